@@ -1,0 +1,217 @@
+/* lama_b200.h -- C-ABI of the B200-native LaMa hot path (liblama_b200.so).
+ *
+ * The reference (iris-ua/iris_lama) has no plugin / FFI layer: the particle-filter SLAM hot path sits
+ * behind plain C++ classes.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  Plain pointers and sizes only; every function returns an
+ * int status (0 = ok, < 0 = error, see LAMA_ERR_*) and lama_last_error() gives the message.
+ * Handles are not thread safe: one host thread per handle (as the reference objects).
+ *
+ * Conventions
+ *   poses       xyr[3] = (x, y, rotation) like lama::Pose2D(x, y, rotation), include/lama/pose2d.h:45
+ *   SE2 states  state[4] = (cos, sin, tx, ty): the raw Sophus SE2 of Pose2D::state, pose2d.h:76
+ *   scans       pts_xyz = N x 3 doubles (PointCloudXYZ::points), sensor_origin[3], sensor_quat_xyzw[4]
+ *               (PointCloudXYZ::sensor_origin_ / sensor_orientation_), include/lama/types.h:111-120
+ *   map cells   absolute unsigned map coordinates as produced by Map::w2m, include/lama/sdm/map.h:125
+ */
+#ifndef LAMA_B200_H
+#define LAMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAMA_OK 0
+#define LAMA_ERR_ARG (-1)
+#define LAMA_ERR_CUDA (-2)
+#define LAMA_ERR_NO_DEVICE (-3)
+#define LAMA_ERR_WINDOW (-4)   /* the map grew outside the device directory window (raise dir_dim) */
+#define LAMA_ERR_POOL (-5)     /* device patch pool exhausted (raise pool_slots) */
+#define LAMA_ERR_OVERFLOW (-6) /* per-scan event log / brushfire heap overflow */
+#define LAMA_ERR_STATE (-7)
+
+/* message of the last failing call on this thread */
+const char* lama_last_error(void);
+/* library / build identification, e.g. "lama_b200 0.1 sm_100a" */
+const char* lama_version(void);
+/* number of visible CUDA devices (0 when none: every create call then fails with LAMA_ERR_NO_DEVICE) */
+int lama_device_count(void);
+
+/* device-side knobs shared by all front ends (no counterpart in the reference) */
+typedef struct lama_device_options {
+    int32_t device;      /* CUDA device ordinal */
+    int32_t dir_dim;     /* map window = dir_dim x dir_dim patches of 32 x 32 cells, power of two, default 64 */
+    int32_t pool_slots;  /* 4 KiB patches in the device pool, 0 = auto */
+    int32_t max_beams;   /* largest scan accepted, default 2048 */
+    int32_t timing;      /* 1: record CUDA-event times per kernel (lama_*_kernel_times) */
+} lama_device_options;
+
+/* ------------------------------------------------------------------------------------------------
+ * PFSlam2D -- include/lama/pf_slam2d.h:132-232, src/pf_slam2d.cpp:106-574
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct lama_pf lama_pf;
+
+typedef struct lama_pf_options { /* PFSlam2D::Options, pf_slam2d.h:132-185 */
+    uint32_t particles;
+    double srr, str, stt, srt;
+    double meas_sigma, meas_sigma_gain;
+    double trans_thresh, rot_thresh;
+    double l2_max;
+    double truncated_ray, truncated_range;
+    double resolution;
+    uint32_t patch_size; /* must be 32 */
+    uint32_t max_iter;
+    int32_t strategy;    /* 0 "gn", 1 "lm" (PFSlam2D::scanMatch always uses Gauss-Newton, pf_slam2d.cpp:423-427) */
+    int32_t threads;     /* accepted for source compatibility; the particle loop runs on the GPU */
+    uint32_t seed;       /* 0 = random_device, pf_slam2d.cpp:131-134 */
+    /* particle sharding over GPUs (one process per GPU): this handle owns particles
+       [shard_rank * particles / shard_count, (shard_rank + 1) * particles / shard_count) */
+    uint32_t shard_rank, shard_count;
+    lama_device_options dev;
+} lama_pf_options;
+
+/* fills the reference defaults (pf_slam2d.h:132-185); `particles` has none there and is set to 1 */
+int lama_pf_options_default(lama_pf_options* o);
+/* PFSlam2D::PFSlam2D(const Options&), pf_slam2d.cpp:106-138 */
+int lama_pf_create(const lama_pf_options* o, lama_pf** out);
+int lama_pf_destroy(lama_pf* h);
+/* PFSlam2D::setPrior, pf_slam2d.cpp:146-149 */
+int lama_pf_set_prior(lama_pf* h, const double xyr[3]);
+/* bool PFSlam2D::update(surface, odometry, timestamp), pf_slam2d.cpp:178-312; *did_update = the bool */
+int lama_pf_update(lama_pf* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                   const double odom_xyr[3], double timestamp, int* did_update);
+/* PFSlam2D::getPose (best particle), pf_slam2d.cpp:332-336 */
+int lama_pf_get_pose(lama_pf* h, double xyr[3]);
+int lama_pf_get_best_particle(lama_pf* h, int* idx);      /* getBestParticleIdx, pf_slam2d.cpp:314-330 */
+int lama_pf_get_neff(lama_pf* h, double* neff);           /* getNeff, pf_slam2d.h:229 */
+/* getParticles(): states P x 4, weights P x 3 = (weight, normalized_weight, weight_sum); either may be NULL */
+int lama_pf_get_particles(lama_pf* h, double* states, double* weights);
+/* Particle::poses history of one particle as xyr triples; returns the length in *count (cap = capacity) */
+int lama_pf_get_trajectory(lama_pf* h, int particle, double* xyr, int cap, int* count);
+/* indices drawn by the last PFSlam2D::resample (pf_slam2d.cpp:537-574); *count = 0 when the last update did not resample */
+int lama_pf_get_last_resample(lama_pf* h, int32_t* idx, int* count);
+/* work counters of the last update and totals: {residual evals (as the reference would count), ray cells,
+   distance-map pops, patches detached, GN iterations, resampled} */
+int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6]);
+/* accumulated CUDA-event kernel times in ms {match, raycast, brushfire, resample} and launches {same + misc} */
+int lama_pf_kernel_times(lama_pf* h, double ms[4], uint64_t launches[5]);
+/* Map::bounds of a particle's map (kind 0 occupancy, 1 distance): min/max cell, *patches = numOfPatches */
+int lama_pf_map_bounds(lama_pf* h, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);
+/* dense window of FrequencyOccupancyMap cells {occupied, visited} + Container "known" bit; arrays may be NULL */
+int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited,
+                             uint8_t* known);
+/* dense window of DynamicDistanceMap::distance_t fields (dynamic_distance_map.h:48-53) + known bit */
+int lama_pf_export_distance(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid,
+                            uint8_t* known, int16_t* ox, int16_t* oy, uint8_t* queued);
+
+/* --- sharded (multi-GPU) operation: the caller moves the small per-scan vectors between ranks ------------
+ * begin : predict (every rank draws the noise of ALL particles, keeping the RNG streams identical) + gate +
+ *         scan matching of the local shard; local_out = P_local x 5 doubles (state[4], log-likelihood)
+ * finish: takes the gathered P x 5 vector, normalises, decides on resampling and returns the systematic
+ *         resampling indices (identical on every rank; rank 0's are broadcast for safety)
+ * apply : applies the indices; new local particle k takes the maps of resident slot local_src[k], which is
+ *         either a local particle (0 .. P_local-1) or a staging slot (P_local .. 2 P_local-1) previously
+ *         filled with lama_pf_particle_unpack from a buffer packed on the ancestor's rank
+ * map   : ray-cast + distance-map update of the local shard
+ * *did_update of begin: 0 = gated (nothing to do), 1 = first scan handled completely, 2 = matched: the
+ * caller must continue with finish [/ apply] / map_update                                                */
+int lama_pf_shard_begin(lama_pf* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                        const double odom_xyr[3], double timestamp, int* did_update, double* local_out);
+int lama_pf_shard_finish(lama_pf* h, const double* all_results, int* resampled, int32_t* idx);
+int lama_pf_shard_apply(lama_pf* h, const int32_t* idx); /* single rank: ancestors are idx themselves */
+int lama_pf_shard_apply_local(lama_pf* h, const int32_t* idx, const int32_t* local_src);
+int lama_pf_shard_map_update(lama_pf* h);
+/* serialise / restore the maps of one resident slot for migration between ranks (host buffers) */
+int lama_pf_particle_pack_size(lama_pf* h, int local_particle, size_t* bytes);
+int lama_pf_particle_pack(lama_pf* h, int local_particle, void* buf, size_t cap, size_t* used);
+int lama_pf_particle_unpack(lama_pf* h, int local_particle, const void* buf, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Slam2D -- include/lama/slam2d.h:91-161, src/slam2d.cpp:92-321
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct lama_slam lama_slam;
+typedef struct lama_slam_options { /* Slam2D::Options, slam2d.h:91-125 */
+    double trans_thresh, rot_thresh, l2_max, truncated_ray, truncated_range, resolution;
+    uint32_t patch_size, max_iter;
+    int32_t strategy; /* 0 "gn", 1 "lm" (slam2d.cpp:226-233) */
+    lama_device_options dev;
+} lama_slam_options;
+int lama_slam_options_default(lama_slam_options* o);
+int lama_slam_create(const lama_slam_options* o, lama_slam** out);
+int lama_slam_destroy(lama_slam* h);
+int lama_slam_set_pose(lama_slam* h, const double xyr[3]);                   /* Slam2D::setPose, slam2d.h:147 */
+int lama_slam_update(lama_slam* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                     const double odom_xyr[3], double timestamp, int* did_update); /* Slam2D::update, slam2d.cpp:143-198 */
+int lama_slam_get_pose(lama_slam* h, double xyr[3]);
+int lama_slam_get_state(lama_slam* h, double state[4]);
+int lama_slam_get_processed_cells(lama_slam* h, uint32_t* n);               /* getNumberOfProcessedCells, slam2d.h:139 */
+int lama_slam_get_counters(lama_slam* h, uint64_t last[6], uint64_t total[6]);
+int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5]);
+int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);
+int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known);
+int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
+                              int16_t* ox, int16_t* oy, uint8_t* queued);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loc2D (match path) -- include/lama/loc2d.h:59-130, src/loc2d.cpp:46-192
+ * The caller fills the public distance_map (loc2d.h:104) through the lama_dm_* grid interface.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct lama_loc lama_loc;
+typedef struct lama_dm lama_dm; /* a device-resident DynamicDistanceMap */
+typedef struct lama_loc_options { /* Loc2D::Options, loc2d.cpp:46-58 */
+    double trans_thresh, rot_thresh, l2_max, resolution;
+    uint32_t patch_size, max_iter;
+    int32_t strategy;
+    double center_xy[2]; /* where to centre the device map window */
+    lama_device_options dev;
+} lama_loc_options;
+int lama_loc_options_default(lama_loc_options* o);
+int lama_loc_create(const lama_loc_options* o, lama_loc** out);              /* Loc2D::Init, loc2d.cpp:61-108 */
+int lama_loc_destroy(lama_loc* h);
+int lama_loc_distance_map(lama_loc* h, lama_dm** dm);                        /* borrowed: Loc2D::distance_map */
+int lama_loc_set_pose(lama_loc* h, const double xyr[3]);                     /* Loc2D::setPose, loc2d.h:117-118 */
+int lama_loc_update(lama_loc* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                    const double odom_xyr[3], double timestamp, int force_update, int* did_update); /* loc2d.cpp:126-192 */
+int lama_loc_get_pose(lama_loc* h, double xyr[3]);
+int lama_loc_get_state(lama_loc* h, double state[4]);
+int lama_loc_get_covar(lama_loc* h, double cov[9]);                          /* Loc2D::getCovar */
+int lama_loc_get_rmse(lama_loc* h, double* rmse);                            /* Loc2D::getRMSE */
+int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2]);                /* {iterations, residual evaluations} */
+
+/* ------------------------------------------------------------------------------------------------
+ * SDM grid interface on a device-resident DynamicDistanceMap
+ * include/lama/sdm/distance_map.h:66-70, dynamic_distance_map.h:55-66
+ * ------------------------------------------------------------------------------------------------ */
+int lama_dm_create(double resolution, uint32_t patch_size, double l2_max, const double center_xy[2], const lama_device_options* dev, lama_dm** out);
+int lama_dm_destroy(lama_dm* dm);
+int lama_dm_max_sqdist(lama_dm* dm, uint32_t* max_sqdist);
+/* addObstacle / removeObstacle on n cells in list order, dynamic_distance_map.cpp:212-242; nothing propagates until update */
+int lama_dm_add_obstacles(lama_dm* dm, const uint32_t* cells_xy, int n);
+int lama_dm_remove_obstacles(lama_dm* dm, const uint32_t* cells_xy, int n);
+/* DynamicDistanceMap::update(), dynamic_distance_map.cpp:160-197; *processed = its return value */
+int lama_dm_update(lama_dm* dm, uint32_t* processed);
+/* DistanceMap::distance(Vector3d, Vector3d* grad) for n points; grad (n x 3) may be NULL */
+int lama_dm_distance(lama_dm* dm, const double* pts_xyz, int n, double* dist, double* grad);
+int lama_dm_bounds(lama_dm* dm, uint32_t mn[2], uint32_t mx[2], int* patches);
+int lama_dm_export(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
+                   int16_t* oy, uint8_t* queued);
+/* upload distance_t fields for a patch-aligned window (x0, y0, w, hgt multiples of 32); cells with known == 0 are left absent */
+int lama_dm_import(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, const uint16_t* sqdist, const uint8_t* valid, const uint8_t* known,
+                   const int16_t* ox, const int16_t* oy, const uint8_t* queued);
+
+/* Solver plug point: the weighted normal equations of MatchSurface2D at `count` SE2 states on one distance
+ * map, so that a host nlls::Strategy (nlls/strategy.h:43-82) can drive the device evaluation.
+ * out = count x 12: {A00,A01,A02,A11,A12,A22, g0,g1,g2, chi2, sum d^2, sum -d^2/meas_sigma} */
+int lama_dm_match_normal_equations(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                                   const double* states, int count, int robust_kind, double robust_param, double meas_sigma, double* out);
+/* Solve(options, MatchSurface2D, cov) for `count` start states (nlls/solver.h:84); states updated in place;
+ * stats = count x 2 {iterations, evaluations}; sums = count x 12 at the final states (may be NULL) */
+int lama_dm_match_solve(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4], double* states,
+                        int count, int strategy, int robust_kind, double robust_param, uint32_t max_iter, uint32_t* stats, double* sums);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMA_B200_H */

@@ -1,0 +1,596 @@
+// capi.cpp -- the extern "C" boundary declared in include/lama_b200.h.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// engine.h declares the status codes as an enum; the C header re-states them as macros, so the C++
+// headers must come first.
+#include "frontend.h"
+
+#include "../../include/lama_b200.h"
+
+using namespace lama_b200;
+
+namespace lama_b200 { int cuda_device_count(); }
+
+namespace {
+thread_local std::string g_err;
+int set_err(const std::string& m, int code)
+{
+    g_err = m;
+    return code;
+}
+DeviceOptions dev_from(const lama_device_options& d)
+{
+    DeviceOptions o;
+    o.device     = d.device;
+    o.dir_dim    = d.dir_dim > 0 ? d.dir_dim : 64;
+    o.pool_slots = d.pool_slots;
+    o.max_beams  = d.max_beams > 0 ? d.max_beams : 2048;
+    o.timing     = d.timing;
+    return o;
+}
+void dev_default(lama_device_options* d)
+{
+    d->device = 0;
+    d->dir_dim = 64;
+    d->pool_slots = 0;
+    d->max_beams = 2048;
+    d->timing = 0;
+}
+void xyr_of(const SE2& s, double xyr[3])
+{
+    xyr[0] = s.tx;
+    xyr[1] = s.ty;
+    xyr[2] = se2_rotation(s);
+}
+void counters_out(const Counters& c, uint64_t o[6])
+{
+    o[0] = c.evals; o[1] = c.ray_cells; o[2] = c.dm_pops; o[3] = c.detached; o[4] = c.gn_iters; o[5] = c.resampled;
+}
+int times_out(Engine* e, double ms[4], uint64_t launches[5])
+{
+    KernelTimes t = e ? e->times() : KernelTimes();
+    if (ms) { ms[0] = t.match_ms; ms[1] = t.raycast_ms; ms[2] = t.brushfire_ms; ms[3] = t.resample_ms; }
+    if (launches) {
+        launches[0] = t.match_launches; launches[1] = t.raycast_launches; launches[2] = t.brushfire_launches; launches[3] = t.resample_launches;
+        launches[4] = t.misc_launches;
+    }
+    return LAMA_OK;
+}
+int export_occ(Engine* e, int particle, uint32_t x0, uint32_t y0, int w, int h, uint16_t* occupied, uint16_t* visited, uint8_t* known)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    std::vector<uint32_t> words((size_t)w * h);
+    int rc = e->export_window(particle, 0, x0, y0, w, h, words.data(), nullptr);
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    for (size_t i = 0; i < words.size(); ++i) {
+        const uint32_t wd = words[i];
+        if (occupied) occupied[i] = (uint16_t)occ_occupied(wd);
+        if (visited) visited[i] = (uint16_t)occ_visited(wd);
+        if (known) known[i] = (wd & ~kOccObstacle) != 0;  // every mutable access counts a visit
+    }
+    return LAMA_OK;
+}
+int export_dm(Engine* e, int particle, bool with_occ, uint32_t x0, uint32_t y0, int w, int h, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
+              int16_t* ox, int16_t* oy, uint8_t* queued)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    std::vector<uint32_t> words((size_t)w * h);
+    int rc = e->export_window(particle, 1, x0, y0, w, h, words.data(), nullptr);
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    std::vector<uint8_t> occ_known;
+    if (with_occ && known) {
+        // The first touch of an occupancy cell always reports "changed" and therefore calls
+        // add/removeObstacle, which marks the distance cell known (frequency_occupancy_map.cpp:65-91,
+        // dynamic_distance_map.cpp:212-242): distance.known = occupancy.known OR touched by the brushfire.
+        std::vector<uint32_t> ow((size_t)w * h);
+        rc = e->export_window(particle, 0, x0, y0, w, h, ow.data(), nullptr);
+        if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+        occ_known.resize(ow.size());
+        for (size_t i = 0; i < ow.size(); ++i) occ_known[i] = (ow[i] & ~kOccObstacle) != 0;
+    }
+    unpack_distance_words(words.data(), occ_known.empty() ? nullptr : occ_known.data(), words.size(), sqdist, valid, known, ox, oy, queued);
+    return LAMA_OK;
+}
+int bounds_out(Engine* e, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    int n = e->bounds(particle, kind, mn, mx);
+    if (n < 0) return set_err("bounds failed", LAMA_ERR_ARG);
+    if (patches) *patches = n;
+    return LAMA_OK;
+}
+}  // namespace
+
+struct lama_pf { PFSlam2D* p; };
+struct lama_slam { Slam2D* s; };
+struct lama_dm { DistanceMapDev* d; bool owned; };
+struct lama_loc { Loc2D* l; lama_dm dm; };
+
+extern "C" {
+
+const char* lama_last_error(void) { return g_err.c_str(); }
+const char* lama_version(void) { return "lama_b200 0.1 sm_100a"; }
+int lama_device_count(void) { return lama_b200::cuda_device_count(); }
+
+// ---- PFSlam2D -------------------------------------------------------------------------------------------
+int lama_pf_options_default(lama_pf_options* o)
+{
+    if (!o) return set_err("null options", LAMA_ERR_ARG);
+    std::memset(o, 0, sizeof(*o));
+    o->particles = 1;
+    o->srr = 0.1; o->str = 0.2; o->stt = 0.1; o->srt = 0.2;
+    o->meas_sigma = 0.05; o->meas_sigma_gain = 3;
+    o->trans_thresh = 0.5; o->rot_thresh = 0.5;
+    o->l2_max = 0.5;
+    o->resolution = 0.05;
+    o->patch_size = 32; o->max_iter = 100;
+    o->strategy = 0; o->threads = -1; o->seed = 0;
+    o->shard_rank = 0; o->shard_count = 1;
+    dev_default(&o->dev);
+    return LAMA_OK;
+}
+int lama_pf_create(const lama_pf_options* o, lama_pf** out)
+{
+    if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
+    PFOptions p;
+    p.particles = o->particles; p.srr = o->srr; p.str = o->str; p.stt = o->stt; p.srt = o->srt;
+    p.meas_sigma = o->meas_sigma; p.meas_sigma_gain = o->meas_sigma_gain; p.trans_thresh = o->trans_thresh; p.rot_thresh = o->rot_thresh;
+    p.l2_max = o->l2_max; p.truncated_ray = o->truncated_ray; p.truncated_range = o->truncated_range; p.resolution = o->resolution;
+    p.patch_size = o->patch_size; p.max_iter = o->max_iter; p.strategy = o->strategy; p.threads = o->threads; p.seed = o->seed;
+    p.shard_rank = o->shard_rank; p.shard_count = o->shard_count ? o->shard_count : 1;
+    p.dev = dev_from(o->dev);
+    std::string err;
+    PFSlam2D* pf = PFSlam2D::create(p, err);
+    if (!pf) return set_err(err, lama_b200::cuda_device_count() < 1 ? LAMA_ERR_NO_DEVICE : LAMA_ERR_ARG);
+    *out = new lama_pf{pf};
+    return LAMA_OK;
+}
+int lama_pf_destroy(lama_pf* h)
+{
+    if (!h) return LAMA_OK;
+    delete h->p;
+    delete h;
+    return LAMA_OK;
+}
+int lama_pf_set_prior(lama_pf* h, const double xyr[3])
+{
+    if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
+    h->p->set_prior(xyr[0], xyr[1], xyr[2]);
+    return LAMA_OK;
+}
+int lama_pf_update(lama_pf* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
+{
+    if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
+    bool did = false;
+    int rc = h->p->update(pts, n, origin, quat, odom, stamp, &did);
+    if (did_update) *did_update = did ? 1 : 0;
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_get_pose(lama_pf* h, double xyr[3])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    xyr_of(h->p->pose((int)h->p->best_particle()), xyr);
+    return LAMA_OK;
+}
+int lama_pf_get_best_particle(lama_pf* h, int* idx)
+{
+    if (!h || !idx) return set_err("null argument", LAMA_ERR_ARG);
+    *idx = (int)h->p->best_particle();
+    return LAMA_OK;
+}
+int lama_pf_get_neff(lama_pf* h, double* neff)
+{
+    if (!h || !neff) return set_err("null argument", LAMA_ERR_ARG);
+    *neff = h->p->neff();
+    return LAMA_OK;
+}
+int lama_pf_get_particles(lama_pf* h, double* states, double* weights)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    for (uint32_t i = 0; i < h->p->particles(); ++i) {
+        if (states) { const SE2& s = h->p->pose(i); states[4 * i] = s.c; states[4 * i + 1] = s.s; states[4 * i + 2] = s.tx; states[4 * i + 3] = s.ty; }
+        if (weights) h->p->weights(i, &weights[3 * i]);
+    }
+    return LAMA_OK;
+}
+int lama_pf_get_trajectory(lama_pf* h, int particle, double* xyr, int cap, int* count)
+{
+    if (!h || particle < 0 || particle >= (int)h->p->particles()) return set_err("bad particle", LAMA_ERR_ARG);
+    std::vector<SE2> t = h->p->has_first_scan() ? h->p->trajectory(particle) : std::vector<SE2>();
+    for (int i = 0; i < (int)t.size() && i < cap && xyr; ++i) xyr_of(t[i], &xyr[3 * i]);
+    if (count) *count = (int)t.size();
+    return LAMA_OK;
+}
+int lama_pf_get_last_resample(lama_pf* h, int32_t* idx, int* count)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    const std::vector<int32_t>& v = h->p->last_resample();
+    if (idx) std::copy(v.begin(), v.end(), idx);
+    if (count) *count = (int)v.size();
+    return LAMA_OK;
+}
+int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    if (last) counters_out(h->p->last_counters(), last);
+    if (total) counters_out(h->p->total_counters(), total);
+    return LAMA_OK;
+}
+int lama_pf_kernel_times(lama_pf* h, double ms[4], uint64_t launches[5])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return times_out(h->p->engine(), ms, launches);
+}
+static int pf_local(lama_pf* h, int particle)
+{
+    int k = particle - h->p->local_begin();
+    return (k < 0 || k >= h->p->local_count()) ? -1 : k;
+}
+int lama_pf_map_bounds(lama_pf* h, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
+{
+    if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
+    return bounds_out(h->p->engine(), pf_local(h, particle), kind, mn, mx, patches);
+}
+int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)
+{
+    if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
+    return export_occ(h->p->engine(), pf_local(h, particle), x0, y0, w, hgt, occupied, visited, known);
+}
+int lama_pf_export_distance(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
+                            int16_t* ox, int16_t* oy, uint8_t* queued)
+{
+    if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
+    return export_dm(h->p->engine(), pf_local(h, particle), true, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
+}
+int lama_pf_shard_begin(lama_pf* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp,
+                        int* did_update, double* local_out)
+{
+    if (!h || !pts || !odom || !local_out) return set_err("null argument", LAMA_ERR_ARG);
+    bool did = false;
+    int rc = h->p->shard_begin(pts, n, origin, quat, odom, stamp, &did, local_out);
+    if (did_update) *did_update = did ? (h->p->last_counters().evals ? 2 : 1) : 0;  // 2 = matched, finish/map pending; 1 = first scan
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_shard_finish(lama_pf* h, const double* all_results, int* resampled, int32_t* idx)
+{
+    if (!h || !all_results || !resampled || !idx) return set_err("null argument", LAMA_ERR_ARG);
+    bool r = false;
+    int rc = h->p->shard_finish(all_results, &r, idx);
+    *resampled = r ? 1 : 0;
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_shard_apply(lama_pf* h, const int32_t* idx)
+{
+    // single-rank form: ancestors are the global indices themselves.  Multi-rank callers use
+    // lama_pf_shard_apply_local below after staging remote ancestors with lama_pf_particle_unpack.
+    if (!h || !idx) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = h->p->shard_apply(idx, idx + h->p->local_begin());
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_shard_apply_local(lama_pf* h, const int32_t* idx, const int32_t* local_src)
+{
+    if (!h || !idx || !local_src) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = h->p->shard_apply(idx, local_src);
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_shard_map_update(lama_pf* h)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = h->p->shard_map_update();
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_particle_pack_size(lama_pf* h, int slot, size_t* bytes)
+{
+    if (!h || !bytes || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
+    int rc = h->p->engine()->pack_size(slot, bytes);
+    return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
+}
+int lama_pf_particle_pack(lama_pf* h, int slot, void* buf, size_t cap, size_t* used)
+{
+    if (!h || !buf || !used || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
+    int rc = h->p->engine()->pack(slot, buf, cap, used);
+    return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
+}
+int lama_pf_particle_unpack(lama_pf* h, int slot, const void* buf, size_t bytes)
+{
+    if (!h || !buf || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
+    int rc = h->p->engine()->unpack(slot, buf, bytes);
+    return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
+}
+
+// ---- Slam2D ---------------------------------------------------------------------------------------------
+int lama_slam_options_default(lama_slam_options* o)
+{
+    if (!o) return set_err("null options", LAMA_ERR_ARG);
+    std::memset(o, 0, sizeof(*o));
+    o->trans_thresh = 0.5; o->rot_thresh = 0.5; o->l2_max = 0.5; o->resolution = 0.05;
+    o->patch_size = 32; o->max_iter = 100; o->strategy = 0;
+    dev_default(&o->dev);
+    return LAMA_OK;
+}
+int lama_slam_create(const lama_slam_options* o, lama_slam** out)
+{
+    if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
+    SlamOptions s;
+    s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
+    s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
+    s.strategy = o->strategy; s.dev = dev_from(o->dev);
+    std::string err;
+    Slam2D* sl = Slam2D::create(s, err);
+    if (!sl) return set_err(err, lama_b200::cuda_device_count() < 1 ? LAMA_ERR_NO_DEVICE : LAMA_ERR_ARG);
+    *out = new lama_slam{sl};
+    return LAMA_OK;
+}
+int lama_slam_destroy(lama_slam* h)
+{
+    if (!h) return LAMA_OK;
+    delete h->s;
+    delete h;
+    return LAMA_OK;
+}
+int lama_slam_set_pose(lama_slam* h, const double xyr[3])
+{
+    if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
+    h->s->set_pose(xyr[0], xyr[1], xyr[2]);
+    return LAMA_OK;
+}
+int lama_slam_update(lama_slam* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
+{
+    if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
+    bool did = false;
+    int rc = h->s->update(pts, n, origin, quat, odom, stamp, &did);
+    if (did_update) *did_update = did ? 1 : 0;
+    return rc == LAMA_OK ? rc : set_err(h->s->error(), rc);
+}
+int lama_slam_get_pose(lama_slam* h, double xyr[3])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    xyr_of(h->s->pose(), xyr);
+    return LAMA_OK;
+}
+int lama_slam_get_state(lama_slam* h, double st[4])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    const SE2& s = h->s->pose();
+    st[0] = s.c; st[1] = s.s; st[2] = s.tx; st[3] = s.ty;
+    return LAMA_OK;
+}
+int lama_slam_get_processed_cells(lama_slam* h, uint32_t* n)
+{
+    if (!h || !n) return set_err("null argument", LAMA_ERR_ARG);
+    *n = h->s->processed_cells();
+    return LAMA_OK;
+}
+int lama_slam_get_counters(lama_slam* h, uint64_t last[6], uint64_t total[6])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    if (last) counters_out(h->s->last_counters(), last);
+    if (total) counters_out(h->s->total_counters(), total);
+    return LAMA_OK;
+}
+int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return times_out(h->s->engine(), ms, launches);
+}
+int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return bounds_out(h->s->engine(), 0, kind, mn, mx, patches);
+}
+int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
+}
+int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
+                              int16_t* oy, uint8_t* queued)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return export_dm(h->s->engine(), 0, true, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
+}
+
+// ---- distance map grid interface --------------------------------------------------------------------------
+int lama_dm_create(double resolution, uint32_t patch_size, double l2_max, const double center_xy[2], const lama_device_options* dev, lama_dm** out)
+{
+    if (!out) return set_err("null argument", LAMA_ERR_ARG);
+    lama_device_options d;
+    if (dev) d = *dev; else dev_default(&d);
+    std::string err;
+    DistanceMapDev* m = DistanceMapDev::create(resolution, patch_size, l2_max, center_xy ? center_xy[0] : 0.0, center_xy ? center_xy[1] : 0.0, dev_from(d), err);
+    if (!m) return set_err(err, lama_b200::cuda_device_count() < 1 ? LAMA_ERR_NO_DEVICE : LAMA_ERR_ARG);
+    *out = new lama_dm{m, true};
+    return LAMA_OK;
+}
+int lama_dm_destroy(lama_dm* dm)
+{
+    if (!dm) return LAMA_OK;
+    if (dm->owned) {
+        delete dm->d;
+        delete dm;
+    }
+    return LAMA_OK;
+}
+int lama_dm_max_sqdist(lama_dm* dm, uint32_t* v)
+{
+    if (!dm || !v) return set_err("null argument", LAMA_ERR_ARG);
+    *v = dm->d->engine()->max_sqdist();
+    return LAMA_OK;
+}
+int lama_dm_add_obstacles(lama_dm* dm, const uint32_t* cells, int n)
+{
+    if (!dm || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
+    return dm->d->add(cells, n, true);
+}
+int lama_dm_remove_obstacles(lama_dm* dm, const uint32_t* cells, int n)
+{
+    if (!dm || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
+    return dm->d->add(cells, n, false);
+}
+int lama_dm_update(lama_dm* dm, uint32_t* processed)
+{
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = dm->d->update(processed);
+    return rc == LAMA_OK ? rc : set_err(dm->d->error(), rc);
+}
+int lama_dm_distance(lama_dm* dm, const double* pts, int n, double* dist, double* grad)
+{
+    if (!dm || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = dm->d->flush_if_pending();
+    if (rc == LAMA_OK) rc = dm->d->engine()->dm_distance(0, pts, n, dist, grad);
+    return rc == LAMA_OK ? rc : set_err(dm->d->engine()->last_error(), rc);
+}
+int lama_dm_bounds(lama_dm* dm, uint32_t mn[2], uint32_t mx[2], int* patches)
+{
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    return bounds_out(dm->d->engine(), 0, 1, mn, mx, patches);
+}
+int lama_dm_export(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox, int16_t* oy,
+                   uint8_t* queued)
+{
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    return export_dm(dm->d->engine(), 0, false, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
+}
+int lama_dm_import(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, const uint16_t* sqdist, const uint8_t* valid, const uint8_t* known,
+                   const int16_t* ox, const int16_t* oy, const uint8_t* queued)
+{
+    if (!dm || !sqdist || !valid || !known) return set_err("null argument", LAMA_ERR_ARG);
+    std::vector<uint32_t> words((size_t)w * hgt);
+    for (size_t i = 0; i < words.size(); ++i) {
+        if (!known[i]) { words[i] = 0; continue; }
+        words[i] = dm_pack(sqdist[i], ox ? ox[i] : 0, oy ? oy[i] : 0, valid[i] != 0, queued && queued[i]);
+    }
+    int rc = dm->d->engine()->import_window(0, 1, x0, y0, w, hgt, words.data());
+    return rc == LAMA_OK ? rc : set_err(dm->d->engine()->last_error(), rc);
+}
+int lama_dm_match_normal_equations(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, const double* states, int count,
+                                   int robust_kind, double robust_param, double meas_sigma, double* out)
+{
+    if (!dm || !pts || !states || !out || count < 1) return set_err("bad argument", LAMA_ERR_ARG);
+    Engine* e = dm->d->engine();
+    int rc = dm->d->flush_if_pending();
+    if (rc == LAMA_OK) rc = e->set_scan(pts, n, origin, quat, 0, 0);
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    SolverOptions so = make_solver(0, 0);
+    so.robust_kind = robust_kind;
+    so.robust_param = robust_param;
+    std::vector<SE2> st((size_t)count);
+    for (int i = 0; i < count; ++i) st[i] = SE2{states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+    std::vector<HostMatchResult> res((size_t)count);
+    rc = e->match(st.data(), count, 0, true, so, meas_sigma, 1, res.data());
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    for (int i = 0; i < count; ++i) std::memcpy(out + (size_t)i * kNumSums, res[i].sums, sizeof(double) * kNumSums);
+    return LAMA_OK;
+}
+int lama_dm_match_solve(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, double* states, int count, int strategy,
+                        int robust_kind, double robust_param, uint32_t max_iter, uint32_t* stats, double* sums)
+{
+    if (!dm || !pts || !states || count < 1) return set_err("bad argument", LAMA_ERR_ARG);
+    Engine* e = dm->d->engine();
+    int rc = dm->d->flush_if_pending();
+    if (rc == LAMA_OK) rc = e->set_scan(pts, n, origin, quat, 0, 0);
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    SolverOptions so = make_solver(strategy, max_iter);
+    so.robust_kind = robust_kind;
+    so.robust_param = robust_param;
+    std::vector<SE2> st((size_t)count);
+    for (int i = 0; i < count; ++i) st[i] = SE2{states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+    std::vector<HostMatchResult> res((size_t)count);
+    rc = e->match(st.data(), count, 0, true, so, 0.05, 0, res.data());
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    for (int i = 0; i < count; ++i) {
+        states[4 * i] = res[i].state.c; states[4 * i + 1] = res[i].state.s; states[4 * i + 2] = res[i].state.tx; states[4 * i + 3] = res[i].state.ty;
+        if (stats) { stats[2 * i] = res[i].iterations; stats[2 * i + 1] = res[i].evals_ref; }
+        if (sums) std::memcpy(sums + (size_t)i * kNumSums, res[i].sums, sizeof(double) * kNumSums);
+    }
+    return LAMA_OK;
+}
+
+// ---- Loc2D ------------------------------------------------------------------------------------------------
+int lama_loc_options_default(lama_loc_options* o)
+{
+    if (!o) return set_err("null options", LAMA_ERR_ARG);
+    std::memset(o, 0, sizeof(*o));
+    o->trans_thresh = 0.5; o->rot_thresh = 0.5; o->l2_max = 1.0; o->resolution = 0.05;
+    o->patch_size = 32; o->max_iter = 100; o->strategy = 0;
+    dev_default(&o->dev);
+    return LAMA_OK;
+}
+int lama_loc_create(const lama_loc_options* o, lama_loc** out)
+{
+    if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
+    LocOptions l;
+    l.trans_thresh = o->trans_thresh; l.rot_thresh = o->rot_thresh; l.l2_max = o->l2_max; l.resolution = o->resolution;
+    l.patch_size = o->patch_size; l.max_iter = o->max_iter; l.strategy = o->strategy; l.center_x = o->center_xy[0]; l.center_y = o->center_xy[1];
+    l.dev = dev_from(o->dev);
+    std::string err;
+    Loc2D* loc = Loc2D::create(l, err);
+    if (!loc) return set_err(err, lama_b200::cuda_device_count() < 1 ? LAMA_ERR_NO_DEVICE : LAMA_ERR_ARG);
+    *out = new lama_loc{loc, lama_dm{loc->distance_map(), false}};
+    return LAMA_OK;
+}
+int lama_loc_destroy(lama_loc* h)
+{
+    if (!h) return LAMA_OK;
+    delete h->l;
+    delete h;
+    return LAMA_OK;
+}
+int lama_loc_distance_map(lama_loc* h, lama_dm** dm)
+{
+    if (!h || !dm) return set_err("null argument", LAMA_ERR_ARG);
+    *dm = &h->dm;
+    return LAMA_OK;
+}
+int lama_loc_set_pose(lama_loc* h, const double xyr[3])
+{
+    if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
+    h->l->set_pose(xyr[0], xyr[1], xyr[2]);
+    return LAMA_OK;
+}
+int lama_loc_update(lama_loc* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int force,
+                    int* did_update)
+{
+    if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
+    bool did = false;
+    int rc = h->l->update(pts, n, origin, quat, odom, stamp, force != 0, &did);
+    if (did_update) *did_update = did ? 1 : 0;
+    return rc == LAMA_OK ? rc : set_err(h->l->error(), rc);
+}
+int lama_loc_get_pose(lama_loc* h, double xyr[3])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    xyr_of(h->l->pose(), xyr);
+    return LAMA_OK;
+}
+int lama_loc_get_state(lama_loc* h, double st[4])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    const SE2& s = h->l->pose();
+    st[0] = s.c; st[1] = s.s; st[2] = s.tx; st[3] = s.ty;
+    return LAMA_OK;
+}
+int lama_loc_get_covar(lama_loc* h, double cov[9])
+{
+    if (!h || !cov) return set_err("null argument", LAMA_ERR_ARG);
+    std::memcpy(cov, h->l->cov(), sizeof(double) * 9);
+    return LAMA_OK;
+}
+int lama_loc_get_rmse(lama_loc* h, double* rmse)
+{
+    if (!h || !rmse) return set_err("null argument", LAMA_ERR_ARG);
+    *rmse = h->l->rmse();
+    return LAMA_OK;
+}
+int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2])
+{
+    if (!h || !stats) return set_err("null argument", LAMA_ERR_ARG);
+    stats[0] = h->l->iterations();
+    stats[1] = h->l->evals();
+    return LAMA_OK;
+}
+
+}  // extern "C"

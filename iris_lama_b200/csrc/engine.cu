@@ -1,0 +1,594 @@
+// engine.cu -- device memory, stream and kernel pipeline behind the front ends.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace lama_b200 {
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e), LAMA_ERR_CUDA); \
+    } while (0)
+
+struct Engine::Impl {
+    cudaStream_t stream = nullptr;
+    StoreView view{};
+    // scan
+    double* d_points = nullptr;
+    ScanParams scan{};
+    // per-launch staging
+    SE2* d_states = nullptr;
+    SE2* h_states = nullptr;  // pinned
+    MatchResult* d_results = nullptr;
+    MatchResult* h_results = nullptr;  // pinned
+    MapUpdateStats* d_stats = nullptr;
+    MapUpdateStats* h_stats = nullptr;  // pinned
+    uint64_t* d_events = nullptr;
+    int32_t* d_idx = nullptr;
+    int32_t* h_idx = nullptr;  // pinned
+    uint32_t* h_status = nullptr;  // pinned
+    int state_cap = 0;
+    RayParams ray{};
+    BrushParams brush{};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // scratch for import/export/distance
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::vector<void*> allocs;
+};
+
+int cuda_device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int Engine::fail(const std::string& what, int code)
+{
+    err_ = what;
+    return code;
+}
+
+static int next_pow2_host(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+Engine* Engine::create(const EngineConfig& cfg, std::string& err)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        err = "no CUDA device available: the lama_b200 hot path has no CPU fallback";
+        return nullptr;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) {
+        err = "invalid device index";
+        return nullptr;
+    }
+    if (cfg.particles < 1 || cfg.dir_dim < 8 || cfg.dir_dim > 128 || (cfg.dir_dim & (cfg.dir_dim - 1)) != 0 || cfg.max_beams < 1 ||
+        cfg.max_beams > 32768 || !(cfg.resolution > 0)) {
+        err = "invalid engine configuration (particles >= 1, dir_dim power of two in [8,128], max_beams <= 32768)";
+        return nullptr;
+    }
+    const double scale = 1.0 / cfg.resolution;
+    uint32_t radius = (uint32_t)std::ceil(cfg.l2_max * scale);  // DynamicDistanceMap::setMaxDistance, dynamic_distance_map.cpp:149-153
+    if (radius > (uint32_t)kDmMaxRadius) {
+        err = "l2_max * scale exceeds 63 cells (packed distance cell limit)";
+        return nullptr;
+    }
+    Engine* e = new Engine();
+    e->cfg_ = cfg;
+    e->max_sqdist_ = radius * radius;
+    if (e->cfg_.pool_slots <= 0) e->cfg_.pool_slots = cfg.particles * 768 + 1024;
+    Impl* d = e->d_ = new Impl();
+    auto bail = [&](const std::string& m) {
+        err = m;
+        delete e;
+        return (Engine*)nullptr;
+    };
+#define CU_NEW(expr)                                                             \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) return bail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    CU_NEW(cudaSetDevice(cfg.device));
+    CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CU_NEW(cudaEventCreate(&d->ev[0]));
+    CU_NEW(cudaEventCreate(&d->ev[1]));
+
+    // directory window centred on (center_x, center_y)
+    const uint32_t cx = w2m(cfg.center_x, scale), cy = w2m(cfg.center_y, scale);
+    e->window_.dim     = cfg.dir_dim;
+    e->window_.base_px = (int32_t)(cx >> kPatchLog2) - cfg.dir_dim / 2;
+    e->window_.base_py = (int32_t)(cy >> kPatchLog2) - cfg.dir_dim / 2;
+
+    StoreView& v = d->view;
+    v.n_slots     = e->cfg_.pool_slots;
+    v.n_particles = cfg.particles;
+    v.window      = e->window_;
+    const size_t dim2 = (size_t)cfg.dir_dim * cfg.dir_dim;
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(p, bytes);
+        if (r == cudaSuccess) d->allocs.push_back(*p);
+        return r;
+    };
+    CU_NEW(dalloc((void**)&v.pool, (size_t)v.n_slots * kPatchBytes));
+    CU_NEW(dalloc((void**)&v.refcount, (size_t)v.n_slots * 4));
+    CU_NEW(dalloc((void**)&v.free_slots, (size_t)v.n_slots * 4));
+    CU_NEW(dalloc((void**)&v.freed, (size_t)v.n_slots * 4));
+    CU_NEW(dalloc((void**)&v.free_count, 64));
+    v.freed_count = v.free_count + 1;
+    v.status      = reinterpret_cast<uint32_t*>(v.free_count + 2);
+    v.counters    = reinterpret_cast<uint64_t*>(v.free_count + 4);
+    CU_NEW(dalloc((void**)&v.dirs, 2 * (size_t)cfg.particles * 2 * dim2 * 4));
+    CU_NEW(dalloc((void**)&d->d_points, (size_t)cfg.max_beams * 3 * 8));
+
+    d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
+    d->ray.hash_cap  = next_pow2_host(std::max(4096, 4 * cfg.max_beams));
+    d->ray.event_cap = next_pow2_host(std::max(2048, cfg.max_beams));
+    d->brush.event_cap = d->ray.event_cap;
+    d->brush.lower_cap = 8192;
+    d->brush.raise_cap = 2048;
+    d->brush.max_sqdist = e->max_sqdist_;
+    CU_NEW(dalloc((void**)&d->d_events, (size_t)cfg.particles * d->ray.event_cap * 8));
+    CU_NEW(dalloc((void**)&d->d_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
+    CU_NEW(dalloc((void**)&d->d_idx, (size_t)cfg.particles * 4));
+    CU_NEW(cudaMallocHost((void**)&d->h_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
+    CU_NEW(cudaMallocHost((void**)&d->h_idx, (size_t)cfg.particles * 4));
+    CU_NEW(cudaMallocHost((void**)&d->h_status, 64));
+
+    const size_t need_ray = raycast_smem_bytes(cfg.dir_dim, d->ray), need_match = match_smem_bytes(cfg.dir_dim, e->max_sqdist_),
+                 need_brush = brushfire_smem_bytes(cfg.dir_dim, d->brush);
+    if (need_ray > 227 * 1024 || need_match > 227 * 1024 || need_brush > 227 * 1024) return bail("shared memory budget exceeded (reduce max_beams / dir_dim)");
+    CU_NEW(configure_kernels(cfg.dir_dim, e->max_sqdist_, d->ray, d->brush));
+
+    launch_init_store(v, 2, d->stream);
+    CU_NEW(cudaGetLastError());
+    CU_NEW(cudaStreamSynchronize(d->stream));
+#undef CU_NEW
+    return e;
+}
+
+Engine::~Engine()
+{
+    if (!d_) return;
+    cudaSetDevice(cfg_.device);
+    if (d_->stream) cudaStreamSynchronize(d_->stream);
+    for (void* p : d_->allocs) cudaFree(p);
+    if (d_->d_states) cudaFree(d_->d_states);
+    if (d_->d_results) cudaFree(d_->d_results);
+    if (d_->h_states) cudaFreeHost(d_->h_states);
+    if (d_->h_results) cudaFreeHost(d_->h_results);
+    if (d_->h_stats) cudaFreeHost(d_->h_stats);
+    if (d_->h_idx) cudaFreeHost(d_->h_idx);
+    if (d_->h_status) cudaFreeHost(d_->h_status);
+    if (d_->d_scratch) cudaFree(d_->d_scratch);
+    if (d_->ev[0]) cudaEventDestroy(d_->ev[0]);
+    if (d_->ev[1]) cudaEventDestroy(d_->ev[1]);
+    if (d_->stream) cudaStreamDestroy(d_->stream);
+    delete d_;
+}
+
+int Engine::synchronize()
+{
+    CU_TRY(cudaSetDevice(cfg_.device));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    return LAMA_OK;
+}
+
+int Engine::set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range)
+{
+    if (!pts || n < 1 || n > cfg_.max_beams) return fail("set_scan: number of beams out of range", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    ScanParams& sp = d_->scan;
+    sp.n_beams         = n;
+    sp.scale           = 1.0 / cfg_.resolution;
+    sp.truncated_ray   = truncated_ray;
+    sp.truncated_range = truncated_range;
+    // Translation3d(sensor_origin) * Quaterniond  (match_surface_2d.cpp:49; Eigen quaternion -> matrix)
+    const double x = quat ? quat[0] : 0, y = quat ? quat[1] : 0, z = quat ? quat[2] : 0, w = quat ? quat[3] : 1;
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    double* l = sp.moving.l;
+    l[0] = 1 - (tyy + tzz); l[1] = txy - twz;       l[2] = txz + twy;
+    l[3] = txy + twz;       l[4] = 1 - (txx + tzz); l[5] = tyz - twx;
+    l[6] = txz - twy;       l[7] = tyz + twx;       l[8] = 1 - (txx + tyy);
+    for (int i = 0; i < 3; ++i) sp.moving.t[i] = origin ? origin[i] : 0.0;
+    // pageable host memory: cudaMemcpyAsync stages through the driver; the copy is tiny (N * 24 B)
+    CU_TRY(cudaMemcpyAsync(d_->d_points, pts, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));  // `pts` may be released by the caller after return
+    return LAMA_OK;
+}
+
+int Engine::ensure_states(int count)
+{
+    if (count <= d_->state_cap) return LAMA_OK;
+    if (d_->d_states) { cudaFree(d_->d_states); cudaFree(d_->d_results); cudaFreeHost(d_->h_states); cudaFreeHost(d_->h_results); }
+    d_->d_states = nullptr; d_->d_results = nullptr; d_->h_states = nullptr; d_->h_results = nullptr;
+    d_->state_cap = 0;
+    const int cap = std::max(count, cfg_.particles);
+    CU_TRY(cudaMalloc((void**)&d_->d_states, (size_t)cap * sizeof(SE2)));
+    CU_TRY(cudaMalloc((void**)&d_->d_results, (size_t)cap * sizeof(MatchResult)));
+    CU_TRY(cudaMallocHost((void**)&d_->h_states, (size_t)cap * sizeof(SE2)));
+    CU_TRY(cudaMallocHost((void**)&d_->h_results, (size_t)cap * sizeof(MatchResult)));
+    d_->state_cap = cap;
+    return LAMA_OK;
+}
+
+int Engine::check_device_status()
+{
+    uint32_t st = *d_->h_status;
+    if (!st) return LAMA_OK;
+    if (st & kErrWindow) return fail("map grew outside the directory window (raise dir_dim)", LAMA_ERR_WINDOW);
+    if (st & kErrPoolEmpty) return fail("patch pool exhausted (raise pool_slots)", LAMA_ERR_POOL);
+    return fail("event log / heap overflow in the map update kernels", LAMA_ERR_OVERFLOW);
+}
+
+uint32_t Engine::device_status()
+{
+    cudaSetDevice(cfg_.device);
+    cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream);
+    cudaStreamSynchronize(d_->stream);
+    return *d_->h_status;
+}
+
+void Engine::store_counters(uint64_t out[4])
+{
+    cudaSetDevice(cfg_.device);
+    uint64_t c[3];
+    int32_t fc = 0;
+    cudaMemcpyAsync(c, d_->view.counters, sizeof(c), cudaMemcpyDeviceToHost, d_->stream);
+    cudaMemcpyAsync(&fc, d_->view.free_count, 4, cudaMemcpyDeviceToHost, d_->stream);
+    cudaStreamSynchronize(d_->stream);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = (uint64_t)fc;
+}
+
+int Engine::match(const SE2* states, int count, int first_particle, bool shared_map, const SolverOptions& so, double meas_sigma, int mode,
+                  HostMatchResult* out)
+{
+    if (count < 1 || first_particle < 0 || (!shared_map && first_particle + count > cfg_.particles) || first_particle >= cfg_.particles)
+        return fail("match: particle range out of bounds", LAMA_ERR_ARG);
+    if (d_->scan.n_beams < 1) return fail("match: no scan uploaded", LAMA_ERR_STATE);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
+    std::memcpy(d_->h_states, states, (size_t)count * sizeof(SE2));
+    CU_TRY(cudaMemcpyAsync(d_->d_states, d_->h_states, (size_t)count * sizeof(SE2), cudaMemcpyHostToDevice, d_->stream));
+    MatchParams mp{};
+    mp.points = d_->d_points;
+    mp.scan = d_->scan;
+    mp.solver = so;
+    mp.meas_sigma = meas_sigma;
+    mp.resolution = cfg_.resolution;
+    mp.max_sqdist = max_sqdist_;
+    mp.set = cur_set_;
+    mp.particle_offset = first_particle;
+    mp.shared_map = shared_map ? 1 : 0;
+    mp.mode = mode;
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
+    launch_match(d_->view, mp, d_->d_states, d_->d_results, count, d_->stream);
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(d_->h_results, d_->d_results, (size_t)count * sizeof(MatchResult), cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    if (timing_) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d_->ev[0], d_->ev[1]);
+        times_.match_ms += ms;
+    }
+    times_.match_launches += 1;
+    static_assert(sizeof(HostMatchResult) == sizeof(MatchResult), "layout");
+    std::memcpy(out, d_->h_results, (size_t)count * sizeof(MatchResult));
+    return LAMA_OK;
+}
+
+int Engine::update_maps(const SE2* states, int first_particle, int count, HostMapStats* out)
+{
+    if (count < 1 || first_particle < 0 || first_particle + count > cfg_.particles) return fail("update_maps: particle range out of bounds", LAMA_ERR_ARG);
+    if (d_->scan.n_beams < 1) return fail("update_maps: no scan uploaded", LAMA_ERR_STATE);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
+    std::memcpy(d_->h_states, states, (size_t)count * sizeof(SE2));
+    CU_TRY(cudaMemcpyAsync(d_->d_states, d_->h_states, (size_t)count * sizeof(SE2), cudaMemcpyHostToDevice, d_->stream));
+    RayParams rp = d_->ray;
+    rp.points = d_->d_points;
+    rp.scan = d_->scan;
+    rp.set = cur_set_;
+    rp.particle_offset = first_particle;
+    BrushParams bp = d_->brush;
+    bp.set = cur_set_;
+    bp.particle_offset = first_particle;
+    cudaEvent_t e2 = nullptr;
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
+    launch_raycast(d_->view, rp, d_->d_states, d_->d_events, d_->d_stats, count, d_->stream);
+    if (timing_) {
+        CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
+        CU_TRY(cudaEventCreate(&e2));
+    }
+    launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
+    if (timing_) CU_TRY(cudaEventRecord(e2, d_->stream));
+    launch_merge_free(d_->view, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(d_->h_stats, d_->d_stats, (size_t)count * sizeof(MapUpdateStats), cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    if (timing_) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, d_->ev[0], d_->ev[1]);
+        cudaEventElapsedTime(&b, d_->ev[1], e2);
+        cudaEventDestroy(e2);
+        times_.raycast_ms += a;
+        times_.brushfire_ms += b;
+    }
+    times_.raycast_launches += 1;
+    times_.brushfire_launches += 1;
+    times_.misc_launches += 1;
+    if (out) {
+        static_assert(sizeof(HostMapStats) == sizeof(MapUpdateStats), "layout");
+        std::memcpy(out, d_->h_stats, (size_t)count * sizeof(MapUpdateStats));
+    }
+    return check_device_status();
+}
+
+int Engine::share_from(int src_particle, int dst_first, int count)
+{
+    if (count == 0) return LAMA_OK;
+    if (src_particle < 0 || src_particle >= cfg_.particles || dst_first < 0 || dst_first + count > cfg_.particles ||
+        (src_particle >= dst_first && src_particle < dst_first + count))
+        return fail("share_from: bad particle range", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    for (int i = 0; i < count; ++i) d_->h_idx[i] = src_particle;
+    CU_TRY(cudaMemcpyAsync(d_->d_idx, d_->h_idx, (size_t)count * 4, cudaMemcpyHostToDevice, d_->stream));
+    launch_release(d_->view, cur_set_, dst_first, count, d_->stream);
+    launch_copy_dirs(d_->view, cur_set_, cur_set_, d_->d_idx, dst_first, count, d_->stream);
+    launch_merge_free(d_->view, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 3;
+    return LAMA_OK;
+}
+
+int Engine::resample(const int32_t* idx)
+{
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const int P = cfg_.particles;
+    for (int i = 0; i < P; ++i) {
+        if (idx[i] < -1 || idx[i] >= P) return fail("resample: index out of range", LAMA_ERR_ARG);
+        d_->h_idx[i] = idx[i];
+    }
+    CU_TRY(cudaMemcpyAsync(d_->d_idx, d_->h_idx, (size_t)P * 4, cudaMemcpyHostToDevice, d_->stream));
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
+    const int other = 1 - cur_set_;
+    launch_copy_dirs(d_->view, cur_set_, other, d_->d_idx, 0, P, d_->stream);  // share first ...
+    launch_release(d_->view, cur_set_, 0, P, d_->stream);                       // ... then drop the old set
+    launch_merge_free(d_->view, d_->stream);
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    if (timing_) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d_->ev[0], d_->ev[1]);
+        times_.resample_ms += ms;
+    }
+    times_.resample_launches += 3;
+    cur_set_ = other;
+    return LAMA_OK;
+}
+
+static int ensure_scratch(Engine::Impl* d, size_t bytes)
+{
+    if (bytes <= d->scratch_bytes) return 0;
+    if (d->d_scratch) cudaFree(d->d_scratch);
+    d->scratch_bytes = 0;
+    if (cudaMalloc(&d->d_scratch, bytes) != cudaSuccess) return -1;
+    d->scratch_bytes = bytes;
+    return 0;
+}
+
+int Engine::dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_add, int n, uint32_t* processed)
+{
+    if (particle < 0 || particle >= cfg_.particles || n < 0) return fail("dm_apply: bad arguments", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    uint32_t total = 0;
+    const int cap = d_->ray.event_cap;
+    std::vector<uint64_t> ev;
+    int done = 0;
+    do {  // event lists longer than the per-particle buffer are applied in chunks; the brushfire runs after each
+          // chunk, which matches the reference only when the whole list fits.  TODO(next): grow the buffer instead.
+        int m = std::min(cap, n - done);
+        ev.resize((size_t)std::max(m, 1));
+        for (int i = 0; i < m; ++i) {
+            uint32_t x = cells_xy[2 * (done + i)], y = cells_xy[2 * (done + i) + 1];
+            if (dir_index(window_, x, y) < 0) return fail("dm_apply: cell outside the directory window", LAMA_ERR_WINDOW);
+            ev[i] = push_record(((uint32_t)i << 1) | (is_add[done + i] ? 1u : 0u), cell_key(window_, x, y));
+        }
+        MapUpdateStats st{};
+        st.events = (uint32_t)m;
+        uint64_t* dev_ev = d_->d_events + (size_t)particle * cap;
+        CU_TRY(cudaMemcpyAsync(dev_ev, ev.data(), (size_t)m * 8, cudaMemcpyHostToDevice, d_->stream));
+        CU_TRY(cudaMemcpyAsync(d_->d_stats + particle, &st, sizeof(st), cudaMemcpyHostToDevice, d_->stream));
+        BrushParams bp = d_->brush;
+        bp.set = cur_set_;
+        bp.particle_offset = particle;
+        // block 0 of this launch must read the event list / stats of `particle`
+        launch_brushfire(d_->view, bp, dev_ev, d_->d_stats + particle, 1, d_->stream);
+        launch_merge_free(d_->view, d_->stream);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(d_->h_stats, d_->d_stats + particle, sizeof(MapUpdateStats), cudaMemcpyDeviceToHost, d_->stream));
+        CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+        CU_TRY(cudaStreamSynchronize(d_->stream));
+        times_.brushfire_launches += 1;
+        times_.misc_launches += 1;
+        total += d_->h_stats[0].dm_pops;
+        done += m;
+        int rc = check_device_status();
+        if (rc != LAMA_OK) return rc;
+    } while (done < n);
+    if (processed) *processed = total;
+    return LAMA_OK;
+}
+
+int Engine::dm_distance(int particle, const double* pts, int n, double* dist, double* grad)
+{
+    if (particle < 0 || particle >= cfg_.particles || n < 1) return fail("dm_distance: bad arguments", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t bp = (size_t)n * 24, bd = (size_t)n * 8, bg = (size_t)n * 24;
+    if (ensure_scratch(d_, bp + bd + bg)) return fail("dm_distance: out of device memory", LAMA_ERR_CUDA);
+    char* base = (char*)d_->d_scratch;
+    CU_TRY(cudaMemcpyAsync(base, pts, bp, cudaMemcpyHostToDevice, d_->stream));
+    launch_distance(d_->view, cur_set_, particle, (const double*)base, n, cfg_.resolution, max_sqdist_, (double*)(base + bp),
+                    grad ? (double*)(base + bp + bd) : nullptr, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(dist, base + bp, bd, cudaMemcpyDeviceToHost, d_->stream));
+    if (grad) CU_TRY(cudaMemcpyAsync(grad, base + bp + bd, bg, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
+int Engine::export_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* words, uint8_t* present)
+{
+    if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1 || w < 1 || h < 1) return fail("export_window: bad arguments", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t bw = (size_t)w * h * 4, bpz = (size_t)w * h;
+    if (ensure_scratch(d_, bw + bpz)) return fail("export_window: out of device memory", LAMA_ERR_CUDA);
+    char* base = (char*)d_->d_scratch;
+    launch_export(d_->view, cur_set_, particle, kind, x0, y0, w, h, (uint32_t*)base, (uint8_t*)(base + bw), d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(words, base, bw, cudaMemcpyDeviceToHost, d_->stream));
+    if (present) CU_TRY(cudaMemcpyAsync(present, base + bw, bpz, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
+int Engine::import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words)
+{
+    if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1 || w < 1 || h < 1 || (x0 | y0 | (uint32_t)w | (uint32_t)h) % kPatchLen)
+        return fail("import_window: window must be patch aligned", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t bw = (size_t)w * h * 4;
+    if (ensure_scratch(d_, bw)) return fail("import_window: out of device memory", LAMA_ERR_CUDA);
+    CU_TRY(cudaMemcpyAsync(d_->d_scratch, words, bw, cudaMemcpyHostToDevice, d_->stream));
+    launch_import(d_->view, cur_set_, particle, kind, x0, y0, w, h, (const uint32_t*)d_->d_scratch, d_->stream);
+    launch_merge_free(d_->view, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 2;
+    return check_device_status();
+}
+
+static const uint32_t kPackMagic = 0x4c414d50u;  // "LAMP"
+
+int Engine::pack_size(int particle, size_t* bytes)
+{
+    if (particle < 0 || particle >= cfg_.particles) return fail("pack_size: bad particle", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
+    std::vector<int32_t> dir(2 * dim2);
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2) * dim2;
+    CU_TRY(cudaMemcpyAsync(dir.data(), src, 2 * dim2 * 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    size_t n = 0;
+    for (int32_t v : dir) n += v >= 0;
+    *bytes = 16 + n * 4 + n * (size_t)kPatchBytes;
+    return LAMA_OK;
+}
+
+int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
+{
+    if (particle < 0 || particle >= cfg_.particles) return fail("pack: bad particle", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
+    std::vector<int32_t> dir(2 * dim2);
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2) * dim2;
+    CU_TRY(cudaMemcpyAsync(dir.data(), src, 2 * dim2 * 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    std::vector<int32_t> entries, slots;
+    uint32_t n_kind[2] = {0, 0};
+    for (int kind = 0; kind < 2; ++kind)
+        for (size_t e = 0; e < dim2; ++e)
+            if (dir[kind * dim2 + e] >= 0) {
+                entries.push_back((int32_t)e);
+                slots.push_back(dir[kind * dim2 + e]);
+                ++n_kind[kind];
+            }
+    const size_t n = slots.size(), need = 16 + n * 4 + n * (size_t)kPatchBytes;
+    if (need > cap) return fail("pack: buffer too small", LAMA_ERR_ARG);
+    uint32_t* hdr = (uint32_t*)buf;
+    hdr[0] = kPackMagic; hdr[1] = (uint32_t)cfg_.dir_dim; hdr[2] = n_kind[0]; hdr[3] = n_kind[1];
+    std::memcpy(hdr + 4, entries.data(), n * 4);
+    if (n) {
+        if (ensure_scratch(d_, n * 4 + n * (size_t)kPatchBytes)) return fail("pack: out of device memory", LAMA_ERR_CUDA);
+        char* base = (char*)d_->d_scratch;
+        uint32_t* d_out = (uint32_t*)base;
+        int32_t* d_slots = (int32_t*)(base + n * (size_t)kPatchBytes);
+        CU_TRY(cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
+        launch_gather_patches(d_->view, d_slots, (int)n, d_out, d_->stream);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync((char*)buf + 16 + n * 4, d_out, n * (size_t)kPatchBytes, cudaMemcpyDeviceToHost, d_->stream));
+        CU_TRY(cudaStreamSynchronize(d_->stream));
+        times_.misc_launches += 1;
+    }
+    *used = need;
+    return LAMA_OK;
+}
+
+int Engine::unpack(int particle, const void* buf, size_t bytes)
+{
+    if (particle < 0 || particle >= cfg_.particles || bytes < 16) return fail("unpack: bad arguments", LAMA_ERR_ARG);
+    const uint32_t* hdr = (const uint32_t*)buf;
+    if (hdr[0] != kPackMagic || hdr[1] != (uint32_t)cfg_.dir_dim) return fail("unpack: incompatible buffer", LAMA_ERR_ARG);
+    const size_t n_occ = hdr[2], n_dm = hdr[3], n = n_occ + n_dm;
+    if (bytes < 16 + n * 4 + n * (size_t)kPatchBytes) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    launch_release(d_->view, cur_set_, particle, 1, d_->stream);
+    launch_merge_free(d_->view, d_->stream);
+    if (n) {
+        if (ensure_scratch(d_, n * 4 + n * (size_t)kPatchBytes)) return fail("unpack: out of device memory", LAMA_ERR_CUDA);
+        char* base = (char*)d_->d_scratch;
+        uint32_t* d_in = (uint32_t*)base;
+        int32_t* d_entries = (int32_t*)(base + n * (size_t)kPatchBytes);
+        CU_TRY(cudaMemcpyAsync(d_entries, hdr + 4, n * 4, cudaMemcpyHostToDevice, d_->stream));
+        CU_TRY(cudaMemcpyAsync(d_in, (const char*)buf + 16 + n * 4, n * (size_t)kPatchBytes, cudaMemcpyHostToDevice, d_->stream));
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)n_occ, d_in, d_->stream);
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + n_occ, (int)n_dm, d_in + n_occ * (size_t)kPatchCells, d_->stream);
+        times_.misc_launches += 2;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    return check_device_status();
+}
+
+int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
+{
+    if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1) return -1;
+    cudaSetDevice(cfg_.device);
+    const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
+    std::vector<int32_t> dir(dim2);
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2 + kind) * dim2;
+    if (cudaMemcpyAsync(dir.data(), src, dim2 * 4, cudaMemcpyDeviceToHost, d_->stream) != cudaSuccess) return -1;
+    cudaStreamSynchronize(d_->stream);
+    int n = 0;
+    mn[0] = mn[1] = 0xffffffffu;
+    mx[0] = mx[1] = 0;
+    for (int py = 0; py < cfg_.dir_dim; ++py)
+        for (int px = 0; px < cfg_.dir_dim; ++px)
+            if (dir[(size_t)py * cfg_.dir_dim + px] >= 0) {
+                uint32_t x = (uint32_t)(window_.base_px + px) << kPatchLog2, y = (uint32_t)(window_.base_py + py) << kPatchLog2;
+                mn[0] = std::min(mn[0], x); mn[1] = std::min(mn[1], y);
+                mx[0] = std::max(mx[0], x + kPatchLen); mx[1] = std::max(mx[1], y + kPatchLen);
+                ++n;
+            }
+    return n;
+}
+
+}  // namespace lama_b200

@@ -1,0 +1,124 @@
+// engine.h -- host-side owner of the device-resident particle maps and the kernel pipeline.
+// Plain C++ interface (no CUDA types) so the front ends and the C-ABI can be compiled by g++.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "lama_core.h"
+#include "match_core.h"
+
+namespace lama_b200 {
+
+struct EngineConfig {
+    int device        = 0;
+    int particles     = 1;      // particles resident on THIS device
+    double resolution = 0.05;
+    double l2_max     = 0.5;
+    int dir_dim       = 64;     // directory window: dir_dim x dir_dim patches of 32 x 32 cells
+    int pool_slots    = 0;      // 0 = auto (particles * 768 + 1024)
+    int max_beams     = 2048;
+    double center_x   = 0.0;    // world position the directory window is centred on
+    double center_y   = 0.0;
+};
+
+struct HostMatchResult {
+    SE2 state;
+    double sums[kNumSums];
+    uint32_t iterations, evals_ref, evals_done, pad;
+};
+
+struct HostMapStats {
+    uint32_t ray_cells, log_records, events, dm_pops;
+};
+
+struct KernelTimes {  // accumulated CUDA-event durations (ms) and launch counts since reset
+    double match_ms = 0, raycast_ms = 0, brushfire_ms = 0, resample_ms = 0;
+    uint64_t match_launches = 0, raycast_launches = 0, brushfire_launches = 0, resample_launches = 0, misc_launches = 0;
+};
+
+class Engine {
+public:
+    static Engine* create(const EngineConfig& cfg, std::string& err);
+    ~Engine();
+
+    const EngineConfig& config() const { return cfg_; }
+    uint32_t max_sqdist() const { return max_sqdist_; }
+    const std::string& last_error() const { return err_; }
+
+    // Uploads one scan (N x 3 doubles, sensor origin, sensor orientation quaternion xyzw).
+    int set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range);
+
+    // Scan matching of `count` states.  Block k uses the map of particle first_particle + k, or, with
+    // shared_map, all of them use the map of first_particle.  mode 0 = solve, 1 = single evaluation.
+    int match(const SE2* states, int count, int first_particle, bool shared_map, const SolverOptions& so, double meas_sigma, int mode,
+              HostMatchResult* out);
+
+    // Ray-cast + distance-map update of particles [first, first+count) at the given poses.
+    int update_maps(const SE2* states, int first_particle, int count, HostMapStats* out);
+
+    // Particles dst_first .. dst_first+count-1 become copy-on-write copies of src_particle (same set).
+    int share_from(int src_particle, int dst_first, int count);
+    // new particle k = old particle idx[k] for all resident slots (PFSlam2D::resample's map copies);
+    // idx[k] == -1 leaves slot k empty.
+    int resample(const int32_t* idx);
+    // Serialise / restore the two maps of one resident slot (particle migration between GPUs).
+    // Layout: {u32 magic, u32 dim, u32 n_occ, u32 n_dm} + (n_occ + n_dm) x u32 directory index + patches (4 KiB each).
+    int pack_size(int particle, size_t* bytes);
+    int pack(int particle, void* buf, size_t cap, size_t* used);
+    int unpack(int particle, const void* buf, size_t bytes);
+
+    // Direct DynamicDistanceMap::addObstacle / removeObstacle calls in list order, then update().
+    int dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_add, int n, uint32_t* processed);
+    // Batched DistanceMap::distance(p, &grad).
+    int dm_distance(int particle, const double* pts, int n, double* dist, double* grad);
+
+    // Dense window export of raw cell words (kind 0 = occupancy, 1 = distance); present may be null.
+    int export_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* words, uint8_t* present);
+    int import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words);
+    // bounding box (in cells) of allocated patches of one map; returns the number of patches
+    int bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2]);
+
+    // sticky device error bits (lama_core.h) -- reads the device word; 0 = ok
+    uint32_t device_status();
+    // {patches allocated, patches detached (COW copies), patches freed, free slots}
+    void store_counters(uint64_t out[4]);
+
+    void enable_timing(bool on) { timing_ = on; }
+    KernelTimes times() const { return times_; }
+    void reset_times() { times_ = KernelTimes(); }
+    int synchronize();
+
+    DirWindow window() const { return window_; }
+
+    struct Impl;
+
+private:
+    Engine() = default;
+    Impl* d_ = nullptr;
+    int ensure_states(int count);
+    EngineConfig cfg_;
+    DirWindow window_{};
+    uint32_t max_sqdist_ = 0;
+    int cur_set_         = 0;
+    bool timing_         = false;
+    KernelTimes times_;
+    std::string err_;
+    int fail(const std::string& what, int code);
+    int check_device_status();
+};
+
+// error codes returned through the C-ABI
+enum : int {
+    LAMA_OK            = 0,
+    LAMA_ERR_ARG       = -1,
+    LAMA_ERR_CUDA      = -2,
+    LAMA_ERR_NO_DEVICE = -3,
+    LAMA_ERR_WINDOW    = -4,   // the map grew outside the directory window
+    LAMA_ERR_POOL      = -5,   // patch pool exhausted
+    LAMA_ERR_OVERFLOW  = -6,   // event log / heap / push-list overflow
+    LAMA_ERR_STATE     = -7,
+};
+
+}  // namespace lama_b200

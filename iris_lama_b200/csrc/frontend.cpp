@@ -1,0 +1,593 @@
+// frontend.cpp -- host orchestration of PFSlam2D / Slam2D / Loc2D over the device Engine.
+#include "frontend.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace lama_b200 {
+
+int cuda_device_count();  // engine.cu
+
+SolverOptions make_solver(int strategy, uint32_t max_iter)
+{
+    SolverOptions so{};
+    so.strategy       = strategy == 1 ? kStrategyLM : kStrategyGN;
+    so.robust_kind    = kRobustCauchy;  // CauchyWeight(0.15): pf_slam2d.cpp:112,426 slam2d.cpp:107 loc2d.cpp:71
+    so.robust_param   = 0.15;
+    so.max_iterations = max_iter;
+    so.eps1 = 1e-4;  // gauss_newton.cpp:40-41 / levenberg_marquardt.cpp:41-43
+    so.eps2 = 1e-4;
+    so.tau  = 1e-4;
+    return so;
+}
+
+static EngineConfig engine_config(const DeviceOptions& dev, int particles, double resolution, double l2_max, double cx, double cy)
+{
+    EngineConfig c;
+    c.device     = dev.device;
+    c.particles  = particles;
+    c.resolution = resolution;
+    c.l2_max     = l2_max;
+    c.dir_dim    = dev.dir_dim > 0 ? dev.dir_dim : 64;
+    c.pool_slots = dev.pool_slots;
+    c.max_beams  = dev.max_beams > 0 ? dev.max_beams : 2048;
+    c.center_x   = cx;
+    c.center_y   = cy;
+    return c;
+}
+
+static double xy_norm(const SE2& s) { return std::sqrt(s.tx * s.tx + s.ty * s.ty); }
+
+// =====================================================================================================
+// PFSlam2D
+// =====================================================================================================
+PFSlam2D* PFSlam2D::create(const PFOptions& o, std::string& err)
+{
+    if (o.particles < 1) { err = "PFSlam2D: Options::particles must be set (>= 1)"; return nullptr; }
+    if (o.patch_size != 32) { err = "PFSlam2D: only patch_size 32 is supported on the device"; return nullptr; }
+    if (o.shard_count < 1 || o.shard_rank >= o.shard_count || o.particles % o.shard_count != 0) {
+        err = "PFSlam2D: particles must divide evenly over shard_count";
+        return nullptr;
+    }
+    if (cuda_device_count() < 1) { err = "no CUDA device available: the lama_b200 hot path has no CPU fallback"; return nullptr; }
+    PFSlam2D* p = new PFSlam2D();
+    p->opt_ = o;
+    p->P_   = o.particles;
+    const int per = (int)(o.particles / o.shard_count);
+    p->lo_ = (int)o.shard_rank * per;
+    p->hi_ = p->lo_ + per;
+    if (p->opt_.seed == 0) p->opt_.seed = std::random_device{}();  // pf_slam2d.cpp:131-132
+    p->gen_.seed(p->opt_.seed);                                    // random::setSeed, pf_slam2d.cpp:134
+    p->pose_.assign(p->P_, SE2{1, 0, 0, 0});
+    p->weight_.assign(p->P_, 0.0);
+    p->nweight_.assign(p->P_, 0.0);
+    p->wsum_.assign(p->P_, 0.0);
+    p->node_of_.assign(p->P_, -1);
+    return p;
+}
+PFSlam2D::~PFSlam2D() = default;
+
+double PFSlam2D::rng_normal(double sigma)  // random::normal, src/random.cpp:69-73
+{
+    std::normal_distribution<double> d(0.0, sigma);
+    return d(gen_);
+}
+double PFSlam2D::rng_uniform()  // random::uniform, src/random.cpp:51-55
+{
+    std::uniform_real_distribution<double> d(0.0, 1.0);
+    return d(gen_);
+}
+
+void PFSlam2D::draw_from_motion(const SE2& delta, SE2& p)
+{
+    const double dx = delta.tx, dy = delta.ty, dr = se2_rotation(delta);
+    double sigma, x, y, yaw;
+    const double sxy = 0.3 * opt_.stt;
+    sigma = opt_.stt * std::fabs(dx) + opt_.str * std::fabs(dr) + sxy * std::fabs(dy);
+    x     = dx + rng_normal(sigma);
+    sigma = opt_.stt * std::fabs(dy) + opt_.str * std::fabs(dr) + sxy * std::fabs(dx);
+    y     = dy + rng_normal(sigma);
+    sigma = opt_.srr * std::fabs(dr) + opt_.srt * xy_norm(delta);
+    yaw   = dr + rng_normal(sigma);
+    yaw   = std::fmod(yaw, 2 * M_PI);
+    if (yaw > M_PI) yaw -= 2 * M_PI;
+    p = se2_mul(p, se2_from_xyr(x, y, yaw));
+}
+
+int PFSlam2D::first_scan(const double odom_xyr[3])
+{
+    // pf_slam2d.cpp:185-228
+    odom_ = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
+    for (uint32_t i = 0; i < P_; ++i) {
+        pose_[i]    = prior_;
+        weight_[i]  = 0.0;
+        wsum_[i]    = 0.0;
+        nodes_.push_back(Node{prior_, -1});
+        node_of_[i] = (int)nodes_.size() - 1;
+    }
+    const int nl = hi_ - lo_;
+    HostMapStats st{};
+    int rc = eng_->update_maps(&prior_, 0, 1, &st);  // particle 0's maps are built from the scan ...
+    if (rc != LAMA_OK) return engine_fail(rc);
+    rc = eng_->share_from(0, 1, nl - 1);              // ... and COW-shared with all the others (:208-216)
+    if (rc != LAMA_OK) return engine_fail(rc);
+    last_.ray_cells = st.ray_cells;
+    last_.dm_pops   = st.dm_pops;
+    has_first_      = true;
+    return LAMA_OK;
+}
+
+bool PFSlam2D::predict_and_gate(const double odom_xyr[3])
+{
+    const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
+    const SE2 odelta   = se2_mul(se2_inv(odom_), odometry);  // Pose2D::operator-, pose2d.cpp:81-84
+    odom_ = odometry;
+    for (uint32_t i = 0; i < P_; ++i) draw_from_motion(odelta, pose_[i]);
+    acc_trans_ += xy_norm(odelta);
+    acc_rot_ += std::fabs(se2_rotation(odelta));
+    if (acc_trans_ <= opt_.trans_thresh && acc_rot_ <= opt_.rot_thresh) return false;
+    acc_trans_ = 0;
+    acc_rot_   = 0;
+    return true;
+}
+
+int PFSlam2D::match_local(double* local_out)
+{
+    const int nl = hi_ - lo_;
+    std::vector<HostMatchResult> res((size_t)nl);
+    // PFSlam2D::scanMatch always uses GaussNewton + CauchyWeight(0.15), pf_slam2d.cpp:423-427
+    SolverOptions so = make_solver(0, opt_.max_iter);
+    int rc = eng_->match(&pose_[lo_], nl, 0, false, so, opt_.meas_sigma, 0, res.data());
+    if (rc != LAMA_OK) return engine_fail(rc);
+    for (int k = 0; k < nl; ++k) {
+        local_out[5 * k + 0] = res[k].state.c;
+        local_out[5 * k + 1] = res[k].state.s;
+        local_out[5 * k + 2] = res[k].state.tx;
+        local_out[5 * k + 3] = res[k].state.ty;
+        local_out[5 * k + 4] = res[k].sums[11];  // calculateLikelihood, pf_slam2d.cpp:393-414
+        last_.evals += res[k].evals_ref + 1;     // + the likelihood pass
+        last_.gn_iters += res[k].iterations;
+    }
+    return LAMA_OK;
+}
+
+void PFSlam2D::absorb_results(const double* all)
+{
+    for (uint32_t i = 0; i < P_; ++i) {
+        pose_[i] = SE2{all[5 * i], all[5 * i + 1], all[5 * i + 2], all[5 * i + 3]};
+        nodes_.push_back(Node{pose_[i], node_of_[i]});  // particle->poses.push_back(pose)
+        node_of_[i] = (int)nodes_.size() - 1;
+        const double l = all[5 * i + 4];
+        wsum_[i] += l;
+        weight_[i] += l;
+    }
+}
+
+void PFSlam2D::normalize()
+{
+    const double gain = 1.0 / (opt_.meas_sigma_gain * opt_.particles);
+    double max_l = weight_[0];
+    for (uint32_t i = 1; i < P_; ++i)
+        if (max_l < weight_[i]) max_l = weight_[i];
+    double sum = 0;
+    for (uint32_t i = 0; i < P_; ++i) {
+        nweight_[i] = std::exp(gain * (weight_[i] - max_l));
+        sum += nweight_[i];
+    }
+    neff_ = 0;
+    for (uint32_t i = 0; i < P_; ++i) {
+        nweight_[i] /= sum;
+        neff_ += nweight_[i] * nweight_[i];
+    }
+    neff_ = 1.0 / neff_;
+}
+
+bool PFSlam2D::compute_resample(std::vector<int32_t>& idx)
+{
+    if (!(neff_ < (opt_.particles * 0.5))) return false;  // pf_slam2d.cpp:279
+    idx.assign(P_, 0);
+    const double interval = 1.0 / (double)P_;
+    double target = interval * rng_uniform();
+    double cw = 0.0;
+    uint32_t n = 0;
+    for (size_t i = 0; i < P_; ++i) {
+        cw += nweight_[i];
+        while (cw > target) {
+            if (n < P_) idx[n] = (int32_t)i;  // the reference writes sample_idx[n++] unguarded (:550-553)
+            ++n;
+            target += interval;
+        }
+    }
+    return true;
+}
+
+void PFSlam2D::apply_resample_host(const std::vector<int32_t>& idx)
+{
+    std::vector<SE2> np(P_);
+    std::vector<double> nw(P_), nn(P_), ns(P_);
+    std::vector<int> nnode(P_);
+    for (uint32_t i = 0; i < P_; ++i) {
+        const int a = idx[i];
+        np[i]    = pose_[a];
+        nw[i]    = 0.0;
+        nn[i]    = nweight_[a];
+        ns[i]    = wsum_[a];
+        nnode[i] = node_of_[a];
+    }
+    pose_.swap(np);
+    weight_.swap(nw);
+    nweight_.swap(nn);
+    wsum_.swap(ns);
+    node_of_.swap(nnode);
+}
+
+void PFSlam2D::finish_counters()
+{
+    uint64_t c[4];
+    eng_->store_counters(c);
+    last_.detached = c[1] - detached_seen_;
+    detached_seen_ = c[1];
+    total_.add(last_);
+}
+
+int PFSlam2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update)
+{
+    if (opt_.shard_count != 1) return fail("PFSlam2D::update on a sharded handle: use the shard_* calls", LAMA_ERR_STATE);
+    std::vector<double> local((size_t)P_ * 5);
+    bool did = false;
+    int rc = shard_begin(pts, n, origin, quat, odom_xyr, stamp, &did, local.data());
+    if (did_update) *did_update = did;
+    if (rc != LAMA_OK || !did || !pending_maps_) return rc;
+    bool resampled = false;
+    std::vector<int32_t> idx(P_);
+    rc = shard_finish(local.data(), &resampled, idx.data());
+    if (rc != LAMA_OK) return rc;
+    if (resampled) {
+        rc = shard_apply(idx.data(), idx.data());
+        if (rc != LAMA_OK) return rc;
+    }
+    return shard_map_update();
+}
+
+int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double, bool* did_update,
+                          double* local_out)
+{
+    *did_update   = false;
+    pending_maps_ = false;
+    last_         = Counters();
+    last_idx_.clear();
+    if (!eng_) {
+        // device state is created on the first scan, centred on the prior
+        std::string e;
+        EngineConfig cfg = engine_config(opt_.dev, 2 * (hi_ - lo_), opt_.resolution, opt_.l2_max, prior_.tx, prior_.ty);
+        if (opt_.shard_count == 1) cfg.particles = hi_ - lo_;  // no staging slots needed without migration
+        cfg.max_beams = std::max(cfg.max_beams, n);
+        Engine* en = Engine::create(cfg, e);
+        if (!en) return fail(e, LAMA_ERR_CUDA);
+        eng_.reset(en);
+        eng_->enable_timing(opt_.dev.timing != 0);
+    }
+    int rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+    if (rc != LAMA_OK) return engine_fail(rc);
+    if (!has_first_) {
+        rc = first_scan(odom_xyr);
+        if (rc != LAMA_OK) return rc;
+        *did_update = true;
+        finish_counters();
+        return LAMA_OK;
+    }
+    if (!predict_and_gate(odom_xyr)) return LAMA_OK;
+    *did_update = true;
+    rc = match_local(local_out);
+    if (rc != LAMA_OK) return rc;
+    pending_maps_ = true;
+    return LAMA_OK;
+}
+
+int PFSlam2D::shard_finish(const double* all_results, bool* resampled, int32_t* idx)
+{
+    if (!pending_maps_) return fail("shard_finish without a pending update", LAMA_ERR_STATE);
+    absorb_results(all_results);
+    normalize();
+    std::vector<int32_t> v;
+    *resampled = compute_resample(v);
+    if (*resampled) std::copy(v.begin(), v.end(), idx);
+    return LAMA_OK;
+}
+
+int PFSlam2D::shard_apply(const int32_t* idx, const int32_t* local_src)
+{
+    if (!pending_maps_) return fail("shard_apply without a pending update", LAMA_ERR_STATE);
+    std::vector<int32_t> v(idx, idx + P_);
+    apply_resample_host(v);
+    last_idx_ = v;
+    last_.resampled = 1;
+    // device side: new local particle k takes the maps of engine slot src[k]
+    const int nl = hi_ - lo_;
+    std::vector<int32_t> src((size_t)eng_->config().particles, 0);
+    for (int k = 0; k < nl; ++k) src[k] = (opt_.shard_count == 1) ? idx[lo_ + k] : local_src[k];
+    for (int k = nl; k < eng_->config().particles; ++k) src[k] = -1;
+    int rc = eng_->resample(src.data());
+    if (rc != LAMA_OK) return engine_fail(rc);
+    return LAMA_OK;
+}
+
+int PFSlam2D::shard_map_update()
+{
+    if (!pending_maps_) return fail("shard_map_update without a pending update", LAMA_ERR_STATE);
+    pending_maps_ = false;
+    const int nl = hi_ - lo_;
+    std::vector<HostMapStats> st((size_t)nl);
+    int rc = eng_->update_maps(&pose_[lo_], 0, nl, st.data());
+    if (rc != LAMA_OK) return engine_fail(rc);
+    for (int k = 0; k < nl; ++k) {
+        last_.ray_cells += st[k].ray_cells;
+        last_.dm_pops += st[k].dm_pops;
+    }
+    finish_counters();
+    return LAMA_OK;
+}
+
+size_t PFSlam2D::best_particle() const
+{
+    size_t best = 0;
+    double ws   = wsum_[0];
+    for (uint32_t i = 1; i < P_; ++i)
+        if (ws < wsum_[i]) {
+            ws   = wsum_[i];
+            best = i;
+        }
+    return best;
+}
+
+std::vector<SE2> PFSlam2D::trajectory(int particle) const
+{
+    std::vector<SE2> out;
+    for (int n = node_of_[particle]; n >= 0; n = nodes_[n].parent) out.push_back(nodes_[n].pose);
+    std::reverse(out.begin(), out.end());
+    return out;
+}
+
+// =====================================================================================================
+// Slam2D
+// =====================================================================================================
+Slam2D* Slam2D::create(const SlamOptions& o, std::string& err)
+{
+    if (o.patch_size != 32) { err = "Slam2D: only patch_size 32 is supported on the device"; return nullptr; }
+    if (cuda_device_count() < 1) { err = "no CUDA device available: the lama_b200 hot path has no CPU fallback"; return nullptr; }
+    Slam2D* s = new Slam2D();
+    s->opt_ = o;
+    return s;
+}
+
+int Slam2D::update_maps()
+{
+    HostMapStats st{};
+    int rc = eng_->update_maps(&pose_, 0, 1, &st);
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    processed_ = st.dm_pops;  // number_of_proccessed_cells_, slam2d.cpp:321
+    last_.ray_cells = st.ray_cells;
+    last_.dm_pops   = st.dm_pops;
+    total_.add(last_);
+    return LAMA_OK;
+}
+
+int Slam2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double, bool* did_update)
+{
+    *did_update = false;
+    last_ = Counters();
+    if (!eng_) {
+        std::string e;
+        EngineConfig cfg = engine_config(opt_.dev, 1, opt_.resolution, opt_.l2_max, pose_.tx, pose_.ty);
+        cfg.max_beams = std::max(cfg.max_beams, n);
+        Engine* en = Engine::create(cfg, e);
+        if (!en) { err_ = e; return LAMA_ERR_CUDA; }
+        eng_.reset(en);
+        eng_->enable_timing(opt_.dev.timing != 0);
+    }
+    const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
+    if (!has_first_) {  // slam2d.cpp:147-161
+        int rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+        if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+        odom_ = odometry;
+        rc = update_maps();
+        if (rc != LAMA_OK) return rc;
+        has_first_  = true;
+        *did_update = true;
+        return LAMA_OK;
+    }
+    const SE2 odelta = se2_mul(se2_inv(odom_), odometry);
+    const SE2 ppose  = se2_mul(pose_, odelta);
+    if (xy_norm(odelta) <= opt_.trans_thresh && std::abs(se2_rotation(odelta)) <= opt_.rot_thresh) return LAMA_OK;  // slam2d.cpp:168-170
+    pose_ = ppose;
+    odom_ = odometry;
+    int rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    HostMatchResult res;
+    rc = eng_->match(&pose_, 1, 0, false, make_solver(opt_.strategy, opt_.max_iter), 0.05, 0, &res);
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    pose_ = res.state;
+    last_.evals    = res.evals_ref;
+    last_.gn_iters = res.iterations;
+    *did_update = true;
+    return update_maps();
+}
+
+// =====================================================================================================
+// DistanceMapDev + Loc2D
+// =====================================================================================================
+DistanceMapDev* DistanceMapDev::create(double resolution, uint32_t patch_size, double l2_max, double cx, double cy, const DeviceOptions& dev,
+                                       std::string& err)
+{
+    if (patch_size != 32) { err = "DynamicDistanceMap: only patch_size 32 is supported on the device"; return nullptr; }
+    if (cuda_device_count() < 1) { err = "no CUDA device available: the lama_b200 hot path has no CPU fallback"; return nullptr; }
+    Engine* en = Engine::create(engine_config(dev, 1, resolution, l2_max, cx, cy), err);
+    if (!en) return nullptr;
+    DistanceMapDev* d = new DistanceMapDev();
+    d->eng_.reset(en);
+    en->enable_timing(dev.timing != 0);
+    return d;
+}
+
+int DistanceMapDev::add(const uint32_t* cells_xy, int n, bool is_add)
+{
+    // addObstacle / removeObstacle only mark cells and queue them; they take effect on the device at
+    // the next update() in call order (the reference's queues are drained by update() as well).
+    for (int i = 0; i < n; ++i) {
+        pend_cells_.push_back(cells_xy[2 * i]);
+        pend_cells_.push_back(cells_xy[2 * i + 1]);
+        pend_kind_.push_back(is_add ? 1 : 0);
+    }
+    return LAMA_OK;
+}
+
+int DistanceMapDev::update(uint32_t* processed)
+{
+    uint32_t p = 0;
+    int rc = eng_->dm_apply(0, pend_cells_.data(), pend_kind_.data(), (int)pend_kind_.size(), &p);
+    pend_cells_.clear();
+    pend_kind_.clear();
+    if (rc != LAMA_OK) err_ = eng_->last_error();
+    if (processed) *processed = p;
+    return rc;
+}
+
+int DistanceMapDev::flush_if_pending()
+{
+    if (pend_kind_.empty()) return LAMA_OK;
+    // Reads of a map with queued-but-unpropagated obstacle changes see the marked cells in the
+    // reference; here the marks are applied lazily, so bring the device up to date first.
+    return update(nullptr);
+}
+
+Loc2D* Loc2D::create(const LocOptions& o, std::string& err)
+{
+    DistanceMapDev* dm = DistanceMapDev::create(o.resolution, o.patch_size, o.l2_max, o.center_x, o.center_y, o.dev, err);
+    if (!dm) return nullptr;
+    Loc2D* l = new Loc2D();
+    l->opt_ = o;
+    l->dm_.reset(dm);
+    return l;
+}
+
+// Solver::calculateCovariance (solver.cpp:133-150): (J^T J)^-1 when J has full column rank, else the
+// thin-SVD pseudo inverse V diag(f(sv)) V^T with f = 1/sv^2 for |sv| > 1e-3 and 3.0 otherwise.
+void covariance_from_sums(const double s[kNumSums], size_t rows, double cov[9])
+{
+    const double A[9] = {s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]};
+    // Jacobi eigen-decomposition of the symmetric 3x3
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = A[i * 3 + j];
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = ((theta >= 0) ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq; }
+            }
+    }
+    double w[3] = {a[0][0], a[1][1], a[2][2]};
+    const double wmax = std::max(w[0], std::max(w[1], w[2])), wmin = std::min(w[0], std::min(w[1], w[2]));
+    const double thr  = 2.220446049250313e-16 * (double)std::max<size_t>(rows, 3);
+    const bool full   = wmax > 0 && std::sqrt(std::max(wmin, 0.0)) > thr * std::sqrt(wmax);
+    if (full) {
+        // Gauss-Jordan with partial pivoting
+        double M[3][6];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { M[i][j] = A[i * 3 + j]; M[i][3 + j] = (i == j) ? 1.0 : 0.0; }
+        bool ok = true;
+        for (int k = 0; k < 3 && ok; ++k) {
+            int piv = k;
+            for (int i = k + 1; i < 3; ++i) if (std::fabs(M[i][k]) > std::fabs(M[piv][k])) piv = i;
+            if (M[piv][k] == 0.0) { ok = false; break; }
+            if (piv != k) for (int j = 0; j < 6; ++j) std::swap(M[k][j], M[piv][j]);
+            double d = M[k][k];
+            for (int j = 0; j < 6; ++j) M[k][j] /= d;
+            for (int i = 0; i < 3; ++i) {
+                if (i == k) continue;
+                double f = M[i][k];
+                for (int j = 0; j < 6; ++j) M[i][j] -= f * M[k][j];
+            }
+        }
+        if (ok) {
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov[i * 3 + j] = M[i][3 + j];
+            return;
+        }
+    }
+    double f[3];
+    for (int i = 0; i < 3; ++i) {
+        double sv = std::sqrt(std::max(w[i], 0.0));
+        f[i] = (std::fabs(sv) > 1.e-3) ? 1.0 / (sv * sv) : 3.0;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += v[i][k] * f[k] * v[j][k];
+            cov[i * 3 + j] = acc;
+        }
+}
+
+int Loc2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double, bool force, bool* did_update)
+{
+    *did_update = false;
+    Engine* eng = dm_->engine();
+    int rc = dm_->flush_if_pending();
+    if (rc != LAMA_OK) { err_ = dm_->error(); return rc; }
+    const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
+    SolverOptions so = make_solver(opt_.strategy, opt_.max_iter);
+    bool scan_set = false;
+    if (!has_first_) {  // loc2d.cpp:128-141
+        odom_      = odometry;
+        has_first_ = true;
+        if (!force) { *did_update = true; return LAMA_OK; }
+        rc = eng->set_scan(pts, n, origin, quat, 0, 0);
+        if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
+        scan_set = true;
+        HostMatchResult r;
+        rc = eng->match(&pose_, 1, 0, false, so, 0.05, 1, &r);
+        if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
+        rmse_ = std::sqrt(r.sums[10] / ((double)((size_t)n - 1)));
+    }
+    const SE2 odelta = se2_mul(se2_inv(odom_), odometry);
+    const SE2 ppose  = se2_mul(pose_, odelta);
+    const bool enough = !(xy_norm(odelta) <= opt_.trans_thresh && std::abs(se2_rotation(odelta)) <= opt_.rot_thresh);
+    if (!force && !enough) return LAMA_OK;
+    pose_ = ppose;
+    odom_ = odometry;
+    if (!scan_set) {
+        rc = eng->set_scan(pts, n, origin, quat, 0, 0);
+        if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
+    }
+    HostMatchResult r;
+    rc = eng->match(&pose_, 1, 0, false, so, 0.05, 0, &r);
+    if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
+    pose_  = r.state;
+    iters_ = r.iterations;
+    evals_ = r.evals_ref + 2;  // + the covariance and rmse evaluations of solver.cpp:110 / loc2d.cpp:178
+    covariance_from_sums(r.sums, (size_t)n, cov_);
+    rmse_ = std::sqrt(r.sums[10] / ((double)((size_t)n - 1)));  // loc2d.cpp:178-180
+    *did_update = true;
+    return LAMA_OK;
+}
+
+void unpack_distance_words(const uint32_t* words, const uint8_t* occ_known, size_t n, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
+                           int16_t* oy, uint8_t* queued)
+{
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t w = words[i];
+        if (sqdist) sqdist[i] = (uint16_t)dm_sqdist(w);
+        if (valid) valid[i] = (w & kDmValid) ? 1 : 0;
+        if (known) known[i] = ((w & kDmKnown) || (occ_known && occ_known[i])) ? 1 : 0;
+        if (ox) ox[i] = (int16_t)dm_ox(w);
+        if (oy) oy[i] = (int16_t)dm_oy(w);
+        if (queued) queued[i] = (w & kDmQueued) ? 1 : 0;
+    }
+}
+
+}  // namespace lama_b200

@@ -1,0 +1,204 @@
+// frontend.h -- host-side mirrors of lama::PFSlam2D / Slam2D / Loc2D on top of the device Engine.
+// The orchestration that the reference keeps on its main thread (odometry sampling with the global
+// mt19937, weight normalisation, systematic resampling, motion gating) stays on the host in fp64 with
+// libstdc++ <random>, so resampling indices are bit-exact with a reference build; the per-particle
+// loops the reference farms to its thread pool (src/pf_slam2d.cpp:254-266,292-302) are the kernels.
+#pragma once
+
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace lama_b200 {
+
+struct DeviceOptions {
+    int device = 0, dir_dim = 64, pool_slots = 0, max_beams = 2048, timing = 0;
+};
+
+// ---- PFSlam2D ---------------------------------------------------------------------------------------
+struct PFOptions {  // include/lama/pf_slam2d.h:132-185
+    uint32_t particles = 1;
+    double srr = 0.1, str = 0.2, stt = 0.1, srt = 0.2;
+    double meas_sigma = 0.05, meas_sigma_gain = 3;
+    double trans_thresh = 0.5, rot_thresh = 0.5;
+    double l2_max = 0.5;
+    double truncated_ray = 0.0, truncated_range = 0.0;
+    double resolution = 0.05;
+    uint32_t patch_size = 32, max_iter = 100;
+    int strategy = 0;
+    int threads = -1;
+    uint32_t seed = 0;
+    uint32_t shard_rank = 0, shard_count = 1;
+    DeviceOptions dev;
+};
+
+struct Counters {
+    uint64_t evals = 0, ray_cells = 0, dm_pops = 0, detached = 0, gn_iters = 0, resampled = 0;
+    void add(const Counters& o)
+    {
+        evals += o.evals; ray_cells += o.ray_cells; dm_pops += o.dm_pops; detached += o.detached; gn_iters += o.gn_iters; resampled += o.resampled;
+    }
+};
+
+class PFSlam2D {
+public:
+    static PFSlam2D* create(const PFOptions& o, std::string& err);
+    ~PFSlam2D();
+
+    void set_prior(double x, double y, double r) { prior_ = se2_from_xyr(x, y, r); }
+    // bool PFSlam2D::update(...)  (src/pf_slam2d.cpp:178-312); returns a LAMA_* status
+    int update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update);
+
+    // sharded split-phase equivalents of update()
+    int shard_begin(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update,
+                    double* local_out);
+    int shard_finish(const double* all_results, bool* resampled, int32_t* idx);
+    int shard_apply(const int32_t* idx, const int32_t* local_src);
+    int shard_map_update();
+
+    size_t best_particle() const;                 // pf_slam2d.cpp:314-330
+    double neff() const { return neff_; }
+    uint32_t particles() const { return P_; }
+    int local_begin() const { return lo_; }
+    int local_count() const { return hi_ - lo_; }
+    const SE2& pose(int i) const { return pose_[i]; }
+    void weights(int i, double w[3]) const { w[0] = weight_[i]; w[1] = nweight_[i]; w[2] = wsum_[i]; }
+    std::vector<SE2> trajectory(int particle) const;
+    const std::vector<int32_t>& last_resample() const { return last_idx_; }
+    const Counters& last_counters() const { return last_; }
+    const Counters& total_counters() const { return total_; }
+    Engine* engine() { return eng_.get(); }
+    const std::string& error() const { return err_; }
+    bool has_first_scan() const { return has_first_; }
+
+private:
+    PFSlam2D() = default;
+    PFOptions opt_;
+    std::unique_ptr<Engine> eng_;
+    std::mt19937 gen_;  // stands in for the reference's process-global generator (src/random.cpp:38-39)
+    uint32_t P_ = 0;
+    int lo_ = 0, hi_ = 0;
+    std::vector<SE2> pose_;
+    std::vector<double> weight_, nweight_, wsum_;
+    struct Node { SE2 pose; int parent; };
+    std::vector<Node> nodes_;       // ancestor-linked pose histories (Particle::poses, pf_slam2d.h:79)
+    std::vector<int> node_of_;
+    SE2 prior_{1, 0, 0, 0}, odom_{1, 0, 0, 0};
+    bool has_first_ = false;
+    double acc_trans_ = 0, acc_rot_ = 0, neff_ = 0;
+    std::vector<int32_t> last_idx_;
+    Counters last_, total_;
+    uint64_t detached_seen_ = 0;
+    std::string err_;
+    bool pending_maps_ = false;
+
+    double rng_normal(double sigma);
+    double rng_uniform();
+    void draw_from_motion(const SE2& delta, SE2& p);     // :365-391
+    bool predict_and_gate(const double odom_xyr[3]);      // :231-249
+    int match_local(double* local_out);                   // :254-266 + scanMatch :416-437
+    void absorb_results(const double* all_results);       // pose/weight bookkeeping of scanMatch
+    void normalize();                                      // :511-535
+    bool compute_resample(std::vector<int32_t>& idx);      // :537-553
+    void apply_resample_host(const std::vector<int32_t>& idx);  // :555-573
+    int first_scan(const double odom_xyr[3]);
+    int fail(const std::string& m, int code) { err_ = m; return code; }
+    int engine_fail(int code) { err_ = eng_->last_error(); return code; }
+    void finish_counters();
+};
+
+// ---- Slam2D -----------------------------------------------------------------------------------------
+struct SlamOptions {  // include/lama/slam2d.h:91-125
+    double trans_thresh = 0.5, rot_thresh = 0.5, l2_max = 0.5, truncated_ray = 0.0, truncated_range = 0.0, resolution = 0.05;
+    uint32_t patch_size = 32, max_iter = 100;
+    int strategy = 0;
+    DeviceOptions dev;
+};
+
+class Slam2D {
+public:
+    static Slam2D* create(const SlamOptions& o, std::string& err);
+    void set_pose(double x, double y, double r) { pose_ = se2_from_xyr(x, y, r); }
+    int update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update);
+    const SE2& pose() const { return pose_; }
+    uint32_t processed_cells() const { return processed_; }
+    const Counters& last_counters() const { return last_; }
+    const Counters& total_counters() const { return total_; }
+    Engine* engine() { return eng_.get(); }
+    const std::string& error() const { return err_; }
+
+private:
+    SlamOptions opt_;
+    std::unique_ptr<Engine> eng_;
+    SE2 pose_{1, 0, 0, 0}, odom_{1, 0, 0, 0};
+    bool has_first_ = false, engine_ready_ = false;
+    uint32_t processed_ = 0;
+    Counters last_, total_;
+    std::string err_;
+    int update_maps();
+};
+
+// ---- device DynamicDistanceMap + Loc2D -------------------------------------------------------------------
+class DistanceMapDev {
+public:
+    static DistanceMapDev* create(double resolution, uint32_t patch_size, double l2_max, double cx, double cy, const DeviceOptions& dev,
+                                  std::string& err);
+    int add(const uint32_t* cells_xy, int n, bool is_add);
+    int update(uint32_t* processed);
+    Engine* engine() { return eng_.get(); }
+    const std::string& error() const { return err_; }
+    int flush_if_pending();
+
+private:
+    std::unique_ptr<Engine> eng_;
+    std::vector<uint32_t> pend_cells_;
+    std::vector<uint8_t> pend_kind_;
+    std::string err_;
+};
+
+struct LocOptions {  // src/loc2d.cpp:46-58
+    double trans_thresh = 0.5, rot_thresh = 0.5, l2_max = 1.0, resolution = 0.05;
+    uint32_t patch_size = 32, max_iter = 100;
+    int strategy = 0;
+    double center_x = 0, center_y = 0;
+    DeviceOptions dev;
+};
+
+class Loc2D {
+public:
+    static Loc2D* create(const LocOptions& o, std::string& err);
+    DistanceMapDev* distance_map() { return dm_.get(); }
+    void set_pose(double x, double y, double r)
+    {
+        pose_      = se2_from_xyr(x, y, r);
+        has_first_ = false;
+    }
+    int update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool force, bool* did_update);
+    const SE2& pose() const { return pose_; }
+    const double* cov() const { return cov_; }
+    double rmse() const { return rmse_; }
+    uint32_t iterations() const { return iters_; }
+    uint32_t evals() const { return evals_; }
+    const std::string& error() const { return err_; }
+
+private:
+    LocOptions opt_;
+    std::unique_ptr<DistanceMapDev> dm_;
+    SE2 pose_{1, 0, 0, 0}, odom_{1, 0, 0, 0};
+    bool has_first_ = false;
+    double cov_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double rmse_ = 0;
+    uint32_t iters_ = 0, evals_ = 0;
+    std::string err_;
+};
+
+// shared helpers
+SolverOptions make_solver(int strategy, uint32_t max_iter);
+void covariance_from_sums(const double sums[kNumSums], size_t rows, double cov[9]);  // Solver::calculateCovariance, solver.cpp:133-150
+void unpack_distance_words(const uint32_t* words, const uint8_t* occ_known, size_t n, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
+                           int16_t* oy, uint8_t* queued);
+
+}  // namespace lama_b200

@@ -1,0 +1,707 @@
+// kernels.cu -- the hand-written sm_100a kernels of the LaMa particle-filter hot path.
+//
+//   k_match      one CTA per particle: the whole Gauss-Newton / LM scan-matching loop
+//                (MatchSurface2D::eval + Solver::solve + GaussNewton, see match_core.h)
+//   k_raycast    one CTA per particle: beam ray-cast into the frequency occupancy map with packed
+//                atomics + ordered replay of threshold crossings (see ray_core.h)
+//   k_brushfire  one warp per particle: DynamicDistanceMap::update() in exact heap order (ddm_core.h)
+//   k_copy_dirs / k_release / k_merge_free   resampling = directory copies with COW reference counts
+//
+// All of them are memory/latency bound integer + fp64 work: no tensor cores.  Directories are staged
+// into shared memory with TMA bulk copies (cp.async.bulk + mbarrier).
+#include "kernels.cuh"
+
+#include "ddm_core.h"
+
+namespace lama_b200 {
+
+namespace {
+
+constexpr int kMatchThreads = 512;
+constexpr int kRayThreads   = 512;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ==================================================================================================
+// k_match
+// ==================================================================================================
+struct MatchShared {
+    uint64_t bar;
+    Affine tf;
+    SE2 state;
+    SolverControl ctl;
+    double warp_part[kMatchThreads / 32][kNumSums];
+    double sums[kNumSums];
+    int done;
+    uint32_t evals_done;
+};
+
+// metric distance of one cell: DynamicDistanceMap::distance(Vector3ui) (dynamic_distance_map.cpp:140-147)
+__device__ __forceinline__ double cell_distance(const uint32_t* __restrict__ pool, const int32_t* dir, const DirWindow& win, uint32_t x, uint32_t y,
+                                                const double* dtab, uint32_t max_sqdist)
+{
+    int di = dir_index(win, x, y);
+    if (di < 0) return dtab[max_sqdist];
+    int slot = dir[di];
+    if (slot < 0) return dtab[max_sqdist];
+    uint32_t w = __ldg(pool + (size_t)slot * kPatchCells + cell_index(x, y));
+    return (w & kDmValid) ? dtab[dm_sqdist(w)] : dtab[max_sqdist];
+}
+
+__device__ __forceinline__ void eval_beam(double s[kNumSums], const Affine& tf, const double* __restrict__ pt, double scale,
+                                          const uint32_t* __restrict__ pool, const int32_t* dir, const DirWindow& win, const double* dtab,
+                                          uint32_t max_sqdist, const SolverOptions& so, double meas_sigma)
+{
+    double hit[3];
+    apply_tf(tf, __ldg(pt), __ldg(pt + 1), __ldg(pt + 2), hit);
+    // hit.z is forced to 0 by eval (match_surface_2d.cpp:71); z never enters the 2-D lookup.
+    const double mx = w2m_nocast(hit[0], scale), my = w2m_nocast(hit[1], scale);
+    const uint32_t dx = (uint32_t)mx, dy = (uint32_t)my;
+    const double mu0 = add_rn(mx, -(double)dx), mu1 = add_rn(my, -(double)dy);
+    double v[4];
+    if ((dx & (kPatchLen - 1)) != kPatchLen - 1 && (dy & (kPatchLen - 1)) != kPatchLen - 1) {
+        // all four stencil cells live in one patch: one directory lookup
+        const double dmax = dtab[max_sqdist];
+        int di = dir_index(win, dx, dy);
+        int slot = di < 0 ? -1 : dir[di];
+        if (slot < 0) {
+            v[0] = v[1] = v[2] = v[3] = dmax;
+        } else {
+            const uint32_t* p = pool + (size_t)slot * kPatchCells + cell_index(dx, dy);
+            uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + kPatchLen), w3 = __ldg(p + kPatchLen + 1);
+            v[0] = (w0 & kDmValid) ? dtab[dm_sqdist(w0)] : dmax;
+            v[1] = (w1 & kDmValid) ? dtab[dm_sqdist(w1)] : dmax;
+            v[2] = (w2 & kDmValid) ? dtab[dm_sqdist(w2)] : dmax;
+            v[3] = (w3 & kDmValid) ? dtab[dm_sqdist(w3)] : dmax;
+        }
+    } else {
+        v[0] = cell_distance(pool, dir, win, dx, dy, dtab, max_sqdist);
+        v[1] = cell_distance(pool, dir, win, dx + 1, dy, dtab, max_sqdist);
+        v[2] = cell_distance(pool, dir, win, dx, dy + 1, dtab, max_sqdist);
+        v[3] = cell_distance(pool, dir, win, dx + 1, dy + 1, dtab, max_sqdist);
+    }
+    BeamEval e = bilinear(v, mu0, mu1, scale, hit[0], hit[1]);
+    accumulate(s, e, so.robust_kind, so.robust_param, meas_sigma);
+}
+
+__global__ void __launch_bounds__(kMatchThreads, 2)
+k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchResult* __restrict__ results)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dim2      = s.window.dim * s.window.dim;
+    int32_t* dir        = reinterpret_cast<int32_t*>(smem_raw);
+    double* dtab        = reinterpret_cast<double*>(smem_raw + (size_t)dim2 * 4);
+    MatchShared& sh     = *reinterpret_cast<MatchShared*>(smem_raw + (size_t)dim2 * 4 + (size_t)(mp.max_sqdist + 1) * 8);
+    const int tid       = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int particle  = mp.shared_map ? mp.particle_offset : mp.particle_offset + blockIdx.x;
+    const int32_t* gdir = dir_of(s, mp.set, particle, kMapDm);
+
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        sh.state = states_in[blockIdx.x];
+        sh.ctl.begin(mp.solver);
+        sh.done       = 0;
+        sh.evals_done = 0;
+    }
+    // sqrt(sqdist) * resolution for every representable squared distance (same expression as
+    // dynamic_distance_map.cpp:143-146, so table entries are bit-identical to the reference's values)
+    for (uint32_t k = tid; k <= mp.max_sqdist; k += blockDim.x) dtab[k] = mul_rn(sqrt((double)k), mp.resolution);
+    __syncthreads();
+    block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
+
+    const int n = mp.scan.n_beams;
+    const bool single = mp.mode == 1;
+    for (;;) {
+        if (tid == 0) sh.tf = compose_tf(sh.state, mp.scan.moving);
+        __syncthreads();
+        double acc[kNumSums];
+#pragma unroll
+        for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
+        const Affine tf = sh.tf;
+        for (int b = tid; b < n; b += blockDim.x)
+            eval_beam(acc, tf, mp.points + 3 * (size_t)b, mp.scan.scale, s.pool, dir, s.window, dtab, mp.max_sqdist, mp.solver, mp.meas_sigma);
+#pragma unroll
+        for (int k = 0; k < kNumSums; ++k) {
+            double v = warp_sum(acc[k]);
+            if (lane == 0) sh.warp_part[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < kNumSums) {
+            double v = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh.warp_part[w][tid];  // fixed order: deterministic
+            sh.sums[tid] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ++sh.evals_done;
+            if (single || sh.done == 1) {
+                sh.done = 2;  // the evaluation just made is the final one
+            } else if (sh.ctl.advance(sh.sums, sh.state)) {
+                // finished.  Unless the last step was reverted, the evaluation just made already is the
+                // one at the final state (likelihood, covariance, rmse); otherwise do one more pass.
+                sh.done = sh.ctl.state_dirty ? 1 : 2;
+            }
+        }
+        __syncthreads();
+        if (sh.done == 2) break;
+    }
+    if (tid == 0) {
+        MatchResult& r = results[blockIdx.x];
+        r.state = sh.state;
+        for (int k = 0; k < kNumSums; ++k) r.sums[k] = sh.sums[k];
+        r.iterations = sh.ctl.iter;
+        r.evals_ref  = sh.ctl.evals_ref;
+        r.evals_done = sh.evals_done;
+        r.pad        = 0;
+    }
+}
+
+// ==================================================================================================
+// k_raycast
+// ==================================================================================================
+struct RayShared {
+    uint64_t bar;
+    Affine tf;
+    uint32_t log_count, event_count, cells, err;
+};
+
+__device__ __forceinline__ void hash_insert(uint32_t* table, int cap, uint32_t key)
+{
+    const uint32_t k1 = key + 1u;  // 0 = empty
+    uint32_t h = (key * 2654435761u) >> 7;
+    for (int i = 0; i < cap; ++i) {
+        uint32_t slot = (h + i) & (cap - 1);
+        uint32_t old  = atomicCAS(&table[slot], 0u, k1);
+        if (old == 0u || old == k1) return;
+    }
+}
+__device__ __forceinline__ bool hash_contains(const uint32_t* table, int cap, uint32_t key)
+{
+    const uint32_t k1 = key + 1u;
+    uint32_t h = (key * 2654435761u) >> 7;
+    for (int i = 0; i < cap; ++i) {
+        uint32_t v = table[(h + i) & (cap - 1)];
+        if (v == k1) return true;
+        if (v == 0u) return false;
+    }
+    return false;
+}
+
+// in-place bitonic sort of n (power of two) 64-bit keys in shared memory by the whole block
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        a[i]   = y;
+                        a[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+__global__ void __launch_bounds__(kRayThreads, 2)
+k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dim2   = s.window.dim * s.window.dim;
+    int32_t* dir     = reinterpret_cast<int32_t*>(smem_raw);
+    uint64_t* log    = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
+    uint64_t* events = log + rp.log_cap;
+    uint32_t* hash   = reinterpret_cast<uint32_t*>(events + rp.event_cap);
+    uint32_t* bitmap = hash + rp.hash_cap;
+    RayShared& sh    = *reinterpret_cast<RayShared*>(bitmap + (dim2 + 31) / 32);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int particle = rp.particle_offset + blockIdx.x;
+    int32_t* gdir      = dir_of(s, rp.set, particle, kMapOcc);
+    const DirWindow win = s.window;
+    const int n = rp.scan.n_beams;
+
+    // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        sh.tf = compose_tf(states[blockIdx.x], rp.scan.moving);
+        sh.log_count = sh.event_count = sh.cells = sh.err = 0;
+    }
+    for (int i = tid; i < rp.hash_cap; i += blockDim.x) hash[i] = 0u;
+    for (int i = tid; i < (dim2 + 31) / 32; i += blockDim.x) bitmap[i] = 0u;
+    __syncthreads();
+    block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
+    const Affine tf = sh.tf;
+
+    // ---- phase 1: mark touched patches, collect the set of hit cells -----------------------------------
+    uint32_t my_err = 0;
+    for (int b = tid; b < n; b += blockDim.x) {
+        const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
+        BeamCells bc = beam_cells(tf, rp.scan, pt);
+        int last = -1;
+        if (bc.mark_hit) {
+            int di = dir_index(win, bc.to[0], bc.to[1]);
+            if (di < 0) my_err |= kErrWindow;
+            else {
+                hash_insert(hash, rp.hash_cap, cell_key(win, bc.to[0], bc.to[1]));
+                atomicOr(&bitmap[di >> 5], 1u << (di & 31));
+            }
+        }
+        RayWalk w(bc);
+        while (w.next()) {
+            int di = dir_index(win, w.x, w.y);
+            if (di < 0) { my_err |= kErrWindow; continue; }
+            if (di != last) {
+                atomicOr(&bitmap[di >> 5], 1u << (di & 31));
+                last = di;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: allocate / detach every touched patch (Map::get mutable + COW) ------------------------
+    for (int w32 = warp; w32 < (dim2 + 31) / 32; w32 += nwarps) {
+        uint32_t bits = bitmap[w32];
+        while (bits) {
+            int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (warp_make_exclusive(s, dir, gdir, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: walk the rays; counters via packed atomics, candidate touches into the log ------------
+    uint32_t my_cells = 0;
+    for (int b = tid; b < n; b += blockDim.x) {
+        const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
+        BeamCells bc = beam_cells(tf, rp.scan, pt);
+        if (bc.mark_hit) {
+            int di = dir_index(win, bc.to[0], bc.to[1]);
+            if (di >= 0 && dir[di] >= 0) {
+                ++my_cells;
+                atomicAdd(patch_ptr(s, dir[di]) + cell_index(bc.to[0], bc.to[1]), kOccHitInc);
+                uint32_t idx = atomicAdd(&sh.log_count, 1u);
+                if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, bc.to[0], bc.to[1]), (uint32_t)b, 0u, true);
+            }
+        }
+        RayWalk w(bc);
+        uint32_t pos = 0;
+        while (w.next()) {
+            ++pos;
+            int di = dir_index(win, w.x, w.y);
+            if (di < 0 || dir[di] < 0) continue;
+            ++my_cells;
+            uint32_t old = atomicAdd(patch_ptr(s, dir[di]) + cell_index(w.x, w.y), kOccMissInc);
+            uint32_t key = cell_key(win, w.x, w.y);
+            if ((old & kOccObstacle) || hash_contains(hash, rp.hash_cap, key)) {
+                uint32_t idx = atomicAdd(&sh.log_count, 1u);
+                if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(key, (uint32_t)b, pos, false);
+            }
+        }
+    }
+    my_cells = __reduce_add_sync(0xffffffffu, my_cells);
+    if (lane == 0 && my_cells) atomicAdd(&sh.cells, my_cells);
+    __syncthreads();
+
+    // ---- phase 4: sort the log by (cell, beam) -------------------------------------------------------------
+    uint32_t count = sh.log_count;
+    if (count > (uint32_t)rp.log_cap) {
+        my_err |= kErrEventLog;
+        count = rp.log_cap;
+    }
+    const int padded = next_pow2((int)count);
+    for (int i = count + tid; i < padded; i += blockDim.x) log[i] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort(log, padded);
+
+    // ---- phase 5: per-cell ordered replay -> obstacle events ----------------------------------------------
+    for (int i = tid; i < (int)count; i += blockDim.x) {
+        const uint32_t key = log_key(log[i]);
+        if (i > 0 && log_key(log[i - 1]) == key) continue;  // not a segment head
+        int end = i + 1;
+        while (end < (int)count && log_key(log[end]) == key) ++end;
+        const uint32_t x = key_x(win, key), y = key_y(win, key);
+        uint32_t* cell = patch_ptr(s, dir[dir_index(win, x, y)]) + cell_index(x, y);
+        const uint32_t final_word = __ldcg(cell);
+        bool obstacle = replay_cell(log, i, end, final_word, [&](bool add, uint32_t seq) {
+            uint32_t idx = atomicAdd(&sh.event_count, 1u);
+            if (idx < (uint32_t)rp.event_cap) events[idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
+        });
+        if (obstacle != ((final_word & kOccObstacle) != 0)) {
+            if (obstacle) atomicOr(cell, kOccObstacle);
+            else atomicAnd(cell, ~kOccObstacle);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 6: order the events like the reference's call sequence and publish them --------------------
+    uint32_t nev = sh.event_count;
+    if (nev > (uint32_t)rp.event_cap) {
+        my_err |= kErrPushOverflow;
+        nev = rp.event_cap;
+    }
+    const int evpad = next_pow2((int)nev);
+    for (int i = nev + tid; i < evpad; i += blockDim.x) events[i] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort(events, evpad);
+    uint64_t* out = events_out + (size_t)blockIdx.x * rp.event_cap;
+    for (int i = tid; i < (int)nev; i += blockDim.x) out[i] = events[i];
+    my_err = __reduce_or_sync(0xffffffffu, my_err);
+    if (lane == 0 && my_err) atomicOr(s.status, my_err);
+    if (tid == 0) {
+        MapUpdateStats& st = stats[blockIdx.x];
+        st.ray_cells   = sh.cells;
+        st.log_records = count;
+        st.events      = nev;
+        st.dm_pops     = 0;
+    }
+}
+
+// ==================================================================================================
+// k_brushfire
+// ==================================================================================================
+struct DeviceDmMap {
+    const StoreView& s;
+    int32_t* dir;       // staged in shared memory
+    int32_t* gdir;
+    uint32_t* excl;     // per directory entry: already verified exclusive during this launch
+    uint32_t* scratch;  // out-of-window accesses land here
+    DirWindow window;
+    int lane;
+    uint32_t err;
+
+    __device__ DeviceDmMap(const StoreView& sv, int32_t* d, int32_t* g, uint32_t* e, uint32_t* sc, int l)
+        : s(sv), dir(d), gdir(g), excl(e), scratch(sc), window(sv.window), lane(l), err(0) {}
+
+    // the mutable Map::get: allocate on touch, copy-on-write detach, mark the cell known
+    __device__ __forceinline__ uint32_t* cell(uint32_t x, uint32_t y)
+    {
+        int di = dir_index(window, x, y);
+        if (di < 0) {
+            err |= kErrWindow;
+            *scratch = 0;
+            return scratch;
+        }
+        if (!((excl[di >> 5] >> (di & 31)) & 1u)) {
+            if (warp_make_exclusive(s, dir, gdir, di, lane) < 0) {
+                err |= kErrPoolEmpty;
+                *scratch = 0;
+                return scratch;
+            }
+            excl[di >> 5] |= 1u << (di & 31);
+            __syncwarp();
+        }
+        uint32_t* p = patch_ptr(s, dir[di]) + cell_index(x, y);
+        uint32_t w  = *p;
+        if (!(w & kDmKnown)) *p = w | kDmKnown;
+        return p;
+    }
+};
+
+// One warp per particle executing the sequential algorithm warp-uniformly: every lane runs the same
+// instruction stream on the same values (loads broadcast, identical stores coalesce), so the 32 lanes
+// are available for the bulk patch zero/copy of allocate-on-touch without any divergence hand-off.
+__global__ void __launch_bounds__(32)
+k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, MapUpdateStats* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dim2    = s.window.dim * s.window.dim;
+    int32_t* dir      = reinterpret_cast<int32_t*>(smem_raw);
+    uint64_t* lower_h = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
+    uint64_t* raise_h = lower_h + bp.lower_cap;
+    uint32_t* excl    = reinterpret_cast<uint32_t*>(raise_h + bp.raise_cap);
+    uint64_t* bar     = reinterpret_cast<uint64_t*>(excl + (dim2 + 31) / 32 + 2);
+    uint32_t* scratch = excl + (dim2 + 31) / 32;
+    const int lane    = threadIdx.x;
+    const int particle = bp.particle_offset + blockIdx.x;
+    int32_t* gdir      = dir_of(s, bp.set, particle, kMapDm);
+
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = lane; i < (dim2 + 31) / 32 + 2; i += 32) excl[i] = 0u;
+    __syncwarp();
+    block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, bar, 0);
+    __syncwarp();
+
+    DeviceDmMap map(s, dir, gdir, excl, scratch, lane);
+    Brushfire<DeviceDmMap> bf(map, Heap{raise_h, 0u, (uint32_t)bp.raise_cap}, Heap{lower_h, 0u, (uint32_t)bp.lower_cap}, bp.max_sqdist);
+
+    const uint32_t nev = stats[blockIdx.x].events;
+    const uint64_t* ev = events + (size_t)blockIdx.x * bp.event_cap;
+    for (uint32_t i = 0; i < nev; ++i) {
+        const uint64_t e   = ev[i];
+        const uint32_t key = (uint32_t)e;
+        const bool add     = ((e >> 32) & 1u) != 0;
+        const uint32_t x = key_x(s.window, key), y = key_y(s.window, key);
+        if (add) bf.add_obstacle(x, y);
+        else bf.remove_obstacle(x, y);
+    }
+    const uint32_t processed = bf.update();
+    const uint32_t err = map.err | bf.err;
+    if (lane == 0) {
+        stats[blockIdx.x].dm_pops = processed;
+        if (err) atomicOr(s.status, err);
+    }
+}
+
+// ==================================================================================================
+// resampling / bookkeeping kernels
+// ==================================================================================================
+__global__ void k_copy_dirs(StoreView s, int src_set, int dst_set, const int32_t* __restrict__ idx, int dst_first)
+{
+    const int p = dst_first + blockIdx.x, kind = blockIdx.y;
+    const int dim2 = s.window.dim * s.window.dim;
+    const int a        = idx[blockIdx.x];
+    const int32_t* src = dir_of(s, src_set, a < 0 ? 0 : a, kind);
+    int32_t* dst       = dir_of(s, dst_set, p, kind);
+    for (int e = threadIdx.x; e < dim2; e += blockDim.x) {
+        int slot = a < 0 ? -1 : src[e];
+        dst[e]   = slot;
+        if (slot >= 0) atomicAdd(&s.refcount[slot], 1);
+    }
+}
+__global__ void k_release(StoreView s, int set, int first)
+{
+    const int p = first + blockIdx.x, kind = blockIdx.y;
+    const int dim2 = s.window.dim * s.window.dim;
+    int32_t* d = dir_of(s, set, p, kind);
+    for (int e = threadIdx.x; e < dim2; e += blockDim.x) {
+        int slot = d[e];
+        if (slot >= 0) {
+            release_slot(s, slot);
+            d[e] = -1;
+        }
+    }
+}
+__global__ void k_merge_free(StoreView s)
+{
+    __shared__ int n, base;
+    if (threadIdx.x == 0) {
+        n    = *s.freed_count;
+        base = *s.free_count;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.free_slots[base + i] = s.freed[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *s.free_count  = base + n;
+        *s.freed_count = 0;
+    }
+}
+__global__ void k_init_store(StoreView s, int n_sets)
+{
+    const size_t total_dir = (size_t)n_sets * s.n_particles * 2 * s.window.dim * s.window.dim;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_dir; i += (size_t)gridDim.x * blockDim.x) s.dirs[i] = -1;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)s.n_slots; i += (size_t)gridDim.x * blockDim.x) {
+        s.free_slots[i] = s.n_slots - 1 - (int)i;  // slot 0 is handed out first
+        s.refcount[i]   = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *s.free_count  = s.n_slots;
+        *s.freed_count = 0;
+        *s.status      = 0;
+        s.counters[0] = s.counters[1] = s.counters[2] = 0;
+    }
+}
+
+__global__ void k_export(StoreView s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* __restrict__ out,
+                         uint8_t* __restrict__ present)
+{
+    const int32_t* d = dir_of(s, set, particle, kind);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < w * h; k += gridDim.x * blockDim.x) {
+        uint32_t x = x0 + (uint32_t)(k % w), y = y0 + (uint32_t)(k / w);
+        int di   = dir_index(s.window, x, y);
+        int slot = di < 0 ? -1 : d[di];
+        out[k]   = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot) + cell_index(x, y));
+        if (present) present[k] = slot >= 0;
+    }
+}
+
+// one warp per patch of the (patch-aligned) window
+__global__ void k_import(StoreView s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* __restrict__ in)
+{
+    const int lane = threadIdx.x & 31;
+    const int pw = w / kPatchLen, ph = h / kPatchLen;
+    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pi >= pw * ph) return;
+    const int px = pi % pw, py = pi / pw;
+    int32_t* d = dir_of(s, set, particle, kind);
+    // does the patch hold anything?
+    uint32_t any = 0;
+    for (int c = lane; c < kPatchCells; c += 32) {
+        int cx = c & (kPatchLen - 1), cy = c >> kPatchLog2;
+        any |= in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
+    }
+    any = __reduce_or_sync(0xffffffffu, any);
+    if (!any) return;
+    const uint32_t x = x0 + px * kPatchLen, y = y0 + py * kPatchLen;
+    int di = dir_index(s.window, x, y);
+    if (di < 0) {
+        if (lane == 0) atomicOr(s.status, kErrWindow);
+        return;
+    }
+    int slot = warp_make_exclusive(s, d, d, di, lane);
+    if (slot < 0) return;
+    uint32_t* dst = patch_ptr(s, slot);
+    for (int c = lane; c < kPatchCells; c += 32) {
+        int cx = c & (kPatchLen - 1), cy = c >> kPatchLog2;
+        dst[c] = in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
+    }
+}
+
+// gather the patches listed in `slots` into a contiguous buffer (particle migration between GPUs)
+__global__ void k_gather_patches(StoreView s, const int32_t* __restrict__ slots, int n, uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pi >= n) return;
+    warp_copy_patch(out + (size_t)pi * kPatchCells, patch_ptr(s, slots[pi]), lane);
+}
+// allocate a patch per listed directory entry of (set, particle, kind) and fill it from `in`
+__global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, const int32_t* __restrict__ entries, int n, const uint32_t* __restrict__ in)
+{
+    const int lane = threadIdx.x & 31;
+    const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pi >= n) return;
+    int32_t* d = dir_of(s, set, particle, kind);
+    int slot = warp_make_exclusive(s, d, d, entries[pi], lane);
+    if (slot < 0) return;
+    warp_copy_patch(patch_ptr(s, slot), in + (size_t)pi * kPatchCells, lane);
+}
+
+__global__ void k_distance(StoreView s, int set, int particle, const double* __restrict__ pts, int n, double resolution, uint32_t max_sqdist,
+                           double* __restrict__ dist, double* __restrict__ grad)
+{
+    const int32_t* d = dir_of(s, set, particle, kMapDm);
+    const double scale = 1.0 / resolution;
+    const double dmax  = mul_rn(sqrt((double)max_sqdist), resolution);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double mx = w2m_nocast(pts[3 * i], scale), my = w2m_nocast(pts[3 * i + 1], scale);
+        const uint32_t dx = (uint32_t)mx, dy = (uint32_t)my;
+        double v[4];
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = dx + (k & 1), y = dy + (k >> 1);
+            int di = dir_index(s.window, x, y);
+            int slot = di < 0 ? -1 : d[di];
+            uint32_t w = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot) + cell_index(x, y));
+            v[k] = (w & kDmValid) ? mul_rn(sqrt((double)dm_sqdist(w)), resolution) : dmax;
+        }
+        BeamEval e = bilinear(v, add_rn(mx, -(double)dx), add_rn(my, -(double)dy), scale, 0, 0);
+        dist[i] = e.dist;
+        if (grad) {
+            grad[3 * i]     = e.gx;
+            grad[3 * i + 1] = e.gy;
+            grad[3 * i + 2] = 0.0;
+        }
+    }
+}
+
+}  // namespace
+
+// ==================================================================================================
+// host-side launch wrappers
+// ==================================================================================================
+size_t match_smem_bytes(int dir_dim, uint32_t max_sqdist)
+{
+    return (size_t)dir_dim * dir_dim * 4 + (size_t)(max_sqdist + 1) * 8 + sizeof(MatchShared) + 16;
+}
+size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
+{
+    const int dim2 = dir_dim * dir_dim;
+    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)rp.hash_cap * 4 + (size_t)((dim2 + 31) / 32) * 4 +
+           sizeof(RayShared) + 16;
+}
+size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
+{
+    const int dim2 = dir_dim * dir_dim;
+    return (size_t)dim2 * 4 + (size_t)(bp.lower_cap + bp.raise_cap) * 8 + (size_t)((dim2 + 31) / 32 + 2) * 4 + 16 + 16;
+}
+
+cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayParams& rp, const BrushParams& bp)
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)match_smem_bytes(dir_dim, max_sqdist_limit));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raycast_smem_bytes(dir_dim, rp));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_brushfire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brushfire_smem_bytes(dir_dim, bp));
+    return e;
+}
+
+void launch_match(const StoreView& s, const MatchParams& mp, const SE2* d_states, MatchResult* d_results, int count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_match<<<count, kMatchThreads, match_smem_bytes(s.window.dim, mp.max_sqdist), st>>>(s, mp, d_states, d_results);
+}
+void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count,
+                    cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_raycast<<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
+}
+void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_brushfire<<<count, 32, brushfire_smem_bytes(s.window.dim, bp), st>>>(s, bp, d_events, d_stats);
+}
+void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_t* d_idx, int dst_first, int count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_copy_dirs<<<dim3(count, 2), 256, 0, st>>>(s, src_set, dst_set, d_idx, dst_first);
+}
+void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_release<<<dim3(count, 2), 256, 0, st>>>(s, set, first);
+}
+void launch_merge_free(const StoreView& s, cudaStream_t st) { k_merge_free<<<1, 256, 0, st>>>(s); }
+void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st) { k_init_store<<<296, 256, 0, st>>>(s, n_sets); }
+void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* d_out, uint8_t* d_present,
+                   cudaStream_t st)
+{
+    int blocks = (w * h + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    k_export<<<blocks, 256, 0, st>>>(s, set, particle, kind, x0, y0, w, h, d_out, d_present);
+}
+void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* d_in, cudaStream_t st)
+{
+    int patches = (w / kPatchLen) * (h / kPatchLen);
+    if (patches <= 0) return;
+    k_import<<<(patches + 3) / 4, 128, 0, st>>>(s, set, particle, kind, x0, y0, w, h, d_in);
+}
+void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, cudaStream_t st)
+{
+    if (n <= 0) return;
+    k_gather_patches<<<(n + 3) / 4, 128, 0, st>>>(s, d_slots, n, d_out);
+}
+void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in, cudaStream_t st)
+{
+    if (n <= 0) return;
+    k_scatter_patches<<<(n + 3) / 4, 128, 0, st>>>(s, set, particle, kind, d_entries, n, d_in);
+}
+void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
+                     double* d_grad, cudaStream_t st)
+{
+    if (n <= 0) return;
+    int blocks = (n + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    k_distance<<<blocks, 256, 0, st>>>(s, set, particle, d_pts, n, resolution, max_sqdist, d_dist, d_grad);
+}
+
+}  // namespace lama_b200

@@ -1,0 +1,85 @@
+// kernels.cuh -- launch interface of the sm_100a kernels (implemented in kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "device_store.cuh"
+#include "match_core.h"
+#include "ray_core.h"
+
+namespace lama_b200 {
+
+struct MatchResult {
+    SE2 state;                 // final state (mode 0) or the evaluated state (mode 1)
+    double sums[kNumSums];     // weighted normal equations, chi2, sum d^2, likelihood at `state`
+    uint32_t iterations;       // Solver iterations performed
+    uint32_t evals_ref;        // residual evaluations the reference's loop performs for this solve
+    uint32_t evals_done;       // residual evaluations this kernel actually performed
+    uint32_t pad;
+};
+
+struct MatchParams {
+    const double* points;  // device, N x 3
+    ScanParams scan;
+    SolverOptions solver;
+    double meas_sigma;
+    double resolution;
+    uint32_t max_sqdist;
+    int set;
+    int particle_offset;   // particle handled by block 0
+    int shared_map;        // 1: every block reads particle `particle_offset`'s map (pose batches on one map)
+    int mode;              // 0 = solve + final evaluation, 1 = single evaluation at the input state
+};
+
+struct RayParams {
+    const double* points;
+    ScanParams scan;
+    int set;
+    int particle_offset;
+    int log_cap, hash_cap, event_cap;  // powers of two
+};
+
+struct BrushParams {
+    int set;
+    int particle_offset;
+    int event_cap;         // stride of the per-particle event lists
+    int lower_cap, raise_cap;
+    uint32_t max_sqdist;
+};
+
+// per-particle outputs of the map update
+struct MapUpdateStats {
+    uint32_t ray_cells;    // cells touched by the ray cast incl. hit cells (work counter C)
+    uint32_t log_records;  // touches that needed ordered replay
+    uint32_t events;       // effective addObstacle/removeObstacle calls
+    uint32_t dm_pops;      // DynamicDistanceMap::update() return value (work counter W)
+};
+
+size_t match_smem_bytes(int dir_dim, uint32_t max_sqdist);
+size_t raycast_smem_bytes(int dir_dim, const RayParams& rp);
+size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp);
+cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayParams& rp, const BrushParams& bp);
+
+void launch_match(const StoreView& s, const MatchParams& mp, const SE2* d_states, MatchResult* d_results, int count, cudaStream_t st);
+void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count,
+                    cudaStream_t st);
+void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st);
+// dst_set[dst_first + k] = src_set[idx[k]] for k in [0, count); bumps reference counts (COW share)
+void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_t* d_idx, int dst_first, int count, cudaStream_t st);
+// releases every patch referenced by particles [first, first+count) of `set` and clears their directories
+void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st);
+void launch_merge_free(const StoreView& s, cudaStream_t st);
+void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st);
+// dense window export: out[j * w + i] = cell word or 0; present[..] = 1 when the patch exists
+void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* d_out,
+                   uint8_t* d_present, cudaStream_t st);
+// dense, patch-aligned window import (x0,y0 multiples of 32; w,h multiples of 32); all-zero patches are skipped
+void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* d_in,
+                   cudaStream_t st);
+void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, cudaStream_t st);
+void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in, cudaStream_t st);
+// batched DistanceMap::distance(point, &grad) on one particle's distance map (SDM grid interface)
+void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
+                     double* d_grad, cudaStream_t st);
+
+}  // namespace lama_b200

@@ -1,0 +1,161 @@
+// ray_core.h -- per-beam geometry, the integer Bresenham walk and the per-cell ordered replay that
+// turns parallel counter updates back into the reference's sequential obstacle events.
+//
+// Reference: PFSlam2D::updateParticleMaps src/pf_slam2d.cpp:439-509 (twin Slam2D::updateMaps
+// src/slam2d.cpp:247-321), Map::computeRay src/sdm/map.cpp:198-227,
+// FrequencyOccupancyMap::setFree/setOccupied src/sdm/frequency_occupancy_map.cpp:65-91.
+//
+// How the parallel kernel stays exact.  The reference walks beams 0..N-1 sequentially; for beam i it
+// first marks the hit cell (setOccupied) and then every interior ray cell (setFree).  Counter updates
+// commute, so all beams add into the packed {occupied, visited} words with atomics.  What does NOT
+// commute is (a) at which touch a cell crosses the 0.25 threshold, which decides the
+// addObstacle/removeObstacle calls, and (b) the order of those calls, which is the push order of the
+// brushfire heaps.  Both only concern cells that receive a hit in this scan or are currently
+// distance-map obstacles; every touch of such a cell is logged as (cell, beam, pos, kind), the log
+// is sorted, and each cell's touches are replayed in beam order from its pre-scan counters.  The
+// obstacle events carry the sequence stamp (beam, pos) of the touch that caused them and are sorted
+// by it, which reproduces the reference's call order exactly.
+#pragma once
+
+#include "lama_core.h"
+
+namespace lama_b200 {
+
+struct ScanParams {
+    MovingTf moving;         // sensor pose in the base frame
+    double scale;            // 1 / resolution
+    double truncated_ray;    // Options::truncated_ray   (pf_slam2d.h:155)
+    double truncated_range;  // Options::truncated_range (pf_slam2d.h:158)
+    int n_beams;
+};
+
+struct BeamCells {
+    uint32_t from[3];
+    uint32_t to[3];
+    bool mark_hit;
+};
+
+// pf_slam2d.cpp:463-499 : world hit / start of one beam and their map cells.
+LAMA_HD BeamCells beam_cells(const Affine& tf, const ScanParams& sp, const double* pt)
+{
+    double start[3] = {tf.t[0], tf.t[1], tf.t[2]};
+    double hit[3], AB[3] = {0, 0, 0};
+    apply_tf(tf, pt[0], pt[1], pt[2], hit);
+    double ray_length = 1.0;
+    BeamCells b;
+    b.mark_hit = true;
+    if (sp.truncated_range > 0.0) {
+        for (int k = 0; k < 3; ++k) AB[k] = add_rn(hit[k], -start[k]);
+        ray_length = sqrt(add_rn(add_rn(mul_rn(AB[0], AB[0]), mul_rn(AB[1], AB[1])), mul_rn(AB[2], AB[2])));
+        if (sp.truncated_range < ray_length) {
+            for (int k = 0; k < 3; ++k) hit[k] = add_rn(start[k], mul_rn(AB[k] / ray_length, sp.truncated_range));
+            b.mark_hit = false;
+        }
+    }
+    if (b.mark_hit && sp.truncated_ray > 0.0) {
+        if (sp.truncated_range == 0.0) {
+            for (int k = 0; k < 3; ++k) AB[k] = add_rn(hit[k], -start[k]);
+            ray_length = sqrt(add_rn(add_rn(mul_rn(AB[0], AB[0]), mul_rn(AB[1], AB[1])), mul_rn(AB[2], AB[2])));
+        }
+        if (sp.truncated_ray < ray_length)
+            for (int k = 0; k < 3; ++k) start[k] = add_rn(hit[k], -mul_rn(AB[k] / ray_length, sp.truncated_ray));
+    }
+    for (int k = 0; k < 3; ++k) {
+        b.to[k]   = w2m(hit[k], sp.scale);
+        b.from[k] = w2m(start[k], sp.scale);
+    }
+    return b;
+}
+
+// Map::computeRay (map.cpp:198-227): integer 3-D Bresenham that emits n-1 cells, excluding both
+// endpoints.  Usage:  RayWalk w(b); while (w.next()) touch(w.x, w.y);
+struct RayWalk {
+    int64_t err[3], coord[3], delta[3], step[3];
+    int n, i;
+    uint32_t x, y;
+    LAMA_HD explicit RayWalk(const BeamCells& b)
+    {
+        n = 0;
+        i = 0;
+        x = y = 0;
+        if (b.from[0] == b.to[0] && b.from[1] == b.to[1] && b.from[2] == b.to[2]) return;
+        for (int j = 0; j < 3; ++j) {
+            err[j]   = 0;
+            coord[j] = (int64_t)b.from[j];
+            delta[j] = (int64_t)b.to[j] - coord[j];
+            step[j]  = delta[j] < 0 ? -1 : 1;
+            delta[j] = delta[j] < 0 ? -delta[j] : delta[j];
+        }
+        int64_t m = delta[0] > delta[1] ? delta[0] : delta[1];
+        n = (int)(m > delta[2] ? m : delta[2]);
+    }
+    LAMA_HD int cells() const { return n > 0 ? n - 1 : 0; }
+    LAMA_HD bool next()
+    {
+        if (i >= n - 1) return false;
+        ++i;
+        for (int j = 0; j < 3; ++j) err[j] += delta[j];
+        for (int j = 0; j < 3; ++j) {
+            if ((err[j] << 1) < n) continue;
+            coord[j] += step[j];
+            err[j] -= n;
+        }
+        x = (uint32_t)coord[0];
+        y = (uint32_t)coord[1];
+        return true;
+    }
+};
+
+// ---- event log ---------------------------------------------------------------------------------------
+// log record: [cell key : 32][beam : 16][pos : 15][kind : 1], kind 1 = hit, 0 = miss.  Sorting the
+// 64-bit records groups touches by cell and orders them by beam (a beam touches a cell at most once).
+LAMA_HD uint64_t log_record(uint32_t key, uint32_t beam, uint32_t pos, bool hit)
+{
+    return ((uint64_t)key << 32) | ((uint64_t)(beam & 0xFFFFu) << 16) | ((uint64_t)(pos & 0x7FFFu) << 1) | (hit ? 1u : 0u);
+}
+LAMA_HD uint32_t log_key(uint64_t r) { return (uint32_t)(r >> 32); }
+LAMA_HD uint32_t log_seq(uint64_t r) { return (uint32_t)r >> 1; }  // (beam << 15) | pos : the order of the reference's calls
+LAMA_HD bool log_is_hit(uint64_t r) { return (r & 1u) != 0; }
+// push record: [seq : 32][cell key : 32]; sorting by it orders obstacle events like the reference.
+LAMA_HD uint64_t push_record(uint32_t seq, uint32_t key) { return ((uint64_t)seq << 32) | key; }
+
+// Replays the sorted touches log[first, last) of ONE cell.  `final_word` is the occupancy word after
+// all of this scan's atomics; returns the new obstacle-mirror bit and emits obstacle events through
+// `emit(kind_is_add, seq)` in call order.
+//   setFree     frequency_occupancy_map.cpp:65-74   setOccupied :81-91
+//   addObstacle / removeObstacle no-op rules: dynamic_distance_map.cpp:217-218,233-234
+template <typename Emit>
+LAMA_HD bool replay_cell(const uint64_t* log, int first, int last, uint32_t final_word, Emit&& emit)
+{
+    uint32_t hits = 0, misses = 0;
+    for (int i = first; i < last; ++i) {
+        if (log_is_hit(log[i])) ++hits;
+        else ++misses;
+    }
+    // counters before this scan (uint16 wrap-around arithmetic like the reference's cells)
+    uint32_t occupied = (occ_occupied(final_word) - hits) & 0x7FFFu;
+    uint32_t visited  = (occ_visited(final_word) - hits - misses) & 0xFFFFu;
+    bool obstacle     = (final_word & kOccObstacle) != 0;
+    for (int i = first; i < last; ++i) {
+        const uint64_t r = log[i];
+        if (log_is_hit(r)) {
+            bool was_occupied = occ_is_occupied(occupied, visited);
+            occupied = (occupied + 1) & 0x7FFFu;
+            visited  = (visited + 1) & 0xFFFFu;
+            if (!was_occupied && occ_is_occupied(occupied, visited) && !obstacle) {
+                obstacle = true;
+                emit(true, log_seq(r));
+            }
+        } else {
+            bool was_free = occ_is_free(occupied, visited);
+            visited = (visited + 1) & 0xFFFFu;
+            if (!was_free && occ_is_free(occupied, visited) && obstacle) {
+                obstacle = false;
+                emit(false, log_seq(r));
+            }
+        }
+    }
+    return obstacle;
+}
+
+}  // namespace lama_b200
