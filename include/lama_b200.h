@@ -46,6 +46,7 @@ typedef struct lama_device_options {
     int32_t pool_slots;  /* 4 KiB patches in the device pool, 0 = auto */
     int32_t max_beams;   /* largest scan accepted, default 2048 */
     int32_t timing;      /* 1: record CUDA-event times per kernel (lama_*_kernel_times) */
+    uint64_t stream;     /* cudaStream_t to launch on (e.g. a torch stream), 0 = the handle creates its own */
 } lama_device_options;
 
 /* ------------------------------------------------------------------------------------------------
@@ -82,6 +83,14 @@ int lama_pf_set_prior(lama_pf* h, const double xyr[3]);
 /* bool PFSlam2D::update(surface, odometry, timestamp), pf_slam2d.cpp:178-312; *did_update = the bool */
 int lama_pf_update(lama_pf* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
                    const double odom_xyr[3], double timestamp, int* did_update);
+/* Device-resident inputs: copy n_scans x n x 3 doubles into HBM once, then run update() on scan `index`
+   without any host->device transfer of points (same semantics as lama_pf_update otherwise) */
+int lama_pf_stage_scans(lama_pf* h, const double* pts_xyz, int n_scans, int n);
+int lama_pf_update_staged(lama_pf* h, int index, const double sensor_origin[3], const double sensor_quat_xyzw[4], const double odom_xyr[3],
+                          double timestamp, int* did_update);
+/* bytes moved host->device [0] and device->host [1] by the update path since the last reset (reset != 0 also
+   clears the kernel timers) */
+int lama_pf_get_traffic(lama_pf* h, uint64_t bytes[2], int reset);
 /* PFSlam2D::getPose (best particle), pf_slam2d.cpp:332-336 */
 int lama_pf_get_pose(lama_pf* h, double xyr[3]);
 int lama_pf_get_best_particle(lama_pf* h, int* idx);      /* getBestParticleIdx, pf_slam2d.cpp:314-330 */

@@ -31,7 +31,8 @@ class LamaError(RuntimeError):
 
 
 class DeviceOptions(C.Structure):
-    _fields_ = [("device", C.c_int32), ("dir_dim", C.c_int32), ("pool_slots", C.c_int32), ("max_beams", C.c_int32), ("timing", C.c_int32)]
+    _fields_ = [("device", C.c_int32), ("dir_dim", C.c_int32), ("pool_slots", C.c_int32), ("max_beams", C.c_int32), ("timing", C.c_int32),
+                ("stream", C.c_uint64)]
 
 
 class PFOptions(C.Structure):
@@ -58,6 +59,7 @@ class LocOptions(C.Structure):
 EXPORTED_SYMBOLS = [
     "lama_last_error", "lama_version", "lama_device_count",
     "lama_pf_options_default", "lama_pf_create", "lama_pf_destroy", "lama_pf_set_prior", "lama_pf_update", "lama_pf_get_pose",
+    "lama_pf_stage_scans", "lama_pf_update_staged", "lama_pf_get_traffic",
     "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample",
     "lama_pf_get_counters", "lama_pf_kernel_times", "lama_pf_map_bounds", "lama_pf_export_occupancy", "lama_pf_export_distance",
     "lama_pf_shard_begin", "lama_pf_shard_finish", "lama_pf_shard_apply", "lama_pf_shard_apply_local", "lama_pf_shard_map_update",
@@ -159,7 +161,7 @@ class PFSlam2D:
         _chk(lib().lama_pf_options_default(C.byref(o)))
         o.particles = particles
         for k, v in kw.items():
-            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing"):
+            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing", "stream"):
                 setattr(o.dev, k, v)
             else:
                 setattr(o, k, v)
@@ -188,6 +190,24 @@ class PFSlam2D:
         did = C.c_int(0)
         _chk(lib().lama_pf_update(self.h, pp, C.c_int(p.size // 3), op, qp, odp, C.c_double(timestamp), C.byref(did)))
         return bool(did.value)
+
+    def stageScans(self, scans):
+        """scans: (T, N, 3) float64, copied into device memory once."""
+        s, sp = _d(scans)
+        _chk(lib().lama_pf_stage_scans(self.h, sp, C.c_int(s.shape[0]), C.c_int(s.shape[1])))
+
+    def updateStaged(self, index, odom, timestamp=0.0, origin=_ID3, quat=_IDQ) -> bool:
+        o, op = _d(origin)
+        q, qp = _d(quat)
+        od, odp = _d(odom)
+        did = C.c_int(0)
+        _chk(lib().lama_pf_update_staged(self.h, C.c_int(index), op, qp, odp, C.c_double(timestamp), C.byref(did)))
+        return bool(did.value)
+
+    def traffic(self, reset=False):
+        b = np.zeros(2, np.uint64)
+        _chk(lib().lama_pf_get_traffic(self.h, _vp(b), C.c_int(int(reset))))
+        return int(b[0]), int(b[1])
 
     def getPose(self):
         out = np.zeros(3)
@@ -294,7 +314,7 @@ class Slam2D:
         o = SlamOptions()
         _chk(lib().lama_slam_options_default(C.byref(o)))
         for k, v in kw.items():
-            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing"):
+            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing", "stream"):
                 setattr(o.dev, k, v)
             else:
                 setattr(o, k, v)
@@ -368,7 +388,7 @@ class DynamicDistanceMap:
             self.h = handle
             self.owned = False
             return
-        d = DeviceOptions(device=0, dir_dim=64, pool_slots=0, max_beams=2048, timing=0)
+        d = DeviceOptions(device=0, dir_dim=64, pool_slots=0, max_beams=2048, timing=0, stream=0)
         for k, v in dev.items():
             setattr(d, k, v)
         c, cp = _d(center)
@@ -454,7 +474,7 @@ class Loc2D:
         o = LocOptions()
         _chk(lib().lama_loc_options_default(C.byref(o)))
         for k, v in kw.items():
-            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing"):
+            if k in ("device", "dir_dim", "pool_slots", "max_beams", "timing", "stream"):
                 setattr(o.dev, k, v)
             elif k == "center":
                 o.center_xy[0], o.center_xy[1] = v

@@ -1,4 +1,5 @@
 // capi.cpp -- the extern "C" boundary declared in include/lama_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -29,6 +30,7 @@ DeviceOptions dev_from(const lama_device_options& d)
     o.pool_slots = d.pool_slots;
     o.max_beams  = d.max_beams > 0 ? d.max_beams : 2048;
     o.timing     = d.timing;
+    o.stream     = d.stream;
     return o;
 }
 void dev_default(lama_device_options* d)
@@ -38,6 +40,7 @@ void dev_default(lama_device_options* d)
     d->pool_slots = 0;
     d->max_beams = 2048;
     d->timing = 0;
+    d->stream = 0;
 }
 void xyr_of(const SE2& s, double xyr[3])
 {
@@ -100,6 +103,22 @@ int bounds_out(Engine* e, int particle, int kind, uint32_t mn[2], uint32_t mx[2]
     int n = e->bounds(particle, kind, mn, mx);
     if (n < 0) return set_err("bounds failed", LAMA_ERR_ARG);
     if (patches) *patches = n;
+    return LAMA_OK;
+}
+// The reference allocates a distance-map patch wherever an occupancy cell was first touched (see
+// export_dm); on the device those cells live only in the occupancy map, so the distance map's
+// bounds are the union of both directories.  *patches counts distance patches proper.
+int bounds_dm_union(Engine* e, int particle, uint32_t mn[2], uint32_t mx[2], int* patches)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    uint32_t a0[2], a1[2], b0[2], b1[2];
+    int nd = e->bounds(particle, 1, a0, a1), no = e->bounds(particle, 0, b0, b1);
+    if (nd < 0 || no < 0) return set_err("bounds failed", LAMA_ERR_ARG);
+    for (int k = 0; k < 2; ++k) {
+        mn[k] = nd && no ? std::min(a0[k], b0[k]) : (nd ? a0[k] : b0[k]);
+        mx[k] = nd && no ? std::max(a1[k], b1[k]) : (nd ? a1[k] : b1[k]);
+    }
+    if (patches) *patches = nd;
     return LAMA_OK;
 }
 }  // namespace
@@ -169,6 +188,29 @@ int lama_pf_update(lama_pf* h, const double* pts, int n, const double* origin, c
     if (did_update) *did_update = did ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+int lama_pf_stage_scans(lama_pf* h, const double* pts, int n_scans, int n)
+{
+    if (!h || !pts) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = h->p->stage_scans(pts, n_scans, n);
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_update_staged(lama_pf* h, int index, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
+{
+    if (!h || !odom) return set_err("null argument", LAMA_ERR_ARG);
+    bool did = false;
+    int rc = h->p->update_staged(index, origin, quat, odom, stamp, &did);
+    if (did_update) *did_update = did ? 1 : 0;
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+int lama_pf_get_traffic(lama_pf* h, uint64_t bytes[2], int reset)
+{
+    if (!h || !bytes) return set_err("null argument", LAMA_ERR_ARG);
+    Engine* e = h->p->engine();
+    bytes[0] = e ? e->h2d_bytes() : 0;
+    bytes[1] = e ? e->d2h_bytes() : 0;
+    if (e && reset) { e->reset_traffic(); e->reset_times(); }
+    return LAMA_OK;
+}
 int lama_pf_get_pose(lama_pf* h, double xyr[3])
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
@@ -232,6 +274,7 @@ static int pf_local(lama_pf* h, int particle)
 int lama_pf_map_bounds(lama_pf* h, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
 {
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
+    if (kind == 1) return bounds_dm_union(h->p->engine(), pf_local(h, particle), mn, mx, patches);
     return bounds_out(h->p->engine(), pf_local(h, particle), kind, mn, mx, patches);
 }
 int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)
@@ -379,6 +422,7 @@ int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5])
 int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    if (kind == 1) return bounds_dm_union(h->s->engine(), 0, mn, mx, patches);
     return bounds_out(h->s->engine(), 0, kind, mn, mx, patches);
 }
 int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)

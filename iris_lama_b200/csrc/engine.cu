@@ -16,9 +16,13 @@ namespace lama_b200 {
 
 struct Engine::Impl {
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     StoreView view{};
     // scan
-    double* d_points = nullptr;
+    double* d_points = nullptr;      // current scan (points into d_scan_buf or d_staged)
+    double* d_scan_buf = nullptr;
+    double* d_staged = nullptr;
+    int staged_scans = 0, staged_beams = 0;
     ScanParams scan{};
     // per-launch staging
     SE2* d_states = nullptr;
@@ -99,7 +103,12 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         if (_e != cudaSuccess) return bail(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
     CU_NEW(cudaSetDevice(cfg.device));
-    CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    if (cfg.stream) {
+        d->stream = reinterpret_cast<cudaStream_t>(cfg.stream);
+        d->own_stream = false;
+    } else {
+        CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    }
     CU_NEW(cudaEventCreate(&d->ev[0]));
     CU_NEW(cudaEventCreate(&d->ev[1]));
 
@@ -128,7 +137,8 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     v.status      = reinterpret_cast<uint32_t*>(v.free_count + 2);
     v.counters    = reinterpret_cast<uint64_t*>(v.free_count + 4);
     CU_NEW(dalloc((void**)&v.dirs, 2 * (size_t)cfg.particles * 2 * dim2 * 4));
-    CU_NEW(dalloc((void**)&d->d_points, (size_t)cfg.max_beams * 3 * 8));
+    CU_NEW(dalloc((void**)&d->d_scan_buf, (size_t)cfg.max_beams * 3 * 8));
+    d->d_points = d->d_scan_buf;
 
     d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
     d->ray.hash_cap  = next_pow2_host(std::max(4096, 4 * cfg.max_beams));
@@ -170,9 +180,10 @@ Engine::~Engine()
     if (d_->h_idx) cudaFreeHost(d_->h_idx);
     if (d_->h_status) cudaFreeHost(d_->h_status);
     if (d_->d_scratch) cudaFree(d_->d_scratch);
+    if (d_->d_staged) cudaFree(d_->d_staged);
     if (d_->ev[0]) cudaEventDestroy(d_->ev[0]);
     if (d_->ev[1]) cudaEventDestroy(d_->ev[1]);
-    if (d_->stream) cudaStreamDestroy(d_->stream);
+    if (d_->stream && d_->own_stream) cudaStreamDestroy(d_->stream);
     delete d_;
 }
 
@@ -183,10 +194,8 @@ int Engine::synchronize()
     return LAMA_OK;
 }
 
-int Engine::set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range)
+void Engine::set_moving(const double origin[3], const double quat[4], double truncated_ray, double truncated_range, int n)
 {
-    if (!pts || n < 1 || n > cfg_.max_beams) return fail("set_scan: number of beams out of range", LAMA_ERR_ARG);
-    CU_TRY(cudaSetDevice(cfg_.device));
     ScanParams& sp = d_->scan;
     sp.n_beams         = n;
     sp.scale           = 1.0 / cfg_.resolution;
@@ -201,9 +210,39 @@ int Engine::set_scan(const double* pts, int n, const double origin[3], const dou
     l[3] = txy + twz;       l[4] = 1 - (txx + tzz); l[5] = tyz - twx;
     l[6] = txz - twy;       l[7] = tyz + twx;       l[8] = 1 - (txx + tyy);
     for (int i = 0; i < 3; ++i) sp.moving.t[i] = origin ? origin[i] : 0.0;
-    // pageable host memory: cudaMemcpyAsync stages through the driver; the copy is tiny (N * 24 B)
+}
+
+int Engine::set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range)
+{
+    if (!pts || n < 1 || n > cfg_.max_beams) return fail("set_scan: number of beams out of range", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    set_moving(origin, quat, truncated_ray, truncated_range, n);
+    d_->d_points = d_->d_scan_buf;
+    // pageable host memory: cudaMemcpyAsync stages through the driver; the copy is small (N * 24 B)
     CU_TRY(cudaMemcpyAsync(d_->d_points, pts, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));  // `pts` may be released by the caller after return
+    h2d_bytes_ += (uint64_t)n * 24;
+    return LAMA_OK;
+}
+
+int Engine::stage_scans(const double* pts, int n_scans, int n)
+{
+    if (!pts || n_scans < 1 || n < 1 || n > cfg_.max_beams) return fail("stage_scans: bad arguments", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    if (d_->d_staged) { cudaFree(d_->d_staged); d_->d_staged = nullptr; }
+    CU_TRY(cudaMalloc((void**)&d_->d_staged, (size_t)n_scans * n * 24));
+    CU_TRY(cudaMemcpyAsync(d_->d_staged, pts, (size_t)n_scans * n * 24, cudaMemcpyHostToDevice, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    d_->staged_scans = n_scans;
+    d_->staged_beams = n;
+    return LAMA_OK;
+}
+
+int Engine::select_staged(int index, const double origin[3], const double quat[4], double truncated_ray, double truncated_range)
+{
+    if (!d_->d_staged || index < 0 || index >= d_->staged_scans) return fail("select_staged: no such staged scan", LAMA_ERR_ARG);
+    set_moving(origin, quat, truncated_ray, truncated_range, d_->staged_beams);
+    d_->d_points = d_->d_staged + (size_t)index * d_->staged_beams * 3;
     return LAMA_OK;
 }
 
@@ -285,6 +324,8 @@ int Engine::match(const SE2* states, int count, int first_particle, bool shared_
     times_.match_launches += 1;
     static_assert(sizeof(HostMatchResult) == sizeof(MatchResult), "layout");
     std::memcpy(out, d_->h_results, (size_t)count * sizeof(MatchResult));
+    h2d_bytes_ += (uint64_t)count * sizeof(SE2);
+    d2h_bytes_ += (uint64_t)count * sizeof(MatchResult);
     return LAMA_OK;
 }
 
@@ -329,6 +370,8 @@ int Engine::update_maps(const SE2* states, int first_particle, int count, HostMa
     times_.raycast_launches += 1;
     times_.brushfire_launches += 1;
     times_.misc_launches += 1;
+    h2d_bytes_ += (uint64_t)count * sizeof(SE2);
+    d2h_bytes_ += (uint64_t)count * sizeof(MapUpdateStats) + 4;
     if (out) {
         static_assert(sizeof(HostMapStats) == sizeof(MapUpdateStats), "layout");
         std::memcpy(out, d_->h_stats, (size_t)count * sizeof(MapUpdateStats));

@@ -21,6 +21,7 @@ struct EngineConfig {
     int max_beams     = 2048;
     double center_x   = 0.0;    // world position the directory window is centred on
     double center_y   = 0.0;
+    uint64_t stream   = 0;      // external cudaStream_t (0 = own non-blocking stream)
 };
 
 struct HostMatchResult {
@@ -49,6 +50,11 @@ public:
 
     // Uploads one scan (N x 3 doubles, sensor origin, sensor orientation quaternion xyzw).
     int set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range);
+
+    // Copies n_scans scans of n beams each into device memory once; select_staged() then makes scan `index`
+    // current without any host->device transfer (inputs resident in HBM).
+    int stage_scans(const double* pts, int n_scans, int n);
+    int select_staged(int index, const double origin[3], const double quat[4], double truncated_ray, double truncated_range);
 
     // Scan matching of `count` states.  Block k uses the map of particle first_particle + k, or, with
     // shared_map, all of them use the map of first_particle.  mode 0 = solve, 1 = single evaluation.
@@ -89,6 +95,9 @@ public:
     KernelTimes times() const { return times_; }
     void reset_times() { times_ = KernelTimes(); }
     int synchronize();
+    uint64_t h2d_bytes() const { return h2d_bytes_; }
+    uint64_t d2h_bytes() const { return d2h_bytes_; }
+    void reset_traffic() { h2d_bytes_ = d2h_bytes_ = 0; }
 
     DirWindow window() const { return window_; }
 
@@ -105,6 +114,8 @@ private:
     bool timing_         = false;
     KernelTimes times_;
     std::string err_;
+    uint64_t h2d_bytes_ = 0, d2h_bytes_ = 0;
+    void set_moving(const double origin[3], const double quat[4], double truncated_ray, double truncated_range, int n);
     int fail(const std::string& what, int code);
     int check_device_status();
 };

@@ -34,6 +34,7 @@ static EngineConfig engine_config(const DeviceOptions& dev, int particles, doubl
     c.max_beams  = dev.max_beams > 0 ? dev.max_beams : 2048;
     c.center_x   = cx;
     c.center_y   = cy;
+    c.stream     = dev.stream;
     return c;
 }
 
@@ -257,18 +258,11 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
     pending_maps_ = false;
     last_         = Counters();
     last_idx_.clear();
-    if (!eng_) {
-        // device state is created on the first scan, centred on the prior
-        std::string e;
-        EngineConfig cfg = engine_config(opt_.dev, 2 * (hi_ - lo_), opt_.resolution, opt_.l2_max, prior_.tx, prior_.ty);
-        if (opt_.shard_count == 1) cfg.particles = hi_ - lo_;  // no staging slots needed without migration
-        cfg.max_beams = std::max(cfg.max_beams, n);
-        Engine* en = Engine::create(cfg, e);
-        if (!en) return fail(e, LAMA_ERR_CUDA);
-        eng_.reset(en);
-        eng_->enable_timing(opt_.dev.timing != 0);
-    }
-    int rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+    int rc = ensure_engine(staged_index_ >= 0 ? staged_beams_ : n);
+    if (rc != LAMA_OK) return rc;
+    if (staged_index_ >= 0) rc = eng_->select_staged(staged_index_, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+    else rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+    staged_index_ = -1;
     if (rc != LAMA_OK) return engine_fail(rc);
     if (!has_first_) {
         rc = first_scan(odom_xyr);
@@ -283,6 +277,47 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
     if (rc != LAMA_OK) return rc;
     pending_maps_ = true;
     return LAMA_OK;
+}
+
+int PFSlam2D::ensure_engine(int n)
+{
+    if (eng_) return LAMA_OK;
+    // device state is created on the first scan, centred on the prior
+    std::string e;
+    EngineConfig cfg = engine_config(opt_.dev, 2 * (hi_ - lo_), opt_.resolution, opt_.l2_max, prior_.tx, prior_.ty);
+    if (opt_.shard_count == 1) cfg.particles = hi_ - lo_;  // no staging slots needed without migration
+    cfg.max_beams = std::max(cfg.max_beams, n);
+    Engine* en = Engine::create(cfg, e);
+    if (!en) return fail(e, LAMA_ERR_CUDA);
+    eng_.reset(en);
+    eng_->enable_timing(opt_.dev.timing != 0);
+    if (!staged_host_.empty()) {
+        int rc = eng_->stage_scans(staged_host_.data(), staged_scans_, staged_beams_);
+        staged_host_.clear();
+        staged_host_.shrink_to_fit();
+        if (rc != LAMA_OK) return engine_fail(rc);
+    }
+    return LAMA_OK;
+}
+
+int PFSlam2D::stage_scans(const double* pts, int n_scans, int n)
+{
+    if (!pts || n_scans < 1 || n < 1) return fail("stage_scans: bad arguments", LAMA_ERR_ARG);
+    staged_scans_ = n_scans;
+    staged_beams_ = n;
+    if (eng_) {
+        int rc = eng_->stage_scans(pts, n_scans, n);
+        return rc == LAMA_OK ? rc : engine_fail(rc);
+    }
+    staged_host_.assign(pts, pts + (size_t)n_scans * n * 3);
+    return LAMA_OK;
+}
+
+int PFSlam2D::update_staged(int index, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update)
+{
+    if (index < 0 || index >= staged_scans_) return fail("update_staged: no such staged scan", LAMA_ERR_ARG);
+    staged_index_ = index;
+    return update(nullptr, staged_beams_, origin, quat, odom_xyr, stamp, did_update);
 }
 
 int PFSlam2D::shard_finish(const double* all_results, bool* resampled, int32_t* idx)

@@ -16,6 +16,7 @@ namespace lama_b200 {
 
 struct DeviceOptions {
     int device = 0, dir_dim = 64, pool_slots = 0, max_beams = 2048, timing = 0;
+    uint64_t stream = 0;
 };
 
 // ---- PFSlam2D ---------------------------------------------------------------------------------------
@@ -51,6 +52,10 @@ public:
     void set_prior(double x, double y, double r) { prior_ = se2_from_xyr(x, y, r); }
     // bool PFSlam2D::update(...)  (src/pf_slam2d.cpp:178-312); returns a LAMA_* status
     int update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update);
+
+    // Scans resident in device memory (bench `value`): stage once, then update by index.  pts = n_scans x n x 3.
+    int stage_scans(const double* pts, int n_scans, int n);
+    int update_staged(int index, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update);
 
     // sharded split-phase equivalents of update()
     int shard_begin(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update,
@@ -94,6 +99,9 @@ private:
     uint64_t detached_seen_ = 0;
     std::string err_;
     bool pending_maps_ = false;
+    std::vector<double> staged_host_;  // kept until the engine exists
+    int staged_scans_ = 0, staged_beams_ = 0, staged_index_ = -1;
+    int ensure_engine(int n);
 
     double rng_normal(double sigma);
     double rng_uniform();

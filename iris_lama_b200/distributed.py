@@ -1,0 +1,115 @@
+"""Multi-GPU particle sharding: one process per GPU, torch.distributed (NCCL) for the plumbing.
+
+Particles shard embarrassingly: particle i lives on rank i // (P / G).  Per scan the only
+exchange is (1) an all-gather of the P x 5 match results (SE2 state + log-likelihood, 10 KB at P = 256) and
+(2) a broadcast of the P resampling indices; on resampling scans the maps of offspring whose ancestor lives on
+another rank migrate point-to-point.  The reference has no distributed layer at all (its only parallelism is the
+thread pool of src/pf_slam2d.cpp:254-266,292-302).
+
+`ShardedPFSlam2D` works with any object implementing the shard* / pack / unpack calls of api.PFSlam2D, which is
+how the gloo CPU tests exercise the orchestration without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def migration_plan(idx: np.ndarray, n_ranks: int):
+    """For every rank, which remote ancestors it needs and where they come from.
+
+    Returns (need, serve): need[r] = sorted unique global ancestor ids rank r must fetch,
+    serve[r] = list of (dst_rank, global_id) rank r must send, in a deterministic order."""
+    P = len(idx)
+    per = P // n_ranks
+    need = []
+    for r in range(n_ranks):
+        anc = np.unique(idx[r * per:(r + 1) * per])
+        need.append([int(a) for a in anc if a // per != r])
+    serve = [[] for _ in range(n_ranks)]
+    for r in range(n_ranks):
+        for a in need[r]:
+            serve[a // per].append((r, a))
+    return need, serve
+
+
+def local_sources(idx: np.ndarray, rank: int, n_ranks: int, need_r):
+    """Engine slot every new local particle copies from: local ancestors map to their own slot, remote ones
+    to the staging slot (P_local + position in need_r) they were unpacked into."""
+    P = len(idx)
+    per = P // n_ranks
+    stage = {a: per + k for k, a in enumerate(need_r)}
+    out = np.zeros(per, np.int32)
+    for k in range(per):
+        a = int(idx[rank * per + k])
+        out[k] = a - rank * per if a // per == rank else stage[a]
+    return out
+
+
+class ShardedPFSlam2D:
+    def __init__(self, pf, particles: int, device=None, group=None):
+        self.pf = pf
+        self.P = particles
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.per = particles // self.world
+        self.device = device if device is not None else torch.device("cpu")
+        self.collectives = 0
+        self.migrated_bytes = 0
+
+    def _t(self, a, dtype):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(self.device)
+
+    def update(self, pts, odom, timestamp=0.0) -> bool:
+        did, local = self.pf.shardBegin(pts, odom, timestamp)
+        if did != 2:
+            return did != 0
+        # (1) all-gather of the local match results
+        mine = self._t(local.reshape(-1), torch.float64)
+        allr = torch.empty(self.P * 5, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(allr, mine, group=self.group)
+        self.collectives += 1
+        all_results = allr.cpu().numpy().reshape(self.P, 5)
+        resampled, idx = self.pf.shardFinish(all_results)
+        # (2) broadcast of rank 0's decision and indices (every rank computes the same ones; rank 0 is authoritative)
+        msg = torch.empty(self.P + 1, dtype=torch.int32, device=self.device)
+        if self.rank == 0:
+            msg[0] = int(resampled)
+            msg[1:] = self._t(idx, torch.int32)
+        dist.broadcast(msg, src=0, group=self.group)
+        self.collectives += 1
+        m = msg.cpu().numpy()
+        if bool(m[0]) != resampled or (resampled and not np.array_equal(m[1:], idx)):
+            raise RuntimeError("resampling decision diverged between ranks")
+        if resampled:
+            self._migrate_and_apply(idx)
+        self.pf.shardMapUpdate()
+        return True
+
+    def _migrate_and_apply(self, idx):
+        need, serve = migration_plan(idx, self.world)
+        # sizes first (all ranks know who sends what; only byte counts are unknown)
+        bufs = [(dst, gid, self.pf.packParticle(gid - self.rank * self.per)) for dst, gid in serve[self.rank]]
+        sizes = torch.zeros(self.world, self.P, dtype=torch.int64, device=self.device)
+        for dst, gid, b in bufs:
+            sizes[dst, gid] = b.size
+        dist.all_reduce(sizes, group=self.group)
+        self.collectives += 1
+        sizes = sizes.cpu().numpy()
+        ops, recv = [], []
+        for dst, gid, b in bufs:
+            t = self._t(b, torch.uint8)
+            ops.append(dist.P2POp(dist.isend, t, dst, group=self.group))
+        for a in need[self.rank]:
+            t = torch.empty(int(sizes[self.rank, a]), dtype=torch.uint8, device=self.device)
+            recv.append((a, t))
+            ops.append(dist.P2POp(dist.irecv, t, a // self.per, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for k, (a, t) in enumerate(recv):
+            self.pf.unpackParticle(self.per + k, t.cpu().numpy())
+            self.migrated_bytes += t.numel()
+        self.pf.shardApply(idx, local_sources(idx, self.rank, self.world, need[self.rank]))

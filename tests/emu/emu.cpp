@@ -1,0 +1,316 @@
+// emu.cpp -- TEST-ONLY host emulation of the CUDA kernels' data flow, built from the product's own core headers
+// (lama_core.h, ddm_core.h, ray_core.h, match_core.h) so that the `-m "not gpu"` suite exercises the exact logic
+// the kernels run: bit-faithful heap, sequential brushfire on packed cells, packed counter updates in an ARBITRARY
+// beam order followed by the ordered per-cell replay, and the fused solver control.  Never linked into the product.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <random>
+#include <vector>
+
+#include "../../iris_lama_b200/csrc/ddm_core.h"
+#include "../../iris_lama_b200/csrc/match_core.h"
+#include "../../iris_lama_b200/csrc/ray_core.h"
+
+using namespace lama_b200;
+
+namespace {
+
+// dense stand-in for directory + patch pool: one word per cell of the window, "known" patches tracked per patch
+struct HostMap {
+    DirWindow window;
+    std::vector<uint32_t> cells;
+    std::vector<uint8_t> patch_present;
+    uint32_t scratch = 0, err = 0;
+    int side() const { return window.dim * kPatchLen; }
+    void init(const DirWindow& w)
+    {
+        window = w;
+        cells.assign((size_t)side() * side(), 0u);
+        patch_present.assign((size_t)w.dim * w.dim, 0);
+    }
+    uint32_t* raw(uint32_t x, uint32_t y, bool touch)
+    {
+        int di = dir_index(window, x, y);
+        if (di < 0) { err |= kErrWindow; scratch = 0; return &scratch; }
+        if (touch) patch_present[di] = 1;
+        uint32_t lx = x - ((uint32_t)window.base_px << kPatchLog2), ly = y - ((uint32_t)window.base_py << kPatchLog2);
+        return &cells[(size_t)ly * side() + lx];
+    }
+};
+struct HostDm : HostMap {
+    uint32_t* cell(uint32_t x, uint32_t y)  // the mutable Map::get of the distance map
+    {
+        uint32_t* p = raw(x, y, true);
+        if (!(*p & kDmKnown)) *p |= kDmKnown;
+        return p;
+    }
+};
+
+struct Emu {
+    double resolution, scale;
+    uint32_t max_sqdist;
+    HostMap occ;
+    HostDm dm;
+    std::vector<uint64_t> heap_l, heap_r;
+    SE2 pose{1, 0, 0, 0}, odom{1, 0, 0, 0};
+    bool has_first = false;
+    double trans_thresh = 0.5, rot_thresh = 0.5;
+    uint32_t max_iter = 100;
+    int strategy = 0;
+    uint32_t last_pops = 0, last_cells = 0, last_events = 0, last_log = 0, last_evals = 0, last_iters = 0;
+};
+
+double cell_dist(const Emu& e, uint32_t x, uint32_t y)
+{
+    HostDm& dm = const_cast<HostDm&>(e.dm);
+    int di = dir_index(dm.window, x, y);
+    uint32_t w = di < 0 ? 0u : *dm.raw(x, y, false);
+    uint32_t sq = (w & kDmValid) ? dm_sqdist(w) : e.max_sqdist;
+    return mul_rn(std::sqrt((double)sq), e.resolution);
+}
+
+void evaluate(const Emu& e, const ScanParams& sp, const double* pts, const SE2& state, const SolverOptions& so, double meas_sigma, double sums[kNumSums])
+{
+    for (int k = 0; k < kNumSums; ++k) sums[k] = 0;
+    Affine tf = compose_tf(state, sp.moving);
+    for (int b = 0; b < sp.n_beams; ++b) {
+        double hit[3];
+        apply_tf(tf, pts[3 * b], pts[3 * b + 1], pts[3 * b + 2], hit);
+        double mx = w2m_nocast(hit[0], sp.scale), my = w2m_nocast(hit[1], sp.scale);
+        uint32_t dx = (uint32_t)mx, dy = (uint32_t)my;
+        double v[4] = {cell_dist(e, dx, dy), cell_dist(e, dx + 1, dy), cell_dist(e, dx, dy + 1), cell_dist(e, dx + 1, dy + 1)};
+        BeamEval be = bilinear(v, add_rn(mx, -(double)dx), add_rn(my, -(double)dy), sp.scale, hit[0], hit[1]);
+        accumulate(sums, be, so.robust_kind, so.robust_param, meas_sigma);
+    }
+}
+
+// k_match: fused solver loop
+void solve(Emu& e, const ScanParams& sp, const double* pts, SE2& state, const SolverOptions& so, double sums[kNumSums])
+{
+    SolverControl ctl;
+    ctl.begin(so);
+    e.last_evals = 0;
+    for (;;) {
+        evaluate(e, sp, pts, state, so, 0.05, sums);
+        if (ctl.advance(sums, state)) break;
+    }
+    if (ctl.state_dirty) evaluate(e, sp, pts, state, so, 0.05, sums);
+    e.last_evals = ctl.evals_ref;
+    e.last_iters = ctl.iter;
+}
+
+// k_raycast + k_brushfire; beams are processed in a shuffled order to prove order independence of the design
+void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pose, uint32_t shuffle_seed)
+{
+    const DirWindow win = e.occ.window;
+    Affine tf = compose_tf(pose, sp.moving);
+    std::vector<int> order(sp.n_beams);
+    for (int i = 0; i < sp.n_beams; ++i) order[i] = i;
+    if (shuffle_seed) {
+        std::mt19937 g(shuffle_seed);
+        std::shuffle(order.begin(), order.end(), g);
+    }
+    // phase 1: hit-cell set
+    std::vector<uint32_t> hitset;
+    for (int b = 0; b < sp.n_beams; ++b) {
+        BeamCells bc = beam_cells(tf, sp, pts + 3 * b);
+        if (bc.mark_hit && dir_index(win, bc.to[0], bc.to[1]) >= 0) hitset.push_back(cell_key(win, bc.to[0], bc.to[1]));
+    }
+    std::sort(hitset.begin(), hitset.end());
+    // phase 3: packed counter updates + candidate log
+    std::vector<uint64_t> log;
+    uint32_t cells = 0;
+    for (int b : order) {
+        BeamCells bc = beam_cells(tf, sp, pts + 3 * b);
+        if (bc.mark_hit && dir_index(win, bc.to[0], bc.to[1]) >= 0) {
+            ++cells;
+            *e.occ.raw(bc.to[0], bc.to[1], true) += kOccHitInc;
+            log.push_back(log_record(cell_key(win, bc.to[0], bc.to[1]), (uint32_t)b, 0u, true));
+        }
+        RayWalk w(bc);
+        uint32_t pos = 0;
+        while (w.next()) {
+            ++pos;
+            if (dir_index(win, w.x, w.y) < 0) continue;
+            ++cells;
+            uint32_t* c = e.occ.raw(w.x, w.y, true);
+            uint32_t old = *c;
+            *c += kOccMissInc;
+            uint32_t key = cell_key(win, w.x, w.y);
+            if ((old & kOccObstacle) || std::binary_search(hitset.begin(), hitset.end(), key)) log.push_back(log_record(key, (uint32_t)b, pos, false));
+        }
+    }
+    // phase 4-6: sort, replay per cell, order the events
+    std::sort(log.begin(), log.end());
+    std::vector<uint64_t> events;
+    for (size_t i = 0; i < log.size();) {
+        size_t j = i + 1;
+        while (j < log.size() && log_key(log[j]) == log_key(log[i])) ++j;
+        uint32_t key = log_key(log[i]);
+        uint32_t* c = e.occ.raw(key_x(win, key), key_y(win, key), false);
+        bool obstacle = replay_cell(log.data(), (int)i, (int)j, *c, [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
+        if (obstacle) *c |= kOccObstacle; else *c &= ~kOccObstacle;
+        i = j;
+    }
+    std::sort(events.begin(), events.end());
+    // k_brushfire
+    e.heap_l.assign(1 << 16, 0);
+    e.heap_r.assign(1 << 16, 0);
+    Brushfire<HostDm> bf(e.dm, Heap{e.heap_r.data(), 0u, (uint32_t)e.heap_r.size()}, Heap{e.heap_l.data(), 0u, (uint32_t)e.heap_l.size()}, e.max_sqdist);
+    for (uint64_t ev : events) {
+        uint32_t key = (uint32_t)ev;
+        if ((ev >> 32) & 1u) bf.add_obstacle(key_x(win, key), key_y(win, key));
+        else bf.remove_obstacle(key_x(win, key), key_y(win, key));
+    }
+    e.last_pops   = bf.update();
+    e.last_cells  = cells;
+    e.last_events = (uint32_t)events.size();
+    e.last_log    = (uint32_t)log.size();
+}
+
+ScanParams scan_params(const Emu& e, int n)
+{
+    ScanParams sp{};
+    sp.n_beams = n;
+    sp.scale = e.scale;
+    for (int i = 0; i < 9; ++i) sp.moving.l[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return sp;
+}
+}  // namespace
+
+extern "C" {
+
+// random push/pop sequence against std::priority_queue with the reference's comparator; returns #mismatches
+int emu_heap_check(uint32_t seed, int n_ops, int prio_range)
+{
+    struct Cmp { bool operator()(const std::pair<int, uint32_t>& l, const std::pair<int, uint32_t>& r) const { return l.first > r.first; } };
+    std::priority_queue<std::pair<int, uint32_t>, std::vector<std::pair<int, uint32_t>>, Cmp> ref;
+    std::vector<uint64_t> buf(n_ops + 1);
+    Heap h{buf.data(), 0u, (uint32_t)buf.size()};
+    std::mt19937 g(seed);
+    int bad = 0;
+    uint32_t id = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        if (h.size == 0 || (g() % 100) < 58) {
+            int p = (int)(g() % prio_range);
+            ref.push({p, id});
+            heap_push(h, heap_entry((uint32_t)p, id));
+            ++id;
+        } else {
+            auto t = ref.top();
+            ref.pop();
+            uint64_t e = heap_pop(h);
+            if ((int)heap_prio(e) != t.first || heap_key(e) != t.second) ++bad;
+        }
+        if (h.size != ref.size()) ++bad;
+    }
+    while (!ref.empty()) {
+        auto t = ref.top();
+        ref.pop();
+        uint64_t e = heap_pop(h);
+        if ((int)heap_prio(e) != t.first || heap_key(e) != t.second) ++bad;
+    }
+    return bad;
+}
+
+void* emu_create(double resolution, double l2_max, double cx, double cy, int dir_dim, double trans_thresh, double rot_thresh, uint32_t max_iter, int strategy)
+{
+    Emu* e = new Emu();
+    e->resolution = resolution;
+    e->scale = 1.0 / resolution;
+    uint32_t r = (uint32_t)std::ceil(l2_max * e->scale);
+    e->max_sqdist = r * r;
+    DirWindow w;
+    w.dim = dir_dim;
+    w.base_px = (int32_t)(w2m(cx, e->scale) >> kPatchLog2) - dir_dim / 2;
+    w.base_py = (int32_t)(w2m(cy, e->scale) >> kPatchLog2) - dir_dim / 2;
+    e->occ.init(w);
+    e->dm.init(w);
+    e->trans_thresh = trans_thresh;
+    e->rot_thresh = rot_thresh;
+    e->max_iter = max_iter;
+    e->strategy = strategy;
+    return e;
+}
+void emu_destroy(void* h) { delete (Emu*)h; }
+void emu_set_pose(void* h, double x, double y, double r) { ((Emu*)h)->pose = se2_from_xyr(x, y, r); }
+void emu_get_state(void* h, double* s) { Emu* e = (Emu*)h; s[0] = e->pose.c; s[1] = e->pose.s; s[2] = e->pose.tx; s[3] = e->pose.ty; }
+void emu_counters(void* h, uint32_t* c) { Emu* e = (Emu*)h; c[0] = e->last_evals; c[1] = e->last_cells; c[2] = e->last_pops; c[3] = e->last_events; c[4] = e->last_log; c[5] = e->last_iters; c[6] = e->occ.err | e->dm.err; }
+
+// Slam2D::update (src/slam2d.cpp:143-198) on top of the emulated kernels
+int emu_slam_update(void* h, const double* pts, int n, const double* odom_xyr, uint32_t shuffle_seed)
+{
+    Emu* e = (Emu*)h;
+    ScanParams sp = scan_params(*e, n);
+    const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
+    if (!e->has_first) {
+        e->odom = odometry;
+        update_maps(*e, sp, pts, e->pose, shuffle_seed);
+        e->has_first = true;
+        return 1;
+    }
+    const SE2 odelta = se2_mul(se2_inv(e->odom), odometry);
+    const SE2 ppose = se2_mul(e->pose, odelta);
+    if (std::sqrt(odelta.tx * odelta.tx + odelta.ty * odelta.ty) <= e->trans_thresh && std::fabs(se2_rotation(odelta)) <= e->rot_thresh) return 0;
+    e->pose = ppose;
+    e->odom = odometry;
+    SolverOptions so{};
+    so.strategy = e->strategy; so.robust_kind = kRobustCauchy; so.robust_param = 0.15; so.max_iterations = e->max_iter;
+    so.eps1 = so.eps2 = so.tau = 1e-4;
+    double sums[kNumSums];
+    solve(*e, sp, pts, e->pose, so, sums);
+    update_maps(*e, sp, pts, e->pose, shuffle_seed);
+    return 1;
+}
+
+void emu_export_dm(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox, int16_t* oy, uint8_t* queued)
+{
+    Emu* e = (Emu*)h;
+    for (int j = 0; j < hh; ++j)
+        for (int i = 0; i < w; ++i) {
+            uint32_t x = x0 + i, y = y0 + j;
+            uint32_t d = dir_index(e->dm.window, x, y) < 0 ? 0u : *e->dm.raw(x, y, false);
+            uint32_t o = dir_index(e->occ.window, x, y) < 0 ? 0u : *e->occ.raw(x, y, false);
+            int k = j * w + i;
+            sqdist[k] = (uint16_t)dm_sqdist(d); valid[k] = (d & kDmValid) != 0; ox[k] = (int16_t)dm_ox(d); oy[k] = (int16_t)dm_oy(d);
+            queued[k] = (d & kDmQueued) != 0;
+            known[k] = (d & kDmKnown) != 0 || (o & ~kOccObstacle) != 0;
+        }
+}
+void emu_export_occ(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* occupied, uint16_t* visited, uint8_t* obstacle)
+{
+    Emu* e = (Emu*)h;
+    for (int j = 0; j < hh; ++j)
+        for (int i = 0; i < w; ++i) {
+            uint32_t x = x0 + i, y = y0 + j;
+            uint32_t o = dir_index(e->occ.window, x, y) < 0 ? 0u : *e->occ.raw(x, y, false);
+            int k = j * w + i;
+            occupied[k] = (uint16_t)occ_occupied(o); visited[k] = (uint16_t)occ_visited(o); obstacle[k] = (o & kOccObstacle) != 0;
+        }
+}
+// direct brushfire calls for the stand-alone DDM comparison
+uint32_t emu_dm_apply(void* h, const uint32_t* cells_xy, const uint8_t* is_add, int n)
+{
+    Emu* e = (Emu*)h;
+    e->heap_l.assign(1 << 16, 0);
+    e->heap_r.assign(1 << 16, 0);
+    Brushfire<HostDm> bf(e->dm, Heap{e->heap_r.data(), 0u, (uint32_t)e->heap_r.size()}, Heap{e->heap_l.data(), 0u, (uint32_t)e->heap_l.size()}, e->max_sqdist);
+    for (int i = 0; i < n; ++i) {
+        if (is_add[i]) bf.add_obstacle(cells_xy[2 * i], cells_xy[2 * i + 1]);
+        else bf.remove_obstacle(cells_xy[2 * i], cells_xy[2 * i + 1]);
+    }
+    return bf.update();
+}
+// SE2 helpers of lama_core.h for comparison with the oracle's
+void emu_se2(int op, const double* a, const double* b, double* out)
+{
+    SE2 A{a[0], a[1], a[2], a[3]}, r{1, 0, 0, 0};
+    if (op == 0) r = se2_mul(A, SE2{b[0], b[1], b[2], b[3]});
+    else if (op == 1) r = se2_inv(A);
+    else if (op == 2) r = se2_exp(a);
+    else if (op == 3) r = se2_from_xyr(a[0], a[1], a[2]);
+    out[0] = r.c; out[1] = r.s; out[2] = r.tx; out[3] = r.ty;
+}
+}

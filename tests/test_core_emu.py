@@ -1,0 +1,133 @@
+"""CPU tests of the product's core logic (lama_core.h / ddm_core.h / ray_core.h / match_core.h) through the
+test-only host emulation in tests/emu: same headers as the CUDA kernels, compared with the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+O = 1321122 * 32
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "emu"), "-s"])
+    L = C.CDLL(os.path.join(HERE, "emu", "_build", "liblama_emu.so"))
+    L.emu_create.restype = C.c_void_p
+    L.emu_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_uint32, C.c_int]
+    L.emu_dm_apply.restype = C.c_uint32
+    for f in ("emu_destroy", "emu_set_pose", "emu_get_state", "emu_counters", "emu_slam_update", "emu_export_dm", "emu_export_occ", "emu_dm_apply"):
+        getattr(L, f).argtypes = None
+    return L
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _export_dm(L, h, x0, y0, w, hh):
+    o = dict(sqdist=np.zeros((hh, w), np.uint16), valid=np.zeros((hh, w), np.uint8), known=np.zeros((hh, w), np.uint8),
+             ox=np.zeros((hh, w), np.int16), oy=np.zeros((hh, w), np.int16), queued=np.zeros((hh, w), np.uint8))
+    L.emu_export_dm(C.c_void_p(h), C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(hh), _vp(o["sqdist"]), _vp(o["valid"]), _vp(o["known"]),
+                    _vp(o["ox"]), _vp(o["oy"]), _vp(o["queued"]))
+    return o
+
+
+def _export_occ(L, h, x0, y0, w, hh):
+    o = dict(occupied=np.zeros((hh, w), np.uint16), visited=np.zeros((hh, w), np.uint16), obstacle=np.zeros((hh, w), np.uint8))
+    L.emu_export_occ(C.c_void_p(h), C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(hh), _vp(o["occupied"]), _vp(o["visited"]), _vp(o["obstacle"]))
+    return o
+
+
+def test_heap_is_bit_faithful_to_std_priority_queue(emu):
+    # many ties (small priority range) are what makes the pop order implementation defined
+    for seed, n, rng in ((1, 20000, 4), (2, 20000, 1), (3, 50000, 100), (4, 3000, 2), (5, 100000, 401)):
+        assert emu.emu_heap_check(C.c_uint32(seed), C.c_int(n), C.c_int(rng)) == 0
+
+
+def test_se2_host_math_equals_oracle_bitwise(emu, po):
+    rng = np.random.default_rng(0)
+    out = np.zeros(4)
+    for _ in range(200):
+        a = po.se2_from_xyr(*rng.uniform(-3, 3, 3))
+        b = po.se2_from_xyr(*rng.uniform(-3, 3, 3))
+        emu.emu_se2(C.c_int(0), _vp(a), _vp(b), _vp(out))
+        assert (out == po.se2_mul(a, b)).all()
+        emu.emu_se2(C.c_int(1), _vp(a), None, _vp(out))
+        assert (out == po.se2_inv(a)).all()
+        h = np.ascontiguousarray(rng.uniform(-0.2, 0.2, 3))
+        emu.emu_se2(C.c_int(2), _vp(h), None, _vp(out))
+        assert (out == po.se2_exp(h)).all()
+
+
+@pytest.mark.parametrize("l2", [0.5, 1.0])
+def test_brushfire_core_equals_oracle_on_add_remove_stress(emu, po, l2):
+    h = emu.emu_create(0.05, l2, 3.2, 3.2, 16, 0.5, 0.5, 100, 0)
+    o = po.DDM(l2_max=l2)
+    rng = np.random.default_rng(7)
+    W = 128
+    occ = np.zeros((W, W), bool)
+    for it in range(60):
+        mode = rng.integers(0, 3)
+        n = int(rng.integers(1, 50))
+        if mode == 0:
+            pts = rng.integers(24, W - 24, size=(n, 2))
+        elif mode == 1:
+            x0, y0 = rng.integers(24, W - 24, 2); dx, dy = rng.integers(-1, 2, 2)
+            pts = np.array([(x0 + k * dx, y0 + k * dy) for k in range(n)]); pts = pts[(pts.min(1) >= 24) & (pts.max(1) < W - 24)]
+        else:
+            pts = np.argwhere(occ)[:, ::-1]
+            if len(pts):
+                pts = pts[rng.choice(len(pts), size=min(len(pts), n), replace=False)]
+        if len(pts) == 0:
+            continue
+        cells = np.ascontiguousarray((pts + O).astype(np.uint32))
+        kinds = np.full(len(cells), 0 if mode == 2 else 1, np.uint8)
+        if mode == 2:
+            o.remove(cells); occ[pts[:, 1], pts[:, 0]] = False
+        else:
+            o.add(cells); occ[pts[:, 1], pts[:, 0]] = True
+        pops_e = emu.emu_dm_apply(C.c_void_p(h), _vp(cells), _vp(kinds), C.c_int(len(cells)))
+        assert pops_e == o.update()
+        a, b = _export_dm(emu, h, O, O, W, W), o.export(O, O, W, W)
+        for k in ("sqdist", "valid", "ox", "oy", "queued"):
+            assert (a[k] == b[k]).all(), (it, k)
+    emu.emu_destroy(C.c_void_p(h))
+
+
+@pytest.mark.parametrize("name,beams,T,shuffle", [("room", 360, 25, 0), ("room", 360, 25, 12345), ("corridor", 240, 20, 99)])
+def test_emulated_slam_equals_oracle(emu, po, synth, name, beams, T, shuffle):
+    """Packed atomics in a SHUFFLED beam order + ordered replay + sequential brushfire == the reference's
+    strictly sequential update (cells bit-exact), and the fused one-evaluation-per-iteration solver == Solver::solve."""
+    ds = synth.make_dataset(name, T, n_beams=beams)
+    t0 = ds.truth[0]
+    h = emu.emu_create(0.05, 0.5, t0[0], t0[1], 64, 0.05, 0.05, 100, 0)
+    emu.emu_set_pose(C.c_void_p(h), C.c_double(t0[0]), C.c_double(t0[1]), C.c_double(t0[2]))
+    o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
+    o.set_pose(*t0)
+    st = np.zeros(4)
+    ctr = np.zeros(7, np.uint32)
+    for t in range(T):
+        pts = np.ascontiguousarray(ds.scans[t]); od = np.ascontiguousarray(ds.odom[t])
+        a = emu.emu_slam_update(C.c_void_p(h), _vp(pts), C.c_int(beams), _vp(od), C.c_uint32(shuffle))
+        b = o.update(ds.scans[t], ds.odom[t])
+        assert bool(a) == b
+        emu.emu_get_state(C.c_void_p(h), _vp(st))
+        assert np.abs(st - o.state()).max() < 1e-12
+        emu.emu_counters(C.c_void_p(h), _vp(ctr))
+        last, _ = o.counters()
+        assert ctr[6] == 0
+        assert (int(ctr[0]), int(ctr[1]), int(ctr[2]), int(ctr[5])) == (last["evals"], last["ray_cells"], last["dm_pops"], last["gn_iters"])
+    n, mn, mx = o.dm_bounds(); w, hh = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    a, b = _export_dm(emu, h, int(mn[0]), int(mn[1]), w, hh), o.export_dm(mn[0], mn[1], w, hh)
+    for k in ("sqdist", "valid", "ox", "oy", "queued", "known"):
+        assert (a[k] == b[k]).all(), k
+    n, mn, mx = o.occ_bounds(); w, hh = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    a, b = _export_occ(emu, h, int(mn[0]), int(mn[1]), w, hh), o.export_occ(mn[0], mn[1], w, hh)
+    assert (a["occupied"] == b["occupied"]).all() and (a["visited"] == b["visited"]).all()
+    # the obstacle mirror bit of the occupancy word equals "distance cell is an obstacle"
+    d = _export_dm(emu, h, int(mn[0]), int(mn[1]), w, hh)
+    assert (a["obstacle"].astype(bool) == ((d["valid"] == 1) & (d["sqdist"] == 0))).all()
+    emu.emu_destroy(C.c_void_p(h))

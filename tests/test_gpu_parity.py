@@ -1,0 +1,291 @@
+"""GPU parity tests proper: the CUDA path through the C-ABI against the oracle on the same seeded inputs and against
+the committed golden fixtures.  Integer / cell data must be bit-exact; poses within 1e-9 (fp64 sums are reduced in a
+different, fixed order on the device)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+O = 1321122 * 32
+POSE_TOL = 1e-9          # BASELINE.json asks for 1e-4 on the trajectory; the device path is ~1e-12 in practice
+
+
+def _room_cells(segments):
+    cells = set()
+    for x1, y1, x2, y2 in segments:
+        n = int(max(abs(x2 - x1), abs(y2 - y1)) / 0.05) + 1
+        for k in range(n + 1):
+            cells.add((int((x1 + (x2 - x1) * k / n) * 20 + O + 0.5), int((y1 + (y2 - y1) * k / n) * 20 + O + 0.5)))
+    return np.array(sorted(cells), np.uint32)
+
+
+def _assert_dm_equal(a, b, fields=("sqdist", "valid", "ox", "oy", "queued", "known")):
+    for k in fields:
+        assert (a[k] == b[k]).all(), f"{k}: {int((a[k] != b[k]).sum())} cells differ"
+
+
+# ---- DynamicDistanceMap grid interface ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("l2", [0.5, 1.0])
+def test_brushfire_add_remove_stress_bit_exact(gpu_api, po, l2):
+    g, o = gpu_api.DynamicDistanceMap(l2_max=l2), po.DDM(l2_max=l2)
+    assert g.max_sqdist == o.max_sqdist
+    rng = np.random.default_rng(11)
+    W = 128
+    occ = np.zeros((W, W), bool)
+    for it in range(50):
+        mode = rng.integers(0, 3)
+        n = int(rng.integers(1, 60))
+        if mode == 0:
+            pts = rng.integers(24, W - 24, size=(n, 2))
+        elif mode == 1:
+            x0, y0 = rng.integers(24, W - 24, 2); dx, dy = rng.integers(-1, 2, 2)
+            pts = np.array([(x0 + k * dx, y0 + k * dy) for k in range(n)]); pts = pts[(pts.min(1) >= 24) & (pts.max(1) < W - 24)]
+        else:
+            pts = np.argwhere(occ)[:, ::-1]
+            if len(pts):
+                pts = pts[rng.choice(len(pts), size=min(len(pts), n), replace=False)]
+        if len(pts) == 0:
+            continue
+        cells = (pts + O).astype(np.uint32)
+        if mode == 2:
+            g.removeObstacle(cells); o.remove(cells); occ[pts[:, 1], pts[:, 0]] = False
+        else:
+            g.addObstacle(cells); o.add(cells); occ[pts[:, 1], pts[:, 0]] = True
+        assert g.update() == o.update()             # DynamicDistanceMap::update() return value
+        _assert_dm_equal(g.export(O, O, W, W), o.export(O, O, W, W))
+    pts = np.zeros((2000, 3)); pts[:, :2] = rng.uniform(0.2, W * 0.05 - 0.2, size=(2000, 2))
+    dg, gg = g.distance(pts); dc, gc = o.distance(pts)
+    assert (dg == dc).all() and (gg == gc).all()   # same fp64 operations in the same order: bit-exact
+
+
+def test_empty_and_degenerate_inputs(gpu_api, po):
+    g, o = gpu_api.DynamicDistanceMap(), po.DDM()
+    assert g.update() == o.update() == 0                                   # empty queues
+    c = np.array([[O + 5, O + 5]], np.uint32)
+    g.removeObstacle(c); o.remove(c)                                       # removing a non-obstacle is a no-op
+    assert g.update() == o.update()
+    g.addObstacle(np.vstack([c, c])); o.add(np.vstack([c, c]))             # duplicate add
+    assert g.update() == o.update()
+    g.addObstacle(c); g.removeObstacle(c); o.add(c); o.remove(c)           # add + remove before update
+    assert g.update() == o.update()
+    _assert_dm_equal(g.export(O - 32, O - 32, 96, 96), o.export(O - 32, O - 32, 96, 96))
+    far = np.array([[100.0, 100.0, 0.0]])                                   # outside every patch: max distance, zero gradient
+    d, gr = g.distance(far)
+    assert d[0] == o.distance(far)[0][0] and np.abs(gr).max() == 0
+
+
+def test_import_export_round_trip(gpu_api, po):
+    o = po.DDM(l2_max=1.0)
+    o.add(np.array([[O + 40 + k, O + 50] for k in range(40)] + [[O + 60, O + 20 + k] for k in range(30)], np.uint32))
+    o.update()
+    e = o.export(O, O, 128, 128)
+    g = gpu_api.DynamicDistanceMap(l2_max=1.0)
+    g.import_(O, O, e)
+    _assert_dm_equal(g.export(O, O, 128, 128), e)
+    # continuing on the imported map behaves like the oracle's own map
+    rm = np.array([[O + 45, O + 50], [O + 60, O + 30]], np.uint32)
+    g.removeObstacle(rm); o.remove(rm)
+    assert g.update() == o.update()
+    _assert_dm_equal(g.export(O, O, 128, 128), o.export(O, O, 128, 128))
+
+
+# ---- MatchSurface2D / Solver -------------------------------------------------------------------------------------------
+def test_normal_equations_and_solve(gpu_api, po, synth):
+    ds = synth.make_dataset("loc_room", 2)
+    cells = _room_cells(ds.segments)
+    g, o = gpu_api.DynamicDistanceMap(l2_max=1.0), po.DDM(l2_max=1.0)
+    g.addObstacle(cells); o.add(cells)
+    assert g.update() == o.update()
+    t = ds.truth[0]
+    rng = np.random.default_rng(3)
+    states = np.array([po.se2_from_xyr(t[0] + dx, t[1] + dy, t[2] + dth) for dx, dy, dth in
+                       [(0.10, -0.07, 0.05), (0, 0, 0), (-0.2, 0.1, -0.08), (0.02, 0.01, 0.3)] + [tuple(rng.uniform(-0.15, 0.15, 3)) for _ in range(28)]])
+    ne = g.matchNormalEquations(ds.scans[0], states)
+    for i, s in enumerate(states):
+        want = o.match_normal_eq(ds.scans[0], s)
+        assert np.allclose(ne[i, :11], want, rtol=1e-11, atol=1e-13), i
+    for strategy in (0, 1):
+        sg, stats, sums = g.matchSolve(ds.scans[0], states, strategy=strategy)
+        for i, s in enumerate(states):
+            sc, _, st = o.match_solve(ds.scans[0], s, strategy=strategy)
+            assert np.abs(sg[i] - sc).max() < POSE_TOL, (strategy, i)
+            assert stats[i, 0] == st[0] and stats[i, 1] == st[1]          # same iteration / evaluation counts
+    # robust kernels other than Cauchy and the max_iter edge cases
+    for robust in ((0, 0.0), (2, 0.15), (3, 4.685), (4, 3.0)):
+        ne = g.matchNormalEquations(ds.scans[0], states[:4], robust=robust)
+        for i in range(4):
+            assert np.allclose(ne[i, :11], o.match_normal_eq(ds.scans[0], states[i], robust=robust), rtol=1e-11, atol=1e-13)
+    for max_iter in (0, 1, 2):
+        sg, stats, _ = g.matchSolve(ds.scans[0], states[:4], max_iter=max_iter)
+        for i in range(4):
+            sc, _, st = o.match_solve(ds.scans[0], states[i], max_iter=max_iter)
+            assert np.abs(sg[i] - sc).max() < POSE_TOL and stats[i, 0] == st[0]
+
+
+def test_match_with_tilted_sensor_and_offset(gpu_api, po, synth):
+    """general sensor pose: PointCloudXYZ::sensor_origin_ / sensor_orientation_ (types.h:117-118)"""
+    ds = synth.make_dataset("loc_room", 1)
+    cells = _room_cells(ds.segments)
+    g, o = gpu_api.DynamicDistanceMap(l2_max=1.0), po.DDM(l2_max=1.0)
+    g.addObstacle(cells); o.add(cells); g.update(); o.update()
+    origin = (0.2, -0.1, 0.3)
+    a = 0.1
+    quat = (0.0, 0.0, np.sin(a / 2), np.cos(a / 2))
+    t = ds.truth[0]
+    s0 = po.se2_from_xyr(t[0] - 0.2, t[1] + 0.1, t[2] - a)
+    ne = g.matchNormalEquations(ds.scans[0], [s0], origin=origin, quat=quat)
+    assert np.allclose(ne[0, :11], o.match_normal_eq(ds.scans[0], s0, origin=origin, quat=quat), rtol=1e-11, atol=1e-13)
+
+
+# ---- Loc2D (config 1) ---------------------------------------------------------------------------------------------------
+def test_loc2d_matches_oracle_and_golden(gpu_api, po, synth):
+    gold = np.load(os.path.join(HERE, "golden", "loc_room.npz"))
+    ds = synth.make_dataset("loc_room", 4)
+    cells = _room_cells(ds.segments)
+    gl = gpu_api.Loc2D(gpu_api.Loc2D.Options(trans_thresh=0.01, rot_thresh=0.01))
+    ol = po.Loc2D(po.LocOptions.defaults(trans_thresh=0.01, rot_thresh=0.01))
+    gl.distance_map.addObstacle(cells)
+    assert gl.distance_map.update() == int(gold["pops"][0])
+    od = ol.dm(); od.add(cells); od.update()
+    t0 = ds.truth[0]
+    gl.setPose(t0[0] + 0.10, t0[1] - 0.07, t0[2] + 0.05); ol.set_pose(t0[0] + 0.10, t0[1] - 0.07, t0[2] + 0.05)
+    for t in range(4):
+        assert gl.update(ds.scans[t], ds.odom[t], force_update=(t == 0)) == ol.update(ds.scans[t], ds.odom[t], force=(t == 0))
+        sc, cov, rmse, _ = ol.get()
+        assert np.abs(gl.state() - sc).max() < POSE_TOL and np.abs(gl.state() - gold["states"][t]).max() < POSE_TOL
+        assert abs(gl.getRMSE() - rmse) < 1e-12 and abs(gl.getRMSE() - gold["rmse"][t]) < 1e-12
+        assert np.allclose(gl.getCovar(), cov, rtol=1e-9) and np.allclose(gl.getCovar(), gold["covs"][t], rtol=1e-9)
+        assert np.hypot(sc[2] - ds.truth[t, 0], sc[3] - ds.truth[t, 1]) < 0.01
+    assert gl.update(ds.scans[3], ds.odom[3]) is False                       # no motion -> gated
+
+
+# ---- Slam2D (config 2 family) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,beams,T", [("room", 360, 30), ("corridor", 720, 40), ("room", 1080, 12)])
+def test_slam2d_matches_oracle(gpu_api, po, synth, name, beams, T):
+    ds = synth.make_dataset(name, T, n_beams=beams)
+    g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05))
+    o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
+    g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+    gold = np.load(os.path.join(HERE, "golden", "slam_room.npz")) if (name, beams, T) == ("room", 360, 30) else None
+    for t in range(T):
+        assert g.update(ds.scans[t], ds.odom[t]) == o.update(ds.scans[t], ds.odom[t])
+        assert np.abs(g.state() - o.state()).max() < POSE_TOL
+        cg, _ = g.counters(); co, _ = o.counters()
+        assert (cg["evals"], cg["ray_cells"], cg["dm_pops"], cg["gn_iters"]) == (co["evals"], co["ray_cells"], co["dm_pops"], co["gn_iters"])
+        assert g.getNumberOfProcessedCells() == co["dm_pops"]
+        if gold is not None:
+            assert np.abs(g.state() - gold["states"][t]).max() < POSE_TOL
+            assert [cg["evals"], cg["ray_cells"], cg["dm_pops"], cg["gn_iters"]] == gold["counters"][t].tolist()
+    n, mn, mx = o.dm_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    _assert_dm_equal(g.exportDistance(int(mn[0]), int(mn[1]), w, h), o.export_dm(mn[0], mn[1], w, h))
+    ng, mng, mxg = g.mapBounds(1)
+    assert (mng == mn).all() and (mxg == mx).all()                            # Map::bounds of the distance map
+    n, mn, mx = o.occ_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    eg, eo = g.exportOccupancy(int(mn[0]), int(mn[1]), w, h), o.export_occ(mn[0], mn[1], w, h)
+    for k in ("occupied", "visited", "known"):
+        assert (eg[k] == eo[k]).all()
+    ng, mng, mxg = g.mapBounds(0)
+    assert ng == n and (mng == mn).all() and (mxg == mx).all()                # numOfPatches / bounds of the occupancy map
+    if gold is not None:
+        lo = gold["origin"]; hh, ww = gold["sqdist"].shape
+        dg = g.exportDistance(int(lo[0]), int(lo[1]), ww, hh); og = g.exportOccupancy(int(lo[0]), int(lo[1]), ww, hh)
+        assert (dg["sqdist"] == gold["sqdist"]).all() and (dg["valid"] == gold["valid"]).all() and (dg["known"] == gold["known"]).all()
+        assert (og["occupied"] == gold["occupied"]).all() and (og["visited"] == gold["visited"]).all()
+
+
+def test_slam2d_truncated_rays(gpu_api, po, synth):
+    """Options::truncated_ray / truncated_range (slam2d.cpp:275-299)"""
+    T = 10
+    ds = synth.make_dataset("room", T, n_beams=360)
+    for kw in (dict(truncated_ray=2.0), dict(truncated_range=6.0), dict(truncated_ray=1.5, truncated_range=8.0)):
+        g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, **kw))
+        o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05, **kw))
+        g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+        for t in range(T):
+            assert g.update(ds.scans[t], ds.odom[t]) == o.update(ds.scans[t], ds.odom[t])
+        assert np.abs(g.state() - o.state()).max() < POSE_TOL
+        n, mn, mx = o.occ_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+        eg, eo = g.exportOccupancy(int(mn[0]), int(mn[1]), w, h), o.export_occ(mn[0], mn[1], w, h)
+        assert (eg["occupied"] == eo["occupied"]).all() and (eg["visited"] == eo["visited"]).all()
+
+
+def test_slam2d_levenberg_marquardt(gpu_api, po, synth):
+    T = 12
+    ds = synth.make_dataset("room", T, n_beams=360)
+    g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, strategy=1))
+    o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05, strategy=1))
+    g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+    for t in range(T):
+        g.update(ds.scans[t], ds.odom[t]); o.update(ds.scans[t], ds.odom[t])
+        assert np.abs(g.state() - o.state()).max() < POSE_TOL
+
+
+# ---- PFSlam2D (config 3 family) -------------------------------------------------------------------------------------------
+def _run_pf_pair(gpu_api, po, ds, P, T, **kw):
+    g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(P, trans_thresh=0.05, rot_thresh=0.05, **kw))
+    o = po.PFSlam2D(po.PFOptions.defaults(P, trans_thresh=0.05, rot_thresh=0.05, threads=8, **kw))
+    g.setPrior(*ds.truth[0]); o.set_prior(*ds.truth[0])
+    n_res = 0
+    for t in range(T):
+        assert g.update(ds.scans[t], ds.odom[t]) == o.update(ds.scans[t], ds.odom[t])
+        rg, ro = g.lastResample(), o.last_resample()
+        assert rg.tolist() == ro.tolist()                                     # resample indices bit-exact
+        n_res += int(len(ro) > 0)
+        sg, wg = g.getParticles(); so, wo = o.particles()
+        assert np.abs(sg - so).max() < POSE_TOL
+        assert np.abs(wg - wo).max() < 1e-6 * max(1.0, np.abs(wo).max())
+        assert abs(g.getNeff() - o.neff) < 1e-6 and g.getBestParticleIdx() == o.best()
+        cg, _ = g.counters(); co, _ = o.counters()
+        assert (cg["evals"], cg["ray_cells"], cg["dm_pops"], cg["gn_iters"]) == (co["evals"], co["ray_cells"], co["dm_pops"], co["gn_iters"])
+    return g, o, n_res
+
+
+def test_pfslam2d_with_forced_resampling_and_golden(gpu_api, po, synth):
+    gold = np.load(os.path.join(HERE, "golden", "pf_room.npz"))
+    P, T = 12, 25
+    ds = synth.make_dataset("room", T, n_beams=180)
+    g, o, n_res = _run_pf_pair(gpu_api, po, ds, P, T, seed=5, meas_sigma_gain=0.02)
+    assert n_res >= 1                                                          # the COW / resample path really ran
+    sg, wg = g.getParticles()
+    assert np.abs(sg - gold["states"]).max() < POSE_TOL and np.abs(wg - gold["weights"]).max() < 1e-6
+    lo = gold["origin"]; h, w = gold["p3_visited"].shape
+    eg = g.exportOccupancy(3, int(lo[0]), int(lo[1]), w, h); dg = g.exportDistance(3, int(lo[0]), int(lo[1]), w, h)
+    assert (eg["visited"] == gold["p3_visited"]).all() and (eg["occupied"] == gold["p3_occupied"]).all()
+    assert (dg["sqdist"] == gold["p3_sqdist"]).all() and (dg["valid"] == gold["p3_valid"]).all()
+    for p in range(P):
+        n, mn, mx = o.dm_bounds(p); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+        _assert_dm_equal(g.exportDistance(p, int(mn[0]), int(mn[1]), w, h), o.export_dm(p, mn[0], mn[1], w, h))
+        n, mn, mx = o.occ_bounds(p); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+        a, b = g.exportOccupancy(p, int(mn[0]), int(mn[1]), w, h), o.export_occ(p, mn[0], mn[1], w, h)
+        assert (a["occupied"] == b["occupied"]).all() and (a["visited"] == b["visited"]).all() and (a["known"] == b["known"]).all()
+    tg, to = g.trajectory(0), o.trajectory(0)
+    assert tg.shape == to.shape and np.abs(tg - to).max() < POSE_TOL and np.abs(tg - gold["trajectory0"]).max() < POSE_TOL
+
+
+def test_pfslam2d_config3_30_particles_1080_beams(gpu_api, po, synth):
+    P, T = 30, 25
+    ds = synth.make_dataset("room", T)
+    assert ds.n_beams == 1080
+    g, o, _ = _run_pf_pair(gpu_api, po, ds, P, T, seed=42)
+    b = g.getBestParticleIdx()
+    assert np.hypot(*(g.getPose()[:2] - ds.truth[T - 1, :2])) < 0.1
+    n, mn, mx = o.dm_bounds(b); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    _assert_dm_equal(g.exportDistance(b, int(mn[0]), int(mn[1]), w, h), o.export_dm(b, mn[0], mn[1], w, h))
+
+
+def test_pfslam2d_motion_gate_and_rng_stream(gpu_api, po, synth):
+    """default thresholds (0.5 m / 0.5 rad): most scans are gated but noise is still drawn on every call"""
+    P, T = 8, 30
+    ds = synth.make_dataset("room", T, n_beams=180)
+    g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(P, seed=9))
+    o = po.PFSlam2D(po.PFOptions.defaults(P, seed=9))
+    g.setPrior(*ds.truth[0]); o.set_prior(*ds.truth[0])
+    ups = 0
+    for t in range(T):
+        a, b = g.update(ds.scans[t], ds.odom[t]), o.update(ds.scans[t], ds.odom[t])
+        assert a == b
+        ups += int(a)
+        assert np.abs(g.getParticles()[0] - o.particles()[0]).max() < POSE_TOL
+    assert 2 <= ups < T
