@@ -140,14 +140,13 @@ def gpu_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the lama_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    sharded = None
     if world > 1:
         import torch.distributed as dist
         from iris_lama_b200.distributed import ShardedPFSlam2D
         dist.init_process_group("nccl", device_id=dev)
 
     steps, warmup = args.steps, args.warmup
-    n_scans = 1 + 2 * (warmup + steps) + (warmup + steps)  # value pass, e2e pass, kernel-timing pass
+    n_scans = 1 + warmup + steps     # scan 0 initialises the maps; every pass replays the SAME scans 1 .. W+K
     ds = make_data(n_scans)
 
     stream = torch.cuda.Stream(device=dev)   # the engine launches on this stream, so torch CUDA events see its kernels
@@ -173,76 +172,61 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    pf = new_pf(False)
-    if world > 1:
-        sharded = ShardedPFSlam2D(pf, PARTICLES, device=dev)
-
-    def step_host(t):   # the public call with HOST buffers (e2e): H2D of the scan + D2H of the results inside
-        if sharded:
-            return sharded.update(ds.scans[t], ds.odom[t])
-        return pf.update(ds.scans[t], ds.odom[t])
+    def timed_pass(staged, timing=False):
+        """one fresh filter over scans 0 .. W+K; returns (device seconds of the K timed steps, wall seconds, pf, extras)"""
+        pf = new_pf(timing)
+        sh = ShardedPFSlam2D(pf, PARTICLES, device=dev) if world > 1 else None
+        if staged and sh is None:
+            pf.stageScans(ds.scans)
+            step = lambda t: pf.updateStaged(t, ds.odom[t])
+        elif sh is not None:
+            step = lambda t: sh.update(ds.scans[t], ds.odom[t])
+        else:
+            step = lambda t: pf.update(ds.scans[t], ds.odom[t])   # the public call with HOST buffers
+        step(0)
+        for t in range(1, 1 + warmup):
+            step(t)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        pf.traffic(reset=True)
+        _, tot0 = pf.counters()
+        if rank == 0 and staged:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        w0 = time.perf_counter()
+        n_upd = 0
+        for t in range(1 + warmup, 1 + warmup + steps):
+            n_upd += int(step(t))
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        dt = max_over_ranks(e0.elapsed_time(e1) * 1e-3)   # device timeline of the launching stream, max over ranks
+        clocks = sampler.stop() if (rank == 0 and staged) else None
+        _, tot1 = pf.counters()
+        return dict(dt=dt, wall=wall, pf=pf, clocks=clocks, n_upd=n_upd, work={k: tot1[k] - tot0[k] for k in tot1})
 
     # ---- pass 1: `value` -- scans resident in HBM (single GPU: staged scans; sharded: host scans, see config) ----
-    cur = 0
-    step_host(cur); cur += 1
-    if not sharded:
-        pf.stageScans(ds.scans)
-        step_value = lambda t: pf.updateStaged(t, ds.odom[t])
-    else:
-        step_value = step_host
-    for _ in range(warmup):
-        step_value(cur); cur += 1
-    sampler = ClockSampler(local_rank)
-    barrier()
-    pf.traffic(reset=True)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    t0 = time.perf_counter()
-    n_upd = 0
-    for _ in range(steps):
-        n_upd += int(step_value(cur)); cur += 1
-    ev1.record(stream)
-    barrier()
-    wall_value = time.perf_counter() - t0
-    dt_value = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)   # device timeline of the launching stream, max over ranks
-    clocks = sampler.stop() if rank == 0 else None
-    _, launches = pf.kernelTimes()
+    r1 = timed_pass(staged=True)
+    dt_value, wall_value, clocks, n_upd = r1["dt"], r1["wall"], r1["clocks"], r1["n_upd"]
+    _, launches = r1["pf"].kernelTimes()
     gpu_launches = int(sum(launches.values()))
-    _, totals_a = pf.counters()
+    work = r1["work"]
+    del r1
 
-    # ---- pass 2: `e2e` -- same metric through the public API with host buffers --------------------------------
-    for _ in range(warmup):
-        step_host(cur); cur += 1
-    barrier()
-    pf.traffic(reset=True)
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record(stream)
-    for _ in range(steps):
-        step_host(cur); cur += 1
-    ev3.record(stream)
-    barrier()
-    dt_e2e = max_over_ranks(ev2.elapsed_time(ev3) * 1e-3)
-    h2d, d2h = pf.traffic()
+    # ---- pass 2: `e2e` -- same metric, same scans, through the public API with host buffers -----------------------
+    r2 = timed_pass(staged=False)
+    dt_e2e = r2["dt"]
+    h2d, d2h = r2["pf"].traffic()
+    del r2
 
     # ---- pass 3: per-kernel CUDA-event durations for the roofline (timing mode adds event records) ------------
     roofline = None
     kernel_ms = None
     if world == 1:
-        pf2 = new_pf(True)
-        k = 0
-        pf2.update(ds.scans[k], ds.odom[k]); k += 1
-        # bring pf2 to the same map state cheaply: replay the scans of pass 1 (same seed -> same filter)
-        for _ in range(warmup + steps):
-            pf2.update(ds.scans[k], ds.odom[k]); k += 1
-        pf2.traffic(reset=True)
-        _, tot0 = pf2.counters()
-        for _ in range(steps):
-            pf2.update(ds.scans[k], ds.odom[k]); k += 1
-        ms, ln = pf2.kernelTimes()
-        _, tot1 = pf2.counters()
-        d = {kk: tot1[kk] - tot0[kk] for kk in tot1}
+        r3 = timed_pass(staged=True, timing=True)
+        ms, ln = r3["pf"].kernelTimes()
+        d = r3["work"]
         peak, peak_kind = load_peaks()
         # algorithmic bytes (SURVEY 8(d)): match E*N*(4 cells x 2 B); ray C*(4 B read + 4 B write); brushfire W*(5x8 B read + 4x8 B write)
         by = {"k_match": d["evals"] * BEAMS * 8.0, "k_raycast": d["ray_cells"] * 8.0, "k_brushfire": d["dm_pops"] * 72.0}
@@ -254,14 +238,14 @@ def gpu_arm(args):
                     "peak_kind": peak_kind, "algorithmic_bytes_per_launch": by[dom] / steps, "avg_launch_ms": tm[dom] / steps,
                     "all_kernels": {kk: {"GBps": (by[kk] / (tm[kk] * 1e-3) / 1e9 if tm[kk] > 0 else 0.0), "ms_per_step": tm[kk] / steps,
                                          "bytes_per_step": by[kk] / steps} for kk in tm}}
-        del pf2
+        del r3
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         cpu_steps = max(4, min(steps, args.cpu_steps))
-        val, dtc, _ = run_cpu(ds, 1, cpu_steps, 2, threads)
+        val, dtc, _ = run_cpu(ds, 1 + warmup - 2, cpu_steps, 2, threads)   # same scans as the GPU's timed region
         cpu = {"value": val, "unit": "scans/s", "cores": threads, "kind": "port",
                "sample": f"{cpu_steps} scans (after 2 warm-up) of the same workload, oracle restatement, thread pool of {threads}"}
 
@@ -280,7 +264,7 @@ def gpu_arm(args):
                 "clocks": clocks,
                 "e2e": {"value": steps / dt_e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps},
                 "gpu_launches": gpu_launches,
-                "counters_per_step": {k: v / max(1, (warmup + steps + 1)) for k, v in totals_a.items()}}
+                "counters_per_step": {k: v / steps for k, v in work.items()}}
         if roofline:
             line["roofline"] = roofline
             line["kernel_ms_per_step"] = kernel_ms

@@ -261,6 +261,8 @@ public:
     double offset;  // (UNIVERSAL_CONSTANT >> 1) * patch_length, map.cpp:55-58
     std::unordered_map<uint64_t, PatchPtr> patches;
     uint64_t detach_count = 0;  // deep patch copies performed by copy-on-write (work counter D)
+    mutable uint64_t prev_idx_ = ~0ull;          // map.h:374-375
+    mutable PatchPtr* prev_patch_ = nullptr;
 
     SparseMap(double res, uint32_t patch_size)
         : resolution(res), scale(1.0 / res), patch_length(1u << ((int)std::log2(patch_size)))
@@ -269,8 +271,12 @@ public:
         log2dim      = (uint32_t)std::log2(patch_length);
         offset       = (double)((kUniversalConstant >> 1) * patch_length);
     }
-    // COW copy: every patch pointer is shared (map.cpp:96-97).
-    SparseMap(const SparseMap& o) = default;
+    // COW copy: every patch pointer is shared (map.cpp:96-97); the patch cache is not carried over.
+    SparseMap(const SparseMap& o)
+        : resolution(o.resolution), scale(o.scale), patch_length(o.patch_length), patch_volume(o.patch_volume), log2dim(o.log2dim), offset(o.offset),
+          patches(o.patches), detach_count(o.detach_count)
+    {
+    }
 
     // map.h:137-138 : tf_ * p with tf_ = Translation(adjust*patch_length) * Scaling(scale)
     void w2m_nocast(const double p[3], double m[3]) const
@@ -305,13 +311,18 @@ public:
         return Vec3u{(uint32_t)((idx / kUniversalConstant) << log2dim), (uint32_t)((idx % kUniversalConstant) << log2dim), 0};
     }
 
-    // Mutable access (map.cpp:371-412): allocate-on-touch, detach shared patch, set the known bit.
+    // Mutable access (map.cpp:371-412): allocate-on-touch, detach shared patch, set the known bit.  The
+    // one-entry patch cache mirrors prev_idx_ / prev_patch_ (map.cpp:400-409): it only saves hash lookups.
     Cell* get(const Vec3u& c)
     {
         uint64_t idx = m2p(c);
-        auto it      = patches.find(idx);
-        if (it == patches.end()) it = patches.emplace(idx, std::make_shared<PatchT>(patch_volume)).first;
-        PatchPtr& p = it->second;
+        if (prev_idx_ != idx || prev_patch_ == nullptr) {
+            auto it = patches.find(idx);
+            if (it == patches.end()) it = patches.emplace(idx, std::make_shared<PatchT>(patch_volume)).first;
+            prev_idx_   = idx;
+            prev_patch_ = &it->second;  // unordered_map never moves its nodes
+        }
+        PatchPtr& p = *prev_patch_;
         if (p.use_count() > 1) {  // cow_ptr.h:104-114
             p = std::make_shared<PatchT>(*p);
             ++detach_count;
@@ -323,11 +334,21 @@ public:
     // Const access (map.cpp:414-455, container.h:119-123): null if patch absent or bit off.
     const Cell* get(const Vec3u& c) const
     {
-        auto it = patches.find(m2p(c));
-        if (it == patches.end()) return nullptr;
+        uint64_t idx = m2p(c);
+        if (prev_idx_ != idx) {
+            auto it = patches.find(idx);
+            prev_idx_ = idx;
+            if (it == patches.end()) {
+                prev_patch_ = nullptr;
+                return nullptr;
+            }
+            prev_patch_ = const_cast<PatchPtr*>(&it->second);
+        } else if (prev_patch_ == nullptr) {
+            return nullptr;
+        }
         uint32_t ci = m2c(c);
-        if (!it->second->is_on(ci)) return nullptr;
-        return &it->second->cells[ci];
+        if (!(*prev_patch_)->is_on(ci)) return nullptr;
+        return &(*prev_patch_)->cells[ci];
     }
 
     // Integer Bresenham, both endpoints excluded (map.cpp:198-227).
