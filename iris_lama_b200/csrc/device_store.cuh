@@ -29,6 +29,14 @@ struct StoreView {
 
 enum MapKind : int { kMapOcc = 0, kMapDm = 1 };
 
+// A directory entry is -1 (patch absent) or slot | flags:
+//   kDirHot   persistent, occupancy directories only: the patch may hold cells whose obstacle-mirror bit is set
+//             (the ray-cast kernel uses fire-and-forget RED atomics on all other patches)
+//   kDirExcl  only ever set in SHARED-MEMORY copies: exclusivity of the patch was verified during this launch
+constexpr int32_t kDirSlotMask = 0x00FFFFFF;
+constexpr int32_t kDirHot      = 1 << 28;
+constexpr int32_t kDirExcl     = 1 << 30;
+
 __device__ __forceinline__ int32_t* dir_of(const StoreView& s, int set, int particle, int kind)
 {
     return s.dirs + (((size_t)set * s.n_particles + particle) * 2 + kind) * (size_t)(s.window.dim * s.window.dim);
@@ -81,7 +89,9 @@ __device__ __forceinline__ void warp_copy_patch(uint32_t* dst, const uint32_t* s
 // of the directory, `dir_gmem` its home.  Returns the (now exclusive) slot or -1 when the pool is empty.
 __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* dir_smem, int32_t* dir_gmem, int di, int lane)
 {
-    int slot = dir_smem[di];
+    const int entry = dir_smem[di];
+    const int slot  = entry < 0 ? -1 : (entry & kDirSlotMask);
+    const int keep  = entry < 0 ? 0 : (entry & kDirHot);
     if (slot < 0) {
         int ns = 0;
         if (lane == 0) {
@@ -93,8 +103,8 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         warp_zero_patch(patch_ptr(s, ns), lane);
         __syncwarp();
         if (lane == 0) {
-            dir_smem[di] = ns;
-            dir_gmem[di] = ns;
+            dir_smem[di] = ns | keep;
+            dir_gmem[di] = ns | keep;
         }
         __syncwarp();
         return ns;
@@ -115,8 +125,8 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         warp_copy_patch(patch_ptr(s, ns), patch_ptr(s, slot), lane);
         __syncwarp();
         if (lane == 0) {
-            dir_smem[di] = ns;
-            dir_gmem[di] = ns;
+            dir_smem[di] = ns | keep;
+            dir_gmem[di] = ns | keep;
             __threadfence();
             release_slot(s, slot);
         }

@@ -342,9 +342,15 @@ int Engine::update_maps(const SE2* states, int first_particle, int count, HostMa
     rp.scan = d_->scan;
     rp.set = cur_set_;
     rp.particle_offset = first_particle;
+    // shared-memory scratch sized for THIS scan (two CTAs per SM at 1080 beams); the maxima were registered at create
+    const int nb = d_->scan.n_beams;
+    rp.log_cap   = std::min(d_->ray.log_cap, next_pow2_host(std::max(1024, 3 * nb)));
+    rp.hash_cap  = std::min(d_->ray.hash_cap, next_pow2_host(std::max(1024, 2 * nb)));
+    rp.event_cap = std::min(d_->ray.event_cap, next_pow2_host(std::max(512, nb)));
     BrushParams bp = d_->brush;
     bp.set = cur_set_;
     bp.particle_offset = first_particle;
+    bp.event_cap = rp.event_cap;
     cudaEvent_t e2 = nullptr;
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
     launch_raycast(d_->view, rp, d_->d_states, d_->d_events, d_->d_stats, count, d_->stream);

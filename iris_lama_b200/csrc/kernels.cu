@@ -11,7 +11,7 @@
 // into shared memory with TMA bulk copies (cp.async.bulk + mbarrier).
 #include "kernels.cuh"
 
-#include "ddm_core.h"
+#include "brushfire_warp.cuh"
 
 namespace lama_b200 {
 
@@ -49,7 +49,7 @@ __device__ __forceinline__ double cell_distance(const uint32_t* __restrict__ poo
     if (di < 0) return dtab[max_sqdist];
     int slot = dir[di];
     if (slot < 0) return dtab[max_sqdist];
-    uint32_t w = __ldg(pool + (size_t)slot * kPatchCells + cell_index(x, y));
+    uint32_t w = __ldg(pool + (size_t)(slot & kDirSlotMask) * kPatchCells + cell_index(x, y));
     return (w & kDmValid) ? dtab[dm_sqdist(w)] : dtab[max_sqdist];
 }
 
@@ -72,7 +72,7 @@ __device__ __forceinline__ void eval_beam(double s[kNumSums], const Affine& tf, 
         if (slot < 0) {
             v[0] = v[1] = v[2] = v[3] = dmax;
         } else {
-            const uint32_t* p = pool + (size_t)slot * kPatchCells + cell_index(dx, dy);
+            const uint32_t* p = pool + (size_t)(slot & kDirSlotMask) * kPatchCells + cell_index(dx, dy);
             uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + kPatchLen), w3 = __ldg(p + kPatchLen + 1);
             v[0] = (w0 & kDmValid) ? dtab[dm_sqdist(w0)] : dmax;
             v[1] = (w1 & kDmValid) ? dtab[dm_sqdist(w1)] : dmax;
@@ -219,17 +219,64 @@ __device__ __forceinline__ int next_pow2(int v)
     return p;
 }
 
+// 2-D integer Bresenham of Map::computeRay for the planar case (from.z == to.z, every 2-D scan): the z axis of the
+// reference's 3-axis loop then never moves (delta_z = 0, 2 * err_z = 0 < n), so dropping it is exact.
+struct RayWalk2 {
+    int ex, ey, dx, dy, sx, sy, n, i;
+    uint32_t x, y;
+    __device__ __forceinline__ explicit RayWalk2(const BeamCells& b)
+    {
+        x = b.from[0];
+        y = b.from[1];
+        const int ddx = (int)(b.to[0] - b.from[0]), ddy = (int)(b.to[1] - b.from[1]);
+        sx = ddx < 0 ? -1 : 1;
+        sy = ddy < 0 ? -1 : 1;
+        dx = ddx < 0 ? -ddx : ddx;
+        dy = ddy < 0 ? -ddy : ddy;
+        n  = dx > dy ? dx : dy;
+        ex = ey = 0;
+        i  = 0;
+    }
+    __device__ __forceinline__ bool next()
+    {
+        if (i >= n - 1) return false;
+        ++i;
+        ex += dx;
+        ey += dy;
+        if (2 * ex >= n) { x += sx; ex -= n; }
+        if (2 * ey >= n) { y += sy; ey -= n; }
+        return true;
+    }
+};
+
+// visits every interior cell of the beam: f(x, y, pos) with pos = 1, 2, ... in the reference's emission order
+template <typename F>
+__device__ __forceinline__ void walk_beam(const BeamCells& bc, F&& f)
+{
+    if (bc.from[2] == bc.to[2]) {
+        RayWalk2 w(bc);
+        uint32_t pos = 0;
+        while (w.next()) f(w.x, w.y, ++pos);
+    } else {  // tilted sensor: the general 3-axis walk
+        RayWalk w(bc);
+        uint32_t pos = 0;
+        while (w.next()) f(w.x, w.y, ++pos);
+    }
+}
+
 __global__ void __launch_bounds__(kRayThreads, 2)
 k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dim2   = s.window.dim * s.window.dim;
+    const int nwords = (dim2 + 31) / 32;
     int32_t* dir     = reinterpret_cast<int32_t*>(smem_raw);
     uint64_t* log    = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
     uint64_t* events = log + rp.log_cap;
     uint32_t* hash   = reinterpret_cast<uint32_t*>(events + rp.event_cap);
-    uint32_t* bitmap = hash + rp.hash_cap;
-    RayShared& sh    = *reinterpret_cast<RayShared*>(bitmap + (dim2 + 31) / 32);
+    uint32_t* bitmap = hash + rp.hash_cap;   // patches touched by this scan
+    uint32_t* hot    = bitmap + nwords;      // patches that need the ordered slow path
+    RayShared& sh    = *reinterpret_cast<RayShared*>(hot + nwords + (nwords & 1));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int particle = rp.particle_offset + blockIdx.x;
@@ -244,42 +291,47 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         sh.log_count = sh.event_count = sh.cells = sh.err = 0;
     }
     for (int i = tid; i < rp.hash_cap; i += blockDim.x) hash[i] = 0u;
-    for (int i = tid; i < (dim2 + 31) / 32; i += blockDim.x) bitmap[i] = 0u;
+    for (int i = tid; i < 2 * nwords; i += blockDim.x) bitmap[i] = 0u;  // bitmap + hot are contiguous
     __syncthreads();
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
     const Affine tf = sh.tf;
+    // patches that already hold obstacle-mirror cells are "hot": their misses need the returned old value
+    for (int di = tid; di < dim2; di += blockDim.x) {
+        const int e = dir[di];
+        if (e >= 0 && (e & kDirHot)) atomicOr(&hot[di >> 5], 1u << (di & 31));
+    }
 
     // ---- phase 1: mark touched patches, collect the set of hit cells -----------------------------------
     uint32_t my_err = 0;
     for (int b = tid; b < n; b += blockDim.x) {
         const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
-        BeamCells bc = beam_cells(tf, rp.scan, pt);
-        int last = -1;
+        const BeamCells bc = beam_cells(tf, rp.scan, pt);
         if (bc.mark_hit) {
-            int di = dir_index(win, bc.to[0], bc.to[1]);
+            const int di = dir_index(win, bc.to[0], bc.to[1]);
             if (di < 0) my_err |= kErrWindow;
             else {
                 hash_insert(hash, rp.hash_cap, cell_key(win, bc.to[0], bc.to[1]));
                 atomicOr(&bitmap[di >> 5], 1u << (di & 31));
+                atomicOr(&hot[di >> 5], 1u << (di & 31));
             }
         }
-        RayWalk w(bc);
-        while (w.next()) {
-            int di = dir_index(win, w.x, w.y);
-            if (di < 0) { my_err |= kErrWindow; continue; }
+        int last = -1;
+        walk_beam(bc, [&](uint32_t x, uint32_t y, uint32_t) {
+            const int di = dir_index(win, x, y);
+            if (di < 0) { my_err |= kErrWindow; return; }
             if (di != last) {
                 atomicOr(&bitmap[di >> 5], 1u << (di & 31));
                 last = di;
             }
-        }
+        });
     }
     __syncthreads();
 
     // ---- phase 2: allocate / detach every touched patch (Map::get mutable + COW) ------------------------
-    for (int w32 = warp; w32 < (dim2 + 31) / 32; w32 += nwarps) {
+    for (int w32 = warp; w32 < nwords; w32 += nwarps) {
         uint32_t bits = bitmap[w32];
         while (bits) {
-            int bit = __ffs(bits) - 1;
+            const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
             if (warp_make_exclusive(s, dir, gdir, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
         }
@@ -290,30 +342,34 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     uint32_t my_cells = 0;
     for (int b = tid; b < n; b += blockDim.x) {
         const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
-        BeamCells bc = beam_cells(tf, rp.scan, pt);
+        const BeamCells bc = beam_cells(tf, rp.scan, pt);
         if (bc.mark_hit) {
-            int di = dir_index(win, bc.to[0], bc.to[1]);
+            const int di = dir_index(win, bc.to[0], bc.to[1]);
             if (di >= 0 && dir[di] >= 0) {
                 ++my_cells;
-                atomicAdd(patch_ptr(s, dir[di]) + cell_index(bc.to[0], bc.to[1]), kOccHitInc);
-                uint32_t idx = atomicAdd(&sh.log_count, 1u);
+                atomicAdd(patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(bc.to[0], bc.to[1]), kOccHitInc);
+                const uint32_t idx = atomicAdd(&sh.log_count, 1u);
                 if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, bc.to[0], bc.to[1]), (uint32_t)b, 0u, true);
             }
         }
-        RayWalk w(bc);
-        uint32_t pos = 0;
-        while (w.next()) {
-            ++pos;
-            int di = dir_index(win, w.x, w.y);
-            if (di < 0 || dir[di] < 0) continue;
+        walk_beam(bc, [&](uint32_t x, uint32_t y, uint32_t pos) {
+            const int di = dir_index(win, x, y);
+            if (di < 0) return;
+            const int e = dir[di];
+            if (e < 0) return;
             ++my_cells;
-            uint32_t old = atomicAdd(patch_ptr(s, dir[di]) + cell_index(w.x, w.y), kOccMissInc);
-            uint32_t key = cell_key(win, w.x, w.y);
+            uint32_t* cell = patch_ptr(s, e & kDirSlotMask) + cell_index(x, y);
+            if (!((hot[di >> 5] >> (di & 31)) & 1u)) {
+                atomicAdd(cell, kOccMissInc);  // result unused: compiles to a fire-and-forget RED
+                return;
+            }
+            const uint32_t old = atomicAdd(cell, kOccMissInc);
+            const uint32_t key = cell_key(win, x, y);
             if ((old & kOccObstacle) || hash_contains(hash, rp.hash_cap, key)) {
-                uint32_t idx = atomicAdd(&sh.log_count, 1u);
+                const uint32_t idx = atomicAdd(&sh.log_count, 1u);
                 if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(key, (uint32_t)b, pos, false);
             }
-        }
+        });
     }
     my_cells = __reduce_add_sync(0xffffffffu, my_cells);
     if (lane == 0 && my_cells) atomicAdd(&sh.cells, my_cells);
@@ -337,15 +393,23 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         int end = i + 1;
         while (end < (int)count && log_key(log[end]) == key) ++end;
         const uint32_t x = key_x(win, key), y = key_y(win, key);
-        uint32_t* cell = patch_ptr(s, dir[dir_index(win, x, y)]) + cell_index(x, y);
+        const int di = dir_index(win, x, y);
+        uint32_t* cell = patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(x, y);
         const uint32_t final_word = __ldcg(cell);
-        bool obstacle = replay_cell(log, i, end, final_word, [&](bool add, uint32_t seq) {
+        const bool obstacle = replay_cell(log, i, end, final_word, [&](bool add, uint32_t seq) {
             uint32_t idx = atomicAdd(&sh.event_count, 1u);
             if (idx < (uint32_t)rp.event_cap) events[idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
         });
         if (obstacle != ((final_word & kOccObstacle) != 0)) {
-            if (obstacle) atomicOr(cell, kOccObstacle);
-            else atomicAnd(cell, ~kOccObstacle);
+            if (obstacle) {
+                atomicOr(cell, kOccObstacle);
+                if (!(dir[di] & kDirHot)) {  // from now on this patch needs the ordered path
+                    atomicOr(&dir[di], kDirHot);
+                    atomicOr(&gdir[di], kDirHot);
+                }
+            } else {
+                atomicAnd(cell, ~kOccObstacle);
+            }
         }
     }
     __syncthreads();
@@ -376,83 +440,39 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
 // ==================================================================================================
 // k_brushfire
 // ==================================================================================================
-struct DeviceDmMap {
-    const StoreView& s;
-    int32_t* dir;       // staged in shared memory
-    int32_t* gdir;
-    uint32_t* excl;     // per directory entry: already verified exclusive during this launch
-    uint32_t* scratch;  // out-of-window accesses land here
-    DirWindow window;
-    int lane;
-    uint32_t err;
-
-    __device__ DeviceDmMap(const StoreView& sv, int32_t* d, int32_t* g, uint32_t* e, uint32_t* sc, int l)
-        : s(sv), dir(d), gdir(g), excl(e), scratch(sc), window(sv.window), lane(l), err(0) {}
-
-    // the mutable Map::get: allocate on touch, copy-on-write detach, mark the cell known
-    __device__ __forceinline__ uint32_t* cell(uint32_t x, uint32_t y)
-    {
-        int di = dir_index(window, x, y);
-        if (di < 0) {
-            err |= kErrWindow;
-            *scratch = 0;
-            return scratch;
-        }
-        if (!((excl[di >> 5] >> (di & 31)) & 1u)) {
-            if (warp_make_exclusive(s, dir, gdir, di, lane) < 0) {
-                err |= kErrPoolEmpty;
-                *scratch = 0;
-                return scratch;
-            }
-            excl[di >> 5] |= 1u << (di & 31);
-            __syncwarp();
-        }
-        uint32_t* p = patch_ptr(s, dir[di]) + cell_index(x, y);
-        uint32_t w  = *p;
-        if (!(w & kDmKnown)) *p = w | kDmKnown;
-        return p;
-    }
-};
-
-// One warp per particle executing the sequential algorithm warp-uniformly: every lane runs the same
-// instruction stream on the same values (loads broadcast, identical stores coalesce), so the 32 lanes
-// are available for the bulk patch zero/copy of allocate-on-touch without any divergence hand-off.
+// One warp per particle (see brushfire_warp.cuh for the schedule and why it is exact).
 __global__ void __launch_bounds__(32)
 k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dim2    = s.window.dim * s.window.dim;
     int32_t* dir      = reinterpret_cast<int32_t*>(smem_raw);
-    uint64_t* lower_h = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
-    uint64_t* raise_h = lower_h + bp.lower_cap;
-    uint32_t* excl    = reinterpret_cast<uint32_t*>(raise_h + bp.raise_cap);
-    uint64_t* bar     = reinterpret_cast<uint64_t*>(excl + (dim2 + 31) / 32 + 2);
-    uint32_t* scratch = excl + (dim2 + 31) / 32;
+    uint64_t* lower_h = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);   // 16-byte aligned: dim2 * 4 is a multiple of 16
+    uint64_t* raise_h = lower_h + bp.lower_cap + 2;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(raise_h + bp.raise_cap + 2);
+    uint64_t* bar     = reinterpret_cast<uint64_t*>(scratch + 32);
     const int lane    = threadIdx.x;
     const int particle = bp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, bp.set, particle, kMapDm);
 
     if (lane == 0) mbar_init(bar, 1);
-    for (int i = lane; i < (dim2 + 31) / 32 + 2; i += 32) excl[i] = 0u;
     __syncwarp();
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, bar, 0);
     __syncwarp();
 
-    DeviceDmMap map(s, dir, gdir, excl, scratch, lane);
-    Brushfire<DeviceDmMap> bf(map, Heap{raise_h, 0u, (uint32_t)bp.raise_cap}, Heap{lower_h, 0u, (uint32_t)bp.lower_cap}, bp.max_sqdist);
-
+    WarpBrushfire bf(s, dir, gdir, scratch, lane, SmemHeap{lower_h, 0u, (uint32_t)bp.lower_cap}, SmemHeap{raise_h, 0u, (uint32_t)bp.raise_cap},
+                     bp.max_sqdist);
     const uint32_t nev = stats[blockIdx.x].events;
     const uint64_t* ev = events + (size_t)blockIdx.x * bp.event_cap;
     for (uint32_t i = 0; i < nev; ++i) {
         const uint64_t e   = ev[i];
         const uint32_t key = (uint32_t)e;
-        const bool add     = ((e >> 32) & 1u) != 0;
         const uint32_t x = key_x(s.window, key), y = key_y(s.window, key);
-        if (add) bf.add_obstacle(x, y);
+        if ((e >> 32) & 1u) bf.add_obstacle(x, y);
         else bf.remove_obstacle(x, y);
     }
     const uint32_t processed = bf.update();
-    const uint32_t err = map.err | bf.err;
+    const uint32_t err = __reduce_or_sync(0xffffffffu, bf.err);
     if (lane == 0) {
         stats[blockIdx.x].dm_pops = processed;
         if (err) atomicOr(s.status, err);
@@ -471,8 +491,8 @@ __global__ void k_copy_dirs(StoreView s, int src_set, int dst_set, const int32_t
     int32_t* dst       = dir_of(s, dst_set, p, kind);
     for (int e = threadIdx.x; e < dim2; e += blockDim.x) {
         int slot = a < 0 ? -1 : src[e];
-        dst[e]   = slot;
-        if (slot >= 0) atomicAdd(&s.refcount[slot], 1);
+        dst[e]   = slot;  // keeps kDirHot
+        if (slot >= 0) atomicAdd(&s.refcount[slot & kDirSlotMask], 1);
     }
 }
 __global__ void k_release(StoreView s, int set, int first)
@@ -483,7 +503,7 @@ __global__ void k_release(StoreView s, int set, int first)
     for (int e = threadIdx.x; e < dim2; e += blockDim.x) {
         int slot = d[e];
         if (slot >= 0) {
-            release_slot(s, slot);
+            release_slot(s, slot & kDirSlotMask);
             d[e] = -1;
         }
     }
@@ -527,7 +547,7 @@ __global__ void k_export(StoreView s, int set, int particle, int kind, uint32_t 
         uint32_t x = x0 + (uint32_t)(k % w), y = y0 + (uint32_t)(k / w);
         int di   = dir_index(s.window, x, y);
         int slot = di < 0 ? -1 : d[di];
-        out[k]   = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot) + cell_index(x, y));
+        out[k]   = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot & kDirSlotMask) + cell_index(x, y));
         if (present) present[k] = slot >= 0;
     }
 }
@@ -558,10 +578,15 @@ __global__ void k_import(StoreView s, int set, int particle, int kind, uint32_t 
     int slot = warp_make_exclusive(s, d, d, di, lane);
     if (slot < 0) return;
     uint32_t* dst = patch_ptr(s, slot);
+    uint32_t obst = 0;
     for (int c = lane; c < kPatchCells; c += 32) {
         int cx = c & (kPatchLen - 1), cy = c >> kPatchLog2;
-        dst[c] = in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
+        uint32_t v = in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
+        dst[c] = v;
+        obst |= v & kOccObstacle;
     }
+    obst = __reduce_or_sync(0xffffffffu, obst);
+    if (kind == kMapOcc && obst && lane == 0) d[di] |= kDirHot;
 }
 
 // gather the patches listed in `slots` into a contiguous buffer (particle migration between GPUs)
@@ -570,7 +595,7 @@ __global__ void k_gather_patches(StoreView s, const int32_t* __restrict__ slots,
     const int lane = threadIdx.x & 31;
     const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pi >= n) return;
-    warp_copy_patch(out + (size_t)pi * kPatchCells, patch_ptr(s, slots[pi]), lane);
+    warp_copy_patch(out + (size_t)pi * kPatchCells, patch_ptr(s, slots[pi] & kDirSlotMask), lane);
 }
 // allocate a patch per listed directory entry of (set, particle, kind) and fill it from `in`
 __global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, const int32_t* __restrict__ entries, int n, const uint32_t* __restrict__ in)
@@ -582,6 +607,8 @@ __global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, 
     int slot = warp_make_exclusive(s, d, d, entries[pi], lane);
     if (slot < 0) return;
     warp_copy_patch(patch_ptr(s, slot), in + (size_t)pi * kPatchCells, lane);
+    // a migrated occupancy patch may hold obstacle-mirror cells: take the ordered ray-cast path (conservative)
+    if (kind == kMapOcc && lane == 0) d[entries[pi]] |= kDirHot;
 }
 
 __global__ void k_distance(StoreView s, int set, int particle, const double* __restrict__ pts, int n, double resolution, uint32_t max_sqdist,
@@ -598,7 +625,7 @@ __global__ void k_distance(StoreView s, int set, int particle, const double* __r
             uint32_t x = dx + (k & 1), y = dy + (k >> 1);
             int di = dir_index(s.window, x, y);
             int slot = di < 0 ? -1 : d[di];
-            uint32_t w = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot) + cell_index(x, y));
+            uint32_t w = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot & kDirSlotMask) + cell_index(x, y));
             v[k] = (w & kDmValid) ? mul_rn(sqrt((double)dm_sqdist(w)), resolution) : dmax;
         }
         BeamEval e = bilinear(v, add_rn(mx, -(double)dx), add_rn(my, -(double)dy), scale, 0, 0);
@@ -623,13 +650,13 @@ size_t match_smem_bytes(int dir_dim, uint32_t max_sqdist)
 size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
 {
     const int dim2 = dir_dim * dir_dim;
-    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)rp.hash_cap * 4 + (size_t)((dim2 + 31) / 32) * 4 +
+    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)rp.hash_cap * 4 + (size_t)((dim2 + 31) / 32 + 1) * 8 +
            sizeof(RayShared) + 16;
 }
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {
     const int dim2 = dir_dim * dir_dim;
-    return (size_t)dim2 * 4 + (size_t)(bp.lower_cap + bp.raise_cap) * 8 + (size_t)((dim2 + 31) / 32 + 2) * 4 + 16 + 16;
+    return (size_t)dim2 * 4 + (size_t)(bp.lower_cap + bp.raise_cap + 4) * 8 + 32 * 4 + 16 + 16;
 }
 
 cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayParams& rp, const BrushParams& bp)
