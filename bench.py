@@ -107,20 +107,40 @@ def run_cpu(ds, first, steps, warmup, threads):
     return n / dt, dt, o
 
 
+def pick_threads(ds):
+    """The reference's thread pool does not scale to every core of a large host (measured on the 128-core GPU box:
+    best around 16-32 threads); give the CPU arm its best thread count, found on a few early scans."""
+    from oracle import pyoracle as po
+    ncpu = os.cpu_count() or 1
+    best, best_v = 1, 0.0
+    for th in sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu} | {min(ncpu, 8)}):
+        o = po.PFSlam2D(po.PFOptions.defaults(PARTICLES, threads=th, **pf_options_kwargs()))
+        o.set_prior(*ds.truth[0])
+        for t in range(3):
+            o.update(ds.scans[t], ds.odom[t])
+        t0 = time.perf_counter()
+        for t in range(3, 7):
+            o.update(ds.scans[t], ds.odom[t])
+        v = 4.0 / (time.perf_counter() - t0)
+        if v > best_v:
+            best, best_v = th, v
+    return best
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    steps, warmup = args.steps, args.warmup
-    ds = make_data(1 + warmup + steps)
-    val, dt, _ = run_cpu(ds, 1, steps, warmup, threads)
+    steps, warmup, pre = args.steps, args.warmup, args.prebuild
+    ds = make_data(max(8, 1 + pre + warmup + steps))
+    threads = pick_threads(ds)
+    val, dt, _ = run_cpu(ds, 1 + pre, steps, warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1000.0 * dt / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": f"PFSlam2D {PARTICLES} particles x {BEAMS} beams, 0.05 m grid, synthetic 30 m loop room",
                                             "particles": PARTICLES, "beams": BEAMS},
             "cpu_baseline": {"value": val, "unit": "scans/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} scans after {warmup} warm-up scans of the same workload; oracle restatement (the reference needs Eigen, absent), "
+                             "sample": f"{steps} scans after {pre} map-building + {warmup} warm-up scans of the same workload; oracle restatement (the reference needs Eigen, absent), "
                                        f"g++ -O3 -march=x86-64-v3, one task per particle per phase on {threads} threads"},
             "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -145,8 +165,10 @@ def gpu_arm(args):
         from iris_lama_b200.distributed import ShardedPFSlam2D
         dist.init_process_group("nccl", device_id=dev)
 
-    steps, warmup = args.steps, args.warmup
-    n_scans = 1 + warmup + steps     # scan 0 initialises the maps; every pass replays the SAME scans 1 .. W+K
+    steps, warmup, pre = args.steps, args.warmup, args.prebuild
+    # scan 0 initialises the maps, scans 1 .. pre build them (untimed, the filter leaves the exploration phase that
+    # only covers the first ~3 % of the 5 000-scan loop), then W warm-up and K timed scans; every pass replays the SAME scans
+    n_scans = max(8, 1 + pre + warmup + steps)
     ds = make_data(n_scans)
 
     stream = torch.cuda.Stream(device=dev)   # the engine launches on this stream, so torch CUDA events see its kernels
@@ -184,7 +206,7 @@ def gpu_arm(args):
         else:
             step = lambda t: pf.update(ds.scans[t], ds.odom[t])   # the public call with HOST buffers
         step(0)
-        for t in range(1, 1 + warmup):
+        for t in range(1, 1 + pre + warmup):
             step(t)
         sampler = ClockSampler(local_rank)
         barrier()
@@ -196,7 +218,7 @@ def gpu_arm(args):
         e0.record(stream)
         w0 = time.perf_counter()
         n_upd = 0
-        for t in range(1 + warmup, 1 + warmup + steps):
+        for t in range(1 + pre + warmup, 1 + pre + warmup + steps):
             n_upd += int(step(t))
         e1.record(stream)
         barrier()
@@ -243,11 +265,12 @@ def gpu_arm(args):
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        threads = pick_threads(ds)
         cpu_steps = max(4, min(steps, args.cpu_steps))
-        val, dtc, _ = run_cpu(ds, 1 + warmup - 2, cpu_steps, 2, threads)   # same scans as the GPU's timed region
+        val, dtc, _ = run_cpu(ds, 1 + pre + warmup - 2, cpu_steps, 2, threads)   # same scans as the GPU's timed region
         cpu = {"value": val, "unit": "scans/s", "cores": threads, "kind": "port",
-               "sample": f"{cpu_steps} scans (after 2 warm-up) of the same workload, oracle restatement, thread pool of {threads}"}
+               "sample": f"{cpu_steps} scans (after {pre} map-building scans) of the same workload, oracle restatement, thread pool of {threads} "
+                         f"(best of 8/16/32/64/{os.cpu_count()} threads on this host)"}
 
     if rank == 0:
         value = steps / dt_value
@@ -258,7 +281,7 @@ def gpu_arm(args):
                            "particles": PARTICLES, "beams": BEAMS, "parallelism": f"particles sharded over {world} GPU(s)",
                            "l2": "per-scan working set (~290 MB of touched map patches over 256 particles) exceeds the 126 MB L2; no explicit flush",
                            "value_inputs": "scans staged in HBM" if world == 1 else "host scans (sharded path)",
-                           "updates_in_timed_region": n_upd,
+                           "updates_in_timed_region": n_upd, "prebuild_scans": pre,
                            "timer": "CUDA events on the launching stream around the K steps (each step also synchronises for its host-side "
                                     "normalise/resample logic); host wall clock of the same region: %.3f s" % wall_value},
                 "clocks": clocks,
@@ -284,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prebuild", type=int, default=300, help="untimed scans that build the map before warm-up (both arms)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

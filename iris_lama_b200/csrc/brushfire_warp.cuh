@@ -86,7 +86,7 @@ struct SmemHeap {
 
 struct WarpBrushfire {
     const StoreView& s;
-    int32_t* dir;        // shared-memory copy of the distance-map directory; kDirExcl marks verified entries
+    int32_t* dir;        // shared-memory copy of the distance-map directory (entries carry kDirOwn)
     int32_t* gdir;
     uint32_t* scratch;   // 32 words: out-of-window / failed accesses land here (one word per lane)
     const DirWindow win;
@@ -100,9 +100,9 @@ struct WarpBrushfire {
         : s(sv), dir(d), gdir(g), scratch(sc), win(sv.window), lane(l), lower_q(lo), raise_q(ra), max_sqdist(msq), err(0), dead(false) {}
 
     // ---- mutable Map::get -------------------------------------------------------------------------------------
-    __device__ __forceinline__ bool entry_ready(int e) const { return e >= 0 && (e & kDirExcl); }
+    __device__ __forceinline__ bool entry_ready(int e) const { return e >= 0 && (e & kDirOwn); }
 
-    // all lanes, identical di: allocate / detach, then mark the shared-memory entry as verified
+    // all lanes, identical di: allocate / detach / verify sole ownership (sets kDirOwn in both directory copies)
     __device__ __forceinline__ bool ensure(int di)
     {
         int slot = warp_make_exclusive(s, dir, gdir, di, lane);
@@ -111,8 +111,6 @@ struct WarpBrushfire {
             dead = true;
             return false;
         }
-        if (lane == 0) dir[di] |= kDirExcl;
-        __syncwarp();
         return true;
     }
     // warp-uniform coordinates

@@ -32,10 +32,12 @@ enum MapKind : int { kMapOcc = 0, kMapDm = 1 };
 // A directory entry is -1 (patch absent) or slot | flags:
 //   kDirHot   persistent, occupancy directories only: the patch may hold cells whose obstacle-mirror bit is set
 //             (the ray-cast kernel uses fire-and-forget RED atomics on all other patches)
-//   kDirExcl  only ever set in SHARED-MEMORY copies: exclusivity of the patch was verified during this launch
+//   kDirOwn   persistent: this particle is the ONLY owner of the slot (reference count verified to be 1), so the
+//             patch can be written in place without looking at the count.  Set on allocation, on copy-on-write
+//             detach and when a count of 1 is observed; cleared on every entry that k_copy_dirs shares.
 constexpr int32_t kDirSlotMask = 0x00FFFFFF;
 constexpr int32_t kDirHot      = 1 << 28;
-constexpr int32_t kDirExcl     = 1 << 30;
+constexpr int32_t kDirOwn      = 1 << 29;
 
 __device__ __forceinline__ int32_t* dir_of(const StoreView& s, int set, int particle, int kind)
 {
@@ -103,12 +105,13 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         warp_zero_patch(patch_ptr(s, ns), lane);
         __syncwarp();
         if (lane == 0) {
-            dir_smem[di] = ns | keep;
-            dir_gmem[di] = ns | keep;
+            dir_smem[di] = ns | keep | kDirOwn;
+            dir_gmem[di] = ns | keep | kDirOwn;
         }
         __syncwarp();
         return ns;
     }
+    if (entry & kDirOwn) return slot;
     int rc = 0;
     if (lane == 0) rc = atomicAdd(&s.refcount[slot], 0);
     rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -125,14 +128,19 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         warp_copy_patch(patch_ptr(s, ns), patch_ptr(s, slot), lane);
         __syncwarp();
         if (lane == 0) {
-            dir_smem[di] = ns | keep;
-            dir_gmem[di] = ns | keep;
+            dir_smem[di] = ns | keep | kDirOwn;
+            dir_gmem[di] = ns | keep | kDirOwn;
             __threadfence();
             release_slot(s, slot);
         }
         __syncwarp();
         return ns;
     }
+    if (lane == 0) {  // sole owner: remember it
+        dir_smem[di] = entry | kDirOwn;
+        dir_gmem[di] = entry | kDirOwn;
+    }
+    __syncwarp();
     return slot;
 }
 

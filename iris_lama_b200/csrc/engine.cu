@@ -143,6 +143,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
     d->ray.hash_cap  = next_pow2_host(std::max(4096, 4 * cfg.max_beams));
     d->ray.event_cap = next_pow2_host(std::max(2048, cfg.max_beams));
+    d->ray.scan.n_beams = cfg.max_beams;  // shared-memory budget is registered for the largest scan
     d->brush.event_cap = d->ray.event_cap;
     d->brush.lower_cap = 8192;
     d->brush.raise_cap = 2048;

@@ -168,6 +168,8 @@ struct RayShared {
     uint64_t bar;
     Affine tf;
     uint32_t log_count, event_count, cells, err;
+    uint32_t work[2];       // work-item counters of the two passes
+    uint32_t any_pending, pad;
 };
 
 __device__ __forceinline__ void hash_insert(uint32_t* table, int cap, uint32_t key)
@@ -219,27 +221,51 @@ __device__ __forceinline__ int next_pow2(int v)
     return p;
 }
 
-// 2-D integer Bresenham of Map::computeRay for the planar case (from.z == to.z, every 2-D scan): the z axis of the
-// reference's 3-axis loop then never moves (delta_z = 0, 2 * err_z = 0 < n), so dropping it is exact.
-struct RayWalk2 {
-    int ex, ey, dx, dy, sx, sy, n, i;
+// ---- ray-cast work decomposition ------------------------------------------------------------------------------
+// Beams are cached in shared memory as their two end cells.  The interior cells of the planar beams (every 2-D
+// scan) are emitted by the 2-axis form of Map::computeRay's integer Bresenham (map.cpp:198-227; with from.z == to.z
+// the z axis of the reference's loop never moves: delta_z = 0 and 2 * err_z = 0 < n).  Its state after i steps has
+// the closed form   k = floor((2 i d + n) / (2 n)),  coord = from + s k,  err = i d - k n,
+// so a walk can start anywhere: work items are (group of 32 adjacent beams, segment of kSegSteps steps), handed to
+// warps through a shared counter.  Lanes of a warp walk angularly adjacent beams in lock step (their atomics fall
+// into the same sectors) and every warp gets the same amount of work, whatever the ray lengths.
+constexpr int kSegSteps = 64;
+
+struct BeamEnds {      // 16 bytes
+    uint32_t fx, fy;   // from cell; bit 31 of fx: mark_hit, bit 31 of fy: non-planar (generic 3-axis walk)
+    uint32_t tx, ty;   // hit cell
+};
+constexpr uint32_t kBeamFlag = 0x80000000u;
+
+struct SegWalk {
+    int ex, ey, dx, dy, sx, sy, n, i, iend;
     uint32_t x, y;
-    __device__ __forceinline__ explicit RayWalk2(const BeamCells& b)
+    __device__ __forceinline__ void init(const BeamEnds& b, int i0, int steps)
     {
-        x = b.from[0];
-        y = b.from[1];
-        const int ddx = (int)(b.to[0] - b.from[0]), ddy = (int)(b.to[1] - b.from[1]);
+        const uint32_t fx = b.fx & ~kBeamFlag, fy = b.fy & ~kBeamFlag;
+        const int ddx = (int)(b.tx - fx), ddy = (int)(b.ty - fy);
         sx = ddx < 0 ? -1 : 1;
         sy = ddy < 0 ? -1 : 1;
         dx = ddx < 0 ? -ddx : ddx;
         dy = ddy < 0 ? -ddy : ddy;
         n  = dx > dy ? dx : dy;
-        ex = ey = 0;
-        i  = 0;
+        i  = i0;
+        iend = min(i0 + steps, n - 1);
+        if (i0 == 0 || n == 0) {
+            x = fx; y = fy; ex = ey = 0;
+        } else {
+            const uint32_t n2 = 2u * (uint32_t)n;
+            const uint32_t kx = (2u * (uint32_t)i0 * (uint32_t)dx + (uint32_t)n) / n2;
+            const uint32_t ky = (2u * (uint32_t)i0 * (uint32_t)dy + (uint32_t)n) / n2;
+            x  = fx + (uint32_t)(sx * (int)kx);
+            y  = fy + (uint32_t)(sy * (int)ky);
+            ex = i0 * dx - (int)kx * n;
+            ey = i0 * dy - (int)ky * n;
+        }
     }
     __device__ __forceinline__ bool next()
     {
-        if (i >= n - 1) return false;
+        if (i >= iend) return false;
         ++i;
         ex += dx;
         ey += dy;
@@ -249,18 +275,109 @@ struct RayWalk2 {
     }
 };
 
-// visits every interior cell of the beam: f(x, y, pos) with pos = 1, 2, ... in the reference's emission order
-template <typename F>
-__device__ __forceinline__ void walk_beam(const BeamCells& bc, F&& f)
+struct RayCtx {
+    const StoreView& s;
+    const RayParams& rp;
+    int32_t* dir;
+    uint32_t* hotmap;    // patches holding a hit cell of this scan
+    uint32_t* pending;   // patches that must be allocated / detached before they can be written
+    uint32_t* hash;
+    uint64_t* log;
+    RayShared& sh;
+    DirWindow win;
+    bool redo;           // second pass: only cells of `pending` patches
+    uint32_t cells, err;
+    // one-entry cache of the current patch
+    uint32_t cpx, cpy;
+    int cdi, centry;
+    bool chot;
+
+    __device__ __forceinline__ void lookup(uint32_t x, uint32_t y)
+    {
+        cpx = x >> kPatchLog2;
+        cpy = y >> kPatchLog2;
+        cdi = dir_index(win, x, y);
+        if (cdi < 0) {
+            err |= kErrWindow;
+            centry = -1;
+            return;
+        }
+        centry = dir[cdi];
+        chot   = (centry >= 0 && (centry & kDirHot)) || ((hotmap[cdi >> 5] >> (cdi & 31)) & 1u);
+        const bool writable = centry >= 0 && (centry & kDirOwn);
+        if (!redo) {
+            if (!writable) {
+                atomicOr(&pending[cdi >> 5], 1u << (cdi & 31));
+                centry = -1;  // handled by the second pass
+            }
+        } else if (!((pending[cdi >> 5] >> (cdi & 31)) & 1u) || !writable) {
+            centry = -1;      // already done in the first pass (or the pool ran dry)
+        }
+    }
+    __device__ __forceinline__ void touch(uint32_t x, uint32_t y, uint32_t beam, uint32_t pos, bool hit)
+    {
+        if ((x >> kPatchLog2) != cpx || (y >> kPatchLog2) != cpy) lookup(x, y);
+        if (centry < 0) return;
+        ++cells;
+        uint32_t* cell = patch_ptr(s, centry & kDirSlotMask) + cell_index(x, y);
+        if (hit) {
+            atomicAdd(cell, kOccHitInc);
+            const uint32_t idx = atomicAdd(&sh.log_count, 1u);
+            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, x, y), beam, 0u, true);
+            return;
+        }
+        if (!chot) {
+            atomicAdd(cell, kOccMissInc);  // result unused: fire-and-forget reduction at the L2
+            return;
+        }
+        const uint32_t old = atomicAdd(cell, kOccMissInc);
+        const uint32_t key = cell_key(win, x, y);
+        if ((old & kOccObstacle) || hash_contains(hash, rp.hash_cap, key)) {
+            const uint32_t idx = atomicAdd(&sh.log_count, 1u);
+            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(key, beam, pos, false);
+        }
+    }
+};
+
+// One pass over all touches of the scan (hits, planar segments, generic beams).
+__device__ __forceinline__ void raycast_pass(RayCtx& c, const BeamEnds* beams, const uint32_t* seg_prefix, int n_beams, int n_groups, uint32_t* work_counter,
+                                             const double* __restrict__ points, const Affine& tf)
 {
-    if (bc.from[2] == bc.to[2]) {
-        RayWalk2 w(bc);
-        uint32_t pos = 0;
-        while (w.next()) f(w.x, w.y, ++pos);
-    } else {  // tilted sensor: the general 3-axis walk
+    const int tid = threadIdx.x, lane = tid & 31;
+    c.cpx = c.cpy = 0xffffffffu;
+    // hits (setOccupied, pf_slam2d.cpp:493-498)
+    for (int b = tid; b < n_beams; b += blockDim.x) {
+        const BeamEnds be = beams[b];
+        if (be.fx & kBeamFlag) c.touch(be.tx, be.ty, (uint32_t)b, 0u, true);
+    }
+    // planar beams: warp-dynamic (group, segment) items
+    const uint32_t total = seg_prefix[n_groups];
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        int g = 0;
+        while (seg_prefix[g + 1] <= item) ++g;
+        const int seg = (int)(item - seg_prefix[g]);
+        const int b = g * 32 + lane;
+        if (b < n_beams) {
+            const BeamEnds be = beams[b];
+            if (!(be.fy & kBeamFlag)) {
+                SegWalk w;
+                w.init(be, seg * kSegSteps, kSegSteps);
+                while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
+            }
+        }
+    }
+    // non-planar beams (tilted sensor): the reference's 3-axis walk, one thread per beam
+    for (int b = tid; b < n_beams; b += blockDim.x) {
+        if (!(beams[b].fy & kBeamFlag)) continue;
+        const double pt[3] = {__ldg(points + 3 * (size_t)b), __ldg(points + 3 * (size_t)b + 1), __ldg(points + 3 * (size_t)b + 2)};
+        const BeamCells bc = beam_cells(tf, c.rp.scan, pt);
         RayWalk w(bc);
         uint32_t pos = 0;
-        while (w.next()) f(w.x, w.y, ++pos);
+        while (w.next()) c.touch(w.x, w.y, (uint32_t)b, ++pos, false);
     }
 }
 
@@ -270,66 +387,88 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dim2   = s.window.dim * s.window.dim;
     const int nwords = (dim2 + 31) / 32;
+    const int n      = rp.scan.n_beams;
+    const int n_groups = (n + 31) / 32;
     int32_t* dir     = reinterpret_cast<int32_t*>(smem_raw);
     uint64_t* log    = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
     uint64_t* events = log + rp.log_cap;
-    uint32_t* hash   = reinterpret_cast<uint32_t*>(events + rp.event_cap);
-    uint32_t* bitmap = hash + rp.hash_cap;   // patches touched by this scan
-    uint32_t* hot    = bitmap + nwords;      // patches that need the ordered slow path
-    RayShared& sh    = *reinterpret_cast<RayShared*>(hot + nwords + (nwords & 1));
+    BeamEnds* beams  = reinterpret_cast<BeamEnds*>(events + rp.event_cap);
+    uint32_t* hash   = reinterpret_cast<uint32_t*>(beams + n_groups * 32);
+    uint32_t* hotmap = hash + rp.hash_cap;
+    uint32_t* pending = hotmap + nwords;
+    uint32_t* seg_prefix = pending + nwords;           // n_groups + 1 entries
+    RayShared& sh    = *reinterpret_cast<RayShared*>(seg_prefix + ((n_groups + 2) & ~1));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int particle = rp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, rp.set, particle, kMapOcc);
     const DirWindow win = s.window;
-    const int n = rp.scan.n_beams;
 
     // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
         sh.tf = compose_tf(states[blockIdx.x], rp.scan.moving);
         sh.log_count = sh.event_count = sh.cells = sh.err = 0;
+        sh.work[0] = sh.work[1] = 0;
+        sh.any_pending = 0;
     }
     for (int i = tid; i < rp.hash_cap; i += blockDim.x) hash[i] = 0u;
-    for (int i = tid; i < 2 * nwords; i += blockDim.x) bitmap[i] = 0u;  // bitmap + hot are contiguous
+    for (int i = tid; i < 2 * nwords; i += blockDim.x) hotmap[i] = 0u;  // hotmap + pending are contiguous
     __syncthreads();
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
     const Affine tf = sh.tf;
-    // patches that already hold obstacle-mirror cells are "hot": their misses need the returned old value
-    for (int di = tid; di < dim2; di += blockDim.x) {
-        const int e = dir[di];
-        if (e >= 0 && (e & kDirHot)) atomicOr(&hot[di >> 5], 1u << (di & 31));
-    }
 
-    // ---- phase 1: mark touched patches, collect the set of hit cells -----------------------------------
+    // ---- phase 1: beam end cells, hit-cell set, segment counts ----------------------------------------
     uint32_t my_err = 0;
-    for (int b = tid; b < n; b += blockDim.x) {
-        const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
-        const BeamCells bc = beam_cells(tf, rp.scan, pt);
-        if (bc.mark_hit) {
-            const int di = dir_index(win, bc.to[0], bc.to[1]);
-            if (di < 0) my_err |= kErrWindow;
-            else {
-                hash_insert(hash, rp.hash_cap, cell_key(win, bc.to[0], bc.to[1]));
-                atomicOr(&bitmap[di >> 5], 1u << (di & 31));
-                atomicOr(&hot[di >> 5], 1u << (di & 31));
+    for (int b = tid; b < n_groups * 32; b += blockDim.x) {
+        BeamEnds be{0u, 0u | kBeamFlag, 0u, 0u};  // padding lanes: flagged non-planar, never walked (b >= n)
+        int segs = 0;
+        if (b < n) {
+            const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
+            const BeamCells bc = beam_cells(tf, rp.scan, pt);
+            be.fx = bc.from[0]; be.fy = bc.from[1]; be.tx = bc.to[0]; be.ty = bc.to[1];
+            if (bc.mark_hit) {
+                const int di = dir_index(win, bc.to[0], bc.to[1]);
+                if (di < 0) my_err |= kErrWindow;
+                else {
+                    be.fx |= kBeamFlag;
+                    hash_insert(hash, rp.hash_cap, cell_key(win, bc.to[0], bc.to[1]));
+                    atomicOr(&hotmap[di >> 5], 1u << (di & 31));
+                }
+            }
+            if (bc.from[2] != bc.to[2]) {
+                be.fy |= kBeamFlag;
+            } else {
+                const int ddx = (int)(bc.to[0] - bc.from[0]), ddy = (int)(bc.to[1] - bc.from[1]);
+                const int nn = max(ddx < 0 ? -ddx : ddx, ddy < 0 ? -ddy : ddy);
+                segs = nn > 1 ? (nn - 1 + kSegSteps - 1) / kSegSteps : 0;
             }
         }
-        int last = -1;
-        walk_beam(bc, [&](uint32_t x, uint32_t y, uint32_t) {
-            const int di = dir_index(win, x, y);
-            if (di < 0) { my_err |= kErrWindow; return; }
-            if (di != last) {
-                atomicOr(&bitmap[di >> 5], 1u << (di & 31));
-                last = di;
-            }
-        });
+        beams[b] = be;
+        // segments of a group = those of its longest beam
+        segs = __reduce_max_sync(0xffffffffu, segs);
+        if (lane == 0) seg_prefix[b >> 5] = (uint32_t)segs;
+    }
+    __syncthreads();
+    if (tid == 0) {  // exclusive scan over <= 128 groups
+        uint32_t acc = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            uint32_t v = seg_prefix[g];
+            seg_prefix[g] = acc;
+            acc += v;
+        }
+        seg_prefix[n_groups] = acc;
     }
     __syncthreads();
 
-    // ---- phase 2: allocate / detach every touched patch (Map::get mutable + COW) ------------------------
+    // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away ------------
+    RayCtx ctx{s, rp, dir, hotmap, pending, hash, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, false};
+    raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[0], rp.points, tf);
+    __syncthreads();
+    // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW), redo them ----
     for (int w32 = warp; w32 < nwords; w32 += nwarps) {
-        uint32_t bits = bitmap[w32];
+        uint32_t bits = pending[w32];
+        if (bits && lane == 0) sh.any_pending = 1;
         while (bits) {
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -337,41 +476,12 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         }
     }
     __syncthreads();
-
-    // ---- phase 3: walk the rays; counters via packed atomics, candidate touches into the log ------------
-    uint32_t my_cells = 0;
-    for (int b = tid; b < n; b += blockDim.x) {
-        const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
-        const BeamCells bc = beam_cells(tf, rp.scan, pt);
-        if (bc.mark_hit) {
-            const int di = dir_index(win, bc.to[0], bc.to[1]);
-            if (di >= 0 && dir[di] >= 0) {
-                ++my_cells;
-                atomicAdd(patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(bc.to[0], bc.to[1]), kOccHitInc);
-                const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-                if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, bc.to[0], bc.to[1]), (uint32_t)b, 0u, true);
-            }
-        }
-        walk_beam(bc, [&](uint32_t x, uint32_t y, uint32_t pos) {
-            const int di = dir_index(win, x, y);
-            if (di < 0) return;
-            const int e = dir[di];
-            if (e < 0) return;
-            ++my_cells;
-            uint32_t* cell = patch_ptr(s, e & kDirSlotMask) + cell_index(x, y);
-            if (!((hot[di >> 5] >> (di & 31)) & 1u)) {
-                atomicAdd(cell, kOccMissInc);  // result unused: compiles to a fire-and-forget RED
-                return;
-            }
-            const uint32_t old = atomicAdd(cell, kOccMissInc);
-            const uint32_t key = cell_key(win, x, y);
-            if ((old & kOccObstacle) || hash_contains(hash, rp.hash_cap, key)) {
-                const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-                if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(key, (uint32_t)b, pos, false);
-            }
-        });
+    if (sh.any_pending) {
+        ctx.redo = true;
+        raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[1], rp.points, tf);
     }
-    my_cells = __reduce_add_sync(0xffffffffu, my_cells);
+    my_err |= ctx.err;
+    uint32_t my_cells = __reduce_add_sync(0xffffffffu, ctx.cells);
     if (lane == 0 && my_cells) atomicAdd(&sh.cells, my_cells);
     __syncthreads();
 
@@ -437,9 +547,6 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     }
 }
 
-// ==================================================================================================
-// k_brushfire
-// ==================================================================================================
 // One warp per particle (see brushfire_warp.cuh for the schedule and why it is exact).
 __global__ void __launch_bounds__(32)
 k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, MapUpdateStats* __restrict__ stats)
@@ -486,13 +593,18 @@ __global__ void k_copy_dirs(StoreView s, int src_set, int dst_set, const int32_t
 {
     const int p = dst_first + blockIdx.x, kind = blockIdx.y;
     const int dim2 = s.window.dim * s.window.dim;
-    const int a        = idx[blockIdx.x];
-    const int32_t* src = dir_of(s, src_set, a < 0 ? 0 : a, kind);
-    int32_t* dst       = dir_of(s, dst_set, p, kind);
+    const int a  = idx[blockIdx.x];
+    int32_t* src = dir_of(s, src_set, a < 0 ? 0 : a, kind);
+    int32_t* dst = dir_of(s, dst_set, p, kind);
     for (int e = threadIdx.x; e < dim2; e += blockDim.x) {
         int slot = a < 0 ? -1 : src[e];
-        dst[e]   = slot;  // keeps kDirHot
-        if (slot >= 0) atomicAdd(&s.refcount[slot & kDirSlotMask], 1);
+        if (slot >= 0) {
+            atomicAdd(&s.refcount[slot & kDirSlotMask], 1);
+            // shared from now on: neither copy owns it (several blocks may clear the same source entry: same value)
+            if ((slot & kDirOwn) && src_set == dst_set) src[e] = slot & ~kDirOwn;
+            slot &= ~kDirOwn;  // keeps kDirHot
+        }
+        dst[e] = slot;
     }
 }
 __global__ void k_release(StoreView s, int set, int first)
@@ -650,8 +762,9 @@ size_t match_smem_bytes(int dir_dim, uint32_t max_sqdist)
 size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
 {
     const int dim2 = dir_dim * dir_dim;
-    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)rp.hash_cap * 4 + (size_t)((dim2 + 31) / 32 + 1) * 8 +
-           sizeof(RayShared) + 16;
+    const int n_groups = (rp.scan.n_beams + 31) / 32;
+    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)n_groups * 32 * 16 + (size_t)rp.hash_cap * 4 +
+           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + sizeof(RayShared) + 32;
 }
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {

@@ -85,29 +85,29 @@ def beam_angles(n_beams: int, fov_deg: float) -> np.ndarray:
 
 
 def loop_trajectory(n: int, radius: float = 6.0, step: float = 0.1, max_turn: float = 0.05) -> np.ndarray:
-    """Rounded-square loop: straight legs of 2*radius joined by quarter turns limited to max_turn
-    rad per step; returns n poses (x, y, theta), starting at (radius, -radius... ) heading +y."""
+    """Rounded square of half side `radius` centred on the origin, driven counter-clockwise: starts at
+    (radius, 0) heading +y, straight legs joined by quarter turns of at most max_turn rad per step (corner radius
+    step / max_turn).  Returns n poses (x, y, theta); laps repeat for as long as n asks."""
+    rt = step / max_turn
+    quarter = int(round((math.pi / 2.0) / max_turn))
     poses = np.zeros((n, 3), dtype=np.float64)
-    x, y, th = radius, -radius * 0.5, math.pi / 2.0
-    leg = 0.0
-    turning = 0.0
-    straight_len = radius
+    x, y, th = radius, 0.0, math.pi / 2.0
+    leg_steps = int(round((radius - rt) / step))        # first leg: from the middle of the right side
+    full_leg = int(round(2.0 * (radius - rt) / step))
+    left, turning = leg_steps, 0
     for i in range(n):
         poses[i] = (x, y, th)
-        if turning > 0.0:
-            d = min(max_turn, turning)
-            th += d
-            turning -= d
-            x += step * math.cos(th)
-            y += step * math.sin(th)
+        if turning > 0:
+            th += (math.pi / 2.0) / quarter
+            turning -= 1
+            if turning == 0:
+                left = full_leg
         else:
-            x += step * math.cos(th)
-            y += step * math.sin(th)
-            leg += step
-            if leg >= straight_len:
-                leg = 0.0
-                turning = math.pi / 2.0
-                straight_len = 2.0 * radius - 2.0 * step / max_turn
+            left -= 1
+            if left == 0:
+                turning = quarter
+        x += step * math.cos(th)
+        y += step * math.sin(th)
     poses[:, 2] = (poses[:, 2] + math.pi) % (2 * math.pi) - math.pi
     return poses
 
