@@ -72,7 +72,7 @@ int export_occ(Engine* e, int particle, uint32_t x0, uint32_t y0, int w, int h, 
         const uint32_t wd = words[i];
         if (occupied) occupied[i] = (uint16_t)occ_occupied(wd);
         if (visited) visited[i] = (uint16_t)occ_visited(wd);
-        if (known) known[i] = (wd & ~kOccObstacle) != 0;  // every mutable access counts a visit
+        if (known) known[i] = wd != 0;  // every mutable access counts a visit
     }
     return LAMA_OK;
 }
@@ -92,7 +92,7 @@ int export_dm(Engine* e, int particle, bool with_occ, uint32_t x0, uint32_t y0, 
         rc = e->export_window(particle, 0, x0, y0, w, h, ow.data(), nullptr);
         if (rc != LAMA_OK) return set_err(e->last_error(), rc);
         occ_known.resize(ow.size());
-        for (size_t i = 0; i < ow.size(); ++i) occ_known[i] = (ow[i] & ~kOccObstacle) != 0;
+        for (size_t i = 0; i < ow.size(); ++i) occ_known[i] = ow[i] != 0;
     }
     unpack_distance_words(words.data(), occ_known.empty() ? nullptr : occ_known.data(), words.size(), sqdist, valid, known, ox, oy, queued);
     return LAMA_OK;

@@ -14,6 +14,7 @@ namespace lama_b200 {
 
 struct StoreView {
     uint32_t* pool;       // n_slots * 1024 words
+    uint32_t* fbits;      // n_slots * 32 words: obstacle-mirror bit of every cell (occupancy patches)
     int32_t* refcount;    // per slot
     int32_t* free_slots;  // stack of free slot ids
     int32_t* free_count;  // number of valid entries in free_slots
@@ -44,6 +45,7 @@ __device__ __forceinline__ int32_t* dir_of(const StoreView& s, int set, int part
     return s.dirs + (((size_t)set * s.n_particles + particle) * 2 + kind) * (size_t)(s.window.dim * s.window.dim);
 }
 __device__ __forceinline__ uint32_t* patch_ptr(const StoreView& s, int slot) { return s.pool + (size_t)slot * kPatchCells; }
+__device__ __forceinline__ uint32_t* fbits_ptr(const StoreView& s, int slot) { return s.fbits + (size_t)slot * 32; }
 
 // ---- slot allocation (one thread) -----------------------------------------------------------------------
 __device__ __forceinline__ int alloc_slot(const StoreView& s)
@@ -103,6 +105,7 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         ns = __shfl_sync(0xffffffffu, ns, 0);
         if (ns < 0) return -1;
         warp_zero_patch(patch_ptr(s, ns), lane);
+        fbits_ptr(s, ns)[lane] = 0u;
         __syncwarp();
         if (lane == 0) {
             dir_smem[di] = ns | keep | kDirOwn;
@@ -126,6 +129,7 @@ __device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* 
         // The source stays immutable while we hold our reference: a sharer only writes in place once
         // it observes refcount == 1, which cannot happen before we drop ours below.
         warp_copy_patch(patch_ptr(s, ns), patch_ptr(s, slot), lane);
+        fbits_ptr(s, ns)[lane] = __ldcg(fbits_ptr(s, slot) + lane);
         __syncwarp();
         if (lane == 0) {
             dir_smem[di] = ns | keep | kDirOwn;

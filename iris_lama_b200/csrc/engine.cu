@@ -129,6 +129,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         return r;
     };
     CU_NEW(dalloc((void**)&v.pool, (size_t)v.n_slots * kPatchBytes));
+    CU_NEW(dalloc((void**)&v.fbits, (size_t)v.n_slots * 128));
     CU_NEW(dalloc((void**)&v.refcount, (size_t)v.n_slots * 4));
     CU_NEW(dalloc((void**)&v.free_slots, (size_t)v.n_slots * 4));
     CU_NEW(dalloc((void**)&v.freed, (size_t)v.n_slots * 4));
@@ -141,7 +142,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     d->d_points = d->d_scan_buf;
 
     d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
-    d->ray.hash_cap  = next_pow2_host(std::max(4096, 4 * cfg.max_beams));
+    d->ray.cand_cap  = 192;
     d->ray.event_cap = next_pow2_host(std::max(2048, cfg.max_beams));
     d->ray.scan.n_beams = cfg.max_beams;  // shared-memory budget is registered for the largest scan
     d->brush.event_cap = d->ray.event_cap;
@@ -346,7 +347,6 @@ int Engine::update_maps(const SE2* states, int first_particle, int count, HostMa
     // shared-memory scratch sized for THIS scan (two CTAs per SM at 1080 beams); the maxima were registered at create
     const int nb = d_->scan.n_beams;
     rp.log_cap   = std::min(d_->ray.log_cap, next_pow2_host(std::max(1024, 3 * nb)));
-    rp.hash_cap  = std::min(d_->ray.hash_cap, next_pow2_host(std::max(1024, 2 * nb)));
     rp.event_cap = std::min(d_->ray.event_cap, next_pow2_host(std::max(512, nb)));
     BrushParams bp = d_->brush;
     bp.set = cur_set_;
@@ -548,7 +548,7 @@ int Engine::pack_size(int particle, size_t* bytes)
     CU_TRY(cudaStreamSynchronize(d_->stream));
     size_t n = 0;
     for (int32_t v : dir) n += v >= 0;
-    *bytes = 16 + n * 4 + n * (size_t)kPatchBytes;
+    *bytes = 16 + n * 4 + n * (size_t)(kPatchBytes + 128);
     return LAMA_OK;
 }
 
@@ -570,20 +570,21 @@ int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
                 slots.push_back(dir[kind * dim2 + e]);
                 ++n_kind[kind];
             }
-    const size_t n = slots.size(), need = 16 + n * 4 + n * (size_t)kPatchBytes;
+    const size_t n = slots.size(), need = 16 + n * 4 + n * (size_t)(kPatchBytes + 128);
     if (need > cap) return fail("pack: buffer too small", LAMA_ERR_ARG);
     uint32_t* hdr = (uint32_t*)buf;
     hdr[0] = kPackMagic; hdr[1] = (uint32_t)cfg_.dir_dim; hdr[2] = n_kind[0]; hdr[3] = n_kind[1];
     std::memcpy(hdr + 4, entries.data(), n * 4);
     if (n) {
-        if (ensure_scratch(d_, n * 4 + n * (size_t)kPatchBytes)) return fail("pack: out of device memory", LAMA_ERR_CUDA);
+        if (ensure_scratch(d_, n * 4 + n * (size_t)(kPatchBytes + 128))) return fail("pack: out of device memory", LAMA_ERR_CUDA);
         char* base = (char*)d_->d_scratch;
-        uint32_t* d_out = (uint32_t*)base;
-        int32_t* d_slots = (int32_t*)(base + n * (size_t)kPatchBytes);
+        uint32_t* d_out = (uint32_t*)base;                                     // n patches, then n x 32 obstacle-mirror words
+        uint32_t* d_fb  = (uint32_t*)(base + n * (size_t)kPatchBytes);
+        int32_t* d_slots = (int32_t*)(base + n * (size_t)(kPatchBytes + 128));
         CU_TRY(cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
-        launch_gather_patches(d_->view, d_slots, (int)n, d_out, d_->stream);
+        launch_gather_patches(d_->view, d_slots, (int)n, d_out, d_fb, d_->stream);
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync((char*)buf + 16 + n * 4, d_out, n * (size_t)kPatchBytes, cudaMemcpyDeviceToHost, d_->stream));
+        CU_TRY(cudaMemcpyAsync((char*)buf + 16 + n * 4, d_out, n * (size_t)(kPatchBytes + 128), cudaMemcpyDeviceToHost, d_->stream));
         CU_TRY(cudaStreamSynchronize(d_->stream));
         times_.misc_launches += 1;
     }
@@ -597,19 +598,21 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
     const uint32_t* hdr = (const uint32_t*)buf;
     if (hdr[0] != kPackMagic || hdr[1] != (uint32_t)cfg_.dir_dim) return fail("unpack: incompatible buffer", LAMA_ERR_ARG);
     const size_t n_occ = hdr[2], n_dm = hdr[3], n = n_occ + n_dm;
-    if (bytes < 16 + n * 4 + n * (size_t)kPatchBytes) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
+    if (bytes < 16 + n * 4 + n * (size_t)(kPatchBytes + 128)) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     launch_release(d_->view, cur_set_, particle, 1, d_->stream);
     launch_merge_free(d_->view, d_->stream);
     if (n) {
-        if (ensure_scratch(d_, n * 4 + n * (size_t)kPatchBytes)) return fail("unpack: out of device memory", LAMA_ERR_CUDA);
+        if (ensure_scratch(d_, n * 4 + n * (size_t)(kPatchBytes + 128))) return fail("unpack: out of device memory", LAMA_ERR_CUDA);
         char* base = (char*)d_->d_scratch;
         uint32_t* d_in = (uint32_t*)base;
-        int32_t* d_entries = (int32_t*)(base + n * (size_t)kPatchBytes);
+        uint32_t* d_fb = (uint32_t*)(base + n * (size_t)kPatchBytes);
+        int32_t* d_entries = (int32_t*)(base + n * (size_t)(kPatchBytes + 128));
         CU_TRY(cudaMemcpyAsync(d_entries, hdr + 4, n * 4, cudaMemcpyHostToDevice, d_->stream));
-        CU_TRY(cudaMemcpyAsync(d_in, (const char*)buf + 16 + n * 4, n * (size_t)kPatchBytes, cudaMemcpyHostToDevice, d_->stream));
-        launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)n_occ, d_in, d_->stream);
-        launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + n_occ, (int)n_dm, d_in + n_occ * (size_t)kPatchCells, d_->stream);
+        CU_TRY(cudaMemcpyAsync(d_in, (const char*)buf + 16 + n * 4, n * (size_t)(kPatchBytes + 128), cudaMemcpyHostToDevice, d_->stream));
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)n_occ, d_in, d_fb, d_->stream);
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + n_occ, (int)n_dm, d_in + n_occ * (size_t)kPatchCells, d_fb + n_occ * 32,
+                               d_->stream);
         times_.misc_launches += 2;
     }
     CU_TRY(cudaGetLastError());

@@ -70,7 +70,7 @@ public:
     // idx[k] == -1 leaves slot k empty.
     int resample(const int32_t* idx);
     // Serialise / restore the two maps of one resident slot (particle migration between GPUs).
-    // Layout: {u32 magic, u32 dim, u32 n_occ, u32 n_dm} + (n_occ + n_dm) x u32 directory index + patches (4 KiB each).
+    // Layout: {u32 magic, u32 dim, u32 n_occ, u32 n_dm} + n x u32 directory index + n patches (4 KiB) + n x 128 B obstacle-mirror bits.
     int pack_size(int particle, size_t* bytes);
     int pack(int particle, void* buf, size_t cap, size_t* used);
     int unpack(int particle, const void* buf, size_t bytes);

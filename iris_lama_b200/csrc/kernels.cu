@@ -169,30 +169,8 @@ struct RayShared {
     Affine tf;
     uint32_t log_count, event_count, cells, err;
     uint32_t work[2];       // work-item counters of the two passes
-    uint32_t any_pending, pad;
+    uint32_t any_pending, n_cand;
 };
-
-__device__ __forceinline__ void hash_insert(uint32_t* table, int cap, uint32_t key)
-{
-    const uint32_t k1 = key + 1u;  // 0 = empty
-    uint32_t h = (key * 2654435761u) >> 7;
-    for (int i = 0; i < cap; ++i) {
-        uint32_t slot = (h + i) & (cap - 1);
-        uint32_t old  = atomicCAS(&table[slot], 0u, k1);
-        if (old == 0u || old == k1) return;
-    }
-}
-__device__ __forceinline__ bool hash_contains(const uint32_t* table, int cap, uint32_t key)
-{
-    const uint32_t k1 = key + 1u;
-    uint32_t h = (key * 2654435761u) >> 7;
-    for (int i = 0; i < cap; ++i) {
-        uint32_t v = table[(h + i) & (cap - 1)];
-        if (v == k1) return true;
-        if (v == 0u) return false;
-    }
-    return false;
-}
 
 // in-place bitonic sort of n (power of two) 64-bit keys in shared memory by the whole block
 __device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n)
@@ -275,22 +253,23 @@ struct SegWalk {
     }
 };
 
+constexpr int kCandNone = 0xFF, kCandOverflow = 0xFE;
+
 struct RayCtx {
     const StoreView& s;
     const RayParams& rp;
     int32_t* dir;
-    uint32_t* hotmap;    // patches holding a hit cell of this scan
-    uint32_t* pending;   // patches that must be allocated / detached before they can be written
-    uint32_t* hash;
+    const uint8_t* cand_idx;   // per directory entry: index of its candidate bitmap, kCandNone or kCandOverflow
+    const uint32_t* cand;      // [cand_cap][32]: bit = cell is a hit cell of this scan or a distance-map obstacle
+    uint32_t* pending;         // patches that must be allocated / detached before they can be written
     uint64_t* log;
     RayShared& sh;
     DirWindow win;
-    bool redo;           // second pass: only cells of `pending` patches
+    bool redo;                 // second pass: only cells of `pending` patches
     uint32_t cells, err;
     // one-entry cache of the current patch
     uint32_t cpx, cpy;
-    int cdi, centry;
-    bool chot;
+    int cdi, centry, ccand;
 
     __device__ __forceinline__ void lookup(uint32_t x, uint32_t y)
     {
@@ -303,7 +282,7 @@ struct RayCtx {
             return;
         }
         centry = dir[cdi];
-        chot   = (centry >= 0 && (centry & kDirHot)) || ((hotmap[cdi >> 5] >> (cdi & 31)) & 1u);
+        ccand  = cand_idx[cdi];
         const bool writable = centry >= 0 && (centry & kDirOwn);
         if (!redo) {
             if (!writable) {
@@ -314,27 +293,18 @@ struct RayCtx {
             centry = -1;      // already done in the first pass (or the pool ran dry)
         }
     }
+    // every counter update is a fire-and-forget reduction at the L2: nothing below waits for a returned value
     __device__ __forceinline__ void touch(uint32_t x, uint32_t y, uint32_t beam, uint32_t pos, bool hit)
     {
         if ((x >> kPatchLog2) != cpx || (y >> kPatchLog2) != cpy) lookup(x, y);
         if (centry < 0) return;
         ++cells;
-        uint32_t* cell = patch_ptr(s, centry & kDirSlotMask) + cell_index(x, y);
-        if (hit) {
-            atomicAdd(cell, kOccHitInc);
+        const uint32_t ci = cell_index(x, y);
+        atomicAdd(patch_ptr(s, centry & kDirSlotMask) + ci, hit ? kOccHitInc : kOccMissInc);
+        if (ccand == kCandNone) return;
+        if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
             const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, x, y), beam, 0u, true);
-            return;
-        }
-        if (!chot) {
-            atomicAdd(cell, kOccMissInc);  // result unused: fire-and-forget reduction at the L2
-            return;
-        }
-        const uint32_t old = atomicAdd(cell, kOccMissInc);
-        const uint32_t key = cell_key(win, x, y);
-        if ((old & kOccObstacle) || hash_contains(hash, rp.hash_cap, key)) {
-            const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(key, beam, pos, false);
+            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, x, y), beam, hit ? 0u : pos, hit);
         }
     }
 };
@@ -391,13 +361,16 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     const int n_groups = (n + 31) / 32;
     int32_t* dir     = reinterpret_cast<int32_t*>(smem_raw);
     uint64_t* log    = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);
-    uint64_t* events = log + rp.log_cap;
-    BeamEnds* beams  = reinterpret_cast<BeamEnds*>(events + rp.event_cap);
-    uint32_t* hash   = reinterpret_cast<uint32_t*>(beams + n_groups * 32);
-    uint32_t* hotmap = hash + rp.hash_cap;
+    BeamEnds* beams  = reinterpret_cast<BeamEnds*>(log + rp.log_cap);
+    uint64_t* events = reinterpret_cast<uint64_t*>(beams);  // overlays the beam cache, which is dead by then
+    const size_t beam_bytes = (size_t)n_groups * 32 * sizeof(BeamEnds), ev_bytes = (size_t)rp.event_cap * 8;
+    uint32_t* cand   = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(beams) + (beam_bytes > ev_bytes ? beam_bytes : ev_bytes));
+    uint32_t* hotmap = cand + rp.cand_cap * 32;
     uint32_t* pending = hotmap + nwords;
     uint32_t* seg_prefix = pending + nwords;           // n_groups + 1 entries
-    RayShared& sh    = *reinterpret_cast<RayShared*>(seg_prefix + ((n_groups + 2) & ~1));
+    uint16_t* cand_di = reinterpret_cast<uint16_t*>(seg_prefix + ((n_groups + 2) & ~1));  // directory entry of every bitmap
+    uint8_t* cand_idx = reinterpret_cast<uint8_t*>(cand_di + ((rp.cand_cap + 3) & ~3));
+    RayShared& sh    = *reinterpret_cast<RayShared*>(cand_idx + dim2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int particle = rp.particle_offset + blockIdx.x;
@@ -411,15 +384,20 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         sh.log_count = sh.event_count = sh.cells = sh.err = 0;
         sh.work[0] = sh.work[1] = 0;
         sh.any_pending = 0;
+        sh.n_cand = 0;
     }
-    for (int i = tid; i < rp.hash_cap; i += blockDim.x) hash[i] = 0u;
     for (int i = tid; i < 2 * nwords; i += blockDim.x) hotmap[i] = 0u;  // hotmap + pending are contiguous
+    for (int i = tid; i < dim2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cand_idx)[i] = 0xFFFFFFFFu;  // kCandNone
     __syncthreads();
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
     const Affine tf = sh.tf;
 
-    // ---- phase 1: beam end cells, hit-cell set, segment counts ----------------------------------------
+    // ---- phase 1a: beam end cells, segment counts, patches that need the ordered path ---------------------
     uint32_t my_err = 0;
+    for (int di = tid; di < dim2; di += blockDim.x) {
+        const int e = dir[di];
+        if (e >= 0 && (e & kDirHot)) atomicOr(&hotmap[di >> 5], 1u << (di & 31));  // holds distance-map obstacles
+    }
     for (int b = tid; b < n_groups * 32; b += blockDim.x) {
         BeamEnds be{0u, 0u | kBeamFlag, 0u, 0u};  // padding lanes: flagged non-planar, never walked (b >= n)
         int segs = 0;
@@ -432,8 +410,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
                 if (di < 0) my_err |= kErrWindow;
                 else {
                     be.fx |= kBeamFlag;
-                    hash_insert(hash, rp.hash_cap, cell_key(win, bc.to[0], bc.to[1]));
-                    atomicOr(&hotmap[di >> 5], 1u << (di & 31));
+                    atomicOr(&hotmap[di >> 5], 1u << (di & 31));  // holds a hit cell of this scan
                 }
             }
             if (bc.from[2] != bc.to[2]) {
@@ -445,24 +422,70 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
             }
         }
         beams[b] = be;
-        // segments of a group = those of its longest beam
-        segs = __reduce_max_sync(0xffffffffu, segs);
+        segs = __reduce_max_sync(0xffffffffu, segs);  // segments of a group = those of its longest beam
         if (lane == 0) seg_prefix[b >> 5] = (uint32_t)segs;
     }
     __syncthreads();
-    if (tid == 0) {  // exclusive scan over <= 128 groups
-        uint32_t acc = 0;
-        for (int g = 0; g < n_groups; ++g) {
-            uint32_t v = seg_prefix[g];
-            seg_prefix[g] = acc;
-            acc += v;
+    // ---- phase 1b: one warp numbers the hot patches and scans the segment counts -----------------------------
+    if (warp == 0) {
+        uint32_t base = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int wi = w0 + lane;
+            const uint32_t bits = wi < nwords ? hotmap[wi] : 0u;
+            const uint32_t cnt = __popc(bits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            uint32_t k = base + incl - cnt;
+            uint32_t b2 = bits;
+            while (b2) {
+                const int bit = __ffs(b2) - 1;
+                b2 &= b2 - 1;
+                const int di = wi * 32 + bit;
+                if (k < (uint32_t)rp.cand_cap) {
+                    cand_idx[di] = (uint8_t)k;
+                    cand_di[k]   = (uint16_t)di;
+                } else {
+                    cand_idx[di] = kCandOverflow;
+                }
+                ++k;
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
-        seg_prefix[n_groups] = acc;
+        if (lane == 0) {
+            sh.n_cand = base < (uint32_t)rp.cand_cap ? base : (uint32_t)rp.cand_cap;
+            uint32_t acc = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                uint32_t v = seg_prefix[g];
+                seg_prefix[g] = acc;
+                acc += v;
+            }
+            seg_prefix[n_groups] = acc;
+        }
+    }
+    __syncthreads();
+    // ---- phase 1c: candidate bitmaps = obstacle-mirror bits of the patch | hit cells of this scan --------------
+    for (int k = warp; k < (int)sh.n_cand; k += nwarps) {
+        const int e = dir[cand_di[k]];
+        cand[k * 32 + lane] = e >= 0 ? __ldcg(fbits_ptr(s, e & kDirSlotMask) + lane) : 0u;
+    }
+    __syncthreads();
+    for (int b = tid; b < n; b += blockDim.x) {
+        const BeamEnds be = beams[b];
+        if (!(be.fx & kBeamFlag)) continue;
+        const int k = cand_idx[dir_index(win, be.tx, be.ty)];
+        if (k < rp.cand_cap) {
+            const uint32_t ci = cell_index(be.tx, be.ty);
+            atomicOr(&cand[k * 32 + (ci >> 5)], 1u << (ci & 31));
+        }
     }
     __syncthreads();
 
     // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away ------------
-    RayCtx ctx{s, rp, dir, hotmap, pending, hash, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, false};
+    RayCtx ctx{s, rp, dir, cand_idx, cand, pending, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, kCandNone};
     raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[0], rp.points, tf);
     __syncthreads();
     // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW), redo them ----
@@ -506,19 +529,22 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         const int di = dir_index(win, x, y);
         uint32_t* cell = patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(x, y);
         const uint32_t final_word = __ldcg(cell);
-        const bool obstacle = replay_cell(log, i, end, final_word, [&](bool add, uint32_t seq) {
+        const uint32_t ci = cell_index(x, y);
+        uint32_t* fword = fbits_ptr(s, dir[di] & kDirSlotMask) + (ci >> 5);
+        const bool before = (__ldcg(fword) >> (ci & 31)) & 1u;
+        const bool obstacle = replay_cell(log, i, end, final_word, before, [&](bool add, uint32_t seq) {
             uint32_t idx = atomicAdd(&sh.event_count, 1u);
             if (idx < (uint32_t)rp.event_cap) events[idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
         });
-        if (obstacle != ((final_word & kOccObstacle) != 0)) {
+        if (obstacle != before) {
             if (obstacle) {
-                atomicOr(cell, kOccObstacle);
+                atomicOr(fword, 1u << (ci & 31));
                 if (!(dir[di] & kDirHot)) {  // from now on this patch needs the ordered path
                     atomicOr(&dir[di], kDirHot);
                     atomicOr(&gdir[di], kDirHot);
                 }
             } else {
-                atomicAnd(cell, ~kOccObstacle);
+                atomicAnd(fword, ~(1u << (ci & 31)));
             }
         }
     }
@@ -690,27 +716,24 @@ __global__ void k_import(StoreView s, int set, int particle, int kind, uint32_t 
     int slot = warp_make_exclusive(s, d, d, di, lane);
     if (slot < 0) return;
     uint32_t* dst = patch_ptr(s, slot);
-    uint32_t obst = 0;
     for (int c = lane; c < kPatchCells; c += 32) {
         int cx = c & (kPatchLen - 1), cy = c >> kPatchLog2;
-        uint32_t v = in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
-        dst[c] = v;
-        obst |= v & kOccObstacle;
+        dst[c] = in[(size_t)(py * kPatchLen + cy) * w + px * kPatchLen + cx];
     }
-    obst = __reduce_or_sync(0xffffffffu, obst);
-    if (kind == kMapOcc && obst && lane == 0) d[di] |= kDirHot;
 }
 
 // gather the patches listed in `slots` into a contiguous buffer (particle migration between GPUs)
-__global__ void k_gather_patches(StoreView s, const int32_t* __restrict__ slots, int n, uint32_t* __restrict__ out)
+__global__ void k_gather_patches(StoreView s, const int32_t* __restrict__ slots, int n, uint32_t* __restrict__ out, uint32_t* __restrict__ out_fbits)
 {
     const int lane = threadIdx.x & 31;
     const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pi >= n) return;
     warp_copy_patch(out + (size_t)pi * kPatchCells, patch_ptr(s, slots[pi] & kDirSlotMask), lane);
+    out_fbits[(size_t)pi * 32 + lane] = __ldcg(fbits_ptr(s, slots[pi] & kDirSlotMask) + lane);
 }
 // allocate a patch per listed directory entry of (set, particle, kind) and fill it from `in`
-__global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, const int32_t* __restrict__ entries, int n, const uint32_t* __restrict__ in)
+__global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, const int32_t* __restrict__ entries, int n, const uint32_t* __restrict__ in,
+                                  const uint32_t* __restrict__ in_fbits)
 {
     const int lane = threadIdx.x & 31;
     const int pi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -719,8 +742,9 @@ __global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, 
     int slot = warp_make_exclusive(s, d, d, entries[pi], lane);
     if (slot < 0) return;
     warp_copy_patch(patch_ptr(s, slot), in + (size_t)pi * kPatchCells, lane);
-    // a migrated occupancy patch may hold obstacle-mirror cells: take the ordered ray-cast path (conservative)
-    if (kind == kMapOcc && lane == 0) d[entries[pi]] |= kDirHot;
+    const uint32_t fb = in_fbits[(size_t)pi * 32 + lane];
+    fbits_ptr(s, slot)[lane] = fb;
+    if (kind == kMapOcc && __any_sync(0xffffffffu, fb != 0u) && lane == 0) d[entries[pi]] |= kDirHot;
 }
 
 __global__ void k_distance(StoreView s, int set, int particle, const double* __restrict__ pts, int n, double resolution, uint32_t max_sqdist,
@@ -763,8 +787,9 @@ size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
 {
     const int dim2 = dir_dim * dir_dim;
     const int n_groups = (rp.scan.n_beams + 31) / 32;
-    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (size_t)rp.event_cap * 8 + (size_t)n_groups * 32 * 16 + (size_t)rp.hash_cap * 4 +
-           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + sizeof(RayShared) + 32;
+    const size_t beam_bytes = (size_t)n_groups * 32 * 16, ev_bytes = (size_t)rp.event_cap * 8;
+    return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (beam_bytes > ev_bytes ? beam_bytes : ev_bytes) + (size_t)rp.cand_cap * 128 +
+           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + (size_t)(rp.cand_cap + 4) * 2 + (size_t)dim2 + sizeof(RayShared) + 32;
 }
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {
@@ -825,15 +850,16 @@ void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t
     if (patches <= 0) return;
     k_import<<<(patches + 3) / 4, 128, 0, st>>>(s, set, particle, kind, x0, y0, w, h, d_in);
 }
-void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, cudaStream_t st)
+void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, uint32_t* d_out_fbits, cudaStream_t st)
 {
     if (n <= 0) return;
-    k_gather_patches<<<(n + 3) / 4, 128, 0, st>>>(s, d_slots, n, d_out);
+    k_gather_patches<<<(n + 3) / 4, 128, 0, st>>>(s, d_slots, n, d_out, d_out_fbits);
 }
-void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in, cudaStream_t st)
+void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in,
+                            const uint32_t* d_in_fbits, cudaStream_t st)
 {
     if (n <= 0) return;
-    k_scatter_patches<<<(n + 3) / 4, 128, 0, st>>>(s, set, particle, kind, d_entries, n, d_in);
+    k_scatter_patches<<<(n + 3) / 4, 128, 0, st>>>(s, set, particle, kind, d_entries, n, d_in, d_in_fbits);
 }
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st)

@@ -36,7 +36,8 @@ struct RayParams {
     ScanParams scan;
     int set;
     int particle_offset;
-    int log_cap, hash_cap, event_cap;  // powers of two
+    int log_cap, event_cap;  // powers of two
+    int cand_cap;            // candidate bitmaps (patches with hit cells or distance-map obstacles), <= 253
 };
 
 struct BrushParams {
@@ -76,8 +77,9 @@ void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t
 // dense, patch-aligned window import (x0,y0 multiples of 32; w,h multiples of 32); all-zero patches are skipped
 void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* d_in,
                    cudaStream_t st);
-void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, cudaStream_t st);
-void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in, cudaStream_t st);
+void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, uint32_t* d_out_fbits, cudaStream_t st);
+void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in,
+                            const uint32_t* d_in_fbits, cudaStream_t st);
 // batched DistanceMap::distance(point, &grad) on one particle's distance map (SDM grid interface)
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st);

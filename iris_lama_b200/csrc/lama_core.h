@@ -35,14 +35,15 @@ constexpr uint32_t kUniversalHalf = 1321122u;        // UNIVERSAL_CONSTANT >> 1 
 constexpr uint32_t kMapOffsetCells = kUniversalHalf * kPatchLen;  // 42 275 904
 
 // ---- occupancy cell: FrequencyOccupancyMap {uint16 occupied; uint16 visited} packed in one word so
-// that a hit is ONE atomicAdd(+0x00010001) and a miss ONE atomicAdd(+0x00010000).  Bit 15 mirrors
-// "this cell is currently an obstacle of the distance map" (valid_obstacle && sqdist == 0), which the
-// ray-cast kernel needs to know whether a miss can trigger removeObstacle.  Hence `occupied` has 15
-// usable bits here (the reference wraps at 2^16); `visited` wraps at 2^16 exactly like the uint16.
+// that a hit is ONE atomicAdd(+0x00010001) and a miss ONE atomicAdd(+0x00010000); `visited` (high half)
+// wraps at 2^16 exactly like the reference's uint16.  (A carry out of `occupied` would need 65 536 hits on
+// one cell while visited, which counts the same hits, has wrapped as well.)
+// Whether a cell is currently an obstacle of the distance map (valid_obstacle && sqdist == 0) -- which
+// decides if a miss can trigger removeObstacle -- is mirrored in a separate bit plane of 32 words per patch
+// (StoreView::fbits), so that the ray-cast kernel never needs the value returned by an atomic.
 constexpr uint32_t kOccHitInc   = 0x00010001u;
 constexpr uint32_t kOccMissInc  = 0x00010000u;
-constexpr uint32_t kOccObstacle = 0x00008000u;
-LAMA_HD uint32_t occ_occupied(uint32_t w) { return w & 0x7FFFu; }
+LAMA_HD uint32_t occ_occupied(uint32_t w) { return w & 0xFFFFu; }
 LAMA_HD uint32_t occ_visited(uint32_t w) { return w >> 16; }
 // prob() < 0.25 / > 0.25 of frequency_occupancy_map.cpp:40-45 in exact integer arithmetic
 // (occupied/visited == 0.25 exactly iff 4*occupied == visited; unvisited cells read 0.25).

@@ -11,7 +11,8 @@
 // commute is (a) at which touch a cell crosses the 0.25 threshold, which decides the
 // addObstacle/removeObstacle calls, and (b) the order of those calls, which is the push order of the
 // brushfire heaps.  Both only concern cells that receive a hit in this scan or are currently
-// distance-map obstacles; every touch of such a cell is logged as (cell, beam, pos, kind), the log
+// distance-map obstacles ("candidate" cells, found with per-patch bitmaps in shared memory); every touch of
+// such a cell is logged as (cell, beam, pos, kind), the log
 // is sorted, and each cell's touches are replayed in beam order from its pre-scan counters.  The
 // obstacle events carry the sequence stamp (beam, pos) of the touch that caused them and are sorted
 // by it, which reproduces the reference's call order exactly.
@@ -120,12 +121,12 @@ LAMA_HD bool log_is_hit(uint64_t r) { return (r & 1u) != 0; }
 LAMA_HD uint64_t push_record(uint32_t seq, uint32_t key) { return ((uint64_t)seq << 32) | key; }
 
 // Replays the sorted touches log[first, last) of ONE cell.  `final_word` is the occupancy word after
-// all of this scan's atomics; returns the new obstacle-mirror bit and emits obstacle events through
-// `emit(kind_is_add, seq)` in call order.
+// all of this scan's atomics, `obstacle` the cell's obstacle-mirror bit before the scan; returns the new
+// mirror bit and emits obstacle events through `emit(kind_is_add, seq)` in call order.
 //   setFree     frequency_occupancy_map.cpp:65-74   setOccupied :81-91
 //   addObstacle / removeObstacle no-op rules: dynamic_distance_map.cpp:217-218,233-234
 template <typename Emit>
-LAMA_HD bool replay_cell(const uint64_t* log, int first, int last, uint32_t final_word, Emit&& emit)
+LAMA_HD bool replay_cell(const uint64_t* log, int first, int last, uint32_t final_word, bool obstacle, Emit&& emit)
 {
     uint32_t hits = 0, misses = 0;
     for (int i = first; i < last; ++i) {
@@ -133,14 +134,13 @@ LAMA_HD bool replay_cell(const uint64_t* log, int first, int last, uint32_t fina
         else ++misses;
     }
     // counters before this scan (uint16 wrap-around arithmetic like the reference's cells)
-    uint32_t occupied = (occ_occupied(final_word) - hits) & 0x7FFFu;
+    uint32_t occupied = (occ_occupied(final_word) - hits) & 0xFFFFu;
     uint32_t visited  = (occ_visited(final_word) - hits - misses) & 0xFFFFu;
-    bool obstacle     = (final_word & kOccObstacle) != 0;
     for (int i = first; i < last; ++i) {
         const uint64_t r = log[i];
         if (log_is_hit(r)) {
             bool was_occupied = occ_is_occupied(occupied, visited);
-            occupied = (occupied + 1) & 0x7FFFu;
+            occupied = (occupied + 1) & 0xFFFFu;
             visited  = (visited + 1) & 0xFFFFu;
             if (!was_occupied && occ_is_occupied(occupied, visited) && !obstacle) {
                 obstacle = true;

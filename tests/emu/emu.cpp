@@ -21,6 +21,7 @@ namespace {
 struct HostMap {
     DirWindow window;
     std::vector<uint32_t> cells;
+    std::vector<uint8_t> fbit;   // obstacle-mirror bit plane (StoreView::fbits on the device)
     std::vector<uint8_t> patch_present;
     uint32_t scratch = 0, err = 0;
     int side() const { return window.dim * kPatchLen; }
@@ -28,6 +29,7 @@ struct HostMap {
     {
         window = w;
         cells.assign((size_t)side() * side(), 0u);
+        fbit.assign((size_t)side() * side(), 0);
         patch_present.assign((size_t)w.dim * w.dim, 0);
     }
     uint32_t* raw(uint32_t x, uint32_t y, bool touch)
@@ -136,10 +138,10 @@ void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pos
             if (dir_index(win, w.x, w.y) < 0) continue;
             ++cells;
             uint32_t* c = e.occ.raw(w.x, w.y, true);
-            uint32_t old = *c;
             *c += kOccMissInc;
             uint32_t key = cell_key(win, w.x, w.y);
-            if ((old & kOccObstacle) || std::binary_search(hitset.begin(), hitset.end(), key)) log.push_back(log_record(key, (uint32_t)b, pos, false));
+            const bool obst = e.occ.fbit[c - e.occ.cells.data()] != 0;
+            if (obst || std::binary_search(hitset.begin(), hitset.end(), key)) log.push_back(log_record(key, (uint32_t)b, pos, false));
         }
     }
     // phase 4-6: sort, replay per cell, order the events
@@ -150,8 +152,8 @@ void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pos
         while (j < log.size() && log_key(log[j]) == log_key(log[i])) ++j;
         uint32_t key = log_key(log[i]);
         uint32_t* c = e.occ.raw(key_x(win, key), key_y(win, key), false);
-        bool obstacle = replay_cell(log.data(), (int)i, (int)j, *c, [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
-        if (obstacle) *c |= kOccObstacle; else *c &= ~kOccObstacle;
+        uint8_t& fb = e.occ.fbit[c - e.occ.cells.data()];
+        fb = replay_cell(log.data(), (int)i, (int)j, *c, fb != 0, [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
         i = j;
     }
     std::sort(events.begin(), events.end());
@@ -276,7 +278,7 @@ void emu_export_dm(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* s
             int k = j * w + i;
             sqdist[k] = (uint16_t)dm_sqdist(d); valid[k] = (d & kDmValid) != 0; ox[k] = (int16_t)dm_ox(d); oy[k] = (int16_t)dm_oy(d);
             queued[k] = (d & kDmQueued) != 0;
-            known[k] = (d & kDmKnown) != 0 || (o & ~kOccObstacle) != 0;
+            known[k] = (d & kDmKnown) != 0 || o != 0;
         }
 }
 void emu_export_occ(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* occupied, uint16_t* visited, uint8_t* obstacle)
@@ -285,9 +287,11 @@ void emu_export_occ(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* 
     for (int j = 0; j < hh; ++j)
         for (int i = 0; i < w; ++i) {
             uint32_t x = x0 + i, y = y0 + j;
-            uint32_t o = dir_index(e->occ.window, x, y) < 0 ? 0u : *e->occ.raw(x, y, false);
+            const bool in = dir_index(e->occ.window, x, y) >= 0;
+            uint32_t* c = in ? e->occ.raw(x, y, false) : nullptr;
+            uint32_t o = in ? *c : 0u;
             int k = j * w + i;
-            occupied[k] = (uint16_t)occ_occupied(o); visited[k] = (uint16_t)occ_visited(o); obstacle[k] = (o & kOccObstacle) != 0;
+            occupied[k] = (uint16_t)occ_occupied(o); visited[k] = (uint16_t)occ_visited(o); obstacle[k] = in ? e->occ.fbit[c - e->occ.cells.data()] : 0;
         }
 }
 // direct brushfire calls for the stand-alone DDM comparison
