@@ -18,7 +18,7 @@ namespace lama_b200 {
 namespace {
 
 constexpr int kMatchThreads = 512;
-constexpr int kRayThreads   = 512;
+constexpr int kRayThreads   = 384;  // 2 CTAs/SM at <= 85 registers: the walk loop must not spill (r01 profile: LDL in the DDA)
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -255,6 +255,32 @@ struct SegWalk {
 
 constexpr int kCandNone = 0xFF, kCandOverflow = 0xFE;
 
+// Map::computeRay's 3-axis walk in 32-bit arithmetic (cell coordinates and deltas are < 2^27): tilted sensors only
+struct RayWalk3 {
+    int e0, e1, e2, d0, d1, d2, s0, s1, s2, n, i;
+    uint32_t x, y, z;
+    __device__ __forceinline__ explicit RayWalk3(const BeamCells& b)
+    {
+        x = b.from[0]; y = b.from[1]; z = b.from[2];
+        const int a0 = (int)(b.to[0] - b.from[0]), a1 = (int)(b.to[1] - b.from[1]), a2 = (int)(b.to[2] - b.from[2]);
+        s0 = a0 < 0 ? -1 : 1; s1 = a1 < 0 ? -1 : 1; s2 = a2 < 0 ? -1 : 1;
+        d0 = a0 < 0 ? -a0 : a0; d1 = a1 < 0 ? -a1 : a1; d2 = a2 < 0 ? -a2 : a2;
+        n = max(d0, max(d1, d2));
+        e0 = e1 = e2 = 0;
+        i = 0;
+    }
+    __device__ __forceinline__ bool next()
+    {
+        if (i >= n - 1) return false;
+        ++i;
+        e0 += d0; e1 += d1; e2 += d2;
+        if (2 * e0 >= n) { x += s0; e0 -= n; }
+        if (2 * e1 >= n) { y += s1; e1 -= n; }
+        if (2 * e2 >= n) { z += s2; e2 -= n; }
+        return true;
+    }
+};
+
 struct RayCtx {
     const StoreView& s;
     const RayParams& rp;
@@ -327,8 +353,12 @@ __device__ __forceinline__ void raycast_pass(RayCtx& c, const BeamEnds* beams, c
         if (lane == 0) item = atomicAdd(work_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
+        // group of the item: number of groups whose segment range ends at or before it (<= 128 groups)
         int g = 0;
-        while (seg_prefix[g + 1] <= item) ++g;
+        for (int g0 = 0; g0 < n_groups; g0 += 32) {
+            const int gi = g0 + lane;
+            g += __popc(__ballot_sync(0xffffffffu, gi < n_groups && seg_prefix[gi + 1] <= item));
+        }
         const int seg = (int)(item - seg_prefix[g]);
         const int b = g * 32 + lane;
         if (b < n_beams) {
@@ -345,9 +375,8 @@ __device__ __forceinline__ void raycast_pass(RayCtx& c, const BeamEnds* beams, c
         if (!(beams[b].fy & kBeamFlag)) continue;
         const double pt[3] = {__ldg(points + 3 * (size_t)b), __ldg(points + 3 * (size_t)b + 1), __ldg(points + 3 * (size_t)b + 2)};
         const BeamCells bc = beam_cells(tf, c.rp.scan, pt);
-        RayWalk w(bc);
-        uint32_t pos = 0;
-        while (w.next()) c.touch(w.x, w.y, (uint32_t)b, ++pos, false);
+        RayWalk3 w(bc);
+        while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
     }
 }
 
@@ -484,24 +513,27 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     }
     __syncthreads();
 
-    // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away ------------
+    // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away;
+    // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW) and redo those ----
     RayCtx ctx{s, rp, dir, cand_idx, cand, pending, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, kCandNone};
-    raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[0], rp.points, tf);
-    __syncthreads();
-    // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW), redo them ----
-    for (int w32 = warp; w32 < nwords; w32 += nwarps) {
-        uint32_t bits = pending[w32];
-        if (bits && lane == 0) sh.any_pending = 1;
-        while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (warp_make_exclusive(s, dir, gdir, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            __syncthreads();
+            for (int w32 = warp; w32 < nwords; w32 += nwarps) {
+                uint32_t bits = pending[w32];
+                if (bits && lane == 0) sh.any_pending = 1;
+                while (bits) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (warp_make_exclusive(s, dir, gdir, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
+                }
+            }
+            __syncthreads();
+            if (!sh.any_pending) break;
+            ctx.redo = true;
         }
-    }
-    __syncthreads();
-    if (sh.any_pending) {
-        ctx.redo = true;
-        raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[1], rp.points, tf);
+        raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[pass], rp.points, tf);
     }
     my_err |= ctx.err;
     uint32_t my_cells = __reduce_add_sync(0xffffffffu, ctx.cells);
