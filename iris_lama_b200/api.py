@@ -174,8 +174,8 @@ class PFSlam2D:
         _chk(lib().lama_pf_create(C.byref(options), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().lama_pf_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.lama_pf_destroy(self.h)
             self.h = None
 
     def setPrior(self, x, y, r):
@@ -326,8 +326,8 @@ class Slam2D:
         _chk(lib().lama_slam_create(C.byref(options), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().lama_slam_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.lama_slam_destroy(self.h)
             self.h = None
 
     def setPose(self, x, y, r):
@@ -397,8 +397,8 @@ class DynamicDistanceMap:
         _chk(lib().lama_dm_create(C.c_double(resolution), C.c_uint32(patch_size), C.c_double(l2_max), cp, C.byref(d), C.byref(self.h)))
 
     def __del__(self):
-        if getattr(self, "owned", False) and getattr(self, "h", None):
-            lib().lama_dm_destroy(self.h)
+        if getattr(self, "owned", False) and getattr(self, "h", None) and _lib is not None:
+            _lib.lama_dm_destroy(self.h)
             self.h = None
 
     @property
@@ -491,8 +491,8 @@ class Loc2D:
         self.distance_map = DynamicDistanceMap(handle=dm, owner=self)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().lama_loc_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.lama_loc_destroy(self.h)
             self.h = None
 
     def setPose(self, x, y, r):

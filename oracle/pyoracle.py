@@ -147,8 +147,9 @@ class Rng:
         self.h = C.c_void_p(lib().orc_rng_create(C.c_uint32(seed)))
 
     def __del__(self):
-        if lib and self.h:
-            lib().orc_rng_destroy(self.h)
+        if self.h and _lib is not None:
+            _lib.orc_rng_destroy(self.h)
+            self.h = None
 
     def uniform(self):
         return lib().orc_rng_uniform(self.h)
@@ -226,8 +227,9 @@ class DDM:
         self.h = C.c_void_p(handle if handle is not None else lib().orc_ddm_create(C.c_double(res), C.c_uint32(patch), C.c_double(l2_max)))
 
     def __del__(self):
-        if getattr(self, "owned", False) and self.h:
-            lib().orc_ddm_destroy(self.h)
+        if getattr(self, "owned", False) and self.h and _lib is not None:
+            _lib.orc_ddm_destroy(self.h)
+            self.h = None
 
     def clone(self):
         d = DDM.__new__(DDM)
@@ -325,8 +327,9 @@ class PFSlam2D:
             lib().orc_pf_set_shuffle(self.h, C.c_uint32(shuffle))
 
     def __del__(self):
-        if self.h:
-            lib().orc_pf_destroy(self.h)
+        if self.h and lib is not None and _lib is not None:
+            _lib.orc_pf_destroy(self.h)
+            self.h = None
 
     def set_prior(self, x, y, r):
         lib().orc_pf_set_prior(self.h, C.c_double(x), C.c_double(y), C.c_double(r))
@@ -397,8 +400,9 @@ class Slam2D:
             lib().orc_slam_set_shuffle(self.h, C.c_uint32(shuffle))
 
     def __del__(self):
-        if self.h:
-            lib().orc_slam_destroy(self.h)
+        if self.h and _lib is not None:
+            _lib.orc_slam_destroy(self.h)
+            self.h = None
 
     def set_pose(self, x, y, r):
         lib().orc_slam_set_pose(self.h, C.c_double(x), C.c_double(y), C.c_double(r))
@@ -444,8 +448,9 @@ class Loc2D:
         self.h = C.c_void_p(lib().orc_loc_create(C.byref(opts)))
 
     def __del__(self):
-        if self.h:
-            lib().orc_loc_destroy(self.h)
+        if self.h and _lib is not None:
+            _lib.orc_loc_destroy(self.h)
+            self.h = None
 
     def dm(self):
         return DDM(handle=lib().orc_loc_dm_handle(self.h), owner=self)
