@@ -89,7 +89,8 @@ struct WarpBrushfire {
     int32_t* dir;        // shared-memory copy of the distance-map directory (entries carry kDirOwn)
     int32_t* gdir;
     uint32_t* scratch;   // 32 words: out-of-window / failed accesses land here (one word per lane)
-    const DirWindow win;
+    const uint32_t side;     // window side in cells (dim * 32); all coordinates below are WINDOW-RELATIVE
+    const int log2dim;
     const int lane;
     SmemHeap lower_q, raise_q;
     const uint32_t max_sqdist;
@@ -97,7 +98,26 @@ struct WarpBrushfire {
     bool dead;           // the pool ran dry: stop touching the map
 
     __device__ WarpBrushfire(const StoreView& sv, int32_t* d, int32_t* g, uint32_t* sc, int l, SmemHeap lo, SmemHeap ra, uint32_t msq)
-        : s(sv), dir(d), gdir(g), scratch(sc), win(sv.window), lane(l), lower_q(lo), raise_q(ra), max_sqdist(msq), err(0), dead(false) {}
+        : s(sv), dir(d), gdir(g), scratch(sc), side((uint32_t)sv.window.dim * kPatchLen), log2dim(ilog2(sv.window.dim)), lane(l), lower_q(lo),
+          raise_q(ra), max_sqdist(msq), err(0), dead(false) {}
+
+    __host__ __device__ static int ilog2(int v)
+    {
+        int l = 0;
+        while ((1 << (l + 1)) <= v) ++l;
+        return l;
+    }
+    // window-relative cell coordinates: key = y << 16 | x (lama_core.h cell_key); unsigned wrap makes x - 1 at the
+    // border fall outside `side`
+    __device__ __forceinline__ static uint32_t key_of(uint32_t x, uint32_t y) { return (y << 16) | (x & 0xFFFFu); }
+    __device__ __forceinline__ int dindex(uint32_t x, uint32_t y) const
+    {
+        return (x < side && y < side) ? (int)(((y >> kPatchLog2) << log2dim) | (x >> kPatchLog2)) : -1;
+    }
+    __device__ __forceinline__ uint32_t* cellptr(int entry, uint32_t x, uint32_t y) const
+    {
+        return s.pool + ((((uint32_t)entry & (uint32_t)kDirSlotMask) << (2 * kPatchLog2)) | cell_index(x, y));
+    }
 
     // ---- mutable Map::get -------------------------------------------------------------------------------------
     __device__ __forceinline__ bool entry_ready(int e) const { return e >= 0 && (e & kDirOwn); }
@@ -116,37 +136,40 @@ struct WarpBrushfire {
     // warp-uniform coordinates
     __device__ __forceinline__ uint32_t* uptr(uint32_t x, uint32_t y)
     {
-        const int di = dir_index(win, x, y);
+        const int di = dindex(x, y);
         if (di < 0 || dead) {
             if (di < 0) err |= kErrWindow;
             scratch[lane] = 0;
             return &scratch[lane];
         }
-        if (!entry_ready(dir[di]) && !ensure(di)) {
-            scratch[lane] = 0;
-            return &scratch[lane];
+        int e = dir[di];
+        if (!entry_ready(e)) {
+            if (!ensure(di)) {
+                scratch[lane] = 0;
+                return &scratch[lane];
+            }
+            e = dir[di];
         }
-        return patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(x, y);
+        return cellptr(e, x, y);
     }
     // per-lane coordinates; inactive lanes get their scratch word
     __device__ __forceinline__ uint32_t* lptr(uint32_t x, uint32_t y, bool active)
     {
-        int di = active ? dir_index(win, x, y) : -1;
+        const int di = active ? dindex(x, y) : -1;
         if (active && di < 0) err |= kErrWindow;
-        bool need = di >= 0 && !entry_ready(dir[di]);
-        unsigned m = __ballot_sync(kFullMask, need);
-        while (m && !dead) {
+        int e = di >= 0 ? dir[di] : -1;
+        unsigned m = __ballot_sync(kFullMask, di >= 0 && !entry_ready(e));
+        while (m && !dead) {  // rare: first touch of a patch by this particle
             const int l = __ffs(m) - 1;
-            const int d = __shfl_sync(kFullMask, di, l);
-            ensure(d);
-            need = di >= 0 && !entry_ready(dir[di]);
-            m = __ballot_sync(kFullMask, need);
+            ensure(__shfl_sync(kFullMask, di, l));
+            e = di >= 0 ? dir[di] : -1;
+            m = __ballot_sync(kFullMask, di >= 0 && !entry_ready(e));
         }
-        if (di < 0 || dead || !entry_ready(dir[di])) {
+        if (!entry_ready(e) || dead) {
             scratch[lane] = 0;
             return &scratch[lane];
         }
-        return patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(x, y);
+        return cellptr(e, x, y);
     }
     // read a cell the way the mutable get does: the Container bit ("known") is switched on
     __device__ __forceinline__ uint32_t touch(uint32_t* p)
@@ -175,7 +198,7 @@ struct WarpBrushfire {
         const uint32_t w = touch(c);
         if ((w & kDmValid) && dm_sqdist(w) == 0) return;
         *c = dm_pack(0, 0, 0, true, true);
-        push_lower(0, cell_key(win, x, y));
+        push_lower(0, key_of(x, y));
     }
     __device__ __forceinline__ void remove_obstacle(uint32_t x, uint32_t y)
     {
@@ -183,7 +206,7 @@ struct WarpBrushfire {
         const uint32_t w = touch(c);
         if (!((w & kDmValid) && dm_sqdist(w) == 0)) return;
         *c = dm_pack(0, 0, 0, false, true);
-        push_raise(0, cell_key(win, x, y));
+        push_raise(0, key_of(x, y));
     }
 
     // :244-279
@@ -200,7 +223,7 @@ struct WarpBrushfire {
         uint32_t* po = lptr(nx + dm_ox(n), ny + dm_oy(n), go);
         if (go) touch(po);
         __syncwarp();
-        const uint32_t key = cell_key(win, nx, ny);
+        const uint32_t key = key_of(nx, ny);
         for (int j = 0; j < 4; ++j) {
             uint32_t o = 0;
             if (lane == j && go) o = *po;  // re-read: an earlier neighbour of this call may have been cleared
@@ -247,7 +270,7 @@ struct WarpBrushfire {
         }
         __syncwarp();
         unsigned m = __ballot_sync(kFullMask, over) & 0xFu;
-        const uint32_t key = cell_key(win, nx, ny);
+        const uint32_t key = key_of(nx, ny);
         while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
@@ -264,7 +287,7 @@ struct WarpBrushfire {
         uint32_t processed = 0;
         while (raise_q.size) {
             const uint32_t key = heap_key(raise_q.pop());
-            const uint32_t x = key_x(win, key), y = key_y(win, key);
+            const uint32_t x = key & 0xFFFFu, y = key >> 16;
             uint32_t* cur = uptr(x, y);
             touch(cur);
             ++processed;
@@ -272,17 +295,8 @@ struct WarpBrushfire {
         }
         while (lower_q.size) {
             const uint32_t key = heap_key(lower_q.pop());
-            const uint32_t x = key_x(win, key), y = key_y(win, key);
+            const uint32_t x = key & 0xFFFFu, y = key >> 16;
             uint32_t* cur = uptr(x, y);
-            // the next pop is already known (pushes of this pop carry strictly larger priorities): start its load
-            if (lower_q.size) {
-                const uint32_t nk = heap_key(lower_q.top());
-                const int di = dir_index(win, key_x(win, nk), key_y(win, nk));
-                if (di >= 0 && dir[di] >= 0) {
-                    const uint32_t* np = patch_ptr(s, dir[di] & kDirSlotMask) + cell_index(key_x(win, nk), key_y(win, nk));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
-                }
-            }
             const uint32_t c = touch(cur);
             ++processed;
             if (c & kDmValid) {

@@ -631,10 +631,9 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
     const uint64_t* ev = events + (size_t)blockIdx.x * bp.event_cap;
     for (uint32_t i = 0; i < nev; ++i) {
         const uint64_t e   = ev[i];
-        const uint32_t key = (uint32_t)e;
-        const uint32_t x = key_x(s.window, key), y = key_y(s.window, key);
-        if ((e >> 32) & 1u) bf.add_obstacle(x, y);
-        else bf.remove_obstacle(x, y);
+        const uint32_t key = (uint32_t)e;  // window-relative cell
+        if ((e >> 32) & 1u) bf.add_obstacle(key & 0xFFFFu, key >> 16);
+        else bf.remove_obstacle(key & 0xFFFFu, key >> 16);
     }
     const uint32_t processed = bf.update();
     const uint32_t err = __reduce_or_sync(0xffffffffu, bf.err);
