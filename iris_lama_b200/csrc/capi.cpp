@@ -205,6 +205,7 @@ int lama_pf_update_staged(lama_pf* h, int index, const double* origin, const dou
 int lama_pf_get_traffic(lama_pf* h, uint64_t bytes[2], int reset)
 {
     if (!h || !bytes) return set_err("null argument", LAMA_ERR_ARG);
+    h->p->settle_counters();
     Engine* e = h->p->engine();
     bytes[0] = e ? e->h2d_bytes() : 0;
     bytes[1] = e ? e->d2h_bytes() : 0;
@@ -264,6 +265,7 @@ int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6])
 int lama_pf_kernel_times(lama_pf* h, double ms[4], uint64_t launches[5])
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    h->p->settle_counters();
     return times_out(h->p->engine(), ms, launches);
 }
 static int pf_local(lama_pf* h, int particle)

@@ -38,7 +38,7 @@ struct Engine::Impl {
     int state_cap = 0;
     RayParams ray{};
     BrushParams brush{};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // scratch for import/export/distance
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -111,6 +111,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     }
     CU_NEW(cudaEventCreate(&d->ev[0]));
     CU_NEW(cudaEventCreate(&d->ev[1]));
+    CU_NEW(cudaEventCreate(&d->ev[2]));
 
     // directory window centred on (center_x, center_y)
     const uint32_t cx = w2m(cfg.center_x, scale), cy = w2m(cfg.center_y, scale);
@@ -185,12 +186,14 @@ Engine::~Engine()
     if (d_->d_staged) cudaFree(d_->d_staged);
     if (d_->ev[0]) cudaEventDestroy(d_->ev[0]);
     if (d_->ev[1]) cudaEventDestroy(d_->ev[1]);
+    if (d_->ev[2]) cudaEventDestroy(d_->ev[2]);
     if (d_->stream && d_->own_stream) cudaStreamDestroy(d_->stream);
     delete d_;
 }
 
 int Engine::synchronize()
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     CU_TRY(cudaSetDevice(cfg_.device));
     CU_TRY(cudaStreamSynchronize(d_->stream));
     return LAMA_OK;
@@ -216,6 +219,7 @@ void Engine::set_moving(const double origin[3], const double quat[4], double tru
 
 int Engine::set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (!pts || n < 1 || n > cfg_.max_beams) return fail("set_scan: number of beams out of range", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     set_moving(origin, quat, truncated_ray, truncated_range, n);
@@ -229,6 +233,7 @@ int Engine::set_scan(const double* pts, int n, const double origin[3], const dou
 
 int Engine::stage_scans(const double* pts, int n_scans, int n)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (!pts || n_scans < 1 || n < 1 || n > cfg_.max_beams) return fail("stage_scans: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     if (d_->d_staged) { cudaFree(d_->d_staged); d_->d_staged = nullptr; }
@@ -274,6 +279,7 @@ int Engine::check_device_status()
 
 uint32_t Engine::device_status()
 {
+    settle(nullptr);
     cudaSetDevice(cfg_.device);
     cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream);
     cudaStreamSynchronize(d_->stream);
@@ -282,6 +288,7 @@ uint32_t Engine::device_status()
 
 void Engine::store_counters(uint64_t out[4])
 {
+    settle(nullptr);
     cudaSetDevice(cfg_.device);
     uint64_t c[3];
     int32_t fc = 0;
@@ -294,6 +301,7 @@ void Engine::store_counters(uint64_t out[4])
 int Engine::match(const SE2* states, int count, int first_particle, bool shared_map, const SolverOptions& so, double meas_sigma, int mode,
                   HostMatchResult* out)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (count < 1 || first_particle < 0 || (!shared_map && first_particle + count > cfg_.particles) || first_particle >= cfg_.particles)
         return fail("match: particle range out of bounds", LAMA_ERR_ARG);
     if (d_->scan.n_beams < 1) return fail("match: no scan uploaded", LAMA_ERR_STATE);
@@ -333,8 +341,18 @@ int Engine::match(const SE2* states, int count, int first_particle, bool shared_
 
 int Engine::update_maps(const SE2* states, int first_particle, int count, HostMapStats* out)
 {
+    int rc = update_maps_async(states, first_particle, count);
+    if (rc != LAMA_OK) return rc;
+    return settle(out);
+}
+
+// Launches ray cast + brushfire and returns without waiting; settle() (called by every later entry point)
+// synchronises, collects the per-particle statistics and surfaces device errors.
+int Engine::update_maps_async(const SE2* states, int first_particle, int count)
+{
     if (count < 1 || first_particle < 0 || first_particle + count > cfg_.particles) return fail("update_maps: particle range out of bounds", LAMA_ERR_ARG);
     if (d_->scan.n_beams < 1) return fail("update_maps: no scan uploaded", LAMA_ERR_STATE);
+    { int rc = settle(nullptr); if (rc != LAMA_OK) return rc; }
     CU_TRY(cudaSetDevice(cfg_.device));
     { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
     std::memcpy(d_->h_states, states, (size_t)count * sizeof(SE2));
@@ -352,42 +370,47 @@ int Engine::update_maps(const SE2* states, int first_particle, int count, HostMa
     bp.set = cur_set_;
     bp.particle_offset = first_particle;
     bp.event_cap = rp.event_cap;
-    cudaEvent_t e2 = nullptr;
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
     launch_raycast(d_->view, rp, d_->d_states, d_->d_events, d_->d_stats, count, d_->stream);
-    if (timing_) {
-        CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
-        CU_TRY(cudaEventCreate(&e2));
-    }
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
     launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
-    if (timing_) CU_TRY(cudaEventRecord(e2, d_->stream));
+    if (timing_) CU_TRY(cudaEventRecord(d_->ev[2], d_->stream));
     launch_merge_free(d_->view, d_->stream);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(d_->h_stats, d_->d_stats, (size_t)count * sizeof(MapUpdateStats), cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
-    CU_TRY(cudaStreamSynchronize(d_->stream));
-    if (timing_) {
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, d_->ev[0], d_->ev[1]);
-        cudaEventElapsedTime(&b, d_->ev[1], e2);
-        cudaEventDestroy(e2);
-        times_.raycast_ms += a;
-        times_.brushfire_ms += b;
-    }
     times_.raycast_launches += 1;
     times_.brushfire_launches += 1;
     times_.misc_launches += 1;
     h2d_bytes_ += (uint64_t)count * sizeof(SE2);
     d2h_bytes_ += (uint64_t)count * sizeof(MapUpdateStats) + 4;
-    if (out) {
-        static_assert(sizeof(HostMapStats) == sizeof(MapUpdateStats), "layout");
-        std::memcpy(out, d_->h_stats, (size_t)count * sizeof(MapUpdateStats));
+    pending_maps_ = count;
+    return LAMA_OK;
+}
+
+int Engine::settle(HostMapStats* out)
+{
+    if (pending_maps_ == 0) return LAMA_OK;
+    const int count = pending_maps_;
+    pending_maps_ = 0;
+    CU_TRY(cudaSetDevice(cfg_.device));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    if (timing_) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, d_->ev[0], d_->ev[1]);
+        cudaEventElapsedTime(&b, d_->ev[1], d_->ev[2]);
+        times_.raycast_ms += a;
+        times_.brushfire_ms += b;
     }
+    static_assert(sizeof(HostMapStats) == sizeof(MapUpdateStats), "layout");
+    last_map_stats_.assign((HostMapStats*)d_->h_stats, (HostMapStats*)d_->h_stats + count);
+    if (out) std::memcpy(out, d_->h_stats, (size_t)count * sizeof(MapUpdateStats));
     return check_device_status();
 }
 
 int Engine::share_from(int src_particle, int dst_first, int count)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (count == 0) return LAMA_OK;
     if (src_particle < 0 || src_particle >= cfg_.particles || dst_first < 0 || dst_first + count > cfg_.particles ||
         (src_particle >= dst_first && src_particle < dst_first + count))
@@ -406,6 +429,7 @@ int Engine::share_from(int src_particle, int dst_first, int count)
 
 int Engine::resample(const int32_t* idx)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     CU_TRY(cudaSetDevice(cfg_.device));
     const int P = cfg_.particles;
     for (int i = 0; i < P; ++i) {
@@ -443,6 +467,7 @@ static int ensure_scratch(Engine::Impl* d, size_t bytes)
 
 int Engine::dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_add, int n, uint32_t* processed)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || n < 0) return fail("dm_apply: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     uint32_t total = 0;
@@ -486,6 +511,7 @@ int Engine::dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_a
 
 int Engine::dm_distance(int particle, const double* pts, int n, double* dist, double* grad)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || n < 1) return fail("dm_distance: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t bp = (size_t)n * 24, bd = (size_t)n * 8, bg = (size_t)n * 24;
@@ -504,6 +530,7 @@ int Engine::dm_distance(int particle, const double* pts, int n, double* dist, do
 
 int Engine::export_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* words, uint8_t* present)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1 || w < 1 || h < 1) return fail("export_window: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t bw = (size_t)w * h * 4, bpz = (size_t)w * h;
@@ -520,6 +547,7 @@ int Engine::export_window(int particle, int kind, uint32_t x0, uint32_t y0, int 
 
 int Engine::import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1 || w < 1 || h < 1 || (x0 | y0 | (uint32_t)w | (uint32_t)h) % kPatchLen)
         return fail("import_window: window must be patch aligned", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
@@ -539,6 +567,7 @@ static const uint32_t kPackMagic = 0x4c414d50u;  // "LAMP"
 
 int Engine::pack_size(int particle, size_t* bytes)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles) return fail("pack_size: bad particle", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
@@ -554,6 +583,7 @@ int Engine::pack_size(int particle, size_t* bytes)
 
 int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles) return fail("pack: bad particle", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
@@ -594,6 +624,7 @@ int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
 
 int Engine::unpack(int particle, const void* buf, size_t bytes)
 {
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || bytes < 16) return fail("unpack: bad arguments", LAMA_ERR_ARG);
     const uint32_t* hdr = (const uint32_t*)buf;
     if (hdr[0] != kPackMagic || hdr[1] != (uint32_t)cfg_.dir_dim) return fail("unpack: incompatible buffer", LAMA_ERR_ARG);
@@ -623,6 +654,7 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
 
 int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
 {
+    if (settle(nullptr) != LAMA_OK) return -1;
     if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1) return -1;
     cudaSetDevice(cfg_.device);
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;

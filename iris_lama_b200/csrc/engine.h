@@ -63,6 +63,11 @@ public:
 
     // Ray-cast + distance-map update of particles [first, first+count) at the given poses.
     int update_maps(const SE2* states, int first_particle, int count, HostMapStats* out);
+    // Same, but returns right after the launches; the work is collected by settle(), which every later entry point
+    // calls first (errors of an asynchronous update therefore surface at the next call).
+    int update_maps_async(const SE2* states, int first_particle, int count);
+    int settle(HostMapStats* out);
+    const std::vector<HostMapStats>& last_map_stats() const { return last_map_stats_; }
 
     // Particles dst_first .. dst_first+count-1 become copy-on-write copies of src_particle (same set).
     int share_from(int src_particle, int dst_first, int count);
@@ -115,6 +120,8 @@ private:
     KernelTimes times_;
     std::string err_;
     uint64_t h2d_bytes_ = 0, d2h_bytes_ = 0;
+    int pending_maps_ = 0;
+    std::vector<HostMapStats> last_map_stats_;
     void set_moving(const double origin[3], const double quat[4], double truncated_ray, double truncated_range, int n);
     int fail(const std::string& what, int code);
     int check_device_status();

@@ -223,6 +223,19 @@ void PFSlam2D::apply_resample_host(const std::vector<int32_t>& idx)
     node_of_.swap(nnode);
 }
 
+int PFSlam2D::settle_counters()
+{
+    if (!counters_pending_) return LAMA_OK;
+    counters_pending_ = false;
+    int rc = eng_->settle(nullptr);
+    for (const HostMapStats& st : eng_->last_map_stats()) {
+        last_.ray_cells += st.ray_cells;
+        last_.dm_pops += st.dm_pops;
+    }
+    finish_counters();
+    return rc == LAMA_OK ? rc : engine_fail(rc);
+}
+
 void PFSlam2D::finish_counters()
 {
     uint64_t c[4];
@@ -256,6 +269,10 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
 {
     *did_update   = false;
     pending_maps_ = false;
+    if (eng_) {
+        int rcs = settle_counters();   // collect the previous scan's asynchronous map update (and its errors)
+        if (rcs != LAMA_OK) return rcs;
+    }
     last_         = Counters();
     last_idx_.clear();
     int rc = ensure_engine(staged_index_ >= 0 ? staged_beams_ : n);
@@ -353,14 +370,10 @@ int PFSlam2D::shard_map_update()
     if (!pending_maps_) return fail("shard_map_update without a pending update", LAMA_ERR_STATE);
     pending_maps_ = false;
     const int nl = hi_ - lo_;
-    std::vector<HostMapStats> st((size_t)nl);
-    int rc = eng_->update_maps(&pose_[lo_], 0, nl, st.data());
+    // asynchronous: the kernels of this scan overlap with the caller's work until the next call into this handle
+    int rc = eng_->update_maps_async(&pose_[lo_], 0, nl);
     if (rc != LAMA_OK) return engine_fail(rc);
-    for (int k = 0; k < nl; ++k) {
-        last_.ray_cells += st[k].ray_cells;
-        last_.dm_pops += st[k].dm_pops;
-    }
-    finish_counters();
+    counters_pending_ = true;
     return LAMA_OK;
 }
 

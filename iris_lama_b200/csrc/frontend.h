@@ -73,11 +73,12 @@ public:
     void weights(int i, double w[3]) const { w[0] = weight_[i]; w[1] = nweight_[i]; w[2] = wsum_[i]; }
     std::vector<SE2> trajectory(int particle) const;
     const std::vector<int32_t>& last_resample() const { return last_idx_; }
-    const Counters& last_counters() const { return last_; }
-    const Counters& total_counters() const { return total_; }
+    const Counters& last_counters() { settle_counters(); return last_; }
+    const Counters& total_counters() { settle_counters(); return total_; }
     Engine* engine() { return eng_.get(); }
     const std::string& error() const { return err_; }
     bool has_first_scan() const { return has_first_; }
+    int settle_counters();
 
 private:
     PFSlam2D() = default;
@@ -98,7 +99,7 @@ private:
     Counters last_, total_;
     uint64_t detached_seen_ = 0;
     std::string err_;
-    bool pending_maps_ = false;
+    bool pending_maps_ = false, counters_pending_ = false;
     std::vector<double> staged_host_;  // kept until the engine exists
     int staged_scans_ = 0, staged_beams_ = 0, staged_index_ = -1;
     int ensure_engine(int n);

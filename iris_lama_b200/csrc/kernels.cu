@@ -326,7 +326,8 @@ struct RayCtx {
         if (centry < 0) return;
         ++cells;
         const uint32_t ci = cell_index(x, y);
-        atomicAdd(patch_ptr(s, centry & kDirSlotMask) + ci, hit ? kOccHitInc : kOccMissInc);
+        // red.global: a reduction with no destination register (SASS RED), nothing waits for it
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(patch_ptr(s, centry & kDirSlotMask) + ci), "r"(hit ? kOccHitInc : kOccMissInc) : "memory");
         if (ccand == kCandNone) return;
         if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
             const uint32_t idx = atomicAdd(&sh.log_count, 1u);
