@@ -91,7 +91,8 @@ __device__ __forceinline__ void warp_copy_patch(uint32_t* dst, const uint32_t* s
 // first touch (Map::get mutable, map.cpp:400-408) or detach a shared one (cow_ptr.h:104-114).
 // Must be called by all 32 lanes of a warp with identical arguments; `dir_smem` is the staged copy
 // of the directory, `dir_gmem` its home.  Returns the (now exclusive) slot or -1 when the pool is empty.
-__device__ __forceinline__ int warp_make_exclusive(const StoreView& s, int32_t* dir_smem, int32_t* dir_gmem, int di, int lane)
+// (cold path: kept out of line so that the hot loops of the callers stay small)
+static __device__ __noinline__ int warp_make_exclusive(const StoreView& s, int32_t* dir_smem, int32_t* dir_gmem, int di, int lane)
 {
     const int entry = dir_smem[di];
     const int slot  = entry < 0 ? -1 : (entry & kDirSlotMask);
