@@ -256,7 +256,12 @@ def gpu_arm(args):
         kernel_ms = {kk: tm[kk] / steps for kk in tm}
         dom = max(tm, key=tm.get)
         ach = by[dom] / (tm[dom] * 1e-3) / 1e9 if tm[dom] > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of that kernel (per launch)
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_kind": peak_kind, "algorithmic_bytes_per_launch": by[dom] / steps, "avg_launch_ms": tm[dom] / steps,
                     "all_kernels": {kk: {"GBps": (by[kk] / (tm[kk] * 1e-3) / 1e9 if tm[kk] > 0 else 0.0), "ms_per_step": tm[kk] / steps,
                                          "bytes_per_step": by[kk] / steps} for kk in tm}}
