@@ -145,6 +145,8 @@ typedef struct lama_slam_options { /* Slam2D::Options, slam2d.h:91-125 */
     double trans_thresh, rot_thresh, l2_max, truncated_ray, truncated_range, resolution;
     uint32_t patch_size, max_iter;
     int32_t strategy; /* 0 "gn", 1 "lm" (slam2d.cpp:226-233) */
+    int32_t occupancy; /* 0 = FrequencyOccupancyMap as in Slam2D (slam2d.cpp:97); 1 = ProbabilisticOccupancyMap, the log-odds map of
+                          src/sdm/probabilistic_occupancy_map.cpp (what LidarOdometry2D pairs with the same update loop) */
     lama_device_options dev;
 } lama_slam_options;
 int lama_slam_options_default(lama_slam_options* o);
@@ -160,6 +162,8 @@ int lama_slam_get_counters(lama_slam* h, uint64_t last[6], uint64_t total[6]);
 int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5]);
 int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);
 int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known);
+/* occupancy == 1 only: dense window of ProbabilisticOccupancyMap cells (float log-odds, prob_tag) + Container known bit */
+int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known);
 int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
                               int16_t* ox, int16_t* oy, uint8_t* queued);
 

@@ -46,7 +46,7 @@ class PFOptions(C.Structure):
 class SlamOptions(C.Structure):
     _fields_ = [("trans_thresh", C.c_double), ("rot_thresh", C.c_double), ("l2_max", C.c_double), ("truncated_ray", C.c_double),
                 ("truncated_range", C.c_double), ("resolution", C.c_double), ("patch_size", C.c_uint32), ("max_iter", C.c_uint32),
-                ("strategy", C.c_int32), ("dev", DeviceOptions)]
+                ("strategy", C.c_int32), ("occupancy", C.c_int32), ("dev", DeviceOptions)]
 
 
 class LocOptions(C.Structure):
@@ -66,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "lama_pf_particle_pack_size", "lama_pf_particle_pack", "lama_pf_particle_unpack",
     "lama_slam_options_default", "lama_slam_create", "lama_slam_destroy", "lama_slam_set_pose", "lama_slam_update", "lama_slam_get_pose",
     "lama_slam_get_state", "lama_slam_get_processed_cells", "lama_slam_get_counters", "lama_slam_kernel_times", "lama_slam_map_bounds",
-    "lama_slam_export_occupancy", "lama_slam_export_distance",
+    "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
@@ -371,6 +371,11 @@ class Slam2D:
         o = _occ_arrays(w, h)
         _chk(lib().lama_slam_export_occupancy(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), _vp(o["occupied"]),
                                               _vp(o["visited"]), _vp(o["known"])))
+        return o
+
+    def exportLogOdds(self, x0, y0, w, h):
+        o = dict(prob=np.zeros((h, w), np.float32), known=np.zeros((h, w), np.uint8))
+        _chk(lib().lama_slam_export_logodds(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), _vp(o["prob"]), _vp(o["known"])))
         return o
 
     def exportDistance(self, x0, y0, w, h):

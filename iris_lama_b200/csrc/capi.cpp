@@ -84,7 +84,11 @@ int export_dm(Engine* e, int particle, bool with_occ, uint32_t x0, uint32_t y0, 
     int rc = e->export_window(particle, 1, x0, y0, w, h, words.data(), nullptr);
     if (rc != LAMA_OK) return set_err(e->last_error(), rc);
     std::vector<uint8_t> occ_known;
-    if (with_occ && known) {
+    if (with_occ && known && e->config().occupancy_kind == 1) {
+        occ_known.resize((size_t)w * h);
+        rc = e->export_bits(particle, 1, x0, y0, w, h, occ_known.data());
+        if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    } else if (with_occ && known) {
         // The first touch of an occupancy cell always reports "changed" and therefore calls
         // add/removeObstacle, which marks the distance cell known (frequency_occupancy_map.cpp:65-91,
         // dynamic_distance_map.cpp:212-242): distance.known = occupancy.known OR touched by the brushfire.
@@ -362,7 +366,7 @@ int lama_slam_create(const lama_slam_options* o, lama_slam** out)
     SlamOptions s;
     s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
     s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
-    s.strategy = o->strategy; s.dev = dev_from(o->dev);
+    s.strategy = o->strategy; s.occupancy = o->occupancy; s.dev = dev_from(o->dev);
     std::string err;
     Slam2D* sl = Slam2D::create(s, err);
     if (!sl) return set_err(err, lama_b200::cuda_device_count() < 1 ? LAMA_ERR_NO_DEVICE : LAMA_ERR_ARG);
@@ -431,6 +435,17 @@ int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, in
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
+}
+int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known)
+{
+    if (!h || !logodds) return set_err("null argument", LAMA_ERR_ARG);
+    Engine* e = h->s->engine();
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    if (e->config().occupancy_kind != 1) return set_err("this Slam2D uses the frequency occupancy map", LAMA_ERR_STATE);
+    static_assert(sizeof(float) == 4, "float cells");
+    int rc = e->export_window(0, 0, x0, y0, w, hgt, reinterpret_cast<uint32_t*>(logodds), nullptr);
+    if (rc == LAMA_OK && known) rc = e->export_bits(0, 1, x0, y0, w, hgt, known);
+    return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
 int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
                               int16_t* oy, uint8_t* queued)

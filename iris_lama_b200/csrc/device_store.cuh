@@ -15,6 +15,7 @@ namespace lama_b200 {
 struct StoreView {
     uint32_t* pool;       // n_slots * 1024 words
     uint32_t* fbits;      // n_slots * 32 words: obstacle-mirror bit of every cell (occupancy patches)
+    uint32_t* kbits;      // n_slots * 32 words: Container 'known' bit of log-odds occupancy patches (null for frequency maps)
     int32_t* refcount;    // per slot
     int32_t* free_slots;  // stack of free slot ids
     int32_t* free_count;  // number of valid entries in free_slots
@@ -25,10 +26,11 @@ struct StoreView {
     int32_t n_slots;
     int32_t* dirs;        // [set][particle][kind][dim*dim]
     int32_t n_particles;
+    int32_t n_kinds;      // 2 (occupancy, distance) or 3 (+ per-scan scratch counters of the log-odds map)
     DirWindow window;
 };
 
-enum MapKind : int { kMapOcc = 0, kMapDm = 1 };
+enum MapKind : int { kMapOcc = 0, kMapDm = 1, kMapScratch = 2 };
 
 // A directory entry is -1 (patch absent) or slot | flags:
 //   kDirHot   persistent, occupancy directories only: the patch may hold cells whose obstacle-mirror bit is set
@@ -42,10 +44,11 @@ constexpr int32_t kDirOwn      = 1 << 29;
 
 __device__ __forceinline__ int32_t* dir_of(const StoreView& s, int set, int particle, int kind)
 {
-    return s.dirs + (((size_t)set * s.n_particles + particle) * 2 + kind) * (size_t)(s.window.dim * s.window.dim);
+    return s.dirs + (((size_t)set * s.n_particles + particle) * s.n_kinds + kind) * (size_t)(s.window.dim * s.window.dim);
 }
 __device__ __forceinline__ uint32_t* patch_ptr(const StoreView& s, int slot) { return s.pool + (size_t)slot * kPatchCells; }
 __device__ __forceinline__ uint32_t* fbits_ptr(const StoreView& s, int slot) { return s.fbits + (size_t)slot * 32; }
+__device__ __forceinline__ uint32_t* kbits_ptr(const StoreView& s, int slot) { return s.kbits + (size_t)slot * 32; }
 
 // ---- slot allocation (one thread) -----------------------------------------------------------------------
 __device__ __forceinline__ int alloc_slot(const StoreView& s)
@@ -107,6 +110,7 @@ static __device__ __noinline__ int warp_make_exclusive(const StoreView& s, int32
         if (ns < 0) return -1;
         warp_zero_patch(patch_ptr(s, ns), lane);
         fbits_ptr(s, ns)[lane] = 0u;
+        if (s.kbits) kbits_ptr(s, ns)[lane] = 0u;
         __syncwarp();
         if (lane == 0) {
             dir_smem[di] = ns | keep | kDirOwn;
@@ -131,6 +135,7 @@ static __device__ __noinline__ int warp_make_exclusive(const StoreView& s, int32
         // it observes refcount == 1, which cannot happen before we drop ours below.
         warp_copy_patch(patch_ptr(s, ns), patch_ptr(s, slot), lane);
         fbits_ptr(s, ns)[lane] = __ldcg(fbits_ptr(s, slot) + lane);
+        if (s.kbits) kbits_ptr(s, ns)[lane] = __ldcg(kbits_ptr(s, slot) + lane);
         __syncwarp();
         if (lane == 0) {
             dir_smem[di] = ns | keep | kDirOwn;

@@ -122,6 +122,8 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     StoreView& v = d->view;
     v.n_slots     = e->cfg_.pool_slots;
     v.n_particles = cfg.particles;
+    v.n_kinds     = cfg.occupancy_kind == 1 ? 3 : 2;
+    v.kbits       = nullptr;
     v.window      = e->window_;
     const size_t dim2 = (size_t)cfg.dir_dim * cfg.dir_dim;
     auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
@@ -131,6 +133,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     };
     CU_NEW(dalloc((void**)&v.pool, (size_t)v.n_slots * kPatchBytes));
     CU_NEW(dalloc((void**)&v.fbits, (size_t)v.n_slots * 128));
+    if (cfg.occupancy_kind == 1) CU_NEW(dalloc((void**)&v.kbits, (size_t)v.n_slots * 128));
     CU_NEW(dalloc((void**)&v.refcount, (size_t)v.n_slots * 4));
     CU_NEW(dalloc((void**)&v.free_slots, (size_t)v.n_slots * 4));
     CU_NEW(dalloc((void**)&v.freed, (size_t)v.n_slots * 4));
@@ -138,12 +141,21 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     v.freed_count = v.free_count + 1;
     v.status      = reinterpret_cast<uint32_t*>(v.free_count + 2);
     v.counters    = reinterpret_cast<uint64_t*>(v.free_count + 4);
-    CU_NEW(dalloc((void**)&v.dirs, 2 * (size_t)cfg.particles * 2 * dim2 * 4));
+    CU_NEW(dalloc((void**)&v.dirs, 2 * (size_t)cfg.particles * v.n_kinds * dim2 * 4));
     CU_NEW(dalloc((void**)&d->d_scan_buf, (size_t)cfg.max_beams * 3 * 8));
     d->d_points = d->d_scan_buf;
 
     d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
     d->ray.cand_cap  = 192;
+    d->ray.prob_mode = cfg.occupancy_kind == 1 ? 1 : 0;
+    {   // ProbabilisticOccupancyMap's constructor (probabilistic_occupancy_map.cpp:43-60): float logods(), stored as doubles
+        auto logods = [](float prob) -> float { return (float)std::log(prob / (1.0 - prob)); };
+        d->ray.prob.miss      = logods(0.4f);
+        d->ray.prob.hit       = logods(0.7f);
+        d->ray.prob.clamp_min = logods(0.12f);
+        d->ray.prob.clamp_max = logods(0.97f);
+        d->ray.prob.thresh    = 0.0 * logods(0.5f);
+    }
     d->ray.event_cap = next_pow2_host(std::max(2048, cfg.max_beams));
     d->ray.scan.n_beams = cfg.max_beams;  // shared-memory budget is registered for the largest scan
     d->brush.event_cap = d->ray.event_cap;
@@ -545,6 +557,20 @@ int Engine::export_window(int particle, int kind, uint32_t x0, uint32_t y0, int 
     return LAMA_OK;
 }
 
+int Engine::export_bits(int particle, int plane, uint32_t x0, uint32_t y0, int w, int h, uint8_t* out)
+{
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
+    if (particle < 0 || particle >= cfg_.particles || plane < 0 || plane > 1 || w < 1 || h < 1) return fail("export_bits: bad arguments", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    if (ensure_scratch(d_, (size_t)w * h)) return fail("export_bits: out of device memory", LAMA_ERR_CUDA);
+    launch_export_bits(d_->view, plane, cur_set_, particle, x0, y0, w, h, (uint8_t*)d_->d_scratch, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, d_->d_scratch, (size_t)w * h, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
 int Engine::import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
@@ -572,7 +598,7 @@ int Engine::pack_size(int particle, size_t* bytes)
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
     std::vector<int32_t> dir(2 * dim2);
-    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2) * dim2;
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * d_->view.n_kinds) * dim2;
     CU_TRY(cudaMemcpyAsync(dir.data(), src, 2 * dim2 * 4, cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));
     size_t n = 0;
@@ -588,7 +614,7 @@ int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
     CU_TRY(cudaSetDevice(cfg_.device));
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
     std::vector<int32_t> dir(2 * dim2);
-    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2) * dim2;
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * d_->view.n_kinds) * dim2;
     CU_TRY(cudaMemcpyAsync(dir.data(), src, 2 * dim2 * 4, cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));
     std::vector<int32_t> entries, slots;
@@ -659,7 +685,7 @@ int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
     cudaSetDevice(cfg_.device);
     const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
     std::vector<int32_t> dir(dim2);
-    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * 2 + kind) * dim2;
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * d_->view.n_kinds + kind) * dim2;
     if (cudaMemcpyAsync(dir.data(), src, dim2 * 4, cudaMemcpyDeviceToHost, d_->stream) != cudaSuccess) return -1;
     cudaStreamSynchronize(d_->stream);
     int n = 0;

@@ -22,6 +22,7 @@ struct EngineConfig {
     double center_x   = 0.0;    // world position the directory window is centred on
     double center_y   = 0.0;
     uint64_t stream   = 0;      // external cudaStream_t (0 = own non-blocking stream)
+    int occupancy_kind = 0;     // 0 = FrequencyOccupancyMap (PFSlam2D, Slam2D), 1 = ProbabilisticOccupancyMap (log-odds)
 };
 
 struct HostMatchResult {
@@ -88,6 +89,8 @@ public:
     // Dense window export of raw cell words (kind 0 = occupancy, 1 = distance); present may be null.
     int export_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* words, uint8_t* present);
     int import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words);
+    // dense window of a bit plane of the occupancy map: 0 = obstacle mirror, 1 = known bits (log-odds maps)
+    int export_bits(int particle, int plane, uint32_t x0, uint32_t y0, int w, int h, uint8_t* out);
     // bounding box (in cells) of allocated patches of one map; returns the number of patches
     int bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2]);
 

@@ -429,6 +429,7 @@ int Slam2D::update(const double* pts, int n, const double* origin, const double*
         std::string e;
         EngineConfig cfg = engine_config(opt_.dev, 1, opt_.resolution, opt_.l2_max, pose_.tx, pose_.ty);
         cfg.max_beams = std::max(cfg.max_beams, n);
+        cfg.occupancy_kind = opt_.occupancy == 1 ? 1 : 0;
         Engine* en = Engine::create(cfg, e);
         if (!en) { err_ = e; return LAMA_ERR_CUDA; }
         eng_.reset(en);

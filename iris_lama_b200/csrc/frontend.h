@@ -124,6 +124,7 @@ struct SlamOptions {  // include/lama/slam2d.h:91-125
     double trans_thresh = 0.5, rot_thresh = 0.5, l2_max = 0.5, truncated_ray = 0.0, truncated_range = 0.0, resolution = 0.05;
     uint32_t patch_size = 32, max_iter = 100;
     int strategy = 0;
+    int occupancy = 0;  // 0 = FrequencyOccupancyMap (the reference's Slam2D), 1 = ProbabilisticOccupancyMap (log-odds)
     DeviceOptions dev;
 };
 

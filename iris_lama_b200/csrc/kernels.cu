@@ -281,10 +281,13 @@ struct RayWalk3 {
     }
 };
 
+template <bool kProb>
 struct RayCtx {
     const StoreView& s;
     const RayParams& rp;
     int32_t* dir;
+    int32_t* dir_s;            // kProb: directory of the per-scan scratch counters
+    uint32_t* touched;         // kProb: scratch patches that received counts in this scan
     const uint8_t* cand_idx;   // per directory entry: index of its candidate bitmap, kCandNone or kCandOverflow
     const uint32_t* cand;      // [cand_cap][32]: bit = cell is a hit cell of this scan or a distance-map obstacle
     uint32_t* pending;         // patches that must be allocated / detached before they can be written
@@ -309,7 +312,12 @@ struct RayCtx {
         }
         centry = dir[cdi];
         ccand  = cand_idx[cdi];
-        const bool writable = centry >= 0 && (centry & kDirOwn);
+        bool writable = centry >= 0 && (centry & kDirOwn);
+        if (kProb) {  // the counts of a log-odds map go to the scratch patch; both patches must be owned
+            const int se = dir_s[cdi];
+            writable = writable && se >= 0 && (se & kDirOwn);
+            if (writable) centry = se;
+        }
         if (!redo) {
             if (!writable) {
                 atomicOr(&pending[cdi >> 5], 1u << (cdi & 31));
@@ -318,6 +326,7 @@ struct RayCtx {
         } else if (!((pending[cdi >> 5] >> (cdi & 31)) & 1u) || !writable) {
             centry = -1;      // already done in the first pass (or the pool ran dry)
         }
+        if (kProb && centry >= 0) atomicOr(&touched[cdi >> 5], 1u << (cdi & 31));
     }
     // every counter update is a fire-and-forget reduction at the L2: nothing below waits for a returned value
     __device__ __forceinline__ void touch(uint32_t x, uint32_t y, uint32_t beam, uint32_t pos, bool hit)
@@ -337,7 +346,8 @@ struct RayCtx {
 };
 
 // One pass over all touches of the scan (hits, planar segments, generic beams).
-__device__ __forceinline__ void raycast_pass(RayCtx& c, const BeamEnds* beams, const uint32_t* seg_prefix, int n_beams, int n_groups, uint32_t* work_counter,
+template <bool kProb>
+__device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* beams, const uint32_t* seg_prefix, int n_beams, int n_groups, uint32_t* work_counter,
                                              const double* __restrict__ points, const Affine& tf)
 {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -381,7 +391,11 @@ __device__ __forceinline__ void raycast_pass(RayCtx& c, const BeamEnds* beams, c
     }
 }
 
-__global__ void __launch_bounds__(kRayThreads, 2)
+// kProb = false: FrequencyOccupancyMap (PFSlam2D / Slam2D); kProb = true: ProbabilisticOccupancyMap -- the walk adds
+// the per-scan {hits, touches} into a scratch map, candidate cells are replayed in order on the float cell, all other
+// touched cells (misses only, never an obstacle) get their k misses applied one by one in a bulk pass.
+template <bool kProb>
+__global__ void __launch_bounds__(kRayThreads, kProb ? 1 : 2)
 k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -401,10 +415,13 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     uint16_t* cand_di = reinterpret_cast<uint16_t*>(seg_prefix + ((n_groups + 2) & ~1));  // directory entry of every bitmap
     uint8_t* cand_idx = reinterpret_cast<uint8_t*>(cand_di + ((rp.cand_cap + 3) & ~3));
     RayShared& sh    = *reinterpret_cast<RayShared*>(cand_idx + dim2);
+    int32_t* dir_s   = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(&sh) + ((sizeof(RayShared) + 15) & ~(size_t)15));  // kProb only
+    uint32_t* touched = reinterpret_cast<uint32_t*>(dir_s + dim2);                                                                  // kProb only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int particle = rp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, rp.set, particle, kMapOcc);
+    int32_t* gdir_s    = kProb ? dir_of(s, rp.set, particle, kMapScratch) : nullptr;
     const DirWindow win = s.window;
 
     // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
@@ -418,8 +435,11 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     }
     for (int i = tid; i < 2 * nwords; i += blockDim.x) hotmap[i] = 0u;  // hotmap + pending are contiguous
     for (int i = tid; i < dim2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cand_idx)[i] = 0xFFFFFFFFu;  // kCandNone
+    if (kProb)
+        for (int i = tid; i < nwords; i += blockDim.x) touched[i] = 0u;
     __syncthreads();
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, &sh.bar, 0);
+    if (kProb) block_stage_tma(dir_s, gdir_s, (uint32_t)dim2 * 4u, &sh.bar, 1);
     const Affine tf = sh.tf;
 
     // ---- phase 1a: beam end cells, segment counts, patches that need the ordered path ---------------------
@@ -516,7 +536,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
 
     // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away;
     // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW) and redo those ----
-    RayCtx ctx{s, rp, dir, cand_idx, cand, pending, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, kCandNone};
+    RayCtx<kProb> ctx{s, rp, dir, dir_s, touched, cand_idx, cand, pending, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, kCandNone};
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
@@ -528,6 +548,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
                     const int bit = __ffs(bits) - 1;
                     bits &= bits - 1;
                     if (warp_make_exclusive(s, dir, gdir, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
+                    if (kProb && warp_make_exclusive(s, dir_s, gdir_s, w32 * 32 + bit, lane) < 0) my_err |= kErrPoolEmpty;
                 }
             }
             __syncthreads();
@@ -565,10 +586,20 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         const uint32_t ci = cell_index(x, y);
         uint32_t* fword = fbits_ptr(s, dir[di] & kDirSlotMask) + (ci >> 5);
         const bool before = (__ldcg(fword) >> (ci & 31)) & 1u;
-        const bool obstacle = replay_cell(log, i, end, final_word, before, [&](bool add, uint32_t seq) {
+        auto emit = [&](bool add, uint32_t seq) {
             uint32_t idx = atomicAdd(&sh.event_count, 1u);
             if (idx < (uint32_t)rp.event_cap) events[idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
-        });
+        };
+        bool obstacle = before;
+        if (kProb) {
+            // the float cell is updated here, touch by touch; the bulk pass must skip it: clear its scratch counter
+            const float p = replay_cell_prob(log, i, end, __uint_as_float(final_word), obstacle, rp.prob, emit);
+            *cell = __float_as_uint(p);
+            patch_ptr(s, dir_s[di] & kDirSlotMask)[ci] = 0u;
+            atomicOr(kbits_ptr(s, dir[di] & kDirSlotMask) + (ci >> 5), 1u << (ci & 31));
+        } else {
+            obstacle = replay_cell(log, i, end, final_word, before, emit);
+        }
         if (obstacle != before) {
             if (obstacle) {
                 atomicOr(fword, 1u << (ci & 31));
@@ -582,6 +613,37 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         }
     }
     __syncthreads();
+
+    // ---- phase 5b (log-odds maps): apply the k misses of every other touched cell, one by one ---------------------
+    if (kProb) {
+        for (int w32 = 0; w32 < nwords; ++w32) {
+            uint32_t bits = touched[w32];
+            int ord = 0;
+            while (bits) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if ((ord++ % nwarps) != warp) continue;  // patches of this word are dealt round-robin to the warps
+                const int di = w32 * 32 + bit;
+                uint32_t* occ = patch_ptr(s, dir[di] & kDirSlotMask);
+                uint32_t* scr = patch_ptr(s, dir_s[di] & kDirSlotMask);
+                uint32_t* kb  = kbits_ptr(s, dir[di] & kDirSlotMask);
+                for (int row = 0; row < kPatchLen; ++row) {
+                    const int ci = row * kPatchLen + lane;
+                    const uint32_t c = __ldcg(scr + ci);
+                    if (c) {
+                        // not a candidate: no hit in this scan and not an obstacle -> misses only, no event possible
+                        float p = __uint_as_float(__ldcg(occ + ci));
+                        for (uint32_t k = occ_visited(c); k > 0; --k) p = prob_miss(p, rp.prob);
+                        occ[ci] = __float_as_uint(p);
+                        scr[ci] = 0u;
+                    }
+                    const uint32_t known = __ballot_sync(0xffffffffu, c != 0u);
+                    if (lane == 0 && known) kb[row] |= known;
+                }
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- phase 6: order the events like the reference's call sequence and publish them --------------------
     uint32_t nev = sh.event_count;
@@ -695,7 +757,7 @@ __global__ void k_merge_free(StoreView s)
 }
 __global__ void k_init_store(StoreView s, int n_sets)
 {
-    const size_t total_dir = (size_t)n_sets * s.n_particles * 2 * s.window.dim * s.window.dim;
+    const size_t total_dir = (size_t)n_sets * s.n_particles * s.n_kinds * s.window.dim * s.window.dim;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_dir; i += (size_t)gridDim.x * blockDim.x) s.dirs[i] = -1;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)s.n_slots; i += (size_t)gridDim.x * blockDim.x) {
         s.free_slots[i] = s.n_slots - 1 - (int)i;  // slot 0 is handed out first
@@ -719,6 +781,23 @@ __global__ void k_export(StoreView s, int set, int particle, int kind, uint32_t 
         int slot = di < 0 ? -1 : d[di];
         out[k]   = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot & kDirSlotMask) + cell_index(x, y));
         if (present) present[k] = slot >= 0;
+    }
+}
+
+__global__ void k_export_bits(StoreView s, int plane, int set, int particle, uint32_t x0, uint32_t y0, int w, int h, uint8_t* __restrict__ out)
+{
+    const int32_t* d = dir_of(s, set, particle, kMapOcc);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < w * h; k += gridDim.x * blockDim.x) {
+        uint32_t x = x0 + (uint32_t)(k % w), y = y0 + (uint32_t)(k / w);
+        int di   = dir_index(s.window, x, y);
+        int slot = di < 0 ? -1 : d[di];
+        uint8_t v = 0;
+        const uint32_t* base = plane == 0 ? s.fbits : s.kbits;
+        if (slot >= 0 && base) {
+            const uint32_t ci = cell_index(x, y);
+            v = (__ldcg(base + (size_t)(slot & kDirSlotMask) * 32 + (ci >> 5)) >> (ci & 31)) & 1u;
+        }
+        out[k] = v;
     }
 }
 
@@ -820,8 +899,9 @@ size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
     const int dim2 = dir_dim * dir_dim;
     const int n_groups = (rp.scan.n_beams + 31) / 32;
     const size_t beam_bytes = (size_t)n_groups * 32 * 16, ev_bytes = (size_t)rp.event_cap * 8;
+    const size_t prob_extra = rp.prob_mode ? (size_t)dim2 * 4 + (size_t)((dim2 + 31) / 32) * 4 + 32 : 0;
     return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (beam_bytes > ev_bytes ? beam_bytes : ev_bytes) + (size_t)rp.cand_cap * 128 +
-           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + (size_t)(rp.cand_cap + 4) * 2 + (size_t)dim2 + sizeof(RayShared) + 32;
+           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + (size_t)(rp.cand_cap + 4) * 2 + (size_t)dim2 + sizeof(RayShared) + 32 + prob_extra;
 }
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {
@@ -834,7 +914,8 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
     cudaError_t e;
     e = cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)match_smem_bytes(dir_dim, max_sqdist_limit));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raycast_smem_bytes(dir_dim, rp));
+    if (rp.prob_mode) e = cudaFuncSetAttribute(k_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raycast_smem_bytes(dir_dim, rp));
+    else e = cudaFuncSetAttribute(k_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raycast_smem_bytes(dir_dim, rp));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_brushfire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brushfire_smem_bytes(dir_dim, bp));
     return e;
@@ -849,7 +930,8 @@ void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states
                     cudaStream_t st)
 {
     if (count <= 0) return;
-    k_raycast<<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
+    if (rp.prob_mode) k_raycast<true><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
+    else k_raycast<false><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
 }
 void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
 {
@@ -864,7 +946,7 @@ void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_
 void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st)
 {
     if (count <= 0) return;
-    k_release<<<dim3(count, 2), 256, 0, st>>>(s, set, first);
+    k_release<<<dim3(count, s.n_kinds), 256, 0, st>>>(s, set, first);
 }
 void launch_merge_free(const StoreView& s, cudaStream_t st) { k_merge_free<<<1, 256, 0, st>>>(s); }
 void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st) { k_init_store<<<296, 256, 0, st>>>(s, n_sets); }
@@ -875,6 +957,13 @@ void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t
     if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
     k_export<<<blocks, 256, 0, st>>>(s, set, particle, kind, x0, y0, w, h, d_out, d_present);
+}
+void launch_export_bits(const StoreView& s, int plane, int set, int particle, uint32_t x0, uint32_t y0, int w, int h, uint8_t* d_out, cudaStream_t st)
+{
+    int blocks = (w * h + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    k_export_bits<<<blocks, 256, 0, st>>>(s, plane, set, particle, x0, y0, w, h, d_out);
 }
 void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* d_in, cudaStream_t st)
 {

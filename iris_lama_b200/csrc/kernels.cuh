@@ -38,6 +38,8 @@ struct RayParams {
     int particle_offset;
     int log_cap, event_cap;  // powers of two
     int cand_cap;            // candidate bitmaps (patches with hit cells or distance-map obstacles), <= 253
+    int prob_mode;           // 1: log-odds occupancy (ProbabilisticOccupancyMap), counts go to the scratch map first
+    ProbParams prob;
 };
 
 struct BrushParams {
@@ -71,6 +73,8 @@ void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_
 void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st);
 void launch_merge_free(const StoreView& s, cudaStream_t st);
 void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st);
+// dense window of one bit plane (0 = obstacle mirror, 1 = known bits of log-odds maps) of an occupancy map, one byte per cell
+void launch_export_bits(const StoreView& s, int plane, int set, int particle, uint32_t x0, uint32_t y0, int w, int h, uint8_t* d_out, cudaStream_t st);
 // dense window export: out[j * w + i] = cell word or 0; present[..] = 1 when the patch exists
 void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* d_out,
                    uint8_t* d_present, cudaStream_t st);

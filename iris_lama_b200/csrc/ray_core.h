@@ -158,4 +158,39 @@ LAMA_HD bool replay_cell(const uint64_t* log, int first, int last, uint32_t fina
     return obstacle;
 }
 
+
+// ---- ProbabilisticOccupancyMap (log-odds float cells) -------------------------------------------------------------
+// src/sdm/probabilistic_occupancy_map.cpp:50-60 (constants), :82-91 setFree, :98-107 setOccupied.  The constants are
+// computed on the host with the reference's float logods() and handed to the device as doubles.
+struct ProbParams {
+    double miss, hit, clamp_min, clamp_max, thresh;
+};
+LAMA_HD float prob_miss(float p, const ProbParams& pp) { return (float)fmax((double)p + pp.miss, pp.clamp_min); }
+LAMA_HD float prob_hit(float p, const ProbParams& pp) { return (float)fmin((double)p + pp.hit, pp.clamp_max); }
+
+// Ordered replay of the touches of one candidate cell of a log-odds map; returns the final cell value.
+template <typename Emit>
+LAMA_HD float replay_cell_prob(const uint64_t* log, int first, int last, float prob, bool& obstacle, const ProbParams& pp, Emit&& emit)
+{
+    for (int i = first; i < last; ++i) {
+        const uint64_t r = log[i];
+        if (log_is_hit(r)) {
+            const bool was_occupied = (double)prob > pp.thresh;
+            prob = prob_hit(prob, pp);
+            if (!was_occupied && (double)prob > pp.thresh && !obstacle) {
+                obstacle = true;
+                emit(true, log_seq(r));
+            }
+        } else {
+            const bool was_free = (double)prob < pp.thresh;
+            prob = prob_miss(prob, pp);
+            if (!was_free && (double)prob < pp.thresh && obstacle) {
+                obstacle = false;
+                emit(false, log_seq(r));
+            }
+        }
+    }
+    return prob;
+}
+
 }  // namespace lama_b200

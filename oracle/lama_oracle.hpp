@@ -1356,18 +1356,22 @@ struct SlamOptions {
     int strategy = 0;  // 0 = "gn", 1 = "lm" (slam2d.cpp:226-233)
 };
 
-class Slam2D {
+// OccMap = FrequencyOccupancyMap is the reference's Slam2D (slam2d.cpp:97); OccMap = ProbabilisticOccupancyMap is the
+// same front end over the log-odds map (the combination LidarOdometry2D uses, lidar_odometry_2d.cpp:46), kept so that
+// row a18 of SURVEY 8(a) has a complete update path to be checked against.
+template <typename OccMap>
+class Slam2DT {
 public:
     SlamOptions opt;
     DynamicDistanceMap dm;
-    FrequencyOccupancyMap occ;
+    OccMap occ;
     SolverOptions so;
     Pose2D pose, odom;
     bool has_first_scan = false;
     uint32_t processed_cells = 0;
     ScanCounters last, total;
 
-    explicit Slam2D(const SlamOptions& o) : opt(o), dm(o.resolution, o.patch_size), occ(o.resolution, o.patch_size)
+    explicit Slam2DT(const SlamOptions& o) : opt(o), dm(o.resolution, o.patch_size), occ(o.resolution, o.patch_size)
     {
         dm.set_max_distance(o.l2_max);
         so.max_iterations = o.max_iter;
@@ -1411,6 +1415,8 @@ private:
         total.gn_iters += last.gn_iters;
     }
 };
+using Slam2D     = Slam2DT<FrequencyOccupancyMap>;
+using Slam2DProb = Slam2DT<ProbabilisticOccupancyMap>;
 
 // ----------------------------------------------------------------------------------------------
 // Loc2D match path (src/loc2d.cpp:46-108,126-192); global localisation / sampling covariance are

@@ -284,6 +284,60 @@ void* orc_slam_create(const orc_slam_options* o)
 void orc_slam_destroy(void* h) { delete (Slam2D*)h; }
 void orc_slam_set_pose(void* h, double x, double y, double r) { ((Slam2D*)h)->pose = Pose2D(x, y, r); }
 void orc_slam_set_shuffle(void* h, uint32_t s) { ((Slam2D*)h)->dm.set_shuffle(s); }
+// ---- Slam2D over the probabilistic (log-odds) occupancy map -------------------------------------------------------
+void* orc_slamp_create(const orc_slam_options* o)
+{
+    SlamOptions s;
+    s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
+    s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
+    s.strategy = o->strategy;
+    return new Slam2DProb(s);
+}
+void orc_slamp_destroy(void* h) { delete (Slam2DProb*)h; }
+void orc_slamp_set_pose(void* h, double x, double y, double r) { ((Slam2DProb*)h)->pose = Pose2D(x, y, r); }
+int orc_slamp_update(void* h, const double* pts, int n, const double* origin, const double* quat, const double* odom_xyr)
+{
+    PointCloud pc = make_cloud(pts, n, origin, quat);
+    return ((Slam2DProb*)h)->update(pc, Pose2D(odom_xyr[0], odom_xyr[1], odom_xyr[2])) ? 1 : 0;
+}
+void orc_slamp_get_state(void* h, double* state) { se2_to(((Slam2DProb*)h)->pose.state, state); }
+void orc_slamp_counters(void* h, uint64_t* last)
+{
+    auto* s = (Slam2DProb*)h;
+    last[0] = s->last.evals; last[1] = s->last.ray_cells; last[2] = s->last.dm_pops; last[3] = 0; last[4] = s->last.gn_iters; last[5] = 0;
+}
+int orc_slamp_dm_bounds(void* h, uint32_t* mn, uint32_t* mx) { return map_bounds(((Slam2DProb*)h)->dm, mn, mx); }
+int orc_slamp_occ_bounds(void* h, uint32_t* mn, uint32_t* mx) { return map_bounds(((Slam2DProb*)h)->occ, mn, mx); }
+void orc_slamp_export_dm(void* h, uint32_t x0, uint32_t y0, int w, int hh, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox, int16_t* oy,
+                         uint8_t* queued)
+{
+    export_dm(((Slam2DProb*)h)->dm, x0, y0, w, hh, sqdist, valid, known, ox, oy, queued);
+}
+void orc_slamp_export_occ(void* h, uint32_t x0, uint32_t y0, int w, int hh, float* prob, uint8_t* known)
+{
+    export_window(((Slam2DProb*)h)->occ, x0, y0, w, hh, [&](int k, const ProbCell* c, bool on) {
+        prob[k]  = c ? c->prob : 0.0f;
+        known[k] = on;
+    });
+}
+// applies a sequence of setOccupied (1) / setFree (0) calls to ONE cell of a fresh ProbabilisticOccupancyMap;
+// prob_out[i] = cell value after call i, changed_out[i] = the call's return value
+void orc_prob_sequence(const uint8_t* kinds, int n, float* prob_out, uint8_t* changed_out)
+{
+    ProbabilisticOccupancyMap m(0.05, 32);
+    Vec3u c{(uint32_t)m.offset + 3, (uint32_t)m.offset + 5, (uint32_t)m.offset};
+    for (int i = 0; i < n; ++i) {
+        changed_out[i] = kinds[i] ? m.set_occupied(c) : m.set_free(c);
+        prob_out[i]    = static_cast<const SparseMap<ProbCell>&>(m).get(c)->prob;
+    }
+}
+// the constants of ProbabilisticOccupancyMap's constructor: {miss, hit, clamp_min, clamp_max, occ_thresh}
+void orc_prob_constants(double* out)
+{
+    ProbabilisticOccupancyMap m(0.05, 32);
+    out[0] = m.miss_; out[1] = m.hit_; out[2] = m.clamp_min_; out[3] = m.clamp_max_; out[4] = m.occ_thresh_;
+}
+
 int orc_slam_update(void* h, const double* pts, int n, const double* origin, const double* quat, const double* odom_xyr)
 {
     PointCloud pc = make_cloud(pts, n, origin, quat);

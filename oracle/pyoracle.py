@@ -83,7 +83,7 @@ def lib():
         L.orc_se2_log_rot.restype = C.c_double
         L.orc_m2p.restype = C.c_uint64
         L.orc_m2c.restype = C.c_uint32
-        for f in ("orc_ddm_create", "orc_ddm_clone", "orc_pf_create", "orc_pf_dm_handle", "orc_slam_create", "orc_slam_dm_handle",
+        for f in ("orc_ddm_create", "orc_ddm_clone", "orc_pf_create", "orc_pf_dm_handle", "orc_slam_create", "orc_slam_dm_handle", "orc_slamp_create",
                   "orc_loc_create", "orc_loc_dm_handle"):
             getattr(L, f).restype = C.c_void_p
         L.orc_ddm_update.restype = C.c_uint32
@@ -440,6 +440,67 @@ class Slam2D:
 
     def dm(self):
         return DDM(handle=lib().orc_slam_dm_handle(self.h), owner=self)
+
+
+class Slam2DProb:
+    """Slam2D over ProbabilisticOccupancyMap (log-odds cells)."""
+
+    def __init__(self, opts: SlamOptions):
+        self.opts = opts
+        self.h = C.c_void_p(lib().orc_slamp_create(C.byref(opts)))
+
+    def __del__(self):
+        if self.h and _lib is not None:
+            _lib.orc_slamp_destroy(self.h)
+            self.h = None
+
+    def set_pose(self, x, y, r):
+        lib().orc_slamp_set_pose(self.h, C.c_double(x), C.c_double(y), C.c_double(r))
+
+    def update(self, pts, odom, origin=_ID3, quat=_IDQ):
+        p, pp = _d(pts)
+        o, op = _d(origin)
+        q, qp = _d(quat)
+        od, odp = _d(odom)
+        return bool(lib().orc_slamp_update(self.h, pp, C.c_int(p.size // 3), op, qp, odp))
+
+    def state(self):
+        s = np.zeros(4)
+        lib().orc_slamp_get_state(self.h, s.ctypes.data_as(c_dp))
+        return s
+
+    def counters(self):
+        last = np.zeros(6, np.uint64)
+        lib().orc_slamp_counters(self.h, _vp(last))
+        return dict(zip(("evals", "ray_cells", "dm_pops", "detached", "gn_iters", "resampled"), last.tolist()))
+
+    def dm_bounds(self):
+        return _bounds(lib().orc_slamp_dm_bounds, (self.h,))
+
+    def occ_bounds(self):
+        return _bounds(lib().orc_slamp_occ_bounds, (self.h,))
+
+    def export_dm(self, x0, y0, w, h):
+        return _export_dm(lib().orc_slamp_export_dm, (self.h,), x0, y0, w, h)
+
+    def export_occ(self, x0, y0, w, h):
+        out = dict(prob=np.zeros((h, w), np.float32), known=np.zeros((h, w), np.uint8))
+        lib().orc_slamp_export_occ(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), _vp(out["prob"]), _vp(out["known"]))
+        return out
+
+
+def prob_sequence(kinds):
+    k = np.ascontiguousarray(kinds, np.uint8)
+    prob = np.zeros(len(k), np.float32)
+    changed = np.zeros(len(k), np.uint8)
+    lib().orc_prob_sequence(_vp(k), C.c_int(len(k)), _vp(prob), _vp(changed))
+    return prob, changed
+
+
+def prob_constants():
+    out = np.zeros(5)
+    lib().orc_prob_constants(out.ctypes.data_as(c_dp))
+    return dict(zip(("miss", "hit", "clamp_min", "clamp_max", "occ_thresh"), out.tolist()))
 
 
 class Loc2D:

@@ -307,6 +307,20 @@ uint32_t emu_dm_apply(void* h, const uint32_t* cells_xy, const uint8_t* is_add, 
     }
     return bf.update();
 }
+// replay_cell_prob (ray_core.h) on one cell: kinds[i] = 1 hit / 0 miss in beam order; events_out[i] = 1 add, 2 remove, 0 none
+float emu_prob_replay(const uint8_t* kinds, int n, const double* constants, int obstacle_in, uint8_t* events_out, int* obstacle_out)
+{
+    std::vector<uint64_t> log((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        log[i] = log_record(7u, (uint32_t)i, kinds[i] ? 0u : 1u, kinds[i] != 0);
+        events_out[i] = 0;
+    }
+    ProbParams pp{constants[0], constants[1], constants[2], constants[3], constants[4]};
+    bool obstacle = obstacle_in != 0;
+    float p = replay_cell_prob(log.data(), 0, n, 0.0f, obstacle, pp, [&](bool add, uint32_t seq) { events_out[seq >> 15] = add ? 1 : 2; });
+    *obstacle_out = obstacle;
+    return p;
+}
 // SE2 helpers of lama_core.h for comparison with the oracle's
 void emu_se2(int op, const double* a, const double* b, double* out)
 {

@@ -18,6 +18,7 @@ def emu():
     L.emu_create.restype = C.c_void_p
     L.emu_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_uint32, C.c_int]
     L.emu_dm_apply.restype = C.c_uint32
+    L.emu_prob_replay.restype = C.c_float
     for f in ("emu_destroy", "emu_set_pose", "emu_get_state", "emu_counters", "emu_slam_update", "emu_export_dm", "emu_export_occ", "emu_dm_apply"):
         getattr(L, f).argtypes = None
     return L
@@ -131,3 +132,27 @@ def test_emulated_slam_equals_oracle(emu, po, synth, name, beams, T, shuffle):
     d = _export_dm(emu, h, int(mn[0]), int(mn[1]), w, hh)
     assert (a["obstacle"].astype(bool) == ((d["valid"] == 1) & (d["sqdist"] == 0))).all()
     emu.emu_destroy(C.c_void_p(h))
+
+
+def test_logodds_replay_equals_probabilistic_occupancy_map(emu, po):
+    """replay_cell_prob == ProbabilisticOccupancyMap::setFree/setOccupied call by call (float cell, clamps, thresholds)"""
+    rng = np.random.default_rng(4)
+    cst = po.prob_constants()
+    constants = np.array([cst["miss"], cst["hit"], cst["clamp_min"], cst["clamp_max"], cst["occ_thresh"]])
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        kinds = (rng.random(n) < rng.choice([0.1, 0.3, 0.5, 0.9])).astype(np.uint8)
+        prob, changed = po.prob_sequence(kinds)
+        # distance-map side of the reference: addObstacle / removeObstacle are no-ops when the flag already matches
+        flag, want = False, np.zeros(n, np.uint8)
+        for i in range(n):
+            if changed[i]:
+                if kinds[i] and not flag:
+                    flag, want[i] = True, 1
+                elif not kinds[i] and flag:
+                    flag, want[i] = False, 2
+        ev = np.zeros(n, np.uint8)
+        ob = C.c_int(0)
+        p = emu.emu_prob_replay(_vp(kinds), C.c_int(n), _vp(constants), C.c_int(0), _vp(ev), C.byref(ob))
+        assert np.float32(p) == prob[-1]
+        assert (ev == want).all() and bool(ob.value) == flag

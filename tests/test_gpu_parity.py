@@ -222,6 +222,26 @@ def test_slam2d_levenberg_marquardt(gpu_api, po, synth):
         assert np.abs(g.state() - o.state()).max() < POSE_TOL
 
 
+def test_slam2d_logodds_occupancy(gpu_api, po, synth):
+    """row a18: ProbabilisticOccupancyMap cells (float log-odds, clamps) under the same update loop"""
+    for name, beams, T in (("room", 360, 30), ("corridor", 720, 25)):
+        ds = synth.make_dataset(name, T, n_beams=beams)
+        g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, occupancy=1))
+        o = po.Slam2DProb(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
+        g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+        for t in range(T):
+            assert g.update(ds.scans[t], ds.odom[t]) == o.update(ds.scans[t], ds.odom[t])
+            assert np.abs(g.state() - o.state()).max() < POSE_TOL
+            cg, _ = g.counters(); co = o.counters()
+            assert (cg["evals"], cg["ray_cells"], cg["dm_pops"], cg["gn_iters"]) == (co["evals"], co["ray_cells"], co["dm_pops"], co["gn_iters"])
+        n, mn, mx = o.occ_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+        eg, eo = g.exportLogOdds(int(mn[0]), int(mn[1]), w, h), o.export_occ(mn[0], mn[1], w, h)
+        assert (eg["prob"] == eo["prob"]).all()          # float cells bit-exact (same IEEE operations in the same order)
+        assert (eg["known"] == eo["known"]).all()
+        n, mn, mx = o.dm_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+        _assert_dm_equal(g.exportDistance(int(mn[0]), int(mn[1]), w, h), o.export_dm(mn[0], mn[1], w, h))
+
+
 # ---- PFSlam2D (config 3 family) -------------------------------------------------------------------------------------------
 def _run_pf_pair(gpu_api, po, ds, P, T, **kw):
     g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(P, trans_thresh=0.05, rot_thresh=0.05, **kw))
