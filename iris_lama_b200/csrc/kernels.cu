@@ -415,7 +415,8 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     uint16_t* cand_di = reinterpret_cast<uint16_t*>(seg_prefix + ((n_groups + 2) & ~1));  // directory entry of every bitmap
     uint8_t* cand_idx = reinterpret_cast<uint8_t*>(cand_di + ((rp.cand_cap + 3) & ~3));
     RayShared& sh    = *reinterpret_cast<RayShared*>(cand_idx + dim2);
-    int32_t* dir_s   = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(&sh) + ((sizeof(RayShared) + 15) & ~(size_t)15));  // kProb only
+    const size_t dir_s_off = ((size_t)(reinterpret_cast<unsigned char*>(&sh) - smem_raw) + sizeof(RayShared) + 15) & ~(size_t)15;  // TMA target: 16-B aligned
+    int32_t* dir_s   = reinterpret_cast<int32_t*>(smem_raw + dir_s_off);                                                                  // kProb only
     uint32_t* touched = reinterpret_cast<uint32_t*>(dir_s + dim2);                                                                  // kProb only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
