@@ -269,11 +269,15 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
 {
     *did_update   = false;
     pending_maps_ = false;
+    // Host-only work first: the odometry sampling of this scan (global mt19937, all particles, in order) does not
+    // depend on the previous scan's map update, which may still be running on the device.
+    bool moved = false;
+    if (has_first_) moved = predict_and_gate(odom_xyr);
     if (eng_) {
-        int rcs = settle_counters();   // collect the previous scan's asynchronous map update (and its errors)
+        int rcs = settle_counters();   // now collect the previous scan's asynchronous map update (and its errors)
         if (rcs != LAMA_OK) return rcs;
     }
-    last_         = Counters();
+    last_ = Counters();
     last_idx_.clear();
     int rc = ensure_engine(staged_index_ >= 0 ? staged_beams_ : n);
     if (rc != LAMA_OK) return rc;
@@ -288,7 +292,7 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
         finish_counters();
         return LAMA_OK;
     }
-    if (!predict_and_gate(odom_xyr)) return LAMA_OK;
+    if (!moved) return LAMA_OK;
     *did_update = true;
     rc = match_local(local_out);
     if (rc != LAMA_OK) return rc;
