@@ -171,6 +171,30 @@ struct WarpBrushfire {
         }
         return cellptr(e, x, y);
     }
+    // Pointer to cell (x + dx, y + dy) given the pointer `base` to cell (x, y), valid when the target lies in the
+    // same patch (which the caller already owns): plain pointer arithmetic, no directory lookup.
+    __device__ __forceinline__ static bool same_patch(uint32_t x, uint32_t y, int dx, int dy)
+    {
+        return (uint32_t)((int)(x & (kPatchLen - 1)) + dx) < (uint32_t)kPatchLen && (uint32_t)((int)(y & (kPatchLen - 1)) + dy) < (uint32_t)kPatchLen;
+    }
+    // neighbour / obstacle pointer: fast path inside the patch of `base`, directory path otherwise
+    __device__ __forceinline__ uint32_t* rel_uptr(uint32_t* base, uint32_t x, uint32_t y, int dx, int dy)
+    {
+        if (same_patch(x, y, dx, dy) && !is_scratch(base)) return base + dx + dy * kPatchLen;
+        return uptr(x + dx, y + dy);
+    }
+    // per-lane variant; `interior` (warp-uniform) = the whole 4-neighbourhood of (x, y) is inside the patch
+    __device__ __forceinline__ uint32_t* rel_lptr(uint32_t* base, bool interior, uint32_t x, uint32_t y, int dx, int dy, bool active)
+    {
+        if (interior && !is_scratch(base)) return active ? base + dx + dy * kPatchLen : &scratch[lane];
+        return lptr(x + dx, y + dy, active);
+    }
+    __device__ __forceinline__ bool is_scratch(const uint32_t* p) const { return p >= scratch && p < scratch + 32; }
+    __device__ __forceinline__ static bool interior_cell(uint32_t x, uint32_t y)
+    {
+        return ((x & (kPatchLen - 1)) - 1u) < (uint32_t)(kPatchLen - 2) && ((y & (kPatchLen - 1)) - 1u) < (uint32_t)(kPatchLen - 2);
+    }
+
     // read a cell the way the mutable get does: the Container bit ("known") is switched on
     __device__ __forceinline__ uint32_t touch(uint32_t* p)
     {
@@ -216,7 +240,7 @@ struct WarpBrushfire {
         const bool act = lane < 4;
         const int dxi = (i == 0) - (i == 2), dyi = (i == 1) - (i == 3);
         const uint32_t nx = x + dxi, ny = y + dyi;
-        uint32_t* p = lptr(nx, ny, act);
+        uint32_t* p = rel_lptr(cur, interior_cell(x, y), x, y, dxi, dyi, act);
         uint32_t n = 0;
         if (act) n = touch(p);
         const bool go = act && !((n & kDmQueued) || !(n & kDmValid));
@@ -253,7 +277,7 @@ struct WarpBrushfire {
         const int dxi = (i == 0) - (i == 2), dyi = (i == 1) - (i == 3);
         const bool go = lane < 4 && !(dxi * cox > 0 || dyi * coy > 0);  // only update away from the obstacle (:296)
         const uint32_t nx = x + dxi, ny = y + dyi;
-        uint32_t* p = lptr(nx, ny, go);
+        uint32_t* p = rel_lptr(cur, interior_cell(x, y), x, y, dxi, dyi, go);
         uint32_t n = 0;
         if (go) n = touch(p);
         const int rx = cox - dxi, ry = coy - dyi;
@@ -300,7 +324,7 @@ struct WarpBrushfire {
             const uint32_t c = touch(cur);
             ++processed;
             if (c & kDmValid) {
-                const uint32_t o = touch(uptr(x + dm_ox(c), y + dm_oy(c)));
+                const uint32_t o = touch(rel_uptr(cur, x, y, dm_ox(c), dm_oy(c)));
                 if (dm_sqdist(o) == 0 && (c & kDmQueued)) lower(x, y, cur, c);
             }
         }
