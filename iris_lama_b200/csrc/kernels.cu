@@ -116,9 +116,9 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
 
     const int n = mp.scan.n_beams;
     const bool single = mp.mode == 1;
+    if (tid == 0) sh.tf = compose_tf(sh.state, mp.scan.moving);
+    __syncthreads();
     for (;;) {
-        if (tid == 0) sh.tf = compose_tf(sh.state, mp.scan.moving);
-        __syncthreads();
         double acc[kNumSums];
 #pragma unroll
         for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
@@ -131,20 +131,25 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
             if (lane == 0) sh.warp_part[warp][k] = v;
         }
         __syncthreads();
-        if (tid < kNumSums) {
-            double v = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh.warp_part[w][tid];  // fixed order: deterministic
-            sh.sums[tid] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            ++sh.evals_done;
-            if (single || sh.done == 1) {
-                sh.done = 2;  // the evaluation just made is the final one
-            } else if (sh.ctl.advance(sh.sums, sh.state)) {
-                // finished.  Unless the last step was reverted, the evaluation just made already is the
-                // one at the final state (likelihood, covariance, rmse); otherwise do one more pass.
-                sh.done = sh.ctl.state_dirty ? 1 : 2;
+        // Two block barriers per evaluation: warp 0 finishes the reduction (fixed order: deterministic), runs the
+        // solver control and already prepares the transform of the next evaluation.
+        if (warp == 0) {
+            if (lane < kNumSums) {
+                double v = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh.warp_part[w][lane];
+                sh.sums[lane] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ++sh.evals_done;
+                if (single || sh.done == 1) {
+                    sh.done = 2;  // the evaluation just made is the final one
+                } else if (sh.ctl.advance(sh.sums, sh.state)) {
+                    // finished.  Unless the last step was reverted, the evaluation just made already is the
+                    // one at the final state (likelihood, covariance, rmse); otherwise do one more pass.
+                    sh.done = sh.ctl.state_dirty ? 1 : 2;
+                }
+                if (sh.done != 2) sh.tf = compose_tf(sh.state, mp.scan.moving);
             }
         }
         __syncthreads();
