@@ -177,6 +177,9 @@ typedef struct lama_loc_options { /* Loc2D::Options, loc2d.cpp:46-58 */
     double trans_thresh, rot_thresh, l2_max, resolution;
     uint32_t patch_size, max_iter;
     int32_t strategy;
+    uint32_t gloc_particles, gloc_iters; /* globalLocalization: candidates per attempt, attempts (loc2d.cpp:53-54) */
+    double gloc_thresh;                  /* RMSE that ends global localisation (loc2d.cpp:55) */
+    double cov_blend;                    /* blend of the sampling covariance into the solver covariance (loc2d.cpp:57,199-247) */
     double center_xy[2]; /* where to centre the device map window */
     lama_device_options dev;
 } lama_loc_options;
@@ -192,6 +195,11 @@ int lama_loc_get_state(lama_loc* h, double state[4]);
 int lama_loc_get_covar(lama_loc* h, double cov[9]);                          /* Loc2D::getCovar */
 int lama_loc_get_rmse(lama_loc* h, double* rmse);                            /* Loc2D::getRMSE */
 int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2]);                /* {iterations, residual evaluations} */
+/* public `occupancy_map` (SimpleOccupancyMap, loc2d.h:103): setFree (state -1) / setUnknown (0) / setOccupied (1) on n cells */
+int lama_loc_occupancy_set(lama_loc* h, const uint32_t* cells_xy, int n, int state);
+int lama_loc_set_seed(lama_loc* h, uint32_t seed);                            /* random::setSeed for the sampling below */
+int lama_loc_trigger_global_localization(lama_loc* h);                        /* Loc2D::triggerGlobalLocalization, loc2d.cpp:194-197 */
+int lama_loc_global_localization_active(lama_loc* h, int* active);
 
 /* ------------------------------------------------------------------------------------------------
  * SDM grid interface on a device-resident DynamicDistanceMap

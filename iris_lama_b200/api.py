@@ -51,7 +51,8 @@ class SlamOptions(C.Structure):
 
 class LocOptions(C.Structure):
     _fields_ = [("trans_thresh", C.c_double), ("rot_thresh", C.c_double), ("l2_max", C.c_double), ("resolution", C.c_double),
-                ("patch_size", C.c_uint32), ("max_iter", C.c_uint32), ("strategy", C.c_int32), ("center_xy", C.c_double * 2),
+                ("patch_size", C.c_uint32), ("max_iter", C.c_uint32), ("strategy", C.c_int32), ("gloc_particles", C.c_uint32),
+                ("gloc_iters", C.c_uint32), ("gloc_thresh", C.c_double), ("cov_blend", C.c_double), ("center_xy", C.c_double * 2),
                 ("dev", DeviceOptions)]
 
 
@@ -69,6 +70,7 @@ EXPORTED_SYMBOLS = [
     "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
+    "lama_loc_occupancy_set", "lama_loc_set_seed", "lama_loc_trigger_global_localization", "lama_loc_global_localization_active",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
     "lama_dm_distance", "lama_dm_bounds", "lama_dm_export", "lama_dm_import", "lama_dm_match_normal_equations", "lama_dm_match_solve",
 ]
@@ -532,6 +534,22 @@ class Loc2D:
         v = C.c_double(0)
         _chk(lib().lama_loc_get_rmse(self.h, C.byref(v)))
         return v.value
+
+    def occupancySet(self, cells, state):
+        """public occupancy_map (SimpleOccupancyMap): state -1 setFree, 0 setUnknown, 1 setOccupied"""
+        c, cp = _u32(cells)
+        _chk(lib().lama_loc_occupancy_set(self.h, cp, C.c_int(c.size // 2), C.c_int(state)))
+
+    def setSeed(self, seed):
+        _chk(lib().lama_loc_set_seed(self.h, C.c_uint32(seed)))
+
+    def triggerGlobalLocalization(self):
+        _chk(lib().lama_loc_trigger_global_localization(self.h))
+
+    def globalLocalizationActive(self) -> bool:
+        a = C.c_int(0)
+        _chk(lib().lama_loc_global_localization_active(self.h, C.byref(a)))
+        return bool(a.value)
 
     def solveStats(self):
         s = np.zeros(2, np.uint32)

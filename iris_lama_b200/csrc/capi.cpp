@@ -577,6 +577,7 @@ int lama_loc_options_default(lama_loc_options* o)
     std::memset(o, 0, sizeof(*o));
     o->trans_thresh = 0.5; o->rot_thresh = 0.5; o->l2_max = 1.0; o->resolution = 0.05;
     o->patch_size = 32; o->max_iter = 100; o->strategy = 0;
+    o->gloc_particles = 3000; o->gloc_iters = 10; o->gloc_thresh = 0.15; o->cov_blend = 0.0;  // loc2d.cpp:53-57
     dev_default(&o->dev);
     return LAMA_OK;
 }
@@ -586,6 +587,7 @@ int lama_loc_create(const lama_loc_options* o, lama_loc** out)
     LocOptions l;
     l.trans_thresh = o->trans_thresh; l.rot_thresh = o->rot_thresh; l.l2_max = o->l2_max; l.resolution = o->resolution;
     l.patch_size = o->patch_size; l.max_iter = o->max_iter; l.strategy = o->strategy; l.center_x = o->center_xy[0]; l.center_y = o->center_xy[1];
+    l.gloc_particles = o->gloc_particles; l.gloc_iters = o->gloc_iters; l.gloc_thresh = o->gloc_thresh; l.cov_blend = o->cov_blend;
     l.dev = dev_from(o->dev);
     std::string err;
     Loc2D* loc = Loc2D::create(l, err);
@@ -644,6 +646,30 @@ int lama_loc_get_rmse(lama_loc* h, double* rmse)
 {
     if (!h || !rmse) return set_err("null argument", LAMA_ERR_ARG);
     *rmse = h->l->rmse();
+    return LAMA_OK;
+}
+int lama_loc_occupancy_set(lama_loc* h, const uint32_t* cells, int n, int state)
+{
+    if (!h || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
+    for (int i = 0; i < n; ++i) h->l->occupancy_map()->set(cells[2 * i], cells[2 * i + 1], state);
+    return LAMA_OK;
+}
+int lama_loc_set_seed(lama_loc* h, uint32_t seed)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    h->l->set_seed(seed);
+    return LAMA_OK;
+}
+int lama_loc_trigger_global_localization(lama_loc* h)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    h->l->trigger_global_localization();
+    return LAMA_OK;
+}
+int lama_loc_global_localization_active(lama_loc* h, int* active)
+{
+    if (!h || !active) return set_err("null argument", LAMA_ERR_ARG);
+    *active = h->l->global_localization_active() ? 1 : 0;
     return LAMA_OK;
 }
 int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2])

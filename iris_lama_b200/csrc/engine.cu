@@ -521,6 +521,24 @@ int Engine::dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_a
     return LAMA_OK;
 }
 
+int Engine::sampling_likelihood(int particle, const SE2& pose, const double* offsets_xy, int n, int stride, double* out)
+{
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
+    if (particle < 0 || particle >= cfg_.particles || n < 1 || stride < 1) return fail("sampling_likelihood: bad arguments", LAMA_ERR_ARG);
+    if (d_->scan.n_beams < 1) return fail("sampling_likelihood: no scan uploaded", LAMA_ERR_STATE);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    if (ensure_scratch(d_, (size_t)n * 24)) return fail("sampling_likelihood: out of device memory", LAMA_ERR_CUDA);
+    double* d_off = (double*)d_->d_scratch;
+    double* d_out = d_off + 2 * (size_t)n;
+    CU_TRY(cudaMemcpyAsync(d_off, offsets_xy, (size_t)n * 16, cudaMemcpyHostToDevice, d_->stream));
+    launch_sampling(d_->view, cur_set_, particle, d_->d_points, d_->scan, pose, d_off, n, stride, cfg_.resolution, max_sqdist_, d_out, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
 int Engine::dm_distance(int particle, const double* pts, int n, double* dist, double* grad)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }

@@ -83,6 +83,8 @@ public:
 
     // Direct DynamicDistanceMap::addObstacle / removeObstacle calls in list order, then update().
     int dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_add, int n, uint32_t* processed);
+    // Likelihoods of Loc2D::addSamplingCovariance for n offsets (x, y pairs) around `pose` on the current scan.
+    int sampling_likelihood(int particle, const SE2& pose, const double* offsets_xy, int n, int stride, double* out);
     // Batched DistanceMap::distance(p, &grad).
     int dm_distance(int particle, const double* pts, int n, double* dist, double* grad);
 

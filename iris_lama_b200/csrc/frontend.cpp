@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 namespace lama_b200 {
 
@@ -514,6 +515,36 @@ int DistanceMapDev::flush_if_pending()
     return update(nullptr);
 }
 
+// ---- SimpleOccupancyHost ---------------------------------------------------------------------------------------
+void SimpleOccupancyHost::set(uint32_t x, uint32_t y, int state)
+{
+    const uint64_t key = (uint64_t)(x >> kPatchLog2) * 2642244ull + (uint64_t)(y >> kPatchLog2);  // Map::m2p, map.h:153-161
+    auto it = patches_.find(key);
+    if (it == patches_.end()) it = patches_.emplace(key, std::vector<int8_t>(kPatchCells, 0)).first;
+    it->second[cell_index(x, y)] = (int8_t)(state < 0 ? -1 : (state > 0 ? 1 : 0));
+}
+bool SimpleOccupancyHost::is_free_world(double wx, double wy) const
+{
+    const uint32_t x = w2m(wx, scale_), y = w2m(wy, scale_);
+    auto it = patches_.find((uint64_t)(x >> kPatchLog2) * 2642244ull + (uint64_t)(y >> kPatchLog2));
+    return it != patches_.end() && it->second[cell_index(x, y)] == -1;
+}
+bool SimpleOccupancyHost::bounds_world(double mn[2], double mx[2]) const
+{
+    if (patches_.empty()) return false;
+    uint32_t lo[2] = {0xffffffffu, 0xffffffffu}, hi[2] = {0, 0};
+    for (auto& kv : patches_) {
+        const uint32_t ax = (uint32_t)(kv.first / 2642244ull) << kPatchLog2, ay = (uint32_t)(kv.first % 2642244ull) << kPatchLog2;  // Map::p2m
+        lo[0] = std::min(lo[0], ax); lo[1] = std::min(lo[1], ay);
+        hi[0] = std::max(hi[0], ax); hi[1] = std::max(hi[1], ay);
+    }
+    for (int k = 0; k < 2; ++k) {
+        mn[k] = ((double)lo[k] - (double)kMapOffsetCells) / scale_;               // Map::m2w
+        mx[k] = ((double)(hi[k] + kPatchLen) - (double)kMapOffsetCells) / scale_;
+    }
+    return true;
+}
+
 Loc2D* Loc2D::create(const LocOptions& o, std::string& err)
 {
     DistanceMapDev* dm = DistanceMapDev::create(o.resolution, o.patch_size, o.l2_max, o.center_x, o.center_y, o.dev, err);
@@ -521,7 +552,74 @@ Loc2D* Loc2D::create(const LocOptions& o, std::string& err)
     Loc2D* l = new Loc2D();
     l->opt_ = o;
     l->dm_.reset(dm);
+    l->occ_.reset(new SimpleOccupancyHost(o.resolution));
+    l->cov_blend_ = std::max(std::min(o.cov_blend, 1.0), 0.0);  // loc2d.cpp:90
+    const double sstep = o.resolution;                           // loc2d.cpp:93-107
+    auto add = [&](double x, double y) { l->sampling_steps_.push_back(x); l->sampling_steps_.push_back(y); };
+    add(0.0, 0.0);
+    for (int i = 1; i <= 20; ++i) {
+        add(i * sstep, 0.0); add(0.0, i * sstep); add(-i * sstep, 0.0); add(0.0, -i * sstep);
+        add(i * sstep, i * sstep); add(-i * sstep, i * sstep); add(i * sstep, -i * sstep); add(-i * sstep, -i * sstep);
+    }
     return l;
+}
+
+// Loc2D::globalLocalization (loc2d.cpp:249-286): candidates are drawn on the host with the reference's rejection
+// sampling (same generator calls in the same order), evaluated in ONE device launch (the same evaluation kernel as
+// scan matching, every block on the same map) and the best is chosen with the reference's strict `<` in index order.
+int Loc2D::global_localization(int n)
+{
+    double mn[2], mx[2];
+    if (!occ_->bounds_world(mn, mx)) return LAMA_OK;
+    const double diff[2] = {mx[0] - mn[0], mx[1] - mn[1]};
+    std::vector<SE2> cand(opt_.gloc_particles);
+    auto uniform = [&]() { std::uniform_real_distribution<double> d(0.0, 1.0); return d(gen_); };
+    for (uint32_t i = 0; i < opt_.gloc_particles; ++i) {
+        double x, y, a;
+        for (;;) {
+            x = mn[0] + uniform() * diff[0];
+            y = mn[1] + uniform() * diff[1];
+            if (!occ_->is_free_world(x, y)) continue;
+            a = uniform() * 2 * M_PI - M_PI;
+            break;
+        }
+        cand[i] = se2_from_xyr(x, y, a);
+    }
+    std::vector<HostMatchResult> res(cand.size());
+    SolverOptions so = make_solver(0, 0);
+    int rc = dm_->engine()->match(cand.data(), (int)cand.size(), 0, true, so, 0.05, 1, res.data());
+    if (rc != LAMA_OK) { err_ = dm_->engine()->last_error(); return rc; }
+    double best = std::numeric_limits<double>::max();
+    for (size_t i = 0; i < cand.size(); ++i)
+        if (res[i].sums[10] < best) {  // residuals.squaredNorm()
+            best  = res[i].sums[10];
+            pose_ = cand[i];
+        }
+    (void)n;
+    return LAMA_OK;
+}
+
+// Loc2D::addSamplingCovariance (loc2d.cpp:199-247)
+int Loc2D::add_sampling_covariance(int n)
+{
+    const int n_off = (int)(sampling_steps_.size() / 2);
+    const int stride = (int)std::max((size_t)n / 100, (size_t)1);
+    std::vector<double> l((size_t)n_off);
+    int rc = dm_->engine()->sampling_likelihood(0, pose_, sampling_steps_.data(), n_off, stride, l.data());
+    if (rc != LAMA_OK) { err_ = dm_->engine()->last_error(); return rc; }
+    double K[4] = {0, 0, 0, 0}, u[2] = {0, 0}, sl = 0;
+    for (int i = 0; i < n_off; ++i) {
+        const double x = pose_.tx + sampling_steps_[2 * i], y = pose_.ty + sampling_steps_[2 * i + 1];
+        K[0] = K[0] + x * x * l[i]; K[1] = K[1] + x * y * l[i]; K[2] = K[2] + y * x * l[i]; K[3] = K[3] + y * y * l[i];
+        u[0] = u[0] + x * l[i]; u[1] = u[1] + y * l[i];
+        sl = sl + l[i];
+    }
+    const double a = 1.0 / sl, b = 1.0 / (sl * sl);
+    const double sc[4] = {a * K[0] - b * u[0] * u[0], a * K[1] - b * u[0] * u[1], a * K[2] - b * u[1] * u[0], a * K[3] - b * u[1] * u[1]};
+    const double alpha = cov_blend_;
+    cov_[0] = alpha * sc[0] + (1.0 - alpha) * cov_[0]; cov_[1] = alpha * sc[1] + (1.0 - alpha) * cov_[1];
+    cov_[3] = alpha * sc[2] + (1.0 - alpha) * cov_[3]; cov_[4] = alpha * sc[3] + (1.0 - alpha) * cov_[4];
+    return LAMA_OK;
 }
 
 // Solver::calculateCovariance (solver.cpp:133-150): (J^T J)^-1 when J has full column rank, else the
@@ -617,6 +715,16 @@ int Loc2D::update(const double* pts, int n, const double* origin, const double* 
         rc = eng->set_scan(pts, n, origin, quat, 0, 0);
         if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
     }
+    if (do_gloc_) {  // loc2d.cpp:154-166
+        if (gloc_cur_iter_ < opt_.gloc_iters) {
+            gloc_cur_iter_++;
+            rc = global_localization(n);
+            if (rc != LAMA_OK) return rc;
+        } else {
+            do_gloc_       = false;
+            gloc_cur_iter_ = 0;
+        }
+    }
     HostMatchResult r;
     rc = eng->match(&pose_, 1, 0, false, so, 0.05, 0, &r);
     if (rc != LAMA_OK) { err_ = eng->last_error(); return rc; }
@@ -624,7 +732,15 @@ int Loc2D::update(const double* pts, int n, const double* origin, const double* 
     iters_ = r.iterations;
     evals_ = r.evals_ref + 2;  // + the covariance and rmse evaluations of solver.cpp:110 / loc2d.cpp:178
     covariance_from_sums(r.sums, (size_t)n, cov_);
+    if (cov_blend_ > 0.0) {     // loc2d.cpp:175-176
+        rc = add_sampling_covariance(n);
+        if (rc != LAMA_OK) return rc;
+    }
     rmse_ = std::sqrt(r.sums[10] / ((double)((size_t)n - 1)));  // loc2d.cpp:178-180
+    if (do_gloc_ && rmse_ < opt_.gloc_thresh) {                 // loc2d.cpp:182-188
+        do_gloc_       = false;
+        gloc_cur_iter_ = 0;
+    }
     *did_update = true;
     return LAMA_OK;
 }

@@ -7,6 +7,7 @@
 
 #include <memory>
 #include <random>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -169,10 +170,25 @@ private:
     std::string err_;
 };
 
+// SimpleOccupancyMap (src/sdm/simple_occupancy_map.cpp:36-149): Loc2D's static tri-state map.  It is only consulted by
+// the host-side rejection sampling of globalLocalization, so it lives on the host.
+class SimpleOccupancyHost {
+public:
+    explicit SimpleOccupancyHost(double resolution) : resolution_(resolution), scale_(1.0 / resolution) {}
+    void set(uint32_t x, uint32_t y, int state);   // -1 setFree, 0 setUnknown, 1 setOccupied
+    bool is_free_world(double wx, double wy) const;
+    bool bounds_world(double mn[2], double mx[2]) const;  // Map::bounds, patch granular (map.cpp:119-138)
+private:
+    double resolution_, scale_;
+    std::unordered_map<uint64_t, std::vector<int8_t>> patches_;
+};
+
 struct LocOptions {  // src/loc2d.cpp:46-58
     double trans_thresh = 0.5, rot_thresh = 0.5, l2_max = 1.0, resolution = 0.05;
     uint32_t patch_size = 32, max_iter = 100;
     int strategy = 0;
+    uint32_t gloc_particles = 3000, gloc_iters = 10;
+    double gloc_thresh = 0.15, cov_blend = 0.0;
     double center_x = 0, center_y = 0;
     DeviceOptions dev;
 };
@@ -181,6 +197,10 @@ class Loc2D {
 public:
     static Loc2D* create(const LocOptions& o, std::string& err);
     DistanceMapDev* distance_map() { return dm_.get(); }
+    SimpleOccupancyHost* occupancy_map() { return occ_.get(); }
+    void set_seed(uint32_t seed) { gen_.seed(seed); }                 // random::setSeed
+    void trigger_global_localization() { do_gloc_ = true; }          // loc2d.cpp:194-197
+    bool global_localization_active() const { return do_gloc_; }
     void set_pose(double x, double y, double r)
     {
         pose_      = se2_from_xyr(x, y, r);
@@ -203,6 +223,14 @@ private:
     double rmse_ = 0;
     uint32_t iters_ = 0, evals_ = 0;
     std::string err_;
+    std::unique_ptr<SimpleOccupancyHost> occ_;
+    std::mt19937 gen_{std::random_device{}()};   // the reference's global generator is seeded from random_device (random.cpp:38-39)
+    bool do_gloc_ = false;
+    uint32_t gloc_cur_iter_ = 0;
+    double cov_blend_ = 0.0;
+    std::vector<double> sampling_steps_;         // 161 (x, y) offsets, loc2d.cpp:93-107
+    int global_localization(int n);               // loc2d.cpp:249-286
+    int add_sampling_covariance(int n);           // loc2d.cpp:199-247
 };
 
 // shared helpers

@@ -864,6 +864,45 @@ __global__ void k_scatter_patches(StoreView s, int set, int particle, int kind, 
     if (kind == kMapOcc && __any_sync(0xffffffffu, fb != 0u) && lane == 0) d[entries[pi]] |= kDirHot;
 }
 
+// Loc2D::addSamplingCovariance (src/loc2d.cpp:199-236): for every sampling offset the likelihood
+//   l = sum over every `stride`-th beam of exp(-d^2 / 0.01)^3,  d = nearest-cell distance at the offset pose.
+// One block per offset; the host accumulates K, u, s in the reference's order.
+__global__ void k_sampling(StoreView s, int set, int particle, const double* __restrict__ points, ScanParams scan, SE2 pose, const double* __restrict__ offsets,
+                           int stride, double resolution, uint32_t max_sqdist, double* __restrict__ out)
+{
+    __shared__ Affine tf;
+    __shared__ double part[8];
+    const int32_t* d = dir_of(s, set, particle, kMapDm);
+    if (threadIdx.x == 0) {
+        SE2 st = pose;
+        st.tx = add_rn(pose.tx, offsets[2 * blockIdx.x]);
+        st.ty = add_rn(pose.ty, offsets[2 * blockIdx.x + 1]);
+        tf = compose_tf(st, scan.moving);
+    }
+    __syncthreads();
+    const double dmax = mul_rn(sqrt((double)max_sqdist), resolution);
+    double l = 0.0;
+    for (int k = threadIdx.x * stride; k < scan.n_beams; k += blockDim.x * stride) {
+        double hit[3];
+        apply_tf(tf, points[3 * k], points[3 * k + 1], points[3 * k + 2], hit);
+        const uint32_t x = w2m(hit[0], scan.scale), y = w2m(hit[1], scan.scale);
+        const int di = dir_index(s.window, x, y);
+        const int slot = di < 0 ? -1 : d[di];
+        const uint32_t w = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot & kDirSlotMask) + cell_index(x, y));
+        const double dist = (w & kDmValid) ? mul_rn(sqrt((double)dm_sqdist(w)), resolution) : dmax;
+        const double e = exp(-mul_rn(dist, dist) / 0.01);
+        l += e * e * e;
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w];
+        out[blockIdx.x] = v;
+    }
+}
+
 __global__ void k_distance(StoreView s, int set, int particle, const double* __restrict__ pts, int n, double resolution, uint32_t max_sqdist,
                            double* __restrict__ dist, double* __restrict__ grad)
 {
@@ -987,6 +1026,12 @@ void launch_scatter_patches(const StoreView& s, int set, int particle, int kind,
 {
     if (n <= 0) return;
     k_scatter_patches<<<(n + 3) / 4, 128, 0, st>>>(s, set, particle, kind, d_entries, n, d_in, d_in_fbits);
+}
+void launch_sampling(const StoreView& s, int set, int particle, const double* d_points, const ScanParams& scan, const SE2& pose, const double* d_offsets,
+                     int n_offsets, int stride, double resolution, uint32_t max_sqdist, double* d_out, cudaStream_t st)
+{
+    if (n_offsets <= 0) return;
+    k_sampling<<<n_offsets, 128, 0, st>>>(s, set, particle, d_points, scan, pose, d_offsets, stride, resolution, max_sqdist, d_out);
 }
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st)

@@ -84,6 +84,9 @@ void launch_import(const StoreView& s, int set, int particle, int kind, uint32_t
 void launch_gather_patches(const StoreView& s, const int32_t* d_slots, int n, uint32_t* d_out, uint32_t* d_out_fbits, cudaStream_t st);
 void launch_scatter_patches(const StoreView& s, int set, int particle, int kind, const int32_t* d_entries, int n, const uint32_t* d_in,
                             const uint32_t* d_in_fbits, cudaStream_t st);
+// Loc2D::addSamplingCovariance likelihoods: out[i] for offset i (offsets = n x 2 doubles)
+void launch_sampling(const StoreView& s, int set, int particle, const double* d_points, const ScanParams& scan, const SE2& pose, const double* d_offsets,
+                     int n_offsets, int stride, double resolution, uint32_t max_sqdist, double* d_out, cudaStream_t st);
 // batched DistanceMap::distance(point, &grad) on one particle's distance map (SDM grid interface)
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st);

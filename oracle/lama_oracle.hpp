@@ -451,6 +451,39 @@ public:
     uint64_t ray_cells = 0;
 };
 
+// src/sdm/simple_occupancy_map.cpp:36-149 : int8 tri-state cell (-1 free, 0 unknown, 1 occupied); Loc2D's static map
+struct SimpleCell {
+    int8_t v;
+};
+class SimpleOccupancyMap : public SparseMap<SimpleCell> {
+public:
+    using SparseMap<SimpleCell>::SparseMap;
+    bool set_free(const Vec3u& c) { SimpleCell* cell = get(c); if (cell->v == -1) return false; cell->v = -1; return true; }      // :51-58
+    bool set_occupied(const Vec3u& c) { SimpleCell* cell = get(c); if (cell->v == 1) return false; cell->v = 1; return true; }    // :66-73
+    bool set_unknown(const Vec3u& c) { SimpleCell* cell = get(c); if (cell->v == 0) return false; cell->v = 0; return true; }     // :81-88
+    bool is_free(const Vec3u& c) const                                                                                             // :96-102
+    {
+        const SimpleCell* cell = static_cast<const SparseMap<SimpleCell>*>(this)->get(c);
+        return cell != nullptr && cell->v == -1;
+    }
+    bool is_free_world(const double p[3]) const { return is_free(w2m(p)); }                                                         // :91-94
+    // Map::bounds (map.cpp:119-138, map.h:208-212): patch-granular, in world coordinates
+    bool bounds_world(double mn[3], double mx[3]) const
+    {
+        if (patches.empty()) return false;
+        uint32_t lo[2] = {0xffffffffu, 0xffffffffu}, hi[2] = {0, 0};
+        for (auto& kv : patches) {
+            Vec3u a = p2m(kv.first);
+            lo[0] = std::min(lo[0], a.x); lo[1] = std::min(lo[1], a.y);
+            hi[0] = std::max(hi[0], a.x); hi[1] = std::max(hi[1], a.y);
+        }
+        hi[0] += patch_length; hi[1] += patch_length;
+        m2w(Vec3u{lo[0], lo[1], 0}, mn);
+        m2w(Vec3u{hi[0], hi[1], patch_length}, mx);
+        return true;
+    }
+};
+
 // ----------------------------------------------------------------------------------------------
 // Dynamic distance map (Lau et al. dynamic brushfire, 4-neighbourhood in 2-D)
 // include/lama/sdm/dynamic_distance_map.h:48-104, src/sdm/dynamic_distance_map.cpp:66-330
@@ -1426,32 +1459,57 @@ struct LocOptions {
     double trans_thresh = 0.5, rot_thresh = 0.5, l2_max = 1.0, resolution = 0.05;
     uint32_t patch_size = 32, max_iter = 100;
     int strategy = 0;
+    uint32_t gloc_particles = 3000, gloc_iters = 10;  // loc2d.cpp:53-55
+    double gloc_thresh = 0.15, cov_blend = 0.0;       // :55,57
 };
 
 class Loc2D {
 public:
     LocOptions opt;
-    DynamicDistanceMap dm;  // public `distance_map`, filled by the caller (loc2d.h:103-104)
+    DynamicDistanceMap dm;      // public `distance_map`, filled by the caller (loc2d.h:103-104)
+    SimpleOccupancyMap occ;     // public `occupancy_map`
     SolverOptions so;
     Pose2D pose, odom;
     bool has_first_scan = false;
     double rmse = 0;
     double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     SolveStats last_stats;
+    Random rng;                 // stands in for the process-global generator (src/random.cpp:38-39)
+    bool do_global_localization = false;
+    uint32_t gloc_cur_iter = 0;
+    double cov_blend;
+    std::vector<std::pair<double, double>> sampling_steps;
+    uint64_t gloc_evals = 0;
 
-    explicit Loc2D(const LocOptions& o) : opt(o), dm(o.resolution, o.patch_size)
+    explicit Loc2D(const LocOptions& o) : opt(o), dm(o.resolution, o.patch_size), occ(o.resolution, o.patch_size)
     {
         dm.set_max_distance(o.l2_max);
         so.max_iterations = o.max_iter;
         so.strategy.kind  = o.strategy == 1 ? Strategy::LevenbergMarquardt : Strategy::GaussNewton;
         so.robust.kind    = RobustCost::Cauchy;
         so.robust.param   = 0.15;
+        cov_blend = std::max(std::min(o.cov_blend, 1.0), 0.0);  // loc2d.cpp:90
+        // sampling steps cache, loc2d.cpp:93-107
+        const double sstep = dm.resolution;
+        sampling_steps.push_back({0.0, 0.0});
+        for (int i = 1; i <= 20; ++i) {
+            sampling_steps.push_back({i * sstep, 0.0});
+            sampling_steps.push_back({0.0, i * sstep});
+            sampling_steps.push_back({-i * sstep, 0.0});
+            sampling_steps.push_back({0.0, -i * sstep});
+            sampling_steps.push_back({i * sstep, i * sstep});
+            sampling_steps.push_back({-i * sstep, i * sstep});
+            sampling_steps.push_back({i * sstep, -i * sstep});
+            sampling_steps.push_back({-i * sstep, -i * sstep});
+        }
     }
     void set_pose(const Pose2D& p)  // loc2d.h:117-118
     {
         pose           = p;
         has_first_scan = false;
     }
+    void trigger_global_localization() { do_global_localization = true; }  // loc2d.cpp:194-197
+
     bool update(const PointCloud& pc, const Pose2D& odometry, bool force_update)  // :126-192
     {
         if (!has_first_scan) {
@@ -1468,13 +1526,88 @@ public:
         if (!force_update && !(odelta.xy_norm() > opt.trans_thresh || std::abs(odelta.rotation()) > opt.rot_thresh)) return false;
         pose = ppose;
         odom = odometry;
+        if (do_global_localization) {  // :154-166
+            if (gloc_cur_iter < opt.gloc_iters) {
+                gloc_cur_iter++;
+                global_localization(pc);
+            } else {
+                do_global_localization = false;
+                gloc_cur_iter          = 0;
+            }
+        }
         MatchSurface2D ms(&dm, &pc, pose.state);
         last_stats = solve(so, ms, cov);
         pose.state = ms.state;
+        if (cov_blend > 0.0) add_sampling_covariance(pc);  // :175-176
         std::vector<double> res;
         ms.eval(res, nullptr);
         rmse = rmse_of(res, pc.size());
+        if (do_global_localization && rmse < opt.gloc_thresh) {  // :182-188
+            do_global_localization = false;
+            gloc_cur_iter          = 0;
+        }
         return true;
+    }
+
+    // loc2d.cpp:199-247
+    void add_sampling_covariance(const PointCloud& pc)
+    {
+        double K[4] = {0, 0, 0, 0}, u[2] = {0, 0}, sl = 0;
+        Affine3 mtf = moving_tf(pc);
+        const size_t num_points = pc.size();
+        const size_t step = std::max(num_points / 100, size_t(1));
+        const double rot = pose.rotation();
+        for (size_t i = 0; i < sampling_steps.size(); ++i) {
+            const double x = pose.x() + sampling_steps[i].first, y = pose.y() + sampling_steps[i].second;
+            Affine3 tf = compose(fixed_tf(x, y, rot), mtf);
+            double l = 0.0;
+            double hit[3];
+            for (size_t k = 0; k < num_points; k += step) {
+                tf.apply(&pc.pts[3 * k], hit);
+                double dist = dm.distance(dm.w2m(hit));  // nearest cell, no interpolation
+                double e = std::exp(-(dist * dist) / 0.01);
+                l += e * e * e;
+            }
+            K[0] = K[0] + x * x * l; K[1] = K[1] + x * y * l; K[2] = K[2] + y * x * l; K[3] = K[3] + y * y * l;
+            u[0] = u[0] + x * l; u[1] = u[1] + y * l;
+            sl = sl + l;
+        }
+        const double a = 1.0 / sl, b = 1.0 / (sl * sl);
+        const double sc[4] = {a * K[0] - b * u[0] * u[0], a * K[1] - b * u[0] * u[1], a * K[2] - b * u[1] * u[0], a * K[3] - b * u[1] * u[1]};
+        const double alpha = cov_blend;
+        cov[0] = alpha * sc[0] + (1.0 - alpha) * cov[0]; cov[1] = alpha * sc[1] + (1.0 - alpha) * cov[1];
+        cov[3] = alpha * sc[2] + (1.0 - alpha) * cov[3]; cov[4] = alpha * sc[3] + (1.0 - alpha) * cov[4];
+    }
+
+    // loc2d.cpp:249-286
+    void global_localization(const PointCloud& pc)
+    {
+        double mn[3], mx[3];
+        if (!occ.bounds_world(mn, mx)) return;
+        const double diff[2] = {mx[0] - mn[0], mx[1] - mn[1]};
+        double best_error = std::numeric_limits<double>::max();
+        for (uint32_t i = 0; i < opt.gloc_particles; ++i) {
+            double x, y, a;
+            for (;;) {
+                x = mn[0] + rng.uniform() * diff[0];
+                y = mn[1] + rng.uniform() * diff[1];
+                const double p[3] = {x, y, 0.0};
+                if (!occ.is_free_world(p)) continue;
+                a = rng.uniform() * 2 * M_PI - M_PI;
+                break;
+            }
+            Pose2D p(x, y, a);
+            MatchSurface2D ms(&dm, &pc, p.state);
+            std::vector<double> res;
+            ms.eval(res, nullptr);
+            ++gloc_evals;
+            double error = 0;
+            for (double v : res) error += v * v;
+            if (error < best_error) {
+                best_error = error;
+                pose       = p;
+            }
+        }
     }
 
 private:

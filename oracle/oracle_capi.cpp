@@ -373,16 +373,33 @@ struct orc_loc_options {
     double trans_thresh, rot_thresh, l2_max, resolution;
     uint32_t patch_size, max_iter;
     int32_t strategy;
+    uint32_t gloc_particles, gloc_iters;
+    double gloc_thresh, cov_blend;
 };
 void* orc_loc_create(const orc_loc_options* o)
 {
     LocOptions l;
     l.trans_thresh = o->trans_thresh; l.rot_thresh = o->rot_thresh; l.l2_max = o->l2_max; l.resolution = o->resolution;
     l.patch_size = o->patch_size; l.max_iter = o->max_iter; l.strategy = o->strategy;
+    l.gloc_particles = o->gloc_particles; l.gloc_iters = o->gloc_iters; l.gloc_thresh = o->gloc_thresh; l.cov_blend = o->cov_blend;
     return new Loc2D(l);
 }
 void orc_loc_destroy(void* h) { delete (Loc2D*)h; }
 void* orc_loc_dm_handle(void* h) { return &((Loc2D*)h)->dm; }
+void orc_loc_set_seed(void* h, uint32_t seed) { ((Loc2D*)h)->rng.seed(seed); }
+void orc_loc_trigger_gloc(void* h) { ((Loc2D*)h)->trigger_global_localization(); }
+int orc_loc_gloc_active(void* h) { return ((Loc2D*)h)->do_global_localization ? 1 : 0; }
+// SimpleOccupancyMap::setFree (-1) / setUnknown (0) / setOccupied (1) on n cells
+void orc_loc_occ_set(void* h, const uint32_t* cells, int n, int state)
+{
+    auto* l = (Loc2D*)h;
+    for (int i = 0; i < n; ++i) {
+        Vec3u c{cells[2 * i], cells[2 * i + 1], (uint32_t)l->occ.offset};
+        if (state < 0) l->occ.set_free(c);
+        else if (state > 0) l->occ.set_occupied(c);
+        else l->occ.set_unknown(c);
+    }
+}
 void orc_loc_set_pose(void* h, double x, double y, double r) { ((Loc2D*)h)->set_pose(Pose2D(x, y, r)); }
 int orc_loc_update(void* h, const double* pts, int n, const double* origin, const double* quat, const double* odom_xyr, int force)
 {

@@ -60,12 +60,14 @@ class SlamOptions(C.Structure):
 
 class LocOptions(C.Structure):
     _fields_ = [("trans_thresh", C.c_double), ("rot_thresh", C.c_double), ("l2_max", C.c_double), ("resolution", C.c_double),
-                ("patch_size", C.c_uint32), ("max_iter", C.c_uint32), ("strategy", C.c_int32)]
+                ("patch_size", C.c_uint32), ("max_iter", C.c_uint32), ("strategy", C.c_int32), ("gloc_particles", C.c_uint32),
+                ("gloc_iters", C.c_uint32), ("gloc_thresh", C.c_double), ("cov_blend", C.c_double)]
 
     @classmethod
     def defaults(cls, **kw):
         # src/loc2d.cpp:46-58
-        o = cls(trans_thresh=0.5, rot_thresh=0.5, l2_max=1.0, resolution=0.05, patch_size=32, max_iter=100, strategy=0)
+        o = cls(trans_thresh=0.5, rot_thresh=0.5, l2_max=1.0, resolution=0.05, patch_size=32, max_iter=100, strategy=0,
+                gloc_particles=3000, gloc_iters=10, gloc_thresh=0.15, cov_blend=0.0)
         for k, v in kw.items():
             setattr(o, k, v)
         return o
@@ -518,6 +520,19 @@ class Loc2D:
 
     def set_pose(self, x, y, r):
         lib().orc_loc_set_pose(self.h, C.c_double(x), C.c_double(y), C.c_double(r))
+
+    def set_seed(self, seed):
+        lib().orc_loc_set_seed(self.h, C.c_uint32(seed))
+
+    def trigger_global_localization(self):
+        lib().orc_loc_trigger_gloc(self.h)
+
+    def gloc_active(self):
+        return bool(lib().orc_loc_gloc_active(self.h))
+
+    def occ_set(self, cells, state):
+        c, cp = _u32(cells)
+        lib().orc_loc_occ_set(self.h, cp, C.c_int(c.size // 2), C.c_int(state))
 
     def update(self, pts, odom, force=False, origin=_ID3, quat=_IDQ):
         p, pp = _d(pts)

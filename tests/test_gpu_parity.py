@@ -161,6 +161,32 @@ def test_loc2d_matches_oracle_and_golden(gpu_api, po, synth):
     assert gl.update(ds.scans[3], ds.odom[3]) is False                       # no motion -> gated
 
 
+def test_loc2d_global_localization_and_sampling_covariance(gpu_api, po, synth):
+    """SURVEY 8(f) row 1: Loc2D::globalLocalization (3000-candidate evaluation in one launch) + addSamplingCovariance"""
+    ds = synth.make_dataset("loc_room", 6)
+    cells = _room_cells(ds.segments)
+    kw = dict(trans_thresh=0.01, rot_thresh=0.01, gloc_particles=3000, cov_blend=0.5)
+    gl = gpu_api.Loc2D(gpu_api.Loc2D.Options(**kw))
+    ol = po.Loc2D(po.LocOptions.defaults(**kw))
+    gl.distance_map.addObstacle(cells); gl.distance_map.update()
+    od = ol.dm(); od.add(cells); od.update()
+    xs = np.arange(int(-9.9 * 20), int(9.9 * 20))
+    free = np.array([(x + O, y + O) for x in xs[::2] for y in xs[::2]], np.uint32)
+    gl.occupancySet(free, -1); gl.occupancySet(cells, 1)
+    ol.occ_set(free, -1); ol.occ_set(cells, 1)
+    gl.setSeed(77); ol.set_seed(77)
+    gl.setPose(0, 0, 0); ol.set_pose(0, 0, 0)
+    gl.triggerGlobalLocalization(); ol.trigger_global_localization()
+    for t in range(6):
+        assert gl.update(ds.scans[t], ds.odom[t], force_update=(t == 0)) == ol.update(ds.scans[t], ds.odom[t], force=(t == 0))
+        sc, cov, rmse, _ = ol.get()
+        assert np.abs(gl.state() - sc).max() < POSE_TOL, t              # same winning candidate, same refinement
+        assert abs(gl.getRMSE() - rmse) < 1e-12
+        assert np.allclose(gl.getCovar(), cov, rtol=1e-8, atol=1e-12)     # incl. the blended sampling covariance
+        assert gl.globalLocalizationActive() == ol.gloc_active()
+    assert gl.getRMSE() < 0.15 and not gl.globalLocalizationActive()
+
+
 # ---- Slam2D (config 2 family) ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,beams,T", [("room", 360, 30), ("corridor", 720, 40), ("room", 1080, 12)])
 def test_slam2d_matches_oracle(gpu_api, po, synth, name, beams, T):
