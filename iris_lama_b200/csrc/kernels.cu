@@ -214,51 +214,57 @@ __device__ __forceinline__ int next_pow2(int v)
 // into the same sectors) and every warp gets the same amount of work, whatever the ray lengths.
 constexpr int kSegSteps = 64;
 
-struct BeamEnds {      // 16 bytes
+struct BeamEnds {      // 16 bytes; WINDOW-RELATIVE cell coordinates (< 2^16)
     uint32_t fx, fy;   // from cell; bit 31 of fx: mark_hit, bit 31 of fy: non-planar (generic 3-axis walk)
     uint32_t tx, ty;   // hit cell
 };
 constexpr uint32_t kBeamFlag = 0x80000000u;
 
+// Map::computeRay for a planar beam, started at any step.  The major axis (delta == n) moves on every step: its
+// error term returns to 0 each time (err += n; 2 err >= n; err -= n), so only the minor axis carries state:
+//   e += d;  if (2 e >= n) { minor coordinate moves; e -= n; }          [2 e >= n  <=>  e >= (n + 1) >> 1]
+// (dx == dy: both axes move on every step, which the same update yields with d == n.)
 struct SegWalk {
-    int ex, ey, dx, dy, sx, sy, n, i, iend;
+    int e, d, n, half, i, iend;
+    int mx, my, nx, ny;  // major / minor step vectors
     uint32_t x, y;
     __device__ __forceinline__ void init(const BeamEnds& b, int i0, int steps)
     {
         const uint32_t fx = b.fx & ~kBeamFlag, fy = b.fy & ~kBeamFlag;
         const int ddx = (int)(b.tx - fx), ddy = (int)(b.ty - fy);
-        sx = ddx < 0 ? -1 : 1;
-        sy = ddy < 0 ? -1 : 1;
-        dx = ddx < 0 ? -ddx : ddx;
-        dy = ddy < 0 ? -ddy : ddy;
-        n  = dx > dy ? dx : dy;
-        i  = i0;
+        const int sx = ddx < 0 ? -1 : 1, sy = ddy < 0 ? -1 : 1;
+        const int dx = ddx < 0 ? -ddx : ddx, dy = ddy < 0 ? -ddy : ddy;
+        const bool xmajor = dx >= dy;
+        n = xmajor ? dx : dy;
+        d = xmajor ? dy : dx;
+        mx = xmajor ? sx : 0; my = xmajor ? 0 : sy;
+        nx = xmajor ? 0 : sx; ny = xmajor ? sy : 0;
+        half = (n + 1) >> 1;
+        i    = i0;
         iend = min(i0 + steps, n - 1);
-        if (i0 == 0 || n == 0) {
-            x = fx; y = fy; ex = ey = 0;
-        } else {
-            const uint32_t n2 = 2u * (uint32_t)n;
-            const uint32_t kx = (2u * (uint32_t)i0 * (uint32_t)dx + (uint32_t)n) / n2;
-            const uint32_t ky = (2u * (uint32_t)i0 * (uint32_t)dy + (uint32_t)n) / n2;
-            x  = fx + (uint32_t)(sx * (int)kx);
-            y  = fy + (uint32_t)(sy * (int)ky);
-            ex = i0 * dx - (int)kx * n;
-            ey = i0 * dy - (int)ky * n;
+        uint32_t k = 0;
+        e = 0;
+        if (i0 != 0 && n != 0) {  // closed form of the state after i0 steps
+            k = (2u * (uint32_t)i0 * (uint32_t)d + (uint32_t)n) / (2u * (uint32_t)n);
+            e = i0 * d - (int)k * n;
         }
+        x = fx + (uint32_t)(mx * i0 + nx * (int)k);
+        y = fy + (uint32_t)(my * i0 + ny * (int)k);
     }
     __device__ __forceinline__ bool next()
     {
         if (i >= iend) return false;
         ++i;
-        ex += dx;
-        ey += dy;
-        if (2 * ex >= n) { x += sx; ex -= n; }
-        if (2 * ey >= n) { y += sy; ey -= n; }
+        e += d;
+        x += mx;
+        y += my;
+        if (e >= half) { x += nx; y += ny; e -= n; }
         return true;
     }
 };
 
-constexpr int kCandNone = 0xFF, kCandOverflow = 0xFE;
+constexpr uint32_t kCandNone = 0xFF, kCandOverflow = 0xFE;
+constexpr uint32_t kInfoSlotMask = 0x00FFFFFFu;   // slot field of a patch-info word; all ones = not writable in this pass
 
 // Map::computeRay's 3-axis walk in 32-bit arithmetic (cell coordinates and deltas are < 2^27): tilted sensors only
 struct RayWalk3 {
@@ -286,66 +292,55 @@ struct RayWalk3 {
     }
 };
 
+// The inner loop of the ray cast: everything it needs to know about a patch is ONE shared-memory word
+//   pinfo[directory index] = [candidate bitmap index : 8][slot the counters go to : 24]
+// (slot all ones: the patch cannot be written in this pass), so a step is walk + index + LDS + RED with no
+// per-lane patch cache and no divergent lookup.
 template <bool kProb>
 struct RayCtx {
     const StoreView& s;
     const RayParams& rp;
-    int32_t* dir;
-    int32_t* dir_s;            // kProb: directory of the per-scan scratch counters
-    uint32_t* touched;         // kProb: scratch patches that received counts in this scan
-    const uint8_t* cand_idx;   // per directory entry: index of its candidate bitmap, kCandNone or kCandOverflow
+    const uint32_t* pinfo;
     const uint32_t* cand;      // [cand_cap][32]: bit = cell is a hit cell of this scan or a distance-map obstacle
     uint32_t* pending;         // patches that must be allocated / detached before they can be written
+    uint32_t* touched;         // kProb: scratch patches that received counts in this scan
     uint64_t* log;
     RayShared& sh;
-    DirWindow win;
-    bool redo;                 // second pass: only cells of `pending` patches
+    uint32_t side;             // window side in cells
+    int log2dim;
+    bool mark;                 // first pass: note the patches that are not writable yet
     uint32_t cells, err;
-    // one-entry cache of the current patch
-    uint32_t cpx, cpy;
-    int cdi, centry, ccand;
+    int last_di;               // kProb
 
-    __device__ __forceinline__ void lookup(uint32_t x, uint32_t y)
+    // (xr, yr) window-relative.  `run` > 0: this lane adds the misses of `run` adjacent lanes that touch the same
+    // cell (see raycast_pass); `run` == 0: another lane carries this lane's count, only the ordered-path log is kept.
+    // Every counter update is a fire-and-forget reduction at the L2 (SASS RED): nothing waits for a returned value.
+    __device__ __forceinline__ void touch(uint32_t xr, uint32_t yr, uint32_t beam, uint32_t pos, bool hit, uint32_t run = 1u)
     {
-        cpx = x >> kPatchLog2;
-        cpy = y >> kPatchLog2;
-        cdi = dir_index(win, x, y);
-        if (cdi < 0) {
+        if ((xr | yr) >= side) {
             err |= kErrWindow;
-            centry = -1;
             return;
         }
-        centry = dir[cdi];
-        ccand  = cand_idx[cdi];
-        bool writable = centry >= 0 && (centry & kDirOwn);
-        if (kProb) {  // the counts of a log-odds map go to the scratch patch; both patches must be owned
-            const int se = dir_s[cdi];
-            writable = writable && se >= 0 && (se & kDirOwn);
-            if (writable) centry = se;
+        const uint32_t di   = ((yr >> kPatchLog2) << log2dim) | (xr >> kPatchLog2);
+        const uint32_t info = pinfo[di];
+        const uint32_t slot = info & kInfoSlotMask;
+        if (slot == kInfoSlotMask) {
+            if (mark) atomicOr(&pending[di >> 5], 1u << (di & 31));
+            return;
         }
-        if (!redo) {
-            if (!writable) {
-                atomicOr(&pending[cdi >> 5], 1u << (cdi & 31));
-                centry = -1;  // handled by the second pass
-            }
-        } else if (!((pending[cdi >> 5] >> (cdi & 31)) & 1u) || !writable) {
-            centry = -1;      // already done in the first pass (or the pool ran dry)
+        if (kProb && (int)di != last_di) {
+            atomicOr(&touched[di >> 5], 1u << (di & 31));
+            last_di = (int)di;
         }
-        if (kProb && centry >= 0) atomicOr(&touched[cdi >> 5], 1u << (cdi & 31));
-    }
-    // every counter update is a fire-and-forget reduction at the L2: nothing below waits for a returned value
-    __device__ __forceinline__ void touch(uint32_t x, uint32_t y, uint32_t beam, uint32_t pos, bool hit)
-    {
-        if ((x >> kPatchLog2) != cpx || (y >> kPatchLog2) != cpy) lookup(x, y);
-        if (centry < 0) return;
-        ++cells;
-        const uint32_t ci = cell_index(x, y);
-        // red.global: a reduction with no destination register (SASS RED), nothing waits for it
-        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(patch_ptr(s, centry & kDirSlotMask) + ci), "r"(hit ? kOccHitInc : kOccMissInc) : "memory");
+        cells += run;
+        const uint32_t ci = (xr & (kPatchLen - 1)) | ((yr & (kPatchLen - 1)) << kPatchLog2);
+        if (run)
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(s.pool + (((size_t)slot << (2 * kPatchLog2)) | ci)), "r"(hit ? kOccHitInc : run * kOccMissInc) : "memory");
+        const uint32_t ccand = info >> 24;
         if (ccand == kCandNone) return;
         if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
             const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(cell_key(win, x, y), beam, hit ? 0u : pos, hit);
+            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record((yr << 16) | xr, beam, hit ? 0u : pos, hit);
         }
     }
 };
@@ -353,10 +348,10 @@ struct RayCtx {
 // One pass over all touches of the scan (hits, planar segments, generic beams).
 template <bool kProb>
 __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* beams, const uint32_t* seg_prefix, int n_beams, int n_groups, uint32_t* work_counter,
-                                             const double* __restrict__ points, const Affine& tf)
+                                             const double* __restrict__ points, const Affine& tf, uint32_t bx0, uint32_t by0)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    c.cpx = c.cpy = 0xffffffffu;
+    c.last_di = -1;
     // hits (setOccupied, pf_slam2d.cpp:493-498)
     for (int b = tid; b < n_beams; b += blockDim.x) {
         const BeamEnds be = beams[b];
@@ -377,13 +372,29 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
         }
         const int seg = (int)(item - seg_prefix[g]);
         const int b = g * 32 + lane;
-        if (b < n_beams) {
-            const BeamEnds be = beams[b];
-            if (!(be.fy & kBeamFlag)) {
-                SegWalk w;
-                w.init(be, seg * kSegSteps, kSegSteps);
-                while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
+        const BeamEnds be = beams[b];   // the cache is padded to whole groups (padding lanes are flagged non-planar)
+        SegWalk w;
+        w.init(be, seg * kSegSteps, (be.fy & kBeamFlag) ? 0 : kSegSteps);
+        if (seg == 0) {
+            // Lanes walk angularly adjacent beams in lock step, so close to the sensor neighbouring lanes sit on the
+            // same cell: runs of equal cells are merged into ONE reduction carrying the run length (counter additions
+            // commute; the visited half-word wraps like the reference's uint16).  The ordered-path log stays per touch.
+            for (;;) {
+                const bool v = w.next();
+                const unsigned valid = __ballot_sync(0xffffffffu, v);
+                if (!valid) break;
+                const uint32_t key = (w.y << 16) | w.x;
+                const uint32_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool head = v && (lane == 0 || !((valid >> (lane - 1)) & 1u) || pkey != key);
+                const unsigned heads = __ballot_sync(0xffffffffu, head);
+                if (v) {
+                    const unsigned stop = (heads | ~valid) & ~((2u << lane) - 1u);   // first lane above that starts another run
+                    const uint32_t run = head ? (uint32_t)((stop ? __ffs(stop) - 1 : 32) - lane) : 0u;
+                    c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false, run);
+                }
             }
+        } else {
+            while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
         }
     }
     // non-planar beams (tilted sensor): the reference's 3-axis walk, one thread per beam
@@ -392,7 +403,7 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
         const double pt[3] = {__ldg(points + 3 * (size_t)b), __ldg(points + 3 * (size_t)b + 1), __ldg(points + 3 * (size_t)b + 2)};
         const BeamCells bc = beam_cells(tf, c.rp.scan, pt);
         RayWalk3 w(bc);
-        while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
+        while (w.next()) c.touch(w.x - bx0, w.y - by0, (uint32_t)b, (uint32_t)w.i, false);
     }
 }
 
@@ -417,9 +428,9 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     uint32_t* hotmap = cand + rp.cand_cap * 32;
     uint32_t* pending = hotmap + nwords;
     uint32_t* seg_prefix = pending + nwords;           // n_groups + 1 entries
-    uint16_t* cand_di = reinterpret_cast<uint16_t*>(seg_prefix + ((n_groups + 2) & ~1));  // directory entry of every bitmap
-    uint8_t* cand_idx = reinterpret_cast<uint8_t*>(cand_di + ((rp.cand_cap + 3) & ~3));
-    RayShared& sh    = *reinterpret_cast<RayShared*>(cand_idx + dim2);
+    uint32_t* pinfo  = seg_prefix + ((n_groups + 2) & ~1);   // per directory entry: [candidate bitmap index : 8][slot : 24]
+    uint16_t* cand_di = reinterpret_cast<uint16_t*>(pinfo + dim2);  // directory entry of every bitmap
+    RayShared& sh    = *reinterpret_cast<RayShared*>(cand_di + ((rp.cand_cap + 3) & ~3));
     const size_t dir_s_off = ((size_t)(reinterpret_cast<unsigned char*>(&sh) - smem_raw) + sizeof(RayShared) + 15) & ~(size_t)15;  // TMA target: 16-B aligned
     int32_t* dir_s   = reinterpret_cast<int32_t*>(smem_raw + dir_s_off);                                                                  // kProb only
     uint32_t* touched = reinterpret_cast<uint32_t*>(dir_s + dim2);                                                                  // kProb only
@@ -429,6 +440,10 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     int32_t* gdir      = dir_of(s, rp.set, particle, kMapOcc);
     int32_t* gdir_s    = kProb ? dir_of(s, rp.set, particle, kMapScratch) : nullptr;
     const DirWindow win = s.window;
+    const uint32_t bx0 = (uint32_t)win.base_px << kPatchLog2, by0 = (uint32_t)win.base_py << kPatchLog2;
+    const uint32_t side = (uint32_t)win.dim << kPatchLog2;
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= win.dim) ++log2dim;
 
     // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
     if (tid == 0) {
@@ -440,7 +455,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         sh.n_cand = 0;
     }
     for (int i = tid; i < 2 * nwords; i += blockDim.x) hotmap[i] = 0u;  // hotmap + pending are contiguous
-    for (int i = tid; i < dim2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cand_idx)[i] = 0xFFFFFFFFu;  // kCandNone
+    for (int i = tid; i < dim2; i += blockDim.x) pinfo[i] = 0xFFFFFFFFu;  // kCandNone, not writable
     if (kProb)
         for (int i = tid; i < nwords; i += blockDim.x) touched[i] = 0u;
     __syncthreads();
@@ -460,21 +475,23 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         if (b < n) {
             const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
             const BeamCells bc = beam_cells(tf, rp.scan, pt);
-            be.fx = bc.from[0]; be.fy = bc.from[1]; be.tx = bc.to[0]; be.ty = bc.to[1];
-            if (bc.mark_hit) {
-                const int di = dir_index(win, bc.to[0], bc.to[1]);
-                if (di < 0) my_err |= kErrWindow;
-                else {
+            be.fx = bc.from[0] - bx0; be.fy = bc.from[1] - by0; be.tx = bc.to[0] - bx0; be.ty = bc.to[1] - by0;
+            if ((be.fx | be.fy | be.tx | be.ty) >= side) {  // the beam leaves the directory window: reported, nothing is written
+                my_err |= kErrWindow;
+                be.fx = be.tx = be.fy = be.ty = 0u;
+            } else {
+                if (bc.mark_hit) {
+                    const int di = (int)(((be.ty >> kPatchLog2) << log2dim) | (be.tx >> kPatchLog2));
                     be.fx |= kBeamFlag;
                     atomicOr(&hotmap[di >> 5], 1u << (di & 31));  // holds a hit cell of this scan
                 }
-            }
-            if (bc.from[2] != bc.to[2]) {
-                be.fy |= kBeamFlag;
-            } else {
-                const int ddx = (int)(bc.to[0] - bc.from[0]), ddy = (int)(bc.to[1] - bc.from[1]);
-                const int nn = max(ddx < 0 ? -ddx : ddx, ddy < 0 ? -ddy : ddy);
-                segs = nn > 1 ? (nn - 1 + kSegSteps - 1) / kSegSteps : 0;
+                if (bc.from[2] != bc.to[2]) {
+                    be.fy |= kBeamFlag;
+                } else {
+                    const int ddx = (int)(bc.to[0] - bc.from[0]), ddy = (int)(bc.to[1] - bc.from[1]);
+                    const int nn = max(ddx < 0 ? -ddx : ddx, ddy < 0 ? -ddy : ddy);
+                    segs = nn > 1 ? (nn - 1 + kSegSteps - 1) / kSegSteps : 0;
+                }
             }
         }
         beams[b] = be;
@@ -502,10 +519,10 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
                 b2 &= b2 - 1;
                 const int di = wi * 32 + bit;
                 if (k < (uint32_t)rp.cand_cap) {
-                    cand_idx[di] = (uint8_t)k;
-                    cand_di[k]   = (uint16_t)di;
+                    pinfo[di]  = (k << 24) | kInfoSlotMask;
+                    cand_di[k] = (uint16_t)di;
                 } else {
-                    cand_idx[di] = kCandOverflow;
+                    pinfo[di] = (kCandOverflow << 24) | kInfoSlotMask;
                 }
                 ++k;
             }
@@ -532,17 +549,28 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     for (int b = tid; b < n; b += blockDim.x) {
         const BeamEnds be = beams[b];
         if (!(be.fx & kBeamFlag)) continue;
-        const int k = cand_idx[dir_index(win, be.tx, be.ty)];
+        const int k = (int)(pinfo[((be.ty >> kPatchLog2) << log2dim) | (be.tx >> kPatchLog2)] >> 24);
         if (k < rp.cand_cap) {
             const uint32_t ci = cell_index(be.tx, be.ty);
             atomicOr(&cand[k * 32 + (ci >> 5)], 1u << (ci & 31));
         }
     }
+    // ---- phase 1d: the slot every patch's counters go to in the first pass (patches this particle owns) -------------
+    for (int di = tid; di < dim2; di += blockDim.x) {
+        int e = dir[di];
+        bool writable = e >= 0 && (e & kDirOwn);
+        if (kProb) {  // the counts of a log-odds map go to the scratch patch; both patches must be owned
+            const int se = dir_s[di];
+            writable = writable && se >= 0 && (se & kDirOwn);
+            e = se;
+        }
+        if (writable) pinfo[di] = (pinfo[di] & 0xFF000000u) | (uint32_t)(e & kDirSlotMask);
+    }
     __syncthreads();
 
     // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away;
     // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW) and redo those ----
-    RayCtx<kProb> ctx{s, rp, dir, dir_s, touched, cand_idx, cand, pending, log, sh, win, false, 0u, 0u, 0u, 0u, -1, -1, kCandNone};
+    RayCtx<kProb> ctx{s, rp, pinfo, cand, pending, touched, log, sh, side, log2dim, true, 0u, 0u, -1};
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
@@ -559,13 +587,30 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
             }
             __syncthreads();
             if (!sh.any_pending) break;
-            ctx.redo = true;
+            // second pass: only the cells of the patches that were pending (the others are done)
+            for (int di = tid; di < dim2; di += blockDim.x) {
+                uint32_t slot = kInfoSlotMask;
+                if ((pending[di >> 5] >> (di & 31)) & 1u) {
+                    int e = dir[di];
+                    bool writable = e >= 0 && (e & kDirOwn);
+                    if (kProb) {
+                        const int se = dir_s[di];
+                        writable = writable && se >= 0 && (se & kDirOwn);
+                        e = se;
+                    }
+                    if (writable) slot = (uint32_t)(e & kDirSlotMask);   // else: the pool ran dry (reported)
+                }
+                pinfo[di] = (pinfo[di] & 0xFF000000u) | slot;
+            }
+            __syncthreads();
+            ctx.mark = false;
         }
-        raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[pass], rp.points, tf);
+        raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[pass], rp.points, tf, bx0, by0);
     }
     my_err |= ctx.err;
     uint32_t my_cells = __reduce_add_sync(0xffffffffu, ctx.cells);
     if (lane == 0 && my_cells) atomicAdd(&sh.cells, my_cells);
+    __threadfence();  // the reductions above must have been performed before the replay reads the counters back
     __syncthreads();
 
     // ---- phase 4: sort the log by (cell, beam) -------------------------------------------------------------
@@ -946,7 +991,7 @@ size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
     const size_t beam_bytes = (size_t)n_groups * 32 * 16, ev_bytes = (size_t)rp.event_cap * 8;
     const size_t prob_extra = rp.prob_mode ? (size_t)dim2 * 4 + (size_t)((dim2 + 31) / 32) * 4 + 32 : 0;
     return (size_t)dim2 * 4 + (size_t)rp.log_cap * 8 + (beam_bytes > ev_bytes ? beam_bytes : ev_bytes) + (size_t)rp.cand_cap * 128 +
-           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + (size_t)(rp.cand_cap + 4) * 2 + (size_t)dim2 + sizeof(RayShared) + 32 + prob_extra;
+           (size_t)((dim2 + 31) / 32) * 8 + (size_t)(n_groups + 4) * 4 + (size_t)(rp.cand_cap + 4) * 2 + (size_t)dim2 * 4 + sizeof(RayShared) + 32 + prob_extra;
 }
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {
