@@ -132,6 +132,9 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         return r;
     };
     CU_NEW(dalloc((void**)&v.pool, (size_t)v.n_slots * kPatchBytes));
+    if (((uintptr_t)v.pool & (kPatchBytes - 1)) != 0) {  // k_raycast ORs cell offsets into patch base addresses
+        return bail("patch pool is not 4 KiB aligned");
+    }
     CU_NEW(dalloc((void**)&v.fbits, (size_t)v.n_slots * 128));
     if (cfg.occupancy_kind == 1) CU_NEW(dalloc((void**)&v.kbits, (size_t)v.n_slots * 128));
     CU_NEW(dalloc((void**)&v.refcount, (size_t)v.n_slots * 4));

@@ -306,21 +306,16 @@ struct RayCtx {
     uint32_t* touched;         // kProb: scratch patches that received counts in this scan
     uint64_t* log;
     RayShared& sh;
-    uint32_t side;             // window side in cells
     int log2dim;
     bool mark;                 // first pass: note the patches that are not writable yet
-    uint32_t cells, err;
     int last_di;               // kProb
 
     // (xr, yr) window-relative.  `run` > 0: this lane adds the misses of `run` adjacent lanes that touch the same
     // cell (see raycast_pass); `run` == 0: another lane carries this lane's count, only the ordered-path log is kept.
     // Every counter update is a fire-and-forget reduction at the L2 (SASS RED): nothing waits for a returned value.
+    // All cells of a beam lie inside the bounding box of its end cells, which phase 1a checked against the window.
     __device__ __forceinline__ void touch(uint32_t xr, uint32_t yr, uint32_t beam, uint32_t pos, bool hit, uint32_t run = 1u)
     {
-        if ((xr | yr) >= side) {
-            err |= kErrWindow;
-            return;
-        }
         const uint32_t di   = ((yr >> kPatchLog2) << log2dim) | (xr >> kPatchLog2);
         const uint32_t info = pinfo[di];
         const uint32_t slot = info & kInfoSlotMask;
@@ -332,10 +327,17 @@ struct RayCtx {
             atomicOr(&touched[di >> 5], 1u << (di & 31));
             last_di = (int)di;
         }
-        cells += run;
         const uint32_t ci = (xr & (kPatchLen - 1)) | ((yr & (kPatchLen - 1)) << kPatchLog2);
-        if (run)
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(s.pool + (((size_t)slot << (2 * kPatchLog2)) | ci)), "r"(hit ? kOccHitInc : run * kOccMissInc) : "memory");
+        if (run) {
+            // the pool is 4 KiB aligned (checked at creation): patch base = pool + slot * 4096, the cell offset is OR-ed in
+            uint64_t addr;
+            uint32_t lo, hi;
+            asm("mad.wide.u32 %0, %1, 4096, %2;" : "=l"(addr) : "r"(slot), "l"(s.pool));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(addr));
+            lo |= ci << 2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(addr) : "r"(lo), "r"(hi));
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(hit ? kOccHitInc : run * kOccMissInc) : "memory");
+        }
         const uint32_t ccand = info >> 24;
         if (ccand == kCandNone) return;
         if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
@@ -464,7 +466,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     const Affine tf = sh.tf;
 
     // ---- phase 1a: beam end cells, segment counts, patches that need the ordered path ---------------------
-    uint32_t my_err = 0;
+    uint32_t my_err = 0, my_cells = 0;   // touches of this scan: every beam's hit + its n - 1 interior cells (each applied exactly once)
     for (int di = tid; di < dim2; di += blockDim.x) {
         const int e = dir[di];
         if (e >= 0 && (e & kDirHot)) atomicOr(&hotmap[di >> 5], 1u << (di & 31));  // holds distance-map obstacles
@@ -484,14 +486,13 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
                     const int di = (int)(((be.ty >> kPatchLog2) << log2dim) | (be.tx >> kPatchLog2));
                     be.fx |= kBeamFlag;
                     atomicOr(&hotmap[di >> 5], 1u << (di & 31));  // holds a hit cell of this scan
+                    my_cells += 1;
                 }
-                if (bc.from[2] != bc.to[2]) {
-                    be.fy |= kBeamFlag;
-                } else {
-                    const int ddx = (int)(bc.to[0] - bc.from[0]), ddy = (int)(bc.to[1] - bc.from[1]);
-                    const int nn = max(ddx < 0 ? -ddx : ddx, ddy < 0 ? -ddy : ddy);
-                    segs = nn > 1 ? (nn - 1 + kSegSteps - 1) / kSegSteps : 0;
-                }
+                const int ddx = (int)(bc.to[0] - bc.from[0]), ddy = (int)(bc.to[1] - bc.from[1]), ddz = (int)(bc.to[2] - bc.from[2]);
+                const int nn = max(max(ddx < 0 ? -ddx : ddx, ddy < 0 ? -ddy : ddy), ddz < 0 ? -ddz : ddz);
+                my_cells += nn > 1 ? (uint32_t)(nn - 1) : 0u;
+                if (ddz != 0) be.fy |= kBeamFlag;
+                else segs = nn > 1 ? (nn - 1 + kSegSteps - 1) / kSegSteps : 0;
             }
         }
         beams[b] = be;
@@ -570,7 +571,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
 
     // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away;
     // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW) and redo those ----
-    RayCtx<kProb> ctx{s, rp, pinfo, cand, pending, touched, log, sh, side, log2dim, true, 0u, 0u, -1};
+    RayCtx<kProb> ctx{s, rp, pinfo, cand, pending, touched, log, sh, log2dim, true, -1};
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
@@ -607,8 +608,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         }
         raycast_pass(ctx, beams, seg_prefix, n, n_groups, &sh.work[pass], rp.points, tf, bx0, by0);
     }
-    my_err |= ctx.err;
-    uint32_t my_cells = __reduce_add_sync(0xffffffffu, ctx.cells);
+    my_cells = __reduce_add_sync(0xffffffffu, my_cells);
     if (lane == 0 && my_cells) atomicAdd(&sh.cells, my_cells);
     __threadfence();  // the reductions above must have been performed before the replay reads the counters back
     __syncthreads();
