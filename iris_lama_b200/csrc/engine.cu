@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -377,6 +378,7 @@ int Engine::update_maps_async(const SE2* states, int first_particle, int count)
     rp.scan = d_->scan;
     rp.set = cur_set_;
     rp.particle_offset = first_particle;
+    { const char* dbg = std::getenv("LAMA_RAY_DEBUG"); rp.debug = dbg ? std::atoi(dbg) : 0; }  // see RayParams::debug
     // shared-memory scratch sized for THIS scan (two CTAs per SM at 1080 beams); the maxima were registered at create
     const int nb = d_->scan.n_beams;
     rp.log_cap   = std::min(d_->ray.log_cap, next_pow2_host(std::max(1024, 3 * nb)));

@@ -11,6 +11,8 @@
 // into shared memory with TMA bulk copies (cp.async.bulk + mbarrier).
 #include "kernels.cuh"
 
+#include <cstdio>
+
 #include "brushfire_warp.cuh"
 
 namespace lama_b200 {
@@ -18,7 +20,7 @@ namespace lama_b200 {
 namespace {
 
 constexpr int kMatchThreads = 512;
-constexpr int kRayThreads   = 384;  // 2 CTAs/SM at <= 85 registers: the walk loop must not spill (r01 profile: LDL in the DDA)
+constexpr int kRayThreads   = 512;  // 2 CTAs/SM at 64 registers (no spills in the walk loop); the kernel is bound by integer issue rate
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -177,24 +179,57 @@ struct RayShared {
     uint32_t any_pending, n_cand;
 };
 
-// in-place bitonic sort of n (power of two) 64-bit keys in shared memory by the whole block
+// In-place ascending bitonic sort of n (power of two) 64-bit keys in shared memory by the whole block.
+// Compare-exchange distances below 32 stay inside aligned 32-key chunks: a warp keeps a chunk in registers and runs
+// those stages with shuffles (no block barrier); only the distances >= 32 go through shared memory with a barrier
+// per stage (21 instead of 66 barriers at n = 2048).  Ends with a block barrier.
+__device__ __forceinline__ uint64_t bitonic_exchange(uint64_t v, int i, int k, int j)
+{
+    const uint64_t p = __shfl_xor_sync(0xffffffffu, v, j);
+    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+    return (p < v) == keep_min ? p : v;
+}
 __device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n)
 {
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    uint64_t x = a[i], y = a[ixj];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        a[i]   = y;
-                        a[ixj] = x;
-                    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (n <= 32) {   // one warp, padded with the maximum key
+        if (warp == 0 && n > 1) {
+            uint64_t v = lane < n ? a[lane] : ~0ull;
+            for (int k = 2; k <= 32; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) v = bitonic_exchange(v, lane, k, j);
+            if (lane < n) a[lane] = v;
+        }
+        __syncthreads();
+        return;
+    }
+    // stages k = 2 .. 32 (every distance < 32)
+    for (int c = warp; c < n / 32; c += nwarps) {
+        const int i = c * 32 + lane;
+        uint64_t v = a[i];
+        for (int k = 2; k <= 32; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) v = bitonic_exchange(v, i, k, j);
+        a[i] = v;
+    }
+    __syncthreads();
+    for (int k = 64; k <= n; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // the lower index of pair t
+                const uint64_t x = a[i], y = a[i | j];
+                if ((x > y) == ((i & k) == 0)) {
+                    a[i]     = y;
+                    a[i | j] = x;
                 }
             }
             __syncthreads();
         }
+        for (int c = warp; c < n / 32; c += nwarps) {
+            const int i = c * 32 + lane;
+            uint64_t v = a[i];
+            for (int j = 16; j > 0; j >>= 1) v = bitonic_exchange(v, i, k, j);
+            a[i] = v;
+        }
+        __syncthreads();
     }
 }
 __device__ __forceinline__ int next_pow2(int v)
@@ -317,7 +352,11 @@ struct RayCtx {
     __device__ __forceinline__ void touch(uint32_t xr, uint32_t yr, uint32_t beam, uint32_t pos, bool hit, uint32_t run = 1u)
     {
         const uint32_t di   = ((yr >> kPatchLog2) << log2dim) | (xr >> kPatchLog2);
+#ifdef LAMA_PHASE_TIMING
+        const uint32_t info = (rp.debug & 2) ? (0xFF000000u | (di & 1023u)) : pinfo[di];
+#else
         const uint32_t info = pinfo[di];
+#endif
         const uint32_t slot = info & kInfoSlotMask;
         if (slot == kInfoSlotMask) {
             if (mark) atomicOr(&pending[di >> 5], 1u << (di & 31));
@@ -336,6 +375,9 @@ struct RayCtx {
             asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(addr));
             lo |= ci << 2;
             asm("mov.b64 %0, {%1, %2};" : "=l"(addr) : "r"(lo), "r"(hi));
+#ifdef LAMA_PHASE_TIMING
+            if (rp.debug & 1) { if (addr == 1) sh.err = lo; } else
+#endif
             asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(hit ? kOccHitInc : run * kOccMissInc) : "memory");
         }
         const uint32_t ccand = info >> 24;
@@ -412,6 +454,12 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
 // kProb = false: FrequencyOccupancyMap (PFSlam2D / Slam2D); kProb = true: ProbabilisticOccupancyMap -- the walk adds
 // the per-scan {hits, touches} into a scratch map, candidate cells are replayed in order on the float cell, all other
 // touched cells (misses only, never an obstacle) get their k misses applied one by one in a bulk pass.
+#ifdef LAMA_PHASE_TIMING   // developer build: per-phase cycle counts of two CTAs (make EXTRA=-DLAMA_PHASE_TIMING)
+#define RAY_MARK(k) do { if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200)) ph[k] = clock64(); } while (0)
+#else
+#define RAY_MARK(k) do { } while (0)
+#endif
+
 template <bool kProb>
 __global__ void __launch_bounds__(kRayThreads, kProb ? 1 : 2)
 k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
@@ -447,6 +495,10 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     int log2dim = 0;
     while ((1 << (log2dim + 1)) <= win.dim) ++log2dim;
 
+#ifdef LAMA_PHASE_TIMING
+    long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    RAY_MARK(0);
     // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
@@ -569,6 +621,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     }
     __syncthreads();
 
+    RAY_MARK(1);
     // ---- phase 2: optimistic pass -- every patch this particle already owns is written right away;
     // ---- phase 3: allocate / detach the patches that were not writable (Map::get mutable + COW) and redo those ----
     RayCtx<kProb> ctx{s, rp, pinfo, cand, pending, touched, log, sh, log2dim, true, -1};
@@ -613,6 +666,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     __threadfence();  // the reductions above must have been performed before the replay reads the counters back
     __syncthreads();
 
+    RAY_MARK(2);
     // ---- phase 4: sort the log by (cell, beam) -------------------------------------------------------------
     uint32_t count = sh.log_count;
     if (count > (uint32_t)rp.log_cap) {
@@ -624,6 +678,8 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     __syncthreads();
     block_bitonic_sort(log, padded);
 
+    __syncthreads();
+    RAY_MARK(3);
     // ---- phase 5: per-cell ordered replay -> obstacle events ----------------------------------------------
     for (int i = tid; i < (int)count; i += blockDim.x) {
         const uint32_t key = log_key(log[i]);
@@ -696,6 +752,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
         __syncthreads();
     }
 
+    RAY_MARK(4);
     // ---- phase 6: order the events like the reference's call sequence and publish them --------------------
     uint32_t nev = sh.event_count;
     if (nev > (uint32_t)rp.event_cap) {
@@ -710,6 +767,13 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     for (int i = tid; i < (int)nev; i += blockDim.x) out[i] = events[i];
     my_err = __reduce_or_sync(0xffffffffu, my_err);
     if (lane == 0 && my_err) atomicOr(s.status, my_err);
+#ifdef LAMA_PHASE_TIMING
+    __syncthreads();
+    RAY_MARK(5);
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 200))
+        printf("ray cta %d: setup %lld walk %lld sort %lld replay %lld events %lld | log %u events %u\n", blockIdx.x, ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2],
+               ph[4] - ph[3], ph[5] - ph[4], sh.log_count, sh.event_count);
+#endif
     if (tid == 0) {
         MapUpdateStats& st = stats[blockIdx.x];
         st.ray_cells   = sh.cells;

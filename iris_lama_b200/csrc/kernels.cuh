@@ -38,6 +38,7 @@ struct RayParams {
     int particle_offset;
     int log_cap, event_cap;  // powers of two
     int cand_cap;            // candidate bitmaps (patches with hit cells or distance-map obstacles), <= 253
+    int debug;               // developer experiments (LAMA_RAY_DEBUG, only honoured by LAMA_PHASE_TIMING builds): 1 no RED, 2 no LDS
     int prob_mode;           // 1: log-odds occupancy (ProbabilisticOccupancyMap), counts go to the scratch map first
     ProbParams prob;
 };
