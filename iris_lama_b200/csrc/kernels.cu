@@ -19,7 +19,7 @@ namespace lama_b200 {
 
 namespace {
 
-constexpr int kMatchThreads = 512;
+constexpr int kMatchThreads = 576;  // upper bound; the launch picks the block size that splits the beams into equal rounds
 constexpr int kRayThreads   = 512;  // 2 CTAs/SM at 64 registers (no spills in the walk loop); the kernel is bound by integer issue rate
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -1078,7 +1078,11 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
 void launch_match(const StoreView& s, const MatchParams& mp, const SE2* d_states, MatchResult* d_results, int count, cudaStream_t st)
 {
     if (count <= 0) return;
-    k_match<<<count, kMatchThreads, match_smem_bytes(s.window.dim, mp.max_sqdist), st>>>(s, mp, d_states, d_results);
+    // every thread evaluates ceil(n / threads) beams: choose the block so that the last round is (almost) full
+    const int n = mp.scan.n_beams, rounds = (n + kMatchThreads - 1) / kMatchThreads;
+    int threads = (((n + rounds - 1) / rounds) + 31) & ~31;
+    threads = threads < 128 ? 128 : threads;
+    k_match<<<count, threads, match_smem_bytes(s.window.dim, mp.max_sqdist), st>>>(s, mp, d_states, d_results);
 }
 void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count,
                     cudaStream_t st)
