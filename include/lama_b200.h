@@ -108,6 +108,13 @@ int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6]);
 int lama_pf_kernel_times(lama_pf* h, double ms[4], uint64_t launches[5]);
 /* Map::bounds of a particle's map (kind 0 occupancy, 1 distance): min/max cell, *patches = numOfPatches */
 int lama_pf_map_bounds(lama_pf* h, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);
+/* Map::write (src/sdm/map.cpp:490-529) of getOccupancyMap(particle) (kind 0) / getDistanceMap(particle) (kind 1): the reference's
+ * ".sdm" file -- IOHeader (map.h:95-103), DynamicDistanceMap's max_sqdist_ (dynamic_distance_map.cpp:200-203), then per patch
+ * its id, its 1024 cells in the reference cell layout and the 128-byte known mask (container.cpp:143-163). */
+int lama_pf_write_map(lama_pf* h, int particle, int kind, const char* path);
+/* the grey image sdm::export_to_png encodes (src/sdm/export.cpp:46-96; PFSlam2D::saveOccImage / saveDistImage use it):
+ * dims = {width, height} = the map's bounds in cells, pixel (u, v) at pixels[u + v * width]; pixels == NULL only sizes. */
+int lama_pf_export_image(lama_pf* h, int particle, int kind, uint8_t* pixels, size_t cap, int dims[2]);
 /* dense window of FrequencyOccupancyMap cells {occupied, visited} + Container "known" bit; arrays may be NULL */
 int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited,
                              uint8_t* known);
@@ -163,6 +170,8 @@ int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5]);
 int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);
 int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known);
 /* occupancy == 1 only: dense window of ProbabilisticOccupancyMap cells (float log-odds, prob_tag) + Container known bit */
+int lama_slam_write_map(lama_slam* h, int kind, const char* path);                                     /* as lama_pf_write_map */
+int lama_slam_export_image(lama_slam* h, int kind, uint8_t* pixels, size_t cap, int dims[2]);           /* as lama_pf_export_image */
 int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known);
 int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
                               int16_t* ox, int16_t* oy, uint8_t* queued);
@@ -197,6 +206,7 @@ int lama_loc_get_rmse(lama_loc* h, double* rmse);                            /* 
 int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2]);                /* {iterations, residual evaluations} */
 /* public `occupancy_map` (SimpleOccupancyMap, loc2d.h:103): setFree (state -1) / setUnknown (0) / setOccupied (1) on n cells */
 int lama_loc_occupancy_set(lama_loc* h, const uint32_t* cells_xy, int n, int state);
+int lama_loc_occupancy_read(lama_loc* h, const char* path);                   /* occupancy_map->read(file): SimpleOccupancyMap, Map::read map.cpp:531-575 */
 int lama_loc_set_seed(lama_loc* h, uint32_t seed);                            /* random::setSeed for the sampling below */
 int lama_loc_trigger_global_localization(lama_loc* h);                        /* Loc2D::triggerGlobalLocalization, loc2d.cpp:194-197 */
 int lama_loc_global_localization_active(lama_loc* h, int* active);
@@ -216,6 +226,9 @@ int lama_dm_update(lama_dm* dm, uint32_t* processed);
 /* DistanceMap::distance(Vector3d, Vector3d* grad) for n points; grad (n x 3) may be NULL */
 int lama_dm_distance(lama_dm* dm, const double* pts_xyz, int n, double* dist, double* grad);
 int lama_dm_bounds(lama_dm* dm, uint32_t mn[2], uint32_t mx[2], int* patches);
+int lama_dm_write(lama_dm* dm, const char* path);   /* Map::write, map.cpp:490-529 */
+int lama_dm_read(lama_dm* dm, const char* path);    /* Map::read, map.cpp:531-575, into an empty map of the same resolution and l2_max */
+int lama_dm_export_image(lama_dm* dm, uint8_t* pixels, size_t cap, int dims[2]);   /* sdm::export_to_png(DistanceMap), export.cpp:75-96 */
 int lama_dm_export(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
                    int16_t* oy, uint8_t* queued);
 /* upload distance_t fields for a patch-aligned window (x0, y0, w, hgt multiples of 32); cells with known == 0 are left absent */

@@ -70,6 +70,8 @@ EXPORTED_SYMBOLS = [
     "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
+    "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
+    "lama_dm_export_image", "lama_loc_occupancy_read",
     "lama_loc_occupancy_set", "lama_loc_set_seed", "lama_loc_trigger_global_localization", "lama_loc_global_localization_active",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
     "lama_dm_distance", "lama_dm_bounds", "lama_dm_export", "lama_dm_import", "lama_dm_match_normal_equations", "lama_dm_match_solve",
@@ -136,6 +138,32 @@ def _counters(fn, h):
     tot = np.zeros(6, np.uint64)
     _chk(fn(h, _vp(last), _vp(tot)))
     return dict(zip(_COUNTER_KEYS, last.tolist())), dict(zip(_COUNTER_KEYS, tot.tolist()))
+
+
+def _image(fn, args):
+    """(height, width) uint8 array of an export_image entry point; pixel (u, v) of the reference image is out[v, u]"""
+    dims = (C.c_int * 2)()
+    _chk(fn(*args, None, C.c_size_t(0), dims))
+    out = np.zeros((dims[1], dims[0]), np.uint8)
+    if out.size:
+        _chk(fn(*args, _vp(out), C.c_size_t(out.size), dims))
+    return out
+
+
+def write_png(path, grey):
+    """8-bit greyscale PNG of a (height, width) uint8 array (the reference hands the same pixels to stb: image_io.cpp:60-68)"""
+    import struct
+    import zlib
+    grey = np.ascontiguousarray(grey, np.uint8)
+    h, w = grey.shape
+    raw = b"".join(b"\x00" + grey[r].tobytes() for r in range(h))
+
+    def chunk(tag, data):
+        body = tag + data
+        return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
 def _times(fn, h):
@@ -265,6 +293,17 @@ class PFSlam2D:
         _chk(lib().lama_pf_export_distance(self.h, C.c_int(particle), C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
 
+    def writeMap(self, particle, kind, path):
+        """Map::write of getOccupancyMap(particle) (kind 0) / getDistanceMap(particle) (kind 1): a reference .sdm file"""
+        _chk(lib().lama_pf_write_map(self.h, C.c_int(particle), C.c_int(kind), str(path).encode()))
+
+    def exportImage(self, particle, kind):
+        return _image(lib().lama_pf_export_image, (self.h, C.c_int(particle), C.c_int(kind)))
+
+    def saveOccImage(self, path):
+        """PFSlam2D::saveOccImage (pf_slam2d.cpp:338-342): the best particle's occupancy map as PNG"""
+        write_png(path, self.exportImage(self.getBestParticleIdx(), 0))
+
     # ---- split-phase calls used by iris_lama_b200.distributed ------------------------------------------
     def shardBegin(self, pts, odom, timestamp=0.0, origin=_ID3, quat=_IDQ):
         p, pp = _d(pts)
@@ -385,6 +424,15 @@ class Slam2D:
         _chk(lib().lama_slam_export_distance(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
 
+    def writeMap(self, kind, path):
+        _chk(lib().lama_slam_write_map(self.h, C.c_int(kind), str(path).encode()))
+
+    def exportImage(self, kind):
+        return _image(lib().lama_slam_export_image, (self.h, C.c_int(kind)))
+
+    def saveOccImage(self, path):
+        write_png(path, self.exportImage(0))
+
 
 class DynamicDistanceMap:
     """Device-resident lama::DynamicDistanceMap (include/lama/sdm/dynamic_distance_map.h:55-66)."""
@@ -447,6 +495,17 @@ class DynamicDistanceMap:
         h, w = fields["sqdist"].shape
         f = {k: np.ascontiguousarray(fields[k]) for k in ("sqdist", "valid", "known", "ox", "oy", "queued")}
         _chk(lib().lama_dm_import(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(f)))
+
+    def write(self, path):
+        """Map::write (map.cpp:490-529): a reference .sdm file"""
+        _chk(lib().lama_dm_write(self.h, str(path).encode()))
+
+    def read(self, path):
+        """Map::read (map.cpp:531-575) into this (empty) map"""
+        _chk(lib().lama_dm_read(self.h, str(path).encode()))
+
+    def exportImage(self):
+        return _image(lib().lama_dm_export_image, (self.h,))
 
     def matchNormalEquations(self, pts, states, robust=(1, 0.15), meas_sigma=0.05, origin=_ID3, quat=_IDQ):
         p, pp = _d(pts)
@@ -534,6 +593,10 @@ class Loc2D:
         v = C.c_double(0)
         _chk(lib().lama_loc_get_rmse(self.h, C.byref(v)))
         return v.value
+
+    def occupancyRead(self, path):
+        """occupancy_map->read(path): a SimpleOccupancyMap .sdm file"""
+        _chk(lib().lama_loc_occupancy_read(self.h, str(path).encode()))
 
     def occupancySet(self, cells, state):
         """public occupancy_map (SimpleOccupancyMap): state -1 setFree, 0 setUnknown, 1 setOccupied"""

@@ -8,6 +8,7 @@
 // engine.h declares the status codes as an enum; the C header re-states them as macros, so the C++
 // headers must come first.
 #include "frontend.h"
+#include "sdm_io.h"
 
 #include "../../include/lama_b200.h"
 
@@ -123,6 +124,101 @@ int bounds_dm_union(Engine* e, int particle, uint32_t mn[2], uint32_t mx[2], int
         mx[k] = nd && no ? std::max(a1[k], b1[k]) : (nd ? a1[k] : b1[k]);
     }
     if (patches) *patches = nd;
+    return LAMA_OK;
+}
+
+// ---- .sdm files and export images (sdm_io.h) ---------------------------------------------------------------------
+struct DmPlanes {
+    SdmWindow win;
+    std::vector<uint16_t> sqdist;
+    std::vector<uint8_t> valid, known, queued;
+    std::vector<int16_t> ox, oy;
+};
+struct OccPlanes {
+    SdmWindow win;
+    std::vector<uint16_t> occupied, visited;   // frequency maps
+    std::vector<float> prob;                   // log-odds maps
+    std::vector<uint8_t> known;
+};
+// kind 1 of a SLAM front end: the reference's distance map also holds the cells first touched through the occupancy map (see export_dm)
+int fetch_dm(Engine* e, int particle, bool with_occ, DmPlanes& p)
+{
+    uint32_t mn[2], mx[2];
+    int n = 0;
+    int rc = with_occ ? bounds_dm_union(e, particle, mn, mx, &n) : bounds_out(e, particle, 1, mn, mx, &n);
+    if (rc != LAMA_OK) return rc;
+    if (mx[0] <= mn[0]) { p.win = SdmWindow(); return LAMA_OK; }   // empty map
+    p.win.x0 = mn[0]; p.win.y0 = mn[1]; p.win.w = (int)(mx[0] - mn[0]); p.win.h = (int)(mx[1] - mn[1]);
+    const size_t cells = (size_t)p.win.w * p.win.h;
+    p.sqdist.resize(cells); p.valid.resize(cells); p.known.resize(cells); p.queued.resize(cells); p.ox.resize(cells); p.oy.resize(cells);
+    return export_dm(e, particle, with_occ, p.win.x0, p.win.y0, p.win.w, p.win.h, p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(),
+                     p.queued.data());
+}
+int fetch_occ(Engine* e, int particle, OccPlanes& p)
+{
+    uint32_t mn[2], mx[2];
+    int n = 0;
+    int rc = bounds_out(e, particle, 0, mn, mx, &n);
+    if (rc != LAMA_OK) return rc;
+    if (mx[0] <= mn[0]) { p.win = SdmWindow(); return LAMA_OK; }
+    p.win.x0 = mn[0]; p.win.y0 = mn[1]; p.win.w = (int)(mx[0] - mn[0]); p.win.h = (int)(mx[1] - mn[1]);
+    const size_t cells = (size_t)p.win.w * p.win.h;
+    p.known.resize(cells);
+    if (e->config().occupancy_kind == 1) {
+        p.prob.resize(cells);
+        rc = e->export_window(particle, 0, p.win.x0, p.win.y0, p.win.w, p.win.h, reinterpret_cast<uint32_t*>(p.prob.data()), nullptr);
+        if (rc == LAMA_OK) rc = e->export_bits(particle, 1, p.win.x0, p.win.y0, p.win.w, p.win.h, p.known.data());
+        return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
+    }
+    p.occupied.resize(cells); p.visited.resize(cells);
+    return export_occ(e, particle, p.win.x0, p.win.y0, p.win.w, p.win.h, p.occupied.data(), p.visited.data(), p.known.data());
+}
+// kind 0: occupancy map, kind 1: distance map
+int write_map(Engine* e, int particle, int kind, bool slam_frontend, const char* path)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    if (!path || kind < 0 || kind > 1) return set_err("bad argument", LAMA_ERR_ARG);
+    SdmFile f;
+    const float res = (float)e->config().resolution;   // Map::write stores a float (map.cpp:502)
+    if (kind == 1) {
+        DmPlanes p;
+        int rc = fetch_dm(e, particle, slam_frontend, p);
+        if (rc != LAMA_OK) return rc;
+        sdm_from_distance(p.win, res, e->max_sqdist(), p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(), p.queued.data(), f);
+    } else {
+        OccPlanes p;
+        int rc = fetch_occ(e, particle, p);
+        if (rc != LAMA_OK) return rc;
+        if (e->config().occupancy_kind == 1) sdm_from_logodds(p.win, res, p.prob.data(), p.known.data(), f);
+        else sdm_from_frequency(p.win, res, p.occupied.data(), p.visited.data(), p.known.data(), f);
+    }
+    std::string err;
+    if (!sdm_write(path, f, err)) return set_err(err, LAMA_ERR_ARG);
+    return LAMA_OK;
+}
+// grey image of sdm::export_to_png; pixels == NULL: only the dimensions
+int export_image(Engine* e, int particle, int kind, bool slam_frontend, uint8_t* pixels, size_t cap, int dims[2])
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    if (!dims || kind < 0 || kind > 1) return set_err("bad argument", LAMA_ERR_ARG);
+    if (kind == 1) {
+        DmPlanes p;
+        int rc = fetch_dm(e, particle, slam_frontend, p);
+        if (rc != LAMA_OK) return rc;
+        dims[0] = p.win.w; dims[1] = p.win.h;
+        if (!pixels) return LAMA_OK;
+        if (cap < (size_t)p.win.w * p.win.h) return set_err("image buffer too small", LAMA_ERR_ARG);
+        sdm_distance_image(p.win, p.sqdist.data(), p.valid.data(), p.known.data(), e->max_sqdist(), e->config().resolution, pixels);
+        return LAMA_OK;
+    }
+    OccPlanes p;
+    int rc = fetch_occ(e, particle, p);
+    if (rc != LAMA_OK) return rc;
+    dims[0] = p.win.w; dims[1] = p.win.h;
+    if (!pixels) return LAMA_OK;
+    if (cap < (size_t)p.win.w * p.win.h) return set_err("image buffer too small", LAMA_ERR_ARG);
+    if (e->config().occupancy_kind == 1) sdm_occupancy_image_logodds(p.win, p.prob.data(), p.known.data(), e->logodds_threshold(), pixels);
+    else sdm_occupancy_image_frequency(p.win, p.occupied.data(), p.visited.data(), p.known.data(), pixels);
     return LAMA_OK;
 }
 }  // namespace
@@ -288,6 +384,16 @@ int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0,
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     return export_occ(h->p->engine(), pf_local(h, particle), x0, y0, w, hgt, occupied, visited, known);
 }
+int lama_pf_write_map(lama_pf* h, int particle, int kind, const char* path)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return write_map(h->p->engine(), pf_local(h, particle), kind, true, path);
+}
+int lama_pf_export_image(lama_pf* h, int particle, int kind, uint8_t* pixels, size_t cap, int dims[2])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return export_image(h->p->engine(), pf_local(h, particle), kind, true, pixels, cap, dims);
+}
 int lama_pf_export_distance(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
                             int16_t* ox, int16_t* oy, uint8_t* queued)
 {
@@ -436,6 +542,16 @@ int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, in
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
 }
+int lama_slam_write_map(lama_slam* h, int kind, const char* path)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return write_map(h->s->engine(), 0, kind, true, path);
+}
+int lama_slam_export_image(lama_slam* h, int kind, uint8_t* pixels, size_t cap, int dims[2])
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return export_image(h->s->engine(), 0, kind, true, pixels, cap, dims);
+}
 int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known)
 {
     if (!h || !logodds) return set_err("null argument", LAMA_ERR_ARG);
@@ -514,6 +630,41 @@ int lama_dm_export(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, uint16
 {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     return export_dm(dm->d->engine(), 0, false, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
+}
+int lama_dm_write(lama_dm* dm, const char* path)
+{
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = dm->d->flush_if_pending();
+    if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
+    return write_map(dm->d->engine(), 0, 1, false, path);
+}
+int lama_dm_export_image(lama_dm* dm, uint8_t* pixels, size_t cap, int dims[2])
+{
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = dm->d->flush_if_pending();
+    if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
+    return export_image(dm->d->engine(), 0, 1, false, pixels, cap, dims);
+}
+// Map::read into an EMPTY device distance map (map.cpp:531-575).  The file must have been written at this map's
+// resolution and maximum distance (the reference adopts the file's values; the device map's are fixed at creation).
+int lama_dm_read(lama_dm* dm, const char* path)
+{
+    if (!dm || !path) return set_err("null argument", LAMA_ERR_ARG);
+    Engine* e = dm->d->engine();
+    SdmFile f;
+    std::string err;
+    if (!sdm_read(path, sizeof(SdmDistanceCell), 4, f, err)) return set_err(err, LAMA_ERR_ARG);
+    uint32_t max_sqdist = 0;
+    std::memcpy(&max_sqdist, f.params.data(), 4);
+    if (max_sqdist != e->max_sqdist()) return set_err("the file's max_sqdist differs from this map's l2_max", LAMA_ERR_ARG);
+    if (f.header.resolution != (float)e->config().resolution) return set_err("the file's resolution differs from this map's", LAMA_ERR_ARG);
+    SdmWindow win;
+    if (!sdm_window_of(f, win)) return LAMA_OK;
+    DmPlanes p;
+    const size_t cells = (size_t)win.w * win.h;
+    p.sqdist.resize(cells); p.valid.resize(cells); p.known.resize(cells); p.queued.resize(cells); p.ox.resize(cells); p.oy.resize(cells);
+    sdm_to_distance(f, win, p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(), p.queued.data());
+    return lama_dm_import(dm, win.x0, win.y0, win.w, win.h, p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(), p.queued.data());
 }
 int lama_dm_import(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, const uint16_t* sqdist, const uint8_t* valid, const uint8_t* known,
                    const int16_t* ox, const int16_t* oy, const uint8_t* queued)
@@ -652,6 +803,22 @@ int lama_loc_occupancy_set(lama_loc* h, const uint32_t* cells, int n, int state)
 {
     if (!h || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
     for (int i = 0; i < n; ++i) h->l->occupancy_map()->set(cells[2 * i], cells[2 * i + 1], state);
+    return LAMA_OK;
+}
+// SimpleOccupancyMap::read (Map::read, map.cpp:531-575; int8 cells: -1 free, 0 unknown, 1 occupied)
+int lama_loc_occupancy_read(lama_loc* h, const char* path)
+{
+    if (!h || !path) return set_err("null argument", LAMA_ERR_ARG);
+    SdmFile f;
+    std::string err;
+    if (!sdm_read(path, 1, 0, f, err)) return set_err(err, LAMA_ERR_ARG);
+    for (size_t i = 0; i < f.ids.size(); ++i) {
+        const uint32_t ax = (uint32_t)(f.ids[i] / 2642244ull) << kPatchLog2, ay = (uint32_t)(f.ids[i] % 2642244ull) << kPatchLog2;
+        const int8_t* c = reinterpret_cast<const int8_t*>(f.cells.data() + i * (size_t)kPatchCells);
+        const uint64_t* mask = f.masks.data() + i * (kPatchCells / 64);
+        for (uint32_t ci = 0; ci < (uint32_t)kPatchCells; ++ci)
+            if ((mask[ci >> 6] >> (ci & 63)) & 1ull) h->l->occupancy_map()->set(ax + (ci & (kPatchLen - 1)), ay + (ci >> kPatchLog2), c[ci]);
+    }
     return LAMA_OK;
 }
 int lama_loc_set_seed(lama_loc* h, uint32_t seed)

@@ -701,6 +701,8 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
     return check_device_status();
 }
 
+double Engine::logodds_threshold() const { return d_->ray.prob.thresh; }
+
 int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
 {
     if (settle(nullptr) != LAMA_OK) return -1;

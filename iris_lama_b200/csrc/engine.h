@@ -47,6 +47,7 @@ public:
 
     const EngineConfig& config() const { return cfg_; }
     uint32_t max_sqdist() const { return max_sqdist_; }
+    double logodds_threshold() const;   // ProbabilisticOccupancyMap::occ_thresh_ (probabilistic_occupancy_map.cpp:59)
     const std::string& last_error() const { return err_; }
 
     // Uploads one scan (N x 3 doubles, sensor origin, sensor orientation quaternion xyzw).

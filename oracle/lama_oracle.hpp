@@ -24,6 +24,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <limits>
 #include <memory>
@@ -311,6 +312,89 @@ public:
         return Vec3u{(uint32_t)((idx / kUniversalConstant) << log2dim), (uint32_t)((idx % kUniversalConstant) << log2dim), 0};
     }
 
+    // ---- persistence (src/sdm/map.cpp:490-575, header include/lama/sdm/map.h:72-75,95-103, patch payload container.cpp:143-176) ----
+    struct IOHeader {  // map.h:95-103, natural alignment: 32 bytes
+        uint32_t magic;
+        uint16_t version;
+        uint32_t cell_size;
+        uint32_t patch_length;
+        size_t num_patches;
+        float resolution;
+        bool is_3d;
+    };
+    static constexpr uint32_t kMagic = 0x6d64732e;   // map.h:72
+    static constexpr uint16_t kIoVersion = 0x0103;   // map.h:75
+    // `params` = what the concrete map's writeParameters emits (DynamicDistanceMap: max_sqdist_, dynamic_distance_map.cpp:200-203)
+    bool write(const std::string& filename, const void* params, size_t nparams) const
+    {
+        std::ofstream f(filename.c_str(), std::ios::out | std::ios::binary | std::ios::trunc);
+        if (!f.is_open()) return false;
+        IOHeader header;
+        std::memset(&header, 0, sizeof(header));
+        header.magic = kMagic; header.version = kIoVersion; header.cell_size = (uint32_t)sizeof(Cell); header.patch_length = patch_length;
+        header.num_patches = patches.size(); header.resolution = (float)resolution; header.is_3d = false;
+        f.write((const char*)&header, sizeof(IOHeader));
+        if (!f) return false;
+        if (nparams) f.write((const char*)params, (std::streamsize)nparams);
+        for (auto it = patches.begin(); it != patches.end(); ++it) {
+            f.write((const char*)&it->first, sizeof(uint64_t));
+            f.write((const char*)it->second->cells.data(), (std::streamsize)(sizeof(Cell) * patch_volume));   // container.cpp:160
+            f.write((const char*)it->second->mask.data(), (std::streamsize)(sizeof(uint64_t) * it->second->mask.size()));
+        }
+        f.close();
+        return true;
+    }
+    bool read(const std::string& filename, void* params, size_t nparams)
+    {
+        std::ifstream f(filename.c_str(), std::ios::in | std::ios::binary);
+        if (!f.is_open()) return false;
+        IOHeader header;
+        f.read((char*)&header, sizeof(IOHeader));
+        if (!f) return false;
+        if (header.magic != kMagic || header.version != kIoVersion) return false;
+        if (header.cell_size != sizeof(Cell) || header.is_3d) return false;
+        resolution   = header.resolution;   // the file holds a float (map.cpp:548)
+        scale        = 1.0 / resolution;
+        patch_length = header.patch_length;
+        patch_volume = patch_length * patch_length;
+        log2dim      = (uint32_t)std::log2(patch_length);
+        offset       = (double)((kUniversalConstant >> 1) * patch_length);
+        if (nparams) f.read((char*)params, (std::streamsize)nparams);
+        prev_idx_ = ~0ull; prev_patch_ = nullptr;
+        for (size_t i = 0; i < header.num_patches; ++i) {
+            uint64_t idx;
+            f.read((char*)&idx, sizeof(idx));
+            if (!f) return false;
+            auto it = patches.insert(std::make_pair(idx, std::make_shared<PatchT>(patch_volume))).first;
+            f.read((char*)it->second->cells.data(), (std::streamsize)(sizeof(Cell) * patch_volume));
+            f.read((char*)it->second->mask.data(), (std::streamsize)(sizeof(uint64_t) * it->second->mask.size()));
+        }
+        return true;
+    }
+    // Map::bounds in cells (map.cpp:139-157): patch granular; false when the map is empty
+    bool bounds(Vec3u& mn, Vec3u& mx) const
+    {
+        if (patches.empty()) return false;
+        mn = Vec3u{0xffffffffu, 0xffffffffu, 0}; mx = Vec3u{0, 0, 0};
+        for (auto& kv : patches) {
+            Vec3u a = p2m(kv.first);
+            mn.x = std::min(mn.x, a.x); mn.y = std::min(mn.y, a.y);
+            mx.x = std::max(mx.x, a.x); mx.y = std::max(mx.y, a.y);
+        }
+        mx.x += patch_length; mx.y += patch_length;
+        return true;
+    }
+    // Map::visit_all_cells (map.cpp:352-359): every cell whose mask bit is on
+    template <typename F>
+    void visit_all_cells(F&& walker) const
+    {
+        for (auto& kv : patches) {
+            Vec3u a = p2m(kv.first);
+            for (uint32_t ci = 0; ci < patch_volume; ++ci)
+                if (kv.second->is_on(ci)) walker(Vec3u{a.x + (ci & (patch_length - 1)), a.y + (ci >> log2dim), 0});
+        }
+    }
+
     // Mutable access (map.cpp:371-412): allocate-on-touch, detach shared patch, set the known bit.  The
     // one-entry patch cache mirrors prev_idx_ / prev_patch_ (map.cpp:400-409): it only saves hash lookups.
     Cell* get(const Vec3u& c)
@@ -413,6 +497,16 @@ public:
         if (occupied) return false;
         return prob(*cell) > occ_thresh;
     }
+    bool is_free(const Vec3u& c) const      // :115-121
+    {
+        const FreqCell* cell = static_cast<const SparseMap<FreqCell>*>(this)->get(c);
+        return cell != nullptr && prob(*cell) < occ_thresh;
+    }
+    bool is_occupied(const Vec3u& c) const  // :128-134
+    {
+        const FreqCell* cell = static_cast<const SparseMap<FreqCell>*>(this)->get(c);
+        return cell != nullptr && prob(*cell) > occ_thresh;
+    }
     uint64_t ray_cells = 0;  // work counter C (cells visited by ray casts incl. hit cells)
 };
 
@@ -447,6 +541,16 @@ public:
         cell->prob     = std::min(cell->prob + hit_, clamp_max_);
         if (occupied) return false;
         return cell->prob > occ_thresh_;
+    }
+    bool is_free(const Vec3u& c) const      // :130-136
+    {
+        const ProbCell* cell = static_cast<const SparseMap<ProbCell>*>(this)->get(c);
+        return cell != nullptr && cell->prob < occ_thresh_;
+    }
+    bool is_occupied(const Vec3u& c) const  // :143-149
+    {
+        const ProbCell* cell = static_cast<const SparseMap<ProbCell>*>(this)->get(c);
+        return cell != nullptr && cell->prob > occ_thresh_;
     }
     uint64_t ray_cells = 0;
 };
@@ -685,6 +789,41 @@ private:
         current.is_queued = false;
     }
 };
+
+// ----------------------------------------------------------------------------------------------
+// Image content of sdm::export_to_png (src/sdm/export.cpp:46-96).  The PNG encoding itself is a library call
+// (stb) in the reference; what is restated here is the grey image it is given: width = bounds x extent,
+// height = bounds y extent, pixel (u, v) at data[u + v * width] (include/lama/image.h:79-80).
+// ----------------------------------------------------------------------------------------------
+template <class Occ>
+inline std::vector<uint8_t> occupancy_image(const Occ& occ, uint32_t& w, uint32_t& h)
+{
+    Vec3u mn, mx;
+    w = h = 0;
+    if (!occ.bounds(mn, mx)) return {};
+    w = mx.x - mn.x; h = mx.y - mn.y;
+    std::vector<uint8_t> img((size_t)w * h, 90);                       // export.cpp:55
+    occ.visit_all_cells([&](const Vec3u& c) {
+        uint8_t& px = img[(size_t)(c.x - mn.x) + (size_t)(c.y - mn.y) * w];
+        if (occ.is_free(c)) px = 255;                                   // :64-69
+        else if (occ.is_occupied(c)) px = 0;
+        else px = 127;
+    });
+    return img;
+}
+template <class Dm>
+inline std::vector<uint8_t> distance_image(const Dm& dm, uint32_t& w, uint32_t& h)
+{
+    Vec3u mn, mx;
+    w = h = 0;
+    if (!dm.bounds(mn, mx)) return {};
+    w = mx.x - mn.x; h = mx.y - mn.y;
+    std::vector<uint8_t> img((size_t)w * h, 127);                      // export.cpp:83
+    dm.visit_all_cells([&](const Vec3u& c) {
+        img[(size_t)(c.x - mn.x) + (size_t)(c.y - mn.y) * w] = (uint8_t)(dm.distance(c) * 255 / dm.max_distance());   // :91
+    });
+    return img;
+}
 
 // ----------------------------------------------------------------------------------------------
 // Scan-to-map residual problem (src/match_surface_2d.cpp:42-122)

@@ -415,4 +415,27 @@ void orc_loc_get(void* h, double* state, double* cov, double* rmse, uint32_t* st
     if (stats) { stats[0] = l->last_stats.iterations; stats[1] = l->last_stats.evals; }
 }
 
+
+// ---- SDM persistence and image export (Map::write/read, sdm::export_to_png content) on map handles -------------------
+void* orc_pf_occ_handle(void* h, int particle) { auto* pf = (PFSlam2D*)h; return pf->particles[pf->cur][particle].occ.get(); }
+void* orc_slam_occ_handle(void* h) { return &((Slam2D*)h)->occ; }
+void* orc_slamp_occ_handle(void* h) { return &((Slam2DProb*)h)->occ; }
+void* orc_slamp_dm_handle(void* h) { return &((Slam2DProb*)h)->dm; }
+void* orc_loc_occ_handle(void* h) { return &((Loc2D*)h)->occ; }
+int orc_ddm_write(void* d, const char* path) { auto* m = (DynamicDistanceMap*)d; return m->write(path, &m->max_sqdist_, sizeof(m->max_sqdist_)) ? 1 : 0; }
+int orc_ddm_read(void* d, const char* path) { auto* m = (DynamicDistanceMap*)d; return m->read(path, &m->max_sqdist_, sizeof(m->max_sqdist_)) ? 1 : 0; }
+int orc_freq_write(void* d, const char* path) { return ((FrequencyOccupancyMap*)d)->write(path, nullptr, 0) ? 1 : 0; }
+int orc_prob_write(void* d, const char* path) { return ((ProbabilisticOccupancyMap*)d)->write(path, nullptr, 0) ? 1 : 0; }
+int orc_simple_write(void* d, const char* path) { return ((SimpleOccupancyMap*)d)->write(path, nullptr, 0) ? 1 : 0; }
+int orc_simple_read(void* d, const char* path) { return ((SimpleOccupancyMap*)d)->read(path, nullptr, 0) ? 1 : 0; }
+static int image_out(const std::vector<uint8_t>& img, uint32_t w, uint32_t h, uint8_t* out, size_t cap, int* dims)
+{
+    dims[0] = (int)w; dims[1] = (int)h;
+    if (out && cap >= img.size()) std::memcpy(out, img.data(), img.size());
+    return 1;
+}
+int orc_ddm_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = distance_image(*(DynamicDistanceMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
+int orc_freq_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = occupancy_image(*(FrequencyOccupancyMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
+int orc_prob_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = occupancy_image(*(ProbabilisticOccupancyMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
+
 }  // extern "C"

@@ -548,3 +548,42 @@ class Loc2D:
         stats = np.zeros(2, np.uint32)
         lib().orc_loc_get(self.h, s.ctypes.data_as(c_dp), cov.ctypes.data_as(c_dp), C.byref(rmse), stats.ctypes.data_as(c_u32p))
         return s, cov, rmse.value, stats
+
+
+# ---- SDM persistence and image export on map handles (oracle_capi.cpp) ------------------------------------------------
+def _hv(h):
+    h = getattr(h, "h", h)
+    return h if isinstance(h, C.c_void_p) else C.c_void_p(h)
+
+
+def map_handle(name, obj, *args):
+    """name: pf_occ | pf_dm | slam_occ | slam_dm | slamp_occ | slamp_dm | loc_occ | loc_dm -> raw map pointer"""
+    fn = getattr(lib(), "orc_%s_handle" % name)
+    fn.restype = C.c_void_p
+    return C.c_void_p(fn(_hv(obj), *[C.c_int(a) for a in args]))
+
+
+def map_write(kind, handle, path):
+    """kind: 'ddm' | 'freq' | 'prob' | 'simple' -- Map::write (map.cpp:490-529) of the map behind `handle`"""
+    fn = getattr(lib(), "orc_%s_write" % kind)
+    fn.restype = C.c_int
+    return fn(_hv(handle), str(path).encode()) == 1
+
+
+def map_read(kind, handle, path):
+    """kind: 'ddm' | 'simple' -- Map::read (map.cpp:531-575)"""
+    fn = getattr(lib(), "orc_%s_read" % kind)
+    fn.restype = C.c_int
+    return fn(_hv(handle), str(path).encode()) == 1
+
+
+def map_image(kind, handle):
+    """kind: 'ddm' | 'freq' | 'prob' -- the grey image of sdm::export_to_png (export.cpp:46-96) as a (height, width) array"""
+    fn = getattr(lib(), "orc_%s_image" % kind)
+    fn.restype = C.c_int
+    dims = (C.c_int * 2)()
+    fn(_hv(handle), None, C.c_size_t(0), dims)
+    out = np.zeros((dims[1], dims[0]), np.uint8)
+    if out.size:
+        fn(_hv(handle), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size), dims)
+    return out
