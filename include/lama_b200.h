@@ -154,6 +154,11 @@ typedef struct lama_slam_options { /* Slam2D::Options, slam2d.h:91-125 */
     int32_t strategy; /* 0 "gn", 1 "lm" (slam2d.cpp:226-233) */
     int32_t occupancy; /* 0 = FrequencyOccupancyMap as in Slam2D (slam2d.cpp:97); 1 = ProbabilisticOccupancyMap, the log-odds map of
                           src/sdm/probabilistic_occupancy_map.cpp (what LidarOdometry2D pairs with the same update loop) */
+    int32_t transient_map;  /* Slam2D::Options::transient_map (slam2d.h:122): after every map update drop the patches that do not
+                               meet the (doubled, pose-centred, 2 * maxDistance grown) AABB of the scan, slam2d.cpp:323-379 */
+    int32_t lidar_odometry; /* run the handle as lama::LidarOdometry2D (src/lidar_odometry_2d.cpp:42-181): odom_xyr is ignored (may be
+                               NULL), log-odds map, l2_max 1.0, rays keep their last metre, map updated after 0.1 m / 0.5 rad of
+                               estimated motion, transient map always on; lama_slam_get_pose returns LidarOdometry2D::odom */
     lama_device_options dev;
 } lama_slam_options;
 int lama_slam_options_default(lama_slam_options* o);
@@ -165,6 +170,7 @@ int lama_slam_update(lama_slam* h, const double* pts_xyz, int n, const double se
 int lama_slam_get_pose(lama_slam* h, double xyr[3]);
 int lama_slam_get_state(lama_slam* h, double state[4]);
 int lama_slam_get_processed_cells(lama_slam* h, uint32_t* n);               /* getNumberOfProcessedCells, slam2d.h:139 */
+int lama_slam_get_map_stats(lama_slam* h, uint64_t stats[2]);                /* {map updates so far, patches deleted by the transient map} */
 int lama_slam_get_counters(lama_slam* h, uint64_t last[6], uint64_t total[6]);
 int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5]);
 int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches);

@@ -46,7 +46,8 @@ class PFOptions(C.Structure):
 class SlamOptions(C.Structure):
     _fields_ = [("trans_thresh", C.c_double), ("rot_thresh", C.c_double), ("l2_max", C.c_double), ("truncated_ray", C.c_double),
                 ("truncated_range", C.c_double), ("resolution", C.c_double), ("patch_size", C.c_uint32), ("max_iter", C.c_uint32),
-                ("strategy", C.c_int32), ("occupancy", C.c_int32), ("dev", DeviceOptions)]
+                ("strategy", C.c_int32), ("occupancy", C.c_int32), ("transient_map", C.c_int32), ("lidar_odometry", C.c_int32),
+                ("dev", DeviceOptions)]
 
 
 class LocOptions(C.Structure):
@@ -70,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
-    "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
+    "lama_slam_get_map_stats", "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
     "lama_dm_export_image", "lama_loc_occupancy_read",
     "lama_loc_occupancy_set", "lama_loc_set_seed", "lama_loc_trigger_global_localization", "lama_loc_global_localization_active",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
@@ -375,14 +376,20 @@ class Slam2D:
         a, ap = _d([x, y, r])
         _chk(lib().lama_slam_set_pose(self.h, ap))
 
-    def update(self, pts, odom, timestamp=0.0, origin=_ID3, quat=_IDQ) -> bool:
+    def update(self, pts, odom=None, timestamp=0.0, origin=_ID3, quat=_IDQ) -> bool:
         p, pp = _d(pts)
         o, op = _d(origin)
         q, qp = _d(quat)
-        od, odp = _d(odom)
+        od, odp = _d(odom) if odom is not None else (None, None)   # LidarOdometry2D mode takes no odometry
         did = C.c_int(0)
         _chk(lib().lama_slam_update(self.h, pp, C.c_int(p.size // 3), op, qp, odp, C.c_double(timestamp), C.byref(did)))
         return bool(did.value)
+
+    def mapStats(self):
+        """(map updates so far, patches deleted by the transient map)"""
+        s = np.zeros(2, np.uint64)
+        _chk(lib().lama_slam_get_map_stats(self.h, _vp(s)))
+        return int(s[0]), int(s[1])
 
     def getPose(self):
         out = np.zeros(3)
@@ -432,6 +439,16 @@ class Slam2D:
 
     def saveOccImage(self, path):
         write_png(path, self.exportImage(0))
+
+
+class LidarOdometry2D(Slam2D):
+    """lama::LidarOdometry2D (include/lama/lidar_odometry_2d.h:45-75): scan-to-map odometry over a transient log-odds map."""
+
+    def __init__(self, resolution=0.05, max_iter=100, **dev):
+        super().__init__(Slam2D.Options(lidar_odometry=1, resolution=resolution, max_iter=max_iter, **dev))
+
+    def update(self, pts, timestamp=0.0, origin=_ID3, quat=_IDQ) -> bool:
+        return super().update(pts, None, timestamp, origin, quat)
 
 
 class DynamicDistanceMap:

@@ -471,6 +471,7 @@ int lama_slam_create(const lama_slam_options* o, lama_slam** out)
     if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
     SlamOptions s;
     s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
+    s.transient_map = o->transient_map != 0; s.lidar_odometry = o->lidar_odometry != 0;
     s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
     s.strategy = o->strategy; s.occupancy = o->occupancy; s.dev = dev_from(o->dev);
     std::string err;
@@ -492,9 +493,16 @@ int lama_slam_set_pose(lama_slam* h, const double xyr[3])
     h->s->set_pose(xyr[0], xyr[1], xyr[2]);
     return LAMA_OK;
 }
+int lama_slam_get_map_stats(lama_slam* h, uint64_t stats[2])
+{
+    if (!h || !stats) return set_err("null argument", LAMA_ERR_ARG);
+    stats[0] = h->s->map_updates();
+    stats[1] = h->s->removed_patches();
+    return LAMA_OK;
+}
 int lama_slam_update(lama_slam* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
 {
-    if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
+    if (!h || !pts) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->s->update(pts, n, origin, quat, odom, stamp, &did);
     if (did_update) *did_update = did ? 1 : 0;

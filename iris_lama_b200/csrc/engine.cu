@@ -168,9 +168,10 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     d->brush.max_sqdist = e->max_sqdist_;
     CU_NEW(dalloc((void**)&d->d_events, (size_t)cfg.particles * d->ray.event_cap * 8));
     CU_NEW(dalloc((void**)&d->d_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
-    CU_NEW(dalloc((void**)&d->d_idx, (size_t)cfg.particles * 4));
+    const size_t idx_ints = std::max((size_t)cfg.particles, (size_t)cfg.dir_dim * cfg.dir_dim);   // resample indices / directory entries to delete
+    CU_NEW(dalloc((void**)&d->d_idx, idx_ints * 4));
     CU_NEW(cudaMallocHost((void**)&d->h_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
-    CU_NEW(cudaMallocHost((void**)&d->h_idx, (size_t)cfg.particles * 4));
+    CU_NEW(cudaMallocHost((void**)&d->h_idx, idx_ints * 4));
     CU_NEW(cudaMallocHost((void**)&d->h_status, 64));
 
     const size_t need_ray = raycast_smem_bytes(cfg.dir_dim, d->ray), need_match = match_smem_bytes(cfg.dir_dim, e->max_sqdist_),
@@ -222,6 +223,7 @@ void Engine::set_moving(const double origin[3], const double quat[4], double tru
     sp.scale           = 1.0 / cfg_.resolution;
     sp.truncated_ray   = truncated_ray;
     sp.truncated_range = truncated_range;
+    sp.lo_ray          = lo_ray_ ? 1 : 0;
     // Translation3d(sensor_origin) * Quaterniond  (match_surface_2d.cpp:49; Eigen quaternion -> matrix)
     const double x = quat ? quat[0] : 0, y = quat ? quat[1] : 0, z = quat ? quat[2] : 0, w = quat ? quat[3] : 1;
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
@@ -702,6 +704,45 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
 }
 
 double Engine::logodds_threshold() const { return d_->ray.prob.thresh; }
+const ScanParams& Engine::scan_params() const { return d_->scan; }
+
+int Engine::prune_outside(int particle, const double center[2], const double hwidth[2], int* removed)
+{
+    { int rc = settle(nullptr); if (rc != LAMA_OK) return rc; }
+    if (particle < 0 || particle >= cfg_.particles) return fail("prune_outside: no such particle", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim;
+    std::vector<int32_t> dirs(2 * dim2);   // kinds 0 (occupancy) and 1 (distance) are adjacent
+    const int32_t* src = d_->view.dirs + (((size_t)cur_set_ * cfg_.particles + particle) * d_->view.n_kinds) * dim2;
+    CU_TRY(cudaMemcpyAsync(dirs.data(), src, 2 * dim2 * 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    const double scale = 1.0 / cfg_.resolution, off = (double)kMapOffsetCells;
+    std::vector<int32_t> list;
+    for (int py = 0; py < cfg_.dir_dim; ++py)
+        for (int px = 0; px < cfg_.dir_dim; ++px) {
+            const size_t di = (size_t)py * cfg_.dir_dim + px;
+            // the reference walks the DISTANCE map's patches, which include every patch of the occupancy map (see capi.cpp: export_dm)
+            if (dirs[di] < 0 && dirs[dim2 + di] < 0) continue;
+            const uint32_t c0[2] = {(uint32_t)(window_.base_px + px) << kPatchLog2, (uint32_t)(window_.base_py + py) << kPatchLog2};
+            bool meets = true;
+            for (int k = 0; k < 2; ++k) {
+                const double ws = ((double)c0[k] - off) / scale, we = ((double)(c0[k] + kPatchLen) - off) / scale;   // Map::m2w, map.h:147
+                const double bh = (we - ws) * 0.5, bc = ws + bh;                                                        // AABB(min, max), aabb.h:50-55
+                meets = meets && (std::abs(center[k] - bc) <= (hwidth[k] + bh));
+            }
+            if (!meets) list.push_back((int32_t)di);
+        }
+    if (removed) *removed = (int)list.size();
+    if (list.empty()) return LAMA_OK;
+    std::memcpy(d_->h_idx, list.data(), list.size() * 4);
+    CU_TRY(cudaMemcpyAsync(d_->d_idx, d_->h_idx, list.size() * 4, cudaMemcpyHostToDevice, d_->stream));
+    launch_delete_patches(d_->view, cur_set_, particle, d_->d_idx, (int)list.size(), d_->stream);
+    launch_merge_free(d_->view, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 2;
+    return LAMA_OK;
+}
 
 int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
 {

@@ -8,6 +8,7 @@
 
 #include "lama_core.h"
 #include "match_core.h"
+#include "ray_core.h"
 
 namespace lama_b200 {
 
@@ -52,6 +53,11 @@ public:
 
     // Uploads one scan (N x 3 doubles, sensor origin, sensor orientation quaternion xyzw).
     int set_scan(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range);
+    void set_lidar_odometry_rays(bool on) { lo_ray_ = on; }   // ScanParams::lo_ray for the scans set from now on
+    const ScanParams& scan_params() const;
+    // Transient map (slam2d.cpp:323-379, lidar_odometry_2d.cpp:130-181): Map::deletePatchAt on the occupancy and the distance map for
+    // every patch whose AABB does not meet the AABB (center, half width) -- AABB::testIntersection, include/lama/aabb.h:65-72
+    int prune_outside(int particle, const double center[2], const double hwidth[2], int* removed);
 
     // Copies n_scans scans of n beams each into device memory once; select_staged() then makes scan `index`
     // current without any host->device transfer (inputs resident in HBM).
@@ -121,6 +127,7 @@ private:
     EngineConfig cfg_;
     DirWindow window_{};
     uint32_t max_sqdist_ = 0;
+    bool lo_ray_ = false;
     int cur_set_         = 0;
     bool timing_         = false;
     KernelTimes times_;

@@ -414,7 +414,7 @@ Slam2D* Slam2D::create(const SlamOptions& o, std::string& err)
     return s;
 }
 
-int Slam2D::update_maps()
+int Slam2D::update_maps(const double* pts, int n)
 {
     HostMapStats st{};
     int rc = eng_->update_maps(&pose_, 0, 1, &st);
@@ -422,6 +422,60 @@ int Slam2D::update_maps()
     processed_ = st.dm_pops;  // number_of_proccessed_cells_, slam2d.cpp:321
     last_.ray_cells = st.ray_cells;
     last_.dm_pops   = st.dm_pops;
+    total_.add(last_);
+    ++map_updates_;
+    if (!opt_.transient_map && !opt_.lidar_odometry) return LAMA_OK;
+    // Transient map (slam2d.cpp:323-379; lidar_odometry_2d.cpp:130-181 without the factor 2): the surface AABB comes from the world
+    // hits of this scan (the same expression the kernel evaluates per beam), the patch test and the deletion run on the device maps.
+    const ScanParams& sp = eng_->scan_params();
+    const Affine tf = compose_tf(pose_, sp.moving);
+    double mn[2] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max()}, mx[2] = {-mn[0], -mn[1]};
+    for (int i = 0; i < n; ++i) {
+        double hit[3], start[3];
+        beam_world(tf, sp, pts + 3 * (size_t)i, hit, start);
+        for (int k = 0; k < 2; ++k) { mn[k] = std::min(mn[k], hit[k]); mx[k] = std::max(mx[k], hit[k]); }
+    }
+    const double stretch = opt_.lidar_odometry ? 1.0 : 2.0;
+    const double xdist = std::max(pose_.tx - mn[0], mx[0] - pose_.tx) * stretch, ydist = std::max(pose_.ty - mn[1], mx[1] - pose_.ty) * stretch;
+    mn[0] = pose_.tx - xdist; mn[1] = pose_.ty - ydist;
+    mx[0] = pose_.tx + xdist; mx[1] = pose_.ty + ydist;
+    double center[2], hwidth[2];
+    const double reach = std::sqrt((double)eng_->max_sqdist()) * opt_.resolution;   // DistanceMap::maxDistance, dynamic_distance_map.cpp:155-158
+    for (int k = 0; k < 2; ++k) {
+        hwidth[k] = (mx[k] - mn[k]) * 0.5;           // AABB(min, max), aabb.h:50-55
+        center[k] = mn[k] + hwidth[k];
+        hwidth[k] += 2.0 * reach;
+    }
+    int removed = 0;
+    rc = eng_->prune_outside(0, center, hwidth, &removed);
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    removed_ += (uint64_t)removed;
+    return LAMA_OK;
+}
+
+// LidarOdometry2D::update (lidar_odometry_2d.cpp:59-83)
+int Slam2D::update_lidar_odometry(const double* pts, int n, const double* origin, const double* quat, bool* did_update)
+{
+    int rc = eng_->set_scan(pts, n, origin, quat, 0.0, 0.0);
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    *did_update = true;
+    if (!has_first_) {
+        rc = update_maps(pts, n);
+        has_first_ = true;
+        return rc;
+    }
+    HostMatchResult res;
+    rc = eng_->match(&pose_, 1, 0, false, make_solver(0, opt_.max_iter), 0.05, 0, &res);   // GaussNewton + CauchyWeight(0.15), :48-50
+    if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
+    pose_ = res.state;
+    last_.evals    = res.evals_ref;
+    last_.gn_iters = res.iterations;
+    const SE2 odelta = se2_mul(se2_inv(map_update_pose_), pose_);   // map_update_odom - odom (pose2d.cpp:81-84)
+    if (xy_norm(odelta) > 0.1 || std::abs(se2_rotation(odelta)) > 0.5) {
+        rc = update_maps(pts, n);
+        map_update_pose_ = pose_;
+        return rc;
+    }
     total_.add(last_);
     return LAMA_OK;
 }
@@ -432,6 +486,10 @@ int Slam2D::update(const double* pts, int n, const double* origin, const double*
     last_ = Counters();
     if (!eng_) {
         std::string e;
+        if (opt_.lidar_odometry) {   // lidar_odometry_2d.cpp:44-46
+            opt_.l2_max    = 1.0;
+            opt_.occupancy = 1;
+        }
         EngineConfig cfg = engine_config(opt_.dev, 1, opt_.resolution, opt_.l2_max, pose_.tx, pose_.ty);
         cfg.max_beams = std::max(cfg.max_beams, n);
         cfg.occupancy_kind = opt_.occupancy == 1 ? 1 : 0;
@@ -439,13 +497,16 @@ int Slam2D::update(const double* pts, int n, const double* origin, const double*
         if (!en) { err_ = e; return LAMA_ERR_CUDA; }
         eng_.reset(en);
         eng_->enable_timing(opt_.dev.timing != 0);
+        eng_->set_lidar_odometry_rays(opt_.lidar_odometry);
     }
+    if (opt_.lidar_odometry) return update_lidar_odometry(pts, n, origin, quat, did_update);
+    if (!odom_xyr) { err_ = "Slam2D::update needs an odometry pose"; return LAMA_ERR_ARG; }
     const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
     if (!has_first_) {  // slam2d.cpp:147-161
         int rc = eng_->set_scan(pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range);
         if (rc != LAMA_OK) { err_ = eng_->last_error(); return rc; }
         odom_ = odometry;
-        rc = update_maps();
+        rc = update_maps(pts, n);
         if (rc != LAMA_OK) return rc;
         has_first_  = true;
         *did_update = true;
@@ -465,7 +526,7 @@ int Slam2D::update(const double* pts, int n, const double* origin, const double*
     last_.evals    = res.evals_ref;
     last_.gn_iters = res.iterations;
     *did_update = true;
-    return update_maps();
+    return update_maps(pts, n);
 }
 
 // =====================================================================================================

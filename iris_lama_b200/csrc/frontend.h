@@ -126,6 +126,9 @@ struct SlamOptions {  // include/lama/slam2d.h:91-125
     uint32_t patch_size = 32, max_iter = 100;
     int strategy = 0;
     int occupancy = 0;  // 0 = FrequencyOccupancyMap (the reference's Slam2D), 1 = ProbabilisticOccupancyMap (log-odds)
+    bool transient_map = false;    // Slam2D::Options::transient_map (slam2d.h:122, slam2d.cpp:323-379)
+    bool lidar_odometry = false;   // run as lama::LidarOdometry2D (src/lidar_odometry_2d.cpp:42-181): no odometry input, log-odds map,
+                                   // l2_max 1.0, 1 m rays, map updated every 0.1 m / 0.5 rad, transient map always on
     DeviceOptions dev;
 };
 
@@ -136,6 +139,8 @@ public:
     int update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update);
     const SE2& pose() const { return pose_; }
     uint32_t processed_cells() const { return processed_; }
+    uint64_t removed_patches() const { return removed_; }
+    uint64_t map_updates() const { return map_updates_; }
     const Counters& last_counters() const { return last_; }
     const Counters& total_counters() const { return total_; }
     Engine* engine() { return eng_.get(); }
@@ -145,11 +150,14 @@ private:
     SlamOptions opt_;
     std::unique_ptr<Engine> eng_;
     SE2 pose_{1, 0, 0, 0}, odom_{1, 0, 0, 0};
+    SE2 map_update_pose_{1, 0, 0, 0};   // LidarOdometry2D::map_update_odom
     bool has_first_ = false, engine_ready_ = false;
     uint32_t processed_ = 0;
+    uint64_t removed_ = 0, map_updates_ = 0;
     Counters last_, total_;
     std::string err_;
-    int update_maps();
+    int update_maps(const double* pts, int n);
+    int update_lidar_odometry(const double* pts, int n, const double* origin, const double* quat, bool* did_update);
 };
 
 // ---- device DynamicDistanceMap + Loc2D -------------------------------------------------------------------

@@ -855,6 +855,21 @@ __global__ void k_release(StoreView s, int set, int first)
         }
     }
 }
+// Map::deletePatchAt (map.cpp:465-488) for a list of directory entries, in every map kind of one particle
+__global__ void k_delete_patches(StoreView s, int set, int particle, const int32_t* __restrict__ list)
+{
+    const int di = list[blockIdx.x];
+    if (threadIdx.x != 0) return;
+    for (int kind = 0; kind < s.n_kinds; ++kind) {
+        int32_t* d = dir_of(s, set, particle, kind);
+        const int e = d[di];
+        if (e >= 0) {
+            release_slot(s, e & kDirSlotMask);
+            d[di] = -1;
+        }
+    }
+}
+
 __global__ void k_merge_free(StoreView s)
 {
     __shared__ int n, base;
@@ -1107,6 +1122,11 @@ void launch_release(const StoreView& s, int set, int first, int count, cudaStrea
     k_release<<<dim3(count, s.n_kinds), 256, 0, st>>>(s, set, first);
 }
 void launch_merge_free(const StoreView& s, cudaStream_t st) { k_merge_free<<<1, 256, 0, st>>>(s); }
+void launch_delete_patches(const StoreView& s, int set, int particle, const int32_t* d_list, int count, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_delete_patches<<<count, 32, 0, st>>>(s, set, particle, d_list);
+}
 void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st) { k_init_store<<<296, 256, 0, st>>>(s, n_sets); }
 void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, uint32_t* d_out, uint8_t* d_present,
                    cudaStream_t st)

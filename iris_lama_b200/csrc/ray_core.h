@@ -28,6 +28,8 @@ struct ScanParams {
     double truncated_ray;    // Options::truncated_ray   (pf_slam2d.h:155)
     double truncated_range;  // Options::truncated_range (pf_slam2d.h:158)
     int n_beams;
+    int lo_ray;              // 1: LidarOdometry2D's rule instead of the two above: rays longer than 1 m keep their last metre
+                             //    (`if (ray_length >= 1.0) start = hit - AB / ray_length`, lidar_odometry_2d.cpp:103-110)
 };
 
 struct BeamCells {
@@ -36,24 +38,30 @@ struct BeamCells {
     bool mark_hit;
 };
 
-// pf_slam2d.cpp:463-499 : world hit / start of one beam and their map cells.
-LAMA_HD BeamCells beam_cells(const Affine& tf, const ScanParams& sp, const double* pt)
+// pf_slam2d.cpp:463-491 : world hit / ray start of one beam; returns mark_hit.
+LAMA_HD bool beam_world(const Affine& tf, const ScanParams& sp, const double* pt, double hit[3], double start[3])
 {
-    double start[3] = {tf.t[0], tf.t[1], tf.t[2]};
-    double hit[3], AB[3] = {0, 0, 0};
+    start[0] = tf.t[0]; start[1] = tf.t[1]; start[2] = tf.t[2];
+    double AB[3] = {0, 0, 0};
     apply_tf(tf, pt[0], pt[1], pt[2], hit);
     double ray_length = 1.0;
-    BeamCells b;
-    b.mark_hit = true;
+    bool mark_hit = true;
+    if (sp.lo_ray) {
+        for (int k = 0; k < 3; ++k) AB[k] = add_rn(hit[k], -start[k]);
+        ray_length = sqrt(add_rn(add_rn(mul_rn(AB[0], AB[0]), mul_rn(AB[1], AB[1])), mul_rn(AB[2], AB[2])));
+        if (ray_length >= 1.0)
+            for (int k = 0; k < 3; ++k) start[k] = add_rn(hit[k], -(AB[k] / ray_length));
+        return true;
+    }
     if (sp.truncated_range > 0.0) {
         for (int k = 0; k < 3; ++k) AB[k] = add_rn(hit[k], -start[k]);
         ray_length = sqrt(add_rn(add_rn(mul_rn(AB[0], AB[0]), mul_rn(AB[1], AB[1])), mul_rn(AB[2], AB[2])));
         if (sp.truncated_range < ray_length) {
             for (int k = 0; k < 3; ++k) hit[k] = add_rn(start[k], mul_rn(AB[k] / ray_length, sp.truncated_range));
-            b.mark_hit = false;
+            mark_hit = false;
         }
     }
-    if (b.mark_hit && sp.truncated_ray > 0.0) {
+    if (mark_hit && sp.truncated_ray > 0.0) {
         if (sp.truncated_range == 0.0) {
             for (int k = 0; k < 3; ++k) AB[k] = add_rn(hit[k], -start[k]);
             ray_length = sqrt(add_rn(add_rn(mul_rn(AB[0], AB[0]), mul_rn(AB[1], AB[1])), mul_rn(AB[2], AB[2])));
@@ -61,6 +69,15 @@ LAMA_HD BeamCells beam_cells(const Affine& tf, const ScanParams& sp, const doubl
         if (sp.truncated_ray < ray_length)
             for (int k = 0; k < 3; ++k) start[k] = add_rn(hit[k], -mul_rn(AB[k] / ray_length, sp.truncated_ray));
     }
+    return mark_hit;
+}
+
+// pf_slam2d.cpp:463-499 : the map cells of one beam's ray start and hit.
+LAMA_HD BeamCells beam_cells(const Affine& tf, const ScanParams& sp, const double* pt)
+{
+    double start[3], hit[3];
+    BeamCells b;
+    b.mark_hit = beam_world(tf, sp, pt, hit, start);
     for (int k = 0; k < 3; ++k) {
         b.to[k]   = w2m(hit[k], sp.scale);
         b.from[k] = w2m(start[k], sp.scale);

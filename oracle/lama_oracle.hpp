@@ -384,6 +384,22 @@ public:
         mx.x += patch_length; mx.y += patch_length;
         return true;
     }
+    // Map::deletePatchAt (map.cpp:465-488)
+    bool delete_patch_at(const Vec3u& c)
+    {
+        auto it = patches.find(m2p(c));
+        if (it == patches.end()) return false;
+        patches.erase(it);
+        prev_idx_ = ~0ull; prev_patch_ = nullptr;   // the reference's cache holds a pointer into the erased node as well; it is never
+                                                    // dereferenced before the next lookup of another patch in the code paths restated here
+        return true;
+    }
+    // Map::visit_all_patches (map.cpp:361-367): the anchor cell of every patch
+    template <typename F>
+    void visit_all_patches(F&& walker) const
+    {
+        for (auto& kv : patches) walker(p2m(kv.first));
+    }
     // Map::visit_all_cells (map.cpp:352-359): every cell whose mask bit is on
     template <typename F>
     void visit_all_cells(F&& walker) const
@@ -1197,10 +1213,16 @@ struct MapUpdateCounters {
     uint64_t dm_pops   = 0;   // W
 };
 
+// `lo_ray`: LidarOdometry2D's own ray shortening (lidar_odometry_2d.cpp:103-110: `if (ray_length >= 1.0) start = hit - AB / ray_length`)
+// instead of the truncated_ray / truncated_range logic; `hit_min` / `hit_max`: the surface AABB of the transient-map code
+// (slam2d.cpp:264-267,303-306, lidar_odometry_2d.cpp:96-99,113-114).
 template <typename OccMap>
 inline uint32_t update_maps(OccMap& occ, DynamicDistanceMap& dm, const PointCloud& surface, const Pose2D& pose,
-                            double truncated_ray, double truncated_range, MapUpdateCounters* ctr)
+                            double truncated_ray, double truncated_range, MapUpdateCounters* ctr, bool lo_ray = false, double* hit_min = nullptr,
+                            double* hit_max = nullptr)
 {
+    if (hit_min)
+        for (int k = 0; k < 3; ++k) { hit_min[k] = std::numeric_limits<double>::max(); hit_max[k] = -std::numeric_limits<double>::max(); }
     Affine3 tf = compose(fixed_tf(pose.x(), pose.y(), pose.rotation()), moving_tf(surface));
     const double wso[3] = {tf.t[0], tf.t[1], tf.t[2]};
     const size_t n = surface.size();
@@ -1227,7 +1249,15 @@ inline uint32_t update_maps(OccMap& occ, DynamicDistanceMap& dm, const PointClou
             if (truncated_ray < ray_length)
                 for (int k = 0; k < 3; ++k) start[k] = hit[k] - AB[k] / ray_length * truncated_ray;
         }
+        if (lo_ray) {
+            for (int k = 0; k < 3; ++k) AB[k] = hit[k] - start[k];
+            ray_length = std::sqrt(AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2]);
+            if (ray_length >= 1.0)
+                for (int k = 0; k < 3; ++k) start[k] = hit[k] - AB[k] / ray_length;
+        }
         Vec3u mhit = occ.w2m(hit);
+        if (hit_min)
+            for (int k = 0; k < 3; ++k) { hit_min[k] = std::min(hit_min[k], hit[k]); hit_max[k] = std::max(hit_max[k], hit[k]); }
         if (mark_hit) {
             ++cells;
             if (occ.set_occupied(mhit)) dm.add_obstacle(mhit);
@@ -1243,6 +1273,41 @@ inline uint32_t update_maps(OccMap& occ, DynamicDistanceMap& dm, const PointClou
         ctr->dm_pops += processed;
     }
     return processed;
+}
+
+// Transient map (slam2d.cpp:323-379 with `stretch` 2, lidar_odometry_2d.cpp:130-181 with `stretch` 1): keep only the patches whose
+// AABB meets the AABB of the latest surface, made symmetric around the pose and grown by twice the distance map's reach.
+// AABB::testIntersection: include/lama/aabb.h:65-72.
+template <typename OccMap>
+inline size_t transient_prune(OccMap& occ, DynamicDistanceMap& dm, double px, double py, double mn[3], double mx[3], double stretch)
+{
+    mn[2] = mx[2] = 0;
+    const double xdist = std::max(px - mn[0], mx[0] - px) * stretch;
+    const double ydist = std::max(py - mn[1], mx[1] - py) * stretch;
+    mn[0] = px - xdist; mn[1] = py - ydist;
+    mx[0] = px + xdist; mx[1] = py + ydist;
+    double ac[3], ah[3];
+    for (int k = 0; k < 3; ++k) { ah[k] = (mx[k] - mn[k]) * 0.5; ac[k] = mn[k] + ah[k]; }       // AABB(min, max), aabb.h:50-55
+    for (int k = 0; k < 3; ++k) ah[k] += 2.0 * dm.max_distance();
+    std::vector<Vec3u> to_remove;
+    dm.visit_all_patches([&](const Vec3u& origin) {
+        const uint32_t length = occ.patch_length;
+        double ws[3], we[3];
+        occ.m2w(origin, ws);
+        occ.m2w(Vec3u{origin.x + length, origin.y + length, origin.z}, we);   // origin + Vector3ui(length, length, 0.0)
+        ws[2] = we[2] = 0.0;
+        bool hitb = true;
+        for (int k = 0; k < 3; ++k) {
+            const double bh = (we[k] - ws[k]) * 0.5, bc = ws[k] + bh;
+            hitb = hitb && (std::abs(ac[k] - bc) <= (ah[k] + bh));
+        }
+        if (!hitb) to_remove.push_back(origin);
+    });
+    for (auto& c : to_remove) {
+        occ.delete_patch_at(c);
+        dm.delete_patch_at(c);
+    }
+    return to_remove.size();
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1526,6 +1591,7 @@ struct SlamOptions {
     double resolution = 0.05;
     uint32_t patch_size = 32, max_iter = 100;
     int strategy = 0;  // 0 = "gn", 1 = "lm" (slam2d.cpp:226-233)
+    bool transient_map = false;  // slam2d.h:122
 };
 
 // OccMap = FrequencyOccupancyMap is the reference's Slam2D (slam2d.cpp:97); OccMap = ProbabilisticOccupancyMap is the
@@ -1541,6 +1607,7 @@ public:
     Pose2D pose, odom;
     bool has_first_scan = false;
     uint32_t processed_cells = 0;
+    uint64_t removed_patches = 0;
     ScanCounters last, total;
 
     explicit Slam2DT(const SlamOptions& o) : opt(o), dm(o.resolution, o.patch_size), occ(o.resolution, o.patch_size)
@@ -1578,7 +1645,10 @@ private:
     void update_maps_(const PointCloud& pc)
     {
         MapUpdateCounters c;
-        processed_cells = update_maps(occ, dm, pc, pose, opt.truncated_ray, opt.truncated_range, &c);
+        double mn[3], mx[3];
+        processed_cells = update_maps(occ, dm, pc, pose, opt.truncated_ray, opt.truncated_range, &c, false, opt.transient_map ? mn : nullptr,
+                                      opt.transient_map ? mx : nullptr);
+        if (opt.transient_map) removed_patches += transient_prune(occ, dm, pose.x(), pose.y(), mn, mx, 2.0);   // slam2d.cpp:329-379
         last.ray_cells += c.ray_cells;
         last.dm_pops += c.dm_pops;
         total.evals += last.evals;
@@ -1589,6 +1659,61 @@ private:
 };
 using Slam2D     = Slam2DT<FrequencyOccupancyMap>;
 using Slam2DProb = Slam2DT<ProbabilisticOccupancyMap>;
+
+// ----------------------------------------------------------------------------------------------
+// LidarOdometry2D (include/lama/lidar_odometry_2d.h:45-75, src/lidar_odometry_2d.cpp:42-181)
+// ----------------------------------------------------------------------------------------------
+class LidarOdometry2D {
+public:
+    DynamicDistanceMap dm;
+    ProbabilisticOccupancyMap occ;
+    SolverOptions so;
+    Pose2D odom, map_update_odom;
+    bool has_first_scan = false;
+    uint64_t removed_patches = 0, map_updates = 0;
+    ScanCounters last;
+
+    explicit LidarOdometry2D(double resolution = 0.05, uint32_t max_iter = 100) : dm(resolution, 32), occ(resolution, 32)
+    {
+        dm.set_max_distance(1.0);                 // :45
+        so.max_iterations = max_iter;             // :48-50
+        so.strategy.kind  = Strategy::GaussNewton;
+        so.robust.kind    = RobustCost::Cauchy;
+        so.robust.param   = 0.15;
+    }
+    bool update(const PointCloud& pc)             // :59-83
+    {
+        last = ScanCounters();
+        if (!has_first_scan) {
+            update_maps_(pc);
+            has_first_scan = true;
+            return true;
+        }
+        MatchSurface2D ms(&dm, &pc, odom.state);
+        SolveStats st = solve(so, ms, nullptr);
+        odom.state    = ms.state;
+        last.evals += st.evals;
+        last.gn_iters += st.iterations;
+        Pose2D odelta = map_update_odom.minus(odom);   // map_update_odom - odom, pose2d.cpp:81-84
+        if (odelta.xy_norm() > 0.1 || std::abs(odelta.rotation()) > 0.5) {
+            update_maps_(pc);
+            map_update_odom = odom;
+        }
+        return true;
+    }
+
+private:
+    void update_maps_(const PointCloud& pc)       // :85-181
+    {
+        MapUpdateCounters c;
+        double mn[3], mx[3];
+        update_maps(occ, dm, pc, odom, 0.0, 0.0, &c, true, mn, mx);
+        removed_patches += transient_prune(occ, dm, odom.x(), odom.y(), mn, mx, 1.0);
+        last.ray_cells += c.ray_cells;
+        last.dm_pops += c.dm_pops;
+        ++map_updates;
+    }
+};
 
 // ----------------------------------------------------------------------------------------------
 // Loc2D match path (src/loc2d.cpp:46-108,126-192); global localisation / sampling covariance are

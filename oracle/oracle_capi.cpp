@@ -272,13 +272,14 @@ struct orc_slam_options {
     double trans_thresh, rot_thresh, l2_max, truncated_ray, truncated_range, resolution;
     uint32_t patch_size, max_iter;
     int32_t strategy;
+    int32_t transient_map;
 };
 void* orc_slam_create(const orc_slam_options* o)
 {
     SlamOptions s;
     s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
     s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
-    s.strategy = o->strategy;
+    s.strategy = o->strategy; s.transient_map = o->transient_map != 0;
     return new Slam2D(s);
 }
 void orc_slam_destroy(void* h) { delete (Slam2D*)h; }
@@ -290,7 +291,7 @@ void* orc_slamp_create(const orc_slam_options* o)
     SlamOptions s;
     s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
     s.truncated_range = o->truncated_range; s.resolution = o->resolution; s.patch_size = o->patch_size; s.max_iter = o->max_iter;
-    s.strategy = o->strategy;
+    s.strategy = o->strategy; s.transient_map = o->transient_map != 0;
     return new Slam2DProb(s);
 }
 void orc_slamp_destroy(void* h) { delete (Slam2DProb*)h; }
@@ -437,5 +438,24 @@ static int image_out(const std::vector<uint8_t>& img, uint32_t w, uint32_t h, ui
 int orc_ddm_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = distance_image(*(DynamicDistanceMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
 int orc_freq_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = occupancy_image(*(FrequencyOccupancyMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
 int orc_prob_image(void* d, uint8_t* out, size_t cap, int* dims) { uint32_t w, h; auto img = occupancy_image(*(ProbabilisticOccupancyMap*)d, w, h); return image_out(img, w, h, out, cap, dims); }
+
+
+// ---- LidarOdometry2D ------------------------------------------------------------------------------------------------
+void* orc_lo_create(double resolution, uint32_t max_iter) { return new LidarOdometry2D(resolution, max_iter); }
+void orc_lo_destroy(void* h) { delete (LidarOdometry2D*)h; }
+int orc_lo_update(void* h, const double* pts, int n, const double* origin, const double* quat)
+{
+    PointCloud pc = make_cloud(pts, n, origin, quat);
+    return ((LidarOdometry2D*)h)->update(pc) ? 1 : 0;
+}
+void orc_lo_get_state(void* h, double* state) { se2_to(((LidarOdometry2D*)h)->odom.state, state); }
+void orc_lo_counters(void* h, uint64_t* out)
+{
+    auto* l = (LidarOdometry2D*)h;
+    out[0] = l->last.evals; out[1] = l->last.ray_cells; out[2] = l->last.dm_pops; out[3] = l->last.gn_iters; out[4] = l->removed_patches; out[5] = l->map_updates;
+}
+void* orc_lo_occ_handle(void* h) { return &((LidarOdometry2D*)h)->occ; }
+void* orc_lo_dm_handle(void* h) { return &((LidarOdometry2D*)h)->dm; }
+uint64_t orc_slam_removed_patches(void* h) { return ((Slam2D*)h)->removed_patches; }
 
 }  // extern "C"

@@ -46,13 +46,13 @@ class PFOptions(C.Structure):
 class SlamOptions(C.Structure):
     _fields_ = [("trans_thresh", C.c_double), ("rot_thresh", C.c_double), ("l2_max", C.c_double), ("truncated_ray", C.c_double),
                 ("truncated_range", C.c_double), ("resolution", C.c_double), ("patch_size", C.c_uint32), ("max_iter", C.c_uint32),
-                ("strategy", C.c_int32)]
+                ("strategy", C.c_int32), ("transient_map", C.c_int32)]
 
     @classmethod
     def defaults(cls, **kw):
         # include/lama/slam2d.h:91-125
         o = cls(trans_thresh=0.5, rot_thresh=0.5, l2_max=0.5, truncated_ray=0.0, truncated_range=0.0, resolution=0.05, patch_size=32,
-                max_iter=100, strategy=0)
+                max_iter=100, strategy=0, transient_map=0)
         for k, v in kw.items():
             setattr(o, k, v)
         return o
@@ -550,6 +550,35 @@ class Loc2D:
         return s, cov, rmse.value, stats
 
 
+class LidarOdometry2D:
+    """lama::LidarOdometry2D (src/lidar_odometry_2d.cpp:42-181)"""
+
+    def __init__(self, resolution=0.05, max_iter=100):
+        lib().orc_lo_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().orc_lo_create(C.c_double(resolution), C.c_uint32(max_iter)))
+
+    def __del__(self):
+        if self.h and _lib is not None:
+            _lib.orc_lo_destroy(self.h)
+            self.h = None
+
+    def update(self, pts, origin=_ID3, quat=_IDQ):
+        p, pp = _d(pts)
+        o, op = _d(origin)
+        q, qp = _d(quat)
+        return bool(lib().orc_lo_update(self.h, pp, C.c_int(p.size // 3), op, qp))
+
+    def state(self):
+        s = np.zeros(4)
+        lib().orc_lo_get_state(self.h, s.ctypes.data_as(c_dp))
+        return s
+
+    def counters(self):
+        c = np.zeros(6, np.uint64)
+        lib().orc_lo_counters(self.h, _vp(c))
+        return dict(zip(("evals", "ray_cells", "dm_pops", "gn_iters", "removed_patches", "map_updates"), c.tolist()))
+
+
 # ---- SDM persistence and image export on map handles (oracle_capi.cpp) ------------------------------------------------
 def _hv(h):
     h = getattr(h, "h", h)
@@ -557,7 +586,7 @@ def _hv(h):
 
 
 def map_handle(name, obj, *args):
-    """name: pf_occ | pf_dm | slam_occ | slam_dm | slamp_occ | slamp_dm | loc_occ | loc_dm -> raw map pointer"""
+    """name: pf_occ | pf_dm | slam_occ | slam_dm | slamp_occ | slamp_dm | loc_occ | loc_dm | lo_occ | lo_dm -> raw map pointer"""
     fn = getattr(lib(), "orc_%s_handle" % name)
     fn.restype = C.c_void_p
     return C.c_void_p(fn(_hv(obj), *[C.c_int(a) for a in args]))

@@ -335,3 +335,49 @@ def test_pfslam2d_motion_gate_and_rng_stream(gpu_api, po, synth):
         ups += int(a)
         assert np.abs(g.getParticles()[0] - o.particles()[0]).max() < POSE_TOL
     assert 2 <= ups < T
+
+
+# ---- SURVEY 8(f) row 4 (front-end half): LidarOdometry2D and Slam2D's transient map ---------------------------------------
+def _near(scan, r):
+    """the beams shorter than r: a short-range sensor, so that the surface AABB moves with the robot"""
+    return np.ascontiguousarray(scan[np.hypot(scan[:, 0], scan[:, 1]) < r])
+
+
+def test_lidar_odometry_2d(gpu_api, po, synth):
+    """LidarOdometry2D::update (lidar_odometry_2d.cpp:59-181): match, 1 m rays into the log-odds map, transient-map pruning"""
+    ds = synth.make_dataset("corridor", 60, n_beams=720)
+    g, o = gpu_api.LidarOdometry2D(), po.LidarOdometry2D()
+    for t in range(60):
+        s = _near(ds.scans[t], 3.0)
+        assert g.update(s) == o.update(s)
+        assert np.abs(g.state() - o.state()).max() < POSE_TOL, t
+    c = o.counters()
+    assert g.mapStats() == (c["map_updates"], c["removed_patches"]) and c["removed_patches"] > 0 and c["map_updates"] > 20
+    n, mn, mx = po._bounds(po.lib().orc_ddm_bounds, (po.map_handle("lo_dm", o),))
+    gb = g.mapBounds(1)
+    assert (gb[1] == mn).all() and (gb[2] == mx).all()                    # the pruned map covers the same patches
+    w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    _assert_dm_equal(g.exportDistance(mn[0], mn[1], w, h), po._export_dm(po.lib().orc_ddm_export, (po.map_handle("lo_dm", o),), mn[0], mn[1], w, h))
+    assert (g.exportImage(0) == po.map_image("prob", po.map_handle("lo_occ", o))).all()
+    assert g.getPose()[0] > 3.0                                            # it follows the forward motion (short-range beams in a corridor: weakly observable)
+
+
+def test_slam2d_transient_map(gpu_api, po, synth):
+    """Slam2D::Options::transient_map (slam2d.cpp:323-379)"""
+    ds = synth.make_dataset("corridor", 90, n_beams=720)
+    kw = dict(trans_thresh=0.05, rot_thresh=0.05, transient_map=1)
+    g, o = gpu_api.Slam2D(gpu_api.Slam2D.Options(**kw)), po.Slam2D(po.SlamOptions.defaults(**kw))
+    g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+    for t in range(90):
+        s = _near(ds.scans[t], 1.5)
+        assert g.update(s, ds.odom[t]) == o.update(s, ds.odom[t])
+        assert np.abs(g.state() - o.state()).max() < POSE_TOL, t
+    po.lib().orc_slam_removed_patches.restype = po.C.c_uint64
+    removed = po.lib().orc_slam_removed_patches(o.h)
+    assert removed > 0 and g.mapStats()[1] == removed
+    n, mn, mx = o.dm_bounds()
+    w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    _assert_dm_equal(g.exportDistance(mn[0], mn[1], w, h), o.export_dm(mn[0], mn[1], w, h))
+    go, oo = g.exportOccupancy(mn[0], mn[1], w, h), o.export_occ(mn[0], mn[1], w, h)
+    for k in ("occupied", "visited", "known"):
+        assert (go[k] == oo[k]).all(), k
