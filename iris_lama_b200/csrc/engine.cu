@@ -31,7 +31,10 @@ struct Engine::Impl {
     MatchResult* d_results = nullptr;
     MatchResult* h_results = nullptr;  // pinned
     MapUpdateStats* d_stats = nullptr;
-    MapUpdateStats* h_stats = nullptr;  // pinned
+    MapUpdateStats* h_stats = nullptr;  // pinned; two halves (ping-pong between consecutive map updates)
+    uint64_t* h_report = nullptr;       // pinned; per half: {status, allocated, detached, freed, free slots}
+    double* h_scan = nullptr;           // pinned staging of a host scan (step_async)
+    cudaEvent_t ev_match = nullptr;
     uint64_t* d_events = nullptr;
     int32_t* d_idx = nullptr;
     int32_t* h_idx = nullptr;  // pinned
@@ -170,7 +173,11 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     CU_NEW(dalloc((void**)&d->d_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
     const size_t idx_ints = std::max((size_t)cfg.particles, (size_t)cfg.dir_dim * cfg.dir_dim);   // resample indices / directory entries to delete
     CU_NEW(dalloc((void**)&d->d_idx, idx_ints * 4));
-    CU_NEW(cudaMallocHost((void**)&d->h_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
+    CU_NEW(cudaMallocHost((void**)&d->h_stats, 2 * (size_t)cfg.particles * sizeof(MapUpdateStats)));
+    CU_NEW(cudaMallocHost((void**)&d->h_report, 2 * 8 * sizeof(uint64_t)));
+    std::memset(d->h_report, 0, 2 * 8 * sizeof(uint64_t));
+    CU_NEW(cudaMallocHost((void**)&d->h_scan, (size_t)cfg.max_beams * 24));
+    CU_NEW(cudaEventCreateWithFlags(&d->ev_match, cudaEventDisableTiming));
     CU_NEW(cudaMallocHost((void**)&d->h_idx, idx_ints * 4));
     CU_NEW(cudaMallocHost((void**)&d->h_status, 64));
 
@@ -197,6 +204,9 @@ Engine::~Engine()
     if (d_->h_states) cudaFreeHost(d_->h_states);
     if (d_->h_results) cudaFreeHost(d_->h_results);
     if (d_->h_stats) cudaFreeHost(d_->h_stats);
+    if (d_->h_report) cudaFreeHost(d_->h_report);
+    if (d_->h_scan) cudaFreeHost(d_->h_scan);
+    if (d_->ev_match) cudaEventDestroy(d_->ev_match);
     if (d_->h_idx) cudaFreeHost(d_->h_idx);
     if (d_->h_status) cudaFreeHost(d_->h_status);
     if (d_->d_scratch) cudaFree(d_->d_scratch);
@@ -380,6 +390,7 @@ int Engine::update_maps_async(const SE2* states, int first_particle, int count)
     rp.scan = d_->scan;
     rp.set = cur_set_;
     rp.particle_offset = first_particle;
+    rp.state_stride = (int)sizeof(SE2);
     { const char* dbg = std::getenv("LAMA_RAY_DEBUG"); rp.debug = dbg ? std::atoi(dbg) : 0; }  // see RayParams::debug
     // shared-memory scratch sized for THIS scan (two CTAs per SM at 1080 beams); the maxima were registered at create
     const int nb = d_->scan.n_beams;
@@ -396,25 +407,113 @@ int Engine::update_maps_async(const SE2* states, int first_particle, int count)
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[2], d_->stream));
     launch_merge_free(d_->view, d_->stream);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(d_->h_stats, d_->d_stats, (size_t)count * sizeof(MapUpdateStats), cudaMemcpyDeviceToHost, d_->stream));
-    CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+    { int rc = enqueue_report(count); if (rc != LAMA_OK) return rc; }
     times_.raycast_launches += 1;
     times_.brushfire_launches += 1;
     times_.misc_launches += 1;
     h2d_bytes_ += (uint64_t)count * sizeof(SE2);
-    d2h_bytes_ += (uint64_t)count * sizeof(MapUpdateStats) + 4;
+    return LAMA_OK;
+}
+
+// device -> host report of a map update into the other half of the ping-pong buffers (the previous half may not have been read yet)
+int Engine::enqueue_report(int count)
+{
+    const int half = 1 - pending_buf_;
+    MapUpdateStats* hs = d_->h_stats + (size_t)half * cfg_.particles;
+    uint64_t* hr = d_->h_report + (size_t)half * 8;
+    CU_TRY(cudaMemcpyAsync(hs, d_->d_stats, (size_t)count * sizeof(MapUpdateStats), cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaMemcpyAsync(hr, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaMemcpyAsync(hr + 1, d_->view.counters, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaMemcpyAsync(hr + 4, d_->view.free_count, 4, cudaMemcpyDeviceToHost, d_->stream));
+    d2h_bytes_ += (uint64_t)count * sizeof(MapUpdateStats) + 4 + 28;
+    pending_buf_  = half;
     pending_maps_ = count;
     return LAMA_OK;
 }
 
-int Engine::settle(HostMapStats* out)
+int Engine::step_async(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
+                       const SE2* predicted, int count, const SolverOptions& so, double meas_sigma, HostMatchResult* out)
+{
+    if (count < 1 || count > cfg_.particles) return fail("step_async: particle range out of bounds", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    // the previous scan's map update may still be running: nothing below waits for it on the host
+    const bool had_pending = pending_maps_ != 0;
+    const int prev_count = pending_maps_, prev_buf = pending_buf_;
+    if (pts) {
+        if (n < 1 || n > cfg_.max_beams) return fail("step_async: number of beams out of range", LAMA_ERR_ARG);
+        set_moving(origin, quat, truncated_ray, truncated_range, n);
+        std::memcpy(d_->h_scan, pts, (size_t)n * 24);   // free again: the previous call returned after its match, which follows its upload
+        d_->d_points = d_->d_scan_buf;
+        CU_TRY(cudaMemcpyAsync(d_->d_points, d_->h_scan, (size_t)n * 24, cudaMemcpyHostToDevice, d_->stream));
+        h2d_bytes_ += (uint64_t)n * 24;
+    }
+    if (d_->scan.n_beams < 1) return fail("step_async: no scan selected", LAMA_ERR_STATE);
+    { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
+    std::memcpy(d_->h_states, predicted, (size_t)count * sizeof(SE2));
+    CU_TRY(cudaMemcpyAsync(d_->d_states, d_->h_states, (size_t)count * sizeof(SE2), cudaMemcpyHostToDevice, d_->stream));
+    MatchParams mp{};
+    mp.points = d_->d_points;
+    mp.scan = d_->scan;
+    mp.solver = so;
+    mp.meas_sigma = meas_sigma;
+    mp.resolution = cfg_.resolution;
+    mp.max_sqdist = max_sqdist_;
+    mp.set = cur_set_;
+    mp.particle_offset = 0;
+    mp.shared_map = 0;
+    mp.mode = 0;
+    launch_match(d_->view, mp, d_->d_states, d_->d_results, count, d_->stream);
+    CU_TRY(cudaMemcpyAsync(d_->h_results, d_->d_results, (size_t)count * sizeof(MatchResult), cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaEventRecord(d_->ev_match, d_->stream));
+    // map update on the matched poses, read from the match results on the device
+    RayParams rp = d_->ray;
+    rp.points = d_->d_points;
+    rp.scan = d_->scan;
+    rp.set = cur_set_;
+    rp.particle_offset = 0;
+    rp.state_stride = (int)sizeof(MatchResult);
+    const int nb = d_->scan.n_beams;
+    rp.log_cap   = std::min(d_->ray.log_cap, next_pow2_host(std::max(1024, 3 * nb)));
+    rp.event_cap = std::min(d_->ray.event_cap, next_pow2_host(std::max(512, nb)));
+    BrushParams bp = d_->brush;
+    bp.set = cur_set_;
+    bp.particle_offset = 0;
+    bp.event_cap = rp.event_cap;
+    launch_raycast(d_->view, rp, reinterpret_cast<const SE2*>(d_->d_results), d_->d_events, d_->d_stats, count, d_->stream);
+    launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
+    launch_merge_free(d_->view, d_->stream);
+    CU_TRY(cudaGetLastError());
+    { int rc = enqueue_report(count); if (rc != LAMA_OK) return rc; }
+    times_.match_launches += 1;
+    times_.raycast_launches += 1;
+    times_.brushfire_launches += 1;
+    times_.misc_launches += 1;
+    h2d_bytes_ += (uint64_t)count * sizeof(SE2);
+    d2h_bytes_ += (uint64_t)count * sizeof(MatchResult);
+    CU_TRY(cudaEventSynchronize(d_->ev_match));
+    static_assert(sizeof(HostMatchResult) == sizeof(MatchResult), "layout");
+    std::memcpy(out, d_->h_results, (size_t)count * sizeof(MatchResult));
+    // everything enqueued before this scan's match has completed: collect the previous map update without waiting
+    if (had_pending) {
+        const int cur_count = pending_maps_, cur_buf = pending_buf_;
+        pending_maps_ = prev_count;
+        pending_buf_  = prev_buf;
+        const int rc = settle(nullptr, true);
+        pending_maps_ = cur_count;
+        pending_buf_  = cur_buf;
+        if (rc != LAMA_OK) return rc;
+    }
+    return LAMA_OK;
+}
+
+int Engine::settle(HostMapStats* out, bool already_complete)
 {
     if (pending_maps_ == 0) return LAMA_OK;
     const int count = pending_maps_;
     pending_maps_ = 0;
     CU_TRY(cudaSetDevice(cfg_.device));
-    CU_TRY(cudaStreamSynchronize(d_->stream));
-    if (timing_) {
+    if (!already_complete) CU_TRY(cudaStreamSynchronize(d_->stream));
+    if (timing_ && !already_complete) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, d_->ev[0], d_->ev[1]);
         cudaEventElapsedTime(&b, d_->ev[1], d_->ev[2]);
@@ -422,8 +521,13 @@ int Engine::settle(HostMapStats* out)
         times_.brushfire_ms += b;
     }
     static_assert(sizeof(HostMapStats) == sizeof(MapUpdateStats), "layout");
-    last_map_stats_.assign((HostMapStats*)d_->h_stats, (HostMapStats*)d_->h_stats + count);
-    if (out) std::memcpy(out, d_->h_stats, (size_t)count * sizeof(MapUpdateStats));
+    const MapUpdateStats* hs = d_->h_stats + (size_t)pending_buf_ * cfg_.particles;
+    const uint64_t* hr = d_->h_report + (size_t)pending_buf_ * 8;
+    last_map_stats_.assign((const HostMapStats*)hs, (const HostMapStats*)hs + count);
+    if (out) std::memcpy(out, hs, (size_t)count * sizeof(MapUpdateStats));
+    settled_counters_[0] = hr[1]; settled_counters_[1] = hr[2]; settled_counters_[2] = hr[3];
+    settled_counters_[3] = (uint64_t)(uint32_t)hr[4];
+    *d_->h_status = (uint32_t)hr[0];
     return check_device_status();
 }
 

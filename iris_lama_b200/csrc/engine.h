@@ -74,7 +74,16 @@ public:
     // Same, but returns right after the launches; the work is collected by settle(), which every later entry point
     // calls first (errors of an asynchronous update therefore surface at the next call).
     int update_maps_async(const SE2* states, int first_particle, int count);
-    int settle(HostMapStats* out);
+    int settle(HostMapStats* out, bool already_complete = false);
+    // One scan of a particle filter enqueued at once: match -> ray cast -> brushfire with no host round trip in between.  The map
+    // update runs on the MATCHED poses straight from the device results, i.e. BEFORE the resampling decision of this scan; a
+    // resampling applied afterwards copies the updated maps, which gives the same maps as the reference's resample-then-update
+    // (update(copy(m), pose) == copy(update(m, pose))).  Returns when the match results are on the host; the map
+    // update keeps running and is collected by the next settle().  `pts` != nullptr: upload that scan first (no synchronisation).
+    int step_async(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
+                   const SE2* predicted, int count, const SolverOptions& so, double meas_sigma, HostMatchResult* out);
+    bool map_update_pending() const { return pending_maps_ != 0; }
+    const uint64_t* settled_store_counters() const { return settled_counters_; }   // {allocated, detached, freed, free slots} at the last settle
     const std::vector<HostMapStats>& last_map_stats() const { return last_map_stats_; }
 
     // Particles dst_first .. dst_first+count-1 become copy-on-write copies of src_particle (same set).
@@ -134,8 +143,11 @@ private:
     std::string err_;
     uint64_t h2d_bytes_ = 0, d2h_bytes_ = 0;
     int pending_maps_ = 0;
+    int pending_buf_ = 0;                 // which half of the ping-pong host buffers the pending map update reports into
+    uint64_t settled_counters_[4] = {0, 0, 0, 0};
     std::vector<HostMapStats> last_map_stats_;
     void set_moving(const double origin[3], const double quat[4], double truncated_ray, double truncated_range, int n);
+    int enqueue_report(int count);
     int fail(const std::string& what, int code);
     int check_device_status();
 };

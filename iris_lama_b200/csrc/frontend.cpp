@@ -246,9 +246,91 @@ void PFSlam2D::finish_counters()
     total_.add(last_);
 }
 
+// The whole scan enqueued at once (Engine::step_async): odometry sampling on the host, then match -> ray cast -> brushfire
+// back to back on the device.  The map update runs on the matched poses BEFORE the resampling decision; a resampling of
+// this scan then shares the UPDATED maps, which is the reference's resample-then-update with the two steps commuted
+// (every copy of an ancestor would apply the same scan at the same pose).  The host only waits for the match results.
+int PFSlam2D::update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update)
+{
+    pending_maps_ = false;
+    const bool moved = predict_and_gate(odom_xyr);
+    if (!moved) {   // motion gate (pf_slam2d.cpp:215-222): nothing else happens for this scan
+        int rcs = settle_counters();
+        last_ = Counters();
+        last_idx_.clear();
+        staged_index_ = -1;
+        return rcs;
+    }
+    *did_update = true;
+    Counters prev = last_;
+    const bool prev_pending = counters_pending_;
+    counters_pending_ = false;
+    last_ = Counters();
+    last_idx_.clear();
+    const int staged = staged_index_;
+    staged_index_ = -1;
+    int rc = LAMA_OK;
+    if (staged >= 0) {
+        rc = eng_->select_staged(staged, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+        if (rc != LAMA_OK) return engine_fail(rc);
+    }
+    std::vector<HostMatchResult> res((size_t)P_);
+    rc = eng_->step_async(staged >= 0 ? nullptr : pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range, &pose_[0], (int)P_,
+                          make_solver(0, opt_.max_iter), opt_.meas_sigma, res.data());   // GaussNewton + CauchyWeight(0.15), pf_slam2d.cpp:423-427
+    if (prev_pending) {   // the previous scan's map update was collected inside step_async (it precedes this scan's match in the stream)
+        collect_map_stats(prev);
+        total_.add(prev);
+    }
+    if (rc != LAMA_OK) return engine_fail(rc);
+    std::vector<double> all((size_t)P_ * 5);
+    for (uint32_t k = 0; k < P_; ++k) {
+        all[5 * k + 0] = res[k].state.c;
+        all[5 * k + 1] = res[k].state.s;
+        all[5 * k + 2] = res[k].state.tx;
+        all[5 * k + 3] = res[k].state.ty;
+        all[5 * k + 4] = res[k].sums[11];        // calculateLikelihood, pf_slam2d.cpp:393-414
+        last_.evals += res[k].evals_ref + 1;     // + the likelihood pass
+        last_.gn_iters += res[k].iterations;
+    }
+    absorb_results(all.data());
+    normalize();
+    std::vector<int32_t> v;
+    counters_pending_ = true;
+    if (compute_resample(v)) {
+        apply_resample_host(v);
+        last_idx_ = v;
+        last_.resampled = 1;
+        std::vector<int32_t> src(v.begin(), v.end());
+        rc = eng_->resample(src.data());   // after this scan's map update in stream order: the offspring share the updated maps
+        if (rc != LAMA_OK) return engine_fail(rc);
+        // resample() waited for the map update and collected it
+        collect_map_stats(last_);
+        total_.add(last_);
+        counters_pending_ = false;
+    }
+    return LAMA_OK;
+}
+
+void PFSlam2D::collect_map_stats(Counters& c)
+{
+    for (const HostMapStats& st : eng_->last_map_stats()) {
+        c.ray_cells += st.ray_cells;
+        c.dm_pops += st.dm_pops;
+    }
+    const uint64_t* sc = eng_->settled_store_counters();
+    c.detached     = sc[1] - detached_seen_;
+    detached_seen_ = sc[1];
+}
+
 int PFSlam2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update)
 {
     if (opt_.shard_count != 1) return fail("PFSlam2D::update on a sharded handle: use the shard_* calls", LAMA_ERR_STATE);
+    if (has_first_ && eng_ && opt_.dev.timing == 0) {
+        bool did = false;
+        int rc = update_pipelined(pts, n, origin, quat, odom_xyr, &did);
+        if (did_update) *did_update = did;
+        return rc;
+    }
     std::vector<double> local((size_t)P_ * 5);
     bool did = false;
     int rc = shard_begin(pts, n, origin, quat, odom_xyr, stamp, &did, local.data());

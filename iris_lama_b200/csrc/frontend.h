@@ -80,6 +80,8 @@ public:
     const std::string& error() const { return err_; }
     bool has_first_scan() const { return has_first_; }
     int settle_counters();
+    int update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update);
+    void collect_map_stats(Counters& c);
 
 private:
     PFSlam2D() = default;

@@ -502,7 +502,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     // ---- phase 0: stage the directory, clear scratch -------------------------------------------------
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
-        sh.tf = compose_tf(states[blockIdx.x], rp.scan.moving);
+        sh.tf = compose_tf(*reinterpret_cast<const SE2*>(reinterpret_cast<const char*>(states) + (size_t)blockIdx.x * (size_t)rp.state_stride), rp.scan.moving);
         sh.log_count = sh.event_count = sh.cells = sh.err = 0;
         sh.work[0] = sh.work[1] = 0;
         sh.any_pending = 0;

@@ -36,6 +36,7 @@ struct RayParams {
     ScanParams scan;
     int set;
     int particle_offset;
+    int state_stride;        // bytes between the poses handed to k_raycast (sizeof(SE2), or sizeof(MatchResult) when it reads k_match's output)
     int log_cap, event_cap;  // powers of two
     int cand_cap;            // candidate bitmaps (patches with hit cells or distance-map obstacles), <= 253
     int debug;               // developer experiments (LAMA_RAY_DEBUG, only honoured by LAMA_PHASE_TIMING builds): 1 no RED, 2 no LDS

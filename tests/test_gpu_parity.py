@@ -284,7 +284,12 @@ def _run_pf_pair(gpu_api, po, ds, P, T, **kw):
         assert np.abs(wg - wo).max() < 1e-6 * max(1.0, np.abs(wo).max())
         assert abs(g.getNeff() - o.neff) < 1e-6 and g.getBestParticleIdx() == o.best()
         cg, _ = g.counters(); co, _ = o.counters()
-        assert (cg["evals"], cg["ray_cells"], cg["dm_pops"], cg["gn_iters"]) == (co["evals"], co["ray_cells"], co["dm_pops"], co["gn_iters"])
+        assert (cg["evals"], cg["gn_iters"]) == (co["evals"], co["gn_iters"])
+        if len(ro) == 0:
+            # The device updates the maps BEFORE a resampling of the same scan and lets the offspring share the updated maps
+            # (same maps as the reference's resample-then-update): on resampling scans its work counters refer to
+            # the particle set before the resampling, the oracle's to the set after it.  The cells themselves are compared below.
+            assert (cg["ray_cells"], cg["dm_pops"]) == (co["ray_cells"], co["dm_pops"])
     return g, o, n_res
 
 
