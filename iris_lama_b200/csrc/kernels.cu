@@ -259,10 +259,13 @@ constexpr uint32_t kBeamFlag = 0x80000000u;
 // error term returns to 0 each time (err += n; 2 err >= n; err -= n), so only the minor axis carries state:
 //   e += d;  if (2 e >= n) { minor coordinate moves; e -= n; }          [2 e >= n  <=>  e >= (n + 1) >> 1]
 // (dx == dy: both axes move on every step, which the same update yields with d == n.)
+// The cell is kept PACKED, P = yr << 16 | xr (window-relative coordinates, each < 2^13): a step is one addition of a packed
+// step vector (sy * 65536 + sx as a signed number; no borrow crosses the halves because all cells of a beam lie inside the
+// bounding box of its end cells, which is inside the window), and P is also the key of the ordered-path log.
 struct SegWalk {
     int e, d, n, half, i, iend;
-    int mx, my, nx, ny;  // major / minor step vectors
-    uint32_t x, y;
+    int M, N;            // packed major / minor step vectors
+    uint32_t P;
     __device__ __forceinline__ void init(const BeamEnds& b, int i0, int steps)
     {
         const uint32_t fx = b.fx & ~kBeamFlag, fy = b.fy & ~kBeamFlag;
@@ -272,8 +275,8 @@ struct SegWalk {
         const bool xmajor = dx >= dy;
         n = xmajor ? dx : dy;
         d = xmajor ? dy : dx;
-        mx = xmajor ? sx : 0; my = xmajor ? 0 : sy;
-        nx = xmajor ? 0 : sx; ny = xmajor ? sy : 0;
+        M = xmajor ? sx : sy * 65536;
+        N = xmajor ? sy * 65536 : sx;
         half = (n + 1) >> 1;
         i    = i0;
         iend = min(i0 + steps, n - 1);
@@ -283,17 +286,15 @@ struct SegWalk {
             k = (2u * (uint32_t)i0 * (uint32_t)d + (uint32_t)n) / (2u * (uint32_t)n);
             e = i0 * d - (int)k * n;
         }
-        x = fx + (uint32_t)(mx * i0 + nx * (int)k);
-        y = fy + (uint32_t)(my * i0 + ny * (int)k);
+        P = (fx | (fy << 16)) + (uint32_t)(M * i0 + N * (int)k);
     }
     __device__ __forceinline__ bool next()
     {
         if (i >= iend) return false;
         ++i;
         e += d;
-        x += mx;
-        y += my;
-        if (e >= half) { x += nx; y += ny; e -= n; }
+        P += (uint32_t)M;
+        if (e >= half) { P += (uint32_t)N; e -= n; }
         return true;
     }
 };
@@ -345,18 +346,14 @@ struct RayCtx {
     bool mark;                 // first pass: note the patches that are not writable yet
     int last_di;               // kProb
 
-    // (xr, yr) window-relative.  `run` > 0: this lane adds the misses of `run` adjacent lanes that touch the same
-    // cell (see raycast_pass); `run` == 0: another lane carries this lane's count, only the ordered-path log is kept.
-    // Every counter update is a fire-and-forget reduction at the L2 (SASS RED): nothing waits for a returned value.
-    // All cells of a beam lie inside the bounding box of its end cells, which phase 1a checked against the window.
-    __device__ __forceinline__ void touch(uint32_t xr, uint32_t yr, uint32_t beam, uint32_t pos, bool hit, uint32_t run = 1u)
+    __device__ __forceinline__ uint32_t dir_of_cell(uint32_t P) const { return ((P >> 21) << log2dim) | ((P >> kPatchLog2) & 0xFFu); }
+
+    // One touch of packed cell P whose patch-info word is `info` (directory entry `di`).  `run` > 0: this lane adds the misses of
+    // `run` adjacent lanes that touch the same cell (see raycast_pass); `run` == 0: another lane carries this lane's count, only
+    // the ordered-path log is kept.  Every counter update is a fire-and-forget reduction at the L2 (SASS RED): nothing waits
+    // for a returned value.
+    __device__ __forceinline__ void cell(uint32_t P, uint32_t info, uint32_t di, uint32_t beam, uint32_t pos, bool hit, uint32_t run)
     {
-        const uint32_t di   = ((yr >> kPatchLog2) << log2dim) | (xr >> kPatchLog2);
-#ifdef LAMA_PHASE_TIMING
-        const uint32_t info = (rp.debug & 2) ? (0xFF000000u | (di & 1023u)) : pinfo[di];
-#else
-        const uint32_t info = pinfo[di];
-#endif
         const uint32_t slot = info & kInfoSlotMask;
         if (slot == kInfoSlotMask) {
             if (mark) atomicOr(&pending[di >> 5], 1u << (di & 31));
@@ -366,14 +363,14 @@ struct RayCtx {
             atomicOr(&touched[di >> 5], 1u << (di & 31));
             last_di = (int)di;
         }
-        const uint32_t ci = (xr & (kPatchLen - 1)) | ((yr & (kPatchLen - 1)) << kPatchLog2);
+        const uint32_t off = ((P << 2) & 0x7Cu) | ((P >> 9) & 0xF80u);   // byte offset of the cell in its patch: (x & 31) * 4 + (y & 31) * 128
         if (run) {
             // the pool is 4 KiB aligned (checked at creation): patch base = pool + slot * 4096, the cell offset is OR-ed in
             uint64_t addr;
             uint32_t lo, hi;
             asm("mad.wide.u32 %0, %1, 4096, %2;" : "=l"(addr) : "r"(slot), "l"(s.pool));
             asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(addr));
-            lo |= ci << 2;
+            lo |= off;
             asm("mov.b64 %0, {%1, %2};" : "=l"(addr) : "r"(lo), "r"(hi));
 #ifdef LAMA_PHASE_TIMING
             if (rp.debug & 1) { if (addr == 1) sh.err = lo; } else
@@ -382,10 +379,22 @@ struct RayCtx {
         }
         const uint32_t ccand = info >> 24;
         if (ccand == kCandNone) return;
+        const uint32_t ci = off >> 2;
         if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
             const uint32_t idx = atomicAdd(&sh.log_count, 1u);
-            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record((yr << 16) | xr, beam, hit ? 0u : pos, hit);
+            if (idx < (uint32_t)rp.log_cap) log[idx] = log_record(P, beam, hit ? 0u : pos, hit);
         }
+    }
+    // All cells of a beam lie inside the bounding box of its end cells, which phase 1a checked against the window.
+    __device__ __forceinline__ void touch(uint32_t P, uint32_t beam, uint32_t pos, bool hit, uint32_t run = 1u)
+    {
+        const uint32_t di = dir_of_cell(P);
+#ifdef LAMA_PHASE_TIMING
+        const uint32_t info = (rp.debug & 2) ? (0xFF000000u | (di & 1023u)) : pinfo[di];
+#else
+        const uint32_t info = pinfo[di];
+#endif
+        cell(P, info, di, beam, pos, hit, run);
     }
 };
 
@@ -399,7 +408,7 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
     // hits (setOccupied, pf_slam2d.cpp:493-498)
     for (int b = tid; b < n_beams; b += blockDim.x) {
         const BeamEnds be = beams[b];
-        if (be.fx & kBeamFlag) c.touch(be.tx, be.ty, (uint32_t)b, 0u, true);
+        if (be.fx & kBeamFlag) c.touch(be.tx | (be.ty << 16), (uint32_t)b, 0u, true);
     }
     // planar beams: warp-dynamic (group, segment) items
     const uint32_t total = seg_prefix[n_groups];
@@ -427,18 +436,29 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
                 const bool v = w.next();
                 const unsigned valid = __ballot_sync(0xffffffffu, v);
                 if (!valid) break;
-                const uint32_t key = (w.y << 16) | w.x;
-                const uint32_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
-                const bool head = v && (lane == 0 || !((valid >> (lane - 1)) & 1u) || pkey != key);
+                const uint32_t pkey = __shfl_up_sync(0xffffffffu, w.P, 1);
+                const bool head = v && (lane == 0 || !((valid >> (lane - 1)) & 1u) || pkey != w.P);
                 const unsigned heads = __ballot_sync(0xffffffffu, head);
                 if (v) {
                     const unsigned stop = (heads | ~valid) & ~((2u << lane) - 1u);   // first lane above that starts another run
                     const uint32_t run = head ? (uint32_t)((stop ? __ffs(stop) - 1 : 32) - lane) : 0u;
-                    c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false, run);
+                    c.touch(w.P, (uint32_t)b, (uint32_t)w.i, false, run);
                 }
             }
         } else {
-            while (w.next()) c.touch(w.x, w.y, (uint32_t)b, (uint32_t)w.i, false);
+            // software pipeline: the patch-info word of the NEXT cell is fetched from shared memory before the current cell is
+            // processed, so the load latency overlaps the address arithmetic and the reduction of the current cell (the kernel is
+            // latency bound: 31 % of its stall samples were waits for this load)
+            bool v = w.next();
+            uint32_t P = w.P, pos = (uint32_t)w.i, di = c.dir_of_cell(P);
+            uint32_t info = c.pinfo[di];
+            while (v) {
+                const bool vn = w.next();                     // w.P stays on the last cell when the segment is finished
+                const uint32_t Pn = w.P, din = c.dir_of_cell(Pn);
+                const uint32_t infon = c.pinfo[din];
+                c.cell(P, info, di, (uint32_t)b, pos, false, 1u);
+                P = Pn; di = din; info = infon; pos = (uint32_t)w.i; v = vn;
+            }
         }
     }
     // non-planar beams (tilted sensor): the reference's 3-axis walk, one thread per beam
@@ -447,7 +467,7 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
         const double pt[3] = {__ldg(points + 3 * (size_t)b), __ldg(points + 3 * (size_t)b + 1), __ldg(points + 3 * (size_t)b + 2)};
         const BeamCells bc = beam_cells(tf, c.rp.scan, pt);
         RayWalk3 w(bc);
-        while (w.next()) c.touch(w.x - bx0, w.y - by0, (uint32_t)b, (uint32_t)w.i, false);
+        while (w.next()) c.touch((w.x - bx0) | ((w.y - by0) << 16), (uint32_t)b, (uint32_t)w.i, false);
     }
 }
 
