@@ -827,6 +827,29 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
                      bp.max_sqdist);
     const uint32_t nev = stats[blockIdx.x].events;
     const uint64_t* ev = events + (size_t)blockIdx.x * bp.event_cap;
+    // The L1 is cold at every launch and the waves started by the events stay within `reach` cells of them: pull the patch of
+    // every event (32 rows = 32 lines, one per lane) and the neighbouring patches a wave can reach into L1 before the sequential
+    // part starts, so that its dependent loads hit (ncu: 24 % of the loads missed L1, 21 % of the stall samples waited for them).
+    {
+        int reach = 0;
+        while ((uint32_t)(reach * reach) < bp.max_sqdist) ++reach;
+        const int dim = s.window.dim;
+        for (uint32_t i = 0; i < nev; ++i) {
+            const uint32_t key = (uint32_t)ev[i];
+            const int x = (int)(key & 0xFFFFu), y = (int)(key >> 16);
+            const int px = x >> kPatchLog2, py = y >> kPatchLog2, cx = x & (kPatchLen - 1), cy = y & (kPatchLen - 1);
+            const int x0 = cx < reach ? -1 : 0, x1 = cx >= kPatchLen - reach ? 1 : 0, y0 = cy < reach ? -1 : 0, y1 = cy >= kPatchLen - reach ? 1 : 0;
+            for (int dy = y0; dy <= y1; ++dy)
+                for (int dx = x0; dx <= x1; ++dx) {
+                    const int qx = px + dx, qy = py + dy;
+                    if ((unsigned)qx >= (unsigned)dim || (unsigned)qy >= (unsigned)dim) continue;
+                    const int e = dir[qy * dim + qx];
+                    if (e < 0) continue;
+                    const uint32_t* row = patch_ptr(s, e & kDirSlotMask) + lane * kPatchLen;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+                }
+        }
+    }
     for (uint32_t i = 0; i < nev; ++i) {
         const uint64_t e   = ev[i];
         const uint32_t key = (uint32_t)e;  // window-relative cell
