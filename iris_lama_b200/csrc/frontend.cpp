@@ -250,11 +250,13 @@ void PFSlam2D::finish_counters()
 // back to back on the device.  The map update runs on the matched poses BEFORE the resampling decision; a resampling of
 // this scan then shares the UPDATED maps, which is the reference's resample-then-update with the two steps commuted
 // (every copy of an ancestor would apply the same scan at the same pose).  The host only waits for the match results.
-int PFSlam2D::update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update)
+// Front half of a pipelined step for the local particles [lo_, hi_): enqueue match + map update, wait for the match results only,
+// then book the previous scan's map statistics (its map update precedes this scan's match in the stream, so it has completed).
+// `moved` false = motion gate (pf_slam2d.cpp:215-222): nothing else happens for this scan.
+int PFSlam2D::pipelined_begin(const double* pts, int n, const double* origin, const double* quat, bool moved, bool* did_update, double* local_out)
 {
     pending_maps_ = false;
-    const bool moved = predict_and_gate(odom_xyr);
-    if (!moved) {   // motion gate (pf_slam2d.cpp:215-222): nothing else happens for this scan
+    if (!moved) {
         int rcs = settle_counters();
         last_ = Counters();
         last_idx_.clear();
@@ -274,24 +276,37 @@ int PFSlam2D::update_pipelined(const double* pts, int n, const double* origin, c
         rc = eng_->select_staged(staged, origin, quat, opt_.truncated_ray, opt_.truncated_range);
         if (rc != LAMA_OK) return engine_fail(rc);
     }
-    std::vector<HostMatchResult> res((size_t)P_);
-    rc = eng_->step_async(staged >= 0 ? nullptr : pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range, &pose_[0], (int)P_,
+    const int nl = hi_ - lo_;
+    std::vector<HostMatchResult> res((size_t)nl);
+    rc = eng_->step_async(staged >= 0 ? nullptr : pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range, &pose_[lo_], nl,
                           make_solver(0, opt_.max_iter), opt_.meas_sigma, res.data());   // GaussNewton + CauchyWeight(0.15), pf_slam2d.cpp:423-427
-    if (prev_pending) {   // the previous scan's map update was collected inside step_async (it precedes this scan's match in the stream)
+    if (prev_pending) {
         collect_map_stats(prev);
         total_.add(prev);
     }
     if (rc != LAMA_OK) return engine_fail(rc);
-    std::vector<double> all((size_t)P_ * 5);
-    for (uint32_t k = 0; k < P_; ++k) {
-        all[5 * k + 0] = res[k].state.c;
-        all[5 * k + 1] = res[k].state.s;
-        all[5 * k + 2] = res[k].state.tx;
-        all[5 * k + 3] = res[k].state.ty;
-        all[5 * k + 4] = res[k].sums[11];        // calculateLikelihood, pf_slam2d.cpp:393-414
+    for (int k = 0; k < nl; ++k) {
+        local_out[5 * k + 0] = res[k].state.c;
+        local_out[5 * k + 1] = res[k].state.s;
+        local_out[5 * k + 2] = res[k].state.tx;
+        local_out[5 * k + 3] = res[k].state.ty;
+        local_out[5 * k + 4] = res[k].sums[11];  // calculateLikelihood, pf_slam2d.cpp:393-414
         last_.evals += res[k].evals_ref + 1;     // + the likelihood pass
         last_.gn_iters += res[k].iterations;
     }
+    return LAMA_OK;
+}
+
+// The whole scan enqueued at once (Engine::step_async): odometry sampling on the host, then match -> ray cast -> brushfire
+// back to back on the device.  The map update runs on the matched poses BEFORE the resampling decision; a resampling of
+// this scan then shares the UPDATED maps, which is the reference's resample-then-update with the two steps commuted
+// (every copy of an ancestor would apply the same scan at the same pose).  The host only waits for the match results.
+int PFSlam2D::update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update)
+{
+    const bool moved = predict_and_gate(odom_xyr);
+    std::vector<double> all((size_t)P_ * 5);
+    int rc = pipelined_begin(pts, n, origin, quat, moved, did_update, all.data());
+    if (rc != LAMA_OK || !moved) return rc;
     absorb_results(all.data());
     normalize();
     std::vector<int32_t> v;
@@ -356,6 +371,16 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
     // depend on the previous scan's map update, which may still be running on the device.
     bool moved = false;
     if (has_first_) moved = predict_and_gate(odom_xyr);
+    if (has_first_ && eng_ && opt_.shard_count > 1 && opt_.dev.timing == 0) {
+        // Sharded ranks: the map update of the local particles is enqueued right behind their match and runs while the ranks
+        // exchange results and decide about resampling; a resampling of this scan then moves / shares the UPDATED maps.
+        maps_enqueued_ = false;
+        int rcp = pipelined_begin(pts, n, origin, quat, moved, did_update, local_out);
+        if (rcp != LAMA_OK || !moved) return rcp;
+        maps_enqueued_ = true;
+        pending_maps_  = true;
+        return LAMA_OK;
+    }
     if (eng_) {
         int rcs = settle_counters();   // now collect the previous scan's asynchronous map update (and its errors)
         if (rcs != LAMA_OK) return rcs;
@@ -377,6 +402,7 @@ int PFSlam2D::shard_begin(const double* pts, int n, const double* origin, const 
     }
     if (!moved) return LAMA_OK;
     *did_update = true;
+    maps_enqueued_ = false;
     rc = match_local(local_out);
     if (rc != LAMA_OK) return rc;
     pending_maps_ = true;
@@ -457,6 +483,11 @@ int PFSlam2D::shard_map_update()
     if (!pending_maps_) return fail("shard_map_update without a pending update", LAMA_ERR_STATE);
     pending_maps_ = false;
     const int nl = hi_ - lo_;
+    if (maps_enqueued_) {   // already running since shard_begin
+        maps_enqueued_    = false;
+        counters_pending_ = true;
+        return LAMA_OK;
+    }
     // asynchronous: the kernels of this scan overlap with the caller's work until the next call into this handle
     int rc = eng_->update_maps_async(&pose_[lo_], 0, nl);
     if (rc != LAMA_OK) return engine_fail(rc);

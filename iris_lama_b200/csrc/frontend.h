@@ -79,7 +79,9 @@ public:
     Engine* engine() { return eng_.get(); }
     const std::string& error() const { return err_; }
     bool has_first_scan() const { return has_first_; }
+    bool maps_enqueued_ = false;   // sharded ranks: this scan's map update was enqueued together with its match
     int settle_counters();
+    int pipelined_begin(const double* pts, int n, const double* origin, const double* quat, bool moved, bool* did_update, double* local_out);
     int update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update);
     void collect_map_stats(Counters& c);
 

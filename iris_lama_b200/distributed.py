@@ -58,6 +58,14 @@ class ShardedPFSlam2D:
         self.device = device if device is not None else torch.device("cpu")
         self.collectives = 0
         self.migrated_bytes = 0
+        # The collectives get their own CUDA stream: NCCL orders itself after the work already enqueued on the stream it is
+        # called from, and the engine's stream holds this scan's map update (enqueued together with the match), which the
+        # exchange of the match results must not wait for.
+        self.comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def _comm(self):
+        import contextlib
+        return torch.cuda.stream(self.comm_stream) if self.comm_stream is not None else contextlib.nullcontext()
 
     def _t(self, a, dtype):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(self.device)
@@ -67,20 +75,22 @@ class ShardedPFSlam2D:
         if did != 2:
             return did != 0
         # (1) all-gather of the local match results
-        mine = self._t(local.reshape(-1), torch.float64)
-        allr = torch.empty(self.P * 5, dtype=torch.float64, device=self.device)
-        dist.all_gather_into_tensor(allr, mine, group=self.group)
-        self.collectives += 1
-        all_results = allr.cpu().numpy().reshape(self.P, 5)
+        with self._comm():
+            mine = self._t(local.reshape(-1), torch.float64)
+            allr = torch.empty(self.P * 5, dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(allr, mine, group=self.group)
+            self.collectives += 1
+            all_results = allr.cpu().numpy().reshape(self.P, 5)
         resampled, idx = self.pf.shardFinish(all_results)
         # (2) broadcast of rank 0's decision and indices (every rank computes the same ones; rank 0 is authoritative)
-        msg = torch.empty(self.P + 1, dtype=torch.int32, device=self.device)
-        if self.rank == 0:
-            msg[0] = int(resampled)
-            msg[1:] = self._t(idx, torch.int32)
-        dist.broadcast(msg, src=0, group=self.group)
-        self.collectives += 1
-        m = msg.cpu().numpy()
+        with self._comm():
+            msg = torch.empty(self.P + 1, dtype=torch.int32, device=self.device)
+            if self.rank == 0:
+                msg[0] = int(resampled)
+                msg[1:] = self._t(idx, torch.int32)
+            dist.broadcast(msg, src=0, group=self.group)
+            self.collectives += 1
+            m = msg.cpu().numpy()
         if bool(m[0]) != resampled or (resampled and not np.array_equal(m[1:], idx)):
             raise RuntimeError("resampling decision diverged between ranks")
         if resampled:
@@ -89,6 +99,10 @@ class ShardedPFSlam2D:
         return True
 
     def _migrate_and_apply(self, idx):
+        with self._comm():
+            self._migrate_and_apply_impl(idx)
+
+    def _migrate_and_apply_impl(self, idx):
         need, serve = migration_plan(idx, self.world)
         # sizes first (all ranks know who sends what; only byte counts are unknown)
         bufs = [(dst, gid, self.pf.packParticle(gid - self.rank * self.per)) for dst, gid in serve[self.rank]]
