@@ -62,6 +62,7 @@ class ShardedPFSlam2D:
         # called from, and the engine's stream holds this scan's map update (enqueued together with the match), which the
         # exchange of the match results must not wait for.
         self.comm_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._digest = 0.0   # of the previous scan's resampling decision (see update)
 
     def _comm(self):
         import contextlib
@@ -74,25 +75,22 @@ class ShardedPFSlam2D:
         did, local = self.pf.shardBegin(pts, odom, timestamp)
         if did != 2:
             return did != 0
-        # (1) all-gather of the local match results
+        # ONE collective per scan: all-gather of the local match results.  Every rank then normalises and resamples on the same
+        # gathered bytes with the same code and RNG state, so all ranks take the same decision; as a cross-check each rank appends
+        # a digest of its PREVIOUS decision to its payload and everybody compares the gathered digests (a divergence is reported
+        # one scan late instead of costing a second collective on every scan).
         with self._comm():
-            mine = self._t(local.reshape(-1), torch.float64)
-            allr = torch.empty(self.P * 5, dtype=torch.float64, device=self.device)
+            payload = np.concatenate([local.reshape(-1), [self._digest]])
+            mine = self._t(payload, torch.float64)
+            allr = torch.empty(self.world * (self.per * 5 + 1), dtype=torch.float64, device=self.device)
             dist.all_gather_into_tensor(allr, mine, group=self.group)
             self.collectives += 1
-            all_results = allr.cpu().numpy().reshape(self.P, 5)
-        resampled, idx = self.pf.shardFinish(all_results)
-        # (2) broadcast of rank 0's decision and indices (every rank computes the same ones; rank 0 is authoritative)
-        with self._comm():
-            msg = torch.empty(self.P + 1, dtype=torch.int32, device=self.device)
-            if self.rank == 0:
-                msg[0] = int(resampled)
-                msg[1:] = self._t(idx, torch.int32)
-            dist.broadcast(msg, src=0, group=self.group)
-            self.collectives += 1
-            m = msg.cpu().numpy()
-        if bool(m[0]) != resampled or (resampled and not np.array_equal(m[1:], idx)):
+            g = allr.cpu().numpy().reshape(self.world, self.per * 5 + 1)
+        if not (g[:, -1] == g[0, -1]).all():
             raise RuntimeError("resampling decision diverged between ranks")
+        all_results = np.ascontiguousarray(g[:, :-1]).reshape(self.P, 5)
+        resampled, idx = self.pf.shardFinish(all_results)
+        self._digest = float(int(resampled) + (int(np.dot(idx.astype(np.int64), np.arange(1, self.P + 1, dtype=np.int64)) % 9007199254740881) if resampled else 0))
         if resampled:
             self._migrate_and_apply(idx)
         self.pf.shardMapUpdate()

@@ -26,19 +26,14 @@ for t in range(T1):
     t0 = time.perf_counter()
     did, local = pf.shardBegin(ds.scans[t], ds.odom[t], 0.0); t0 = tick("shardBegin (sampling, enqueue, wait for match)", t0)
     with sh._comm():
-        mine = sh._t(local.reshape(-1), torch.float64)
-        allr = torch.empty(P * 5, dtype=torch.float64, device=dev)
+        payload = np.concatenate([local.reshape(-1), [0.0]])
+        mine = sh._t(payload, torch.float64)
+        allr = torch.empty(world * (P // world * 5 + 1), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine)
-        all_results = allr.cpu().numpy().reshape(P, 5)
+        g = allr.cpu().numpy().reshape(world, P // world * 5 + 1)
+    all_results = np.ascontiguousarray(g[:, :-1]).reshape(P, 5)
     t0 = tick("all_gather incl. copies", t0)
     resampled, idx = pf.shardFinish(all_results); t0 = tick("shardFinish (normalise, resampling decision)", t0)
-    with sh._comm():
-        msg = torch.empty(P + 1, dtype=torch.int32, device=dev)
-        if rank == 0:
-            msg[0] = int(resampled); msg[1:] = sh._t(idx, torch.int32)
-        dist.broadcast(msg, src=0)
-        m = msg.cpu().numpy()
-    t0 = tick("broadcast incl. copies", t0)
     pf.shardMapUpdate(); t0 = tick("shardMapUpdate", t0)
 torch.cuda.synchronize(); dist.barrier()
 tot = time.perf_counter() - t_all

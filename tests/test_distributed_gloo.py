@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the particle-sharding orchestration (iris_lama_b200/distributed.py): all-gather of match
-results, broadcast of resampling indices, point-to-point migration of ancestor maps.  The device object is replaced by
+results (+ the digest of the previous resampling decision), point-to-point migration of ancestor maps.  The device object is replaced by
 a stub that implements the same shard*/pack/unpack calls, so the host-side plan is tested without a GPU."""
 import os
 import sys
