@@ -386,3 +386,36 @@ def test_slam2d_transient_map(gpu_api, po, synth):
     go, oo = g.exportOccupancy(mn[0], mn[1], w, h), o.export_occ(mn[0], mn[1], w, h)
     for k in ("occupied", "visited", "known"):
         assert (go[k] == oo[k]).all(), k
+
+
+# ---- failures are loud (no silent truncation, no fallback) ------------------------------------------------------------------
+def test_errors_are_reported_not_swallowed(gpu_api, synth):
+    ds = synth.make_dataset("room", 4, n_beams=360)
+    # a directory window of 8 x 8 patches (12.8 m) cannot hold a 20 m room: LAMA_ERR_WINDOW
+    g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, dir_dim=8))
+    g.setPose(*ds.truth[0])
+    with pytest.raises(gpu_api.LamaError) as e:
+        for t in range(3):
+            g.update(ds.scans[t], ds.odom[t])
+    assert e.value.code == -4 and "window" in str(e.value)
+    # a pool of 24 patches cannot hold the first scan of the same room: LAMA_ERR_POOL
+    g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, pool_slots=24))
+    g.setPose(*ds.truth[0])
+    with pytest.raises(gpu_api.LamaError) as e:
+        for t in range(3):
+            g.update(ds.scans[t], ds.odom[t])
+    assert e.value.code == -5
+    # the particle filter runs its map update asynchronously: the failure surfaces at the next call into the handle
+    pf = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(4, trans_thresh=0.05, rot_thresh=0.05, seed=3, dir_dim=8))
+    pf.setPrior(*ds.truth[0])
+    with pytest.raises(gpu_api.LamaError) as e:
+        for t in range(4):
+            pf.update(ds.scans[t], ds.odom[t])
+        pf.counters()
+    assert e.value.code == -4
+    # more beams than the engine was created for
+    g = gpu_api.Slam2D(gpu_api.Slam2D.Options(trans_thresh=0.05, rot_thresh=0.05, max_beams=360))
+    g.setPose(*ds.truth[0])
+    g.update(ds.scans[0], ds.odom[0])
+    with pytest.raises(gpu_api.LamaError):
+        g.update(np.zeros((400, 3)), ds.odom[1])
