@@ -71,6 +71,19 @@ public:
     void getPose(double xyr[3]) const { check(lama_pf_get_pose(h_, xyr)); }       // pf_slam2d.cpp:332-336
     size_t getBestParticleIdx() const { int i = 0; check(lama_pf_get_best_particle(h_, &i)); return (size_t)i; }
     double getNeff() const { double v = 0; check(lama_pf_get_neff(h_, &v)); return v; }
+    // Map::write of a particle's occupancy (kind 0) / distance (kind 1) map: a reference .sdm file (map.cpp:490-529)
+    void writeMap(int particle, int kind, const std::string& path) const { check(lama_pf_write_map(h_, particle, kind, path.c_str())); }
+    // the grey image PFSlam2D::saveOccImage hands to sdm::export_to_png (pf_slam2d.cpp:338-342, export.cpp:46-73), row-major
+    std::vector<uint8_t> occImage(int& width, int& height) const
+    {
+        int dims[2] = {0, 0};
+        const int best = (int)getBestParticleIdx();
+        check(lama_pf_export_image(h_, best, 0, nullptr, 0, dims));
+        std::vector<uint8_t> img((size_t)dims[0] * dims[1]);
+        if (!img.empty()) check(lama_pf_export_image(h_, best, 0, img.data(), img.size(), dims));
+        width = dims[0]; height = dims[1];
+        return img;
+    }
     lama_pf* handle() const { return h_; }
 
 private:
@@ -99,7 +112,40 @@ public:
     }
     void getPose(double xyr[3]) const { check(lama_slam_get_pose(h_, xyr)); }
     uint32_t getNumberOfProcessedCells() const { uint32_t n = 0; check(lama_slam_get_processed_cells(h_, &n)); return n; }
+    void writeMap(int kind, const std::string& path) const { check(lama_slam_write_map(h_, kind, path.c_str())); }
     lama_slam* handle() const { return h_; }
+
+protected:
+    lama_slam* h_ = nullptr;
+};
+
+// lama::LidarOdometry2D (include/lama/lidar_odometry_2d.h:45-75): the Slam2D handle in its lidar-odometry mode
+class LidarOdometry2D {
+public:
+    struct Options {
+        double resolution;
+        uint32_t max_iter;
+        Options() : resolution(0.05), max_iter(100) {}   // lidar_odometry_2d.h:62-68
+    };
+    explicit LidarOdometry2D(const Options& o = Options())
+    {
+        lama_slam_options s;
+        check(lama_slam_options_default(&s));
+        s.lidar_odometry = 1; s.resolution = o.resolution; s.max_iter = o.max_iter;
+        check(lama_slam_create(&s, &h_));
+    }
+    ~LidarOdometry2D() { lama_slam_destroy(h_); }
+    LidarOdometry2D(const LidarOdometry2D&) = delete;
+    LidarOdometry2D& operator=(const LidarOdometry2D&) = delete;
+    template <typename CloudPtr>
+    bool update(const CloudPtr& surface, double timestamp)  // lidar_odometry_2d.h:73
+    {
+        FlatCloud<typename std::remove_reference<decltype(*surface)>::type> f(*surface);
+        int did = 0;
+        check(lama_slam_update(h_, f.pts.data(), (int)(f.pts.size() / 3), f.origin, f.quat, nullptr, timestamp, &did));
+        return did != 0;
+    }
+    void getOdom(double xyr[3]) const { check(lama_slam_get_pose(h_, xyr)); }   // the public member `odom`
 
 private:
     lama_slam* h_ = nullptr;
@@ -127,6 +173,9 @@ public:
     void getPose(double xyr[3]) const { check(lama_loc_get_pose(h_, xyr)); }
     void getCovar(double cov[9]) const { check(lama_loc_get_covar(h_, cov)); }
     double getRMSE() const { double v = 0; check(lama_loc_get_rmse(h_, &v)); return v; }
+    void triggerGlobalLocalization() { check(lama_loc_trigger_global_localization(h_)); }   // loc2d.cpp:194-197
+    void readOccupancyMap(const std::string& path) { check(lama_loc_occupancy_read(h_, path.c_str())); }    // occupancy_map->read(path)
+    void readDistanceMap(const std::string& path) { check(lama_dm_read(distance_map(), path.c_str())); }    // distance_map->read(path)
 
 private:
     lama_loc* h_ = nullptr;

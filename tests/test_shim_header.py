@@ -19,6 +19,10 @@ int main() {
     pf.setPrior(Pose{0,0,0});
     bool u = pf.update(c, Pose{0,0,0}, 0.0);
     std::printf("updated %d\n", (int)u);
+    lama_b200_shim::LidarOdometry2D lo;            // instantiate every template of the header
+    lo.update(c, 0.0);
+    double xyr[3]; lo.getOdom(xyr);
+    lama_b200_shim::Loc2D loc; loc.Init(lama_b200_shim::Loc2D::defaults()); loc.triggerGlobalLocalization();
   } catch (const std::exception& e) { std::printf("%s\n", e.what()); }
   return 0; }
 '''
