@@ -287,8 +287,10 @@ def gpu_arm(args):
                            "l2": "per-scan working set (~290 MB of touched map patches over 256 particles) exceeds the 126 MB L2; no explicit flush",
                            "value_inputs": "scans staged in HBM" if world == 1 else "host scans (sharded path)",
                            "updates_in_timed_region": n_upd, "prebuild_scans": pre,
-                           "timer": "CUDA events on the launching stream around the K steps (each step also synchronises for its host-side "
-                                    "normalise/resample logic); host wall clock of the same region: %.3f s" % wall_value},
+                           "timer": "CUDA events on the launching stream around the K steps (every step enqueues match + map update at once and "
+                                    "the host waits for the match results only, for its normalise/resample logic; the roofline kernel "
+                                    "times come from a separate pass with per-kernel event records); host wall clock of the same "
+                                    "region: %.3f s" % wall_value},
                 "clocks": clocks,
                 "e2e": {"value": steps / dt_e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps},
                 "gpu_launches": gpu_launches,
