@@ -71,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
-    "lama_slam_get_map_stats", "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
+    "lama_pf_occupancy_query", "lama_slam_occupancy_query", "lama_w2m", "lama_slam_get_map_stats", "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
     "lama_dm_export_image", "lama_loc_occupancy_read",
     "lama_loc_occupancy_set", "lama_loc_set_seed", "lama_loc_trigger_global_localization", "lama_loc_global_localization_active",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
@@ -148,6 +148,15 @@ def _image(fn, args):
     out = np.zeros((dims[1], dims[0]), np.uint8)
     if out.size:
         _chk(fn(*args, _vp(out), C.c_size_t(out.size), dims))
+    return out
+
+
+def w2m(resolution, pts):
+    """Map::w2m (map.h:125-126): world points (n, 3) -> cells (n, 2)"""
+    p, pp = _d(pts)
+    n = p.size // 3
+    out = np.zeros((n, 2), np.uint32)
+    _chk(lib().lama_w2m(C.c_double(resolution), pp, C.c_int(n), _vp(out)))
     return out
 
 
@@ -294,6 +303,14 @@ class PFSlam2D:
         _chk(lib().lama_pf_export_distance(self.h, C.c_int(particle), C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
 
+    def occupancyQuery(self, particle, cells):
+        """(getProbability, flags) of getOccupancyMap(particle) for n cells; flags bit 0 isFree, bit 1 isOccupied, bit 2 isUnknown"""
+        c, cp = _u32(cells)
+        n = c.size // 2
+        prob, flags = np.zeros(n), np.zeros(n, np.uint8)
+        _chk(lib().lama_pf_occupancy_query(self.h, C.c_int(particle), cp, C.c_int(n), prob.ctypes.data_as(c_dp), _vp(flags)))
+        return prob, flags
+
     def writeMap(self, particle, kind, path):
         """Map::write of getOccupancyMap(particle) (kind 0) / getDistanceMap(particle) (kind 1): a reference .sdm file"""
         _chk(lib().lama_pf_write_map(self.h, C.c_int(particle), C.c_int(kind), str(path).encode()))
@@ -430,6 +447,13 @@ class Slam2D:
         o = _dm_arrays(w, h)
         _chk(lib().lama_slam_export_distance(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
+
+    def occupancyQuery(self, cells):
+        c, cp = _u32(cells)
+        n = c.size // 2
+        prob, flags = np.zeros(n), np.zeros(n, np.uint8)
+        _chk(lib().lama_slam_occupancy_query(self.h, cp, C.c_int(n), prob.ctypes.data_as(c_dp), _vp(flags)))
+        return prob, flags
 
     def writeMap(self, kind, path):
         _chk(lib().lama_slam_write_map(self.h, C.c_int(kind), str(path).encode()))

@@ -173,6 +173,36 @@ int fetch_occ(Engine* e, int particle, OccPlanes& p)
     p.occupied.resize(cells); p.visited.resize(cells);
     return export_occ(e, particle, p.win.x0, p.win.y0, p.win.w, p.win.h, p.occupied.data(), p.visited.data(), p.known.data());
 }
+// OccupancyMap::{getProbability, isFree, isOccupied, isUnknown}(Vector3ui) of n cells (frequency_occupancy_map.cpp:110-172,
+// probabilistic_occupancy_map.cpp:38-41,125-175); flags bit 0 free, bit 1 occupied, bit 2 unknown
+int occupancy_query(Engine* e, int particle, const uint32_t* cells, int n, double* prob, uint8_t* flags)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    if (n < 0 || (n && (!cells || !prob || !flags))) return set_err("bad argument", LAMA_ERR_ARG);
+    std::vector<uint32_t> words((size_t)n);
+    std::vector<uint8_t> fl((size_t)n);
+    int rc = e->gather_cells(particle, 0, cells, n, words.data(), fl.data());
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    const bool logodds = e->config().occupancy_kind == 1;
+    const double thr = e->logodds_threshold();
+    auto prob_of = [](float l) -> float { return 1.0 - 1.0 / (1.0 + std::exp(l)); };   // probabilistic_occupancy_map.cpp:38-41 (float in, float out)
+    for (int i = 0; i < n; ++i) {
+        if (logodds) {
+            const bool known = (fl[i] & 2) != 0;
+            float l;
+            std::memcpy(&l, &words[i], 4);
+            prob[i]  = known ? prob_of(l) : prob_of((float)thr);
+            flags[i] = (uint8_t)((known && (double)l < thr ? 1 : 0) | (known && (double)l > thr ? 2 : 0) | (!known || (double)l == thr ? 4 : 0));
+        } else {
+            const bool known = words[i] != 0;   // every mutable access counts a visit
+            const uint32_t occ = occ_occupied(words[i]), vis = occ_visited(words[i]);
+            const double p = vis == 0 ? 0.25 : ((double)occ) / ((double)vis);   // frequency_occupancy_map.cpp:40-45
+            prob[i]  = known ? p : 0.25;
+            flags[i] = (uint8_t)((known && p < 0.25 ? 1 : 0) | (known && p > 0.25 ? 2 : 0) | (!known || vis == 0 ? 4 : 0));
+        }
+    }
+    return LAMA_OK;
+}
 // kind 0: occupancy map, kind 1: distance map
 int write_map(Engine* e, int particle, int kind, bool slam_frontend, const char* path)
 {
@@ -384,6 +414,11 @@ int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0,
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     return export_occ(h->p->engine(), pf_local(h, particle), x0, y0, w, hgt, occupied, visited, known);
 }
+int lama_pf_occupancy_query(lama_pf* h, int particle, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return occupancy_query(h->p->engine(), pf_local(h, particle), cells_xy, n, prob, flags);
+}
 int lama_pf_write_map(lama_pf* h, int particle, int kind, const char* path)
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
@@ -549,6 +584,21 @@ int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, in
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
+}
+int lama_slam_occupancy_query(lama_slam* h, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
+{
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return occupancy_query(h->s->engine(), 0, cells_xy, n, prob, flags);
+}
+int lama_w2m(double resolution, const double* pts_xyz, int n, uint32_t* cells_xy)
+{
+    if (!(resolution > 0) || n < 0 || (n && (!pts_xyz || !cells_xy))) return set_err("bad argument", LAMA_ERR_ARG);
+    const double scale = 1.0 / resolution;
+    for (int i = 0; i < n; ++i) {
+        cells_xy[2 * i]     = w2m(pts_xyz[3 * i], scale);
+        cells_xy[2 * i + 1] = w2m(pts_xyz[3 * i + 1], scale);
+    }
+    return LAMA_OK;
 }
 int lama_slam_write_map(lama_slam* h, int kind, const char* path)
 {

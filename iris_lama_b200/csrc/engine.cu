@@ -686,6 +686,26 @@ int Engine::export_window(int particle, int kind, uint32_t x0, uint32_t y0, int 
     return LAMA_OK;
 }
 
+int Engine::gather_cells(int particle, int kind, const uint32_t* cells_xy, int n, uint32_t* words, uint8_t* flags)
+{
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
+    if (particle < 0 || particle >= cfg_.particles || kind < 0 || kind > 1 || n < 0 || (n && (!cells_xy || !words || !flags)))
+        return fail("gather_cells: bad arguments", LAMA_ERR_ARG);
+    if (n == 0) return LAMA_OK;
+    CU_TRY(cudaSetDevice(cfg_.device));
+    const size_t bc = (size_t)n * 8, bw = (size_t)n * 4, bf = (size_t)n;
+    if (ensure_scratch(d_, bc + bw + bf)) return fail("gather_cells: out of device memory", LAMA_ERR_CUDA);
+    char* base = (char*)d_->d_scratch;
+    CU_TRY(cudaMemcpyAsync(base, cells_xy, bc, cudaMemcpyHostToDevice, d_->stream));
+    launch_gather_cells(d_->view, cur_set_, particle, kind, (const uint32_t*)base, n, (uint32_t*)(base + bc), (uint8_t*)(base + bc + bw), d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(words, base + bc, bw, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaMemcpyAsync(flags, base + bc + bw, bf, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
 int Engine::export_bits(int particle, int plane, uint32_t x0, uint32_t y0, int w, int h, uint8_t* out)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }

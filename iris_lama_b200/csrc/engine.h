@@ -109,6 +109,8 @@ public:
     int import_window(int particle, int kind, uint32_t x0, uint32_t y0, int w, int h, const uint32_t* words);
     // dense window of a bit plane of the occupancy map: 0 = obstacle mirror, 1 = known bits (log-odds maps)
     int export_bits(int particle, int plane, uint32_t x0, uint32_t y0, int w, int h, uint8_t* out);
+    // raw words of n scattered cells (x, y pairs) of one map; flags bit 0: patch exists, bit 1: known bit of a log-odds map
+    int gather_cells(int particle, int kind, const uint32_t* cells_xy, int n, uint32_t* words, uint8_t* flags);
     // bounding box (in cells) of allocated patches of one map; returns the number of patches
     int bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2]);
 

@@ -957,6 +957,28 @@ __global__ void k_export(StoreView s, int set, int particle, int kind, uint32_t 
     }
 }
 
+// the words of n scattered cells of one map; flags bit 0: the patch exists, bit 1: the cell's bit in the `known` plane (log-odds maps)
+__global__ void k_gather_cells(StoreView s, int set, int particle, int kind, const uint32_t* __restrict__ cells, int n, uint32_t* __restrict__ words,
+                               uint8_t* __restrict__ flags)
+{
+    const int32_t* d = dir_of(s, set, particle, kind);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t x = cells[2 * k], y = cells[2 * k + 1];
+        const int di   = dir_index(s.window, x, y);
+        const int slot = di < 0 ? -1 : d[di];
+        uint32_t w = 0;
+        uint8_t f = 0;
+        if (slot >= 0) {
+            const uint32_t ci = cell_index(x, y);
+            w = __ldcg(patch_ptr(s, slot & kDirSlotMask) + ci);
+            f = 1;
+            if (kind == kMapOcc && s.kbits && ((__ldcg(kbits_ptr(s, slot & kDirSlotMask) + (ci >> 5)) >> (ci & 31)) & 1u)) f |= 2;
+        }
+        words[k] = w;
+        flags[k] = f;
+    }
+}
+
 __global__ void k_export_bits(StoreView s, int plane, int set, int particle, uint32_t x0, uint32_t y0, int w, int h, uint8_t* __restrict__ out)
 {
     const int32_t* d = dir_of(s, set, particle, kMapOcc);
@@ -1178,6 +1200,12 @@ void launch_export(const StoreView& s, int set, int particle, int kind, uint32_t
     if (blocks > 1184) blocks = 1184;
     if (blocks < 1) blocks = 1;
     k_export<<<blocks, 256, 0, st>>>(s, set, particle, kind, x0, y0, w, h, d_out, d_present);
+}
+void launch_gather_cells(const StoreView& s, int set, int particle, int kind, const uint32_t* d_cells, int n, uint32_t* d_words, uint8_t* d_flags,
+                         cudaStream_t st)
+{
+    if (n <= 0) return;
+    k_gather_cells<<<(n + 255) / 256 < 592 ? (n + 255) / 256 : 592, 256, 0, st>>>(s, set, particle, kind, d_cells, n, d_words, d_flags);
 }
 void launch_export_bits(const StoreView& s, int plane, int set, int particle, uint32_t x0, uint32_t y0, int w, int h, uint8_t* d_out, cudaStream_t st)
 {

@@ -74,6 +74,8 @@ void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_
 // releases every patch referenced by particles [first, first+count) of `set` and clears their directories
 void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st);
 void launch_merge_free(const StoreView& s, cudaStream_t st);
+void launch_gather_cells(const StoreView& s, int set, int particle, int kind, const uint32_t* d_cells, int n, uint32_t* d_words, uint8_t* d_flags,
+                         cudaStream_t st);
 void launch_delete_patches(const StoreView& s, int set, int particle, const int32_t* d_list, int count, cudaStream_t st);
 void launch_init_store(const StoreView& s, int n_sets, cudaStream_t st);
 // dense window of one bit plane (0 = obstacle mirror, 1 = known bits of log-odds maps) of an occupancy map, one byte per cell

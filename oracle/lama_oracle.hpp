@@ -523,6 +523,16 @@ public:
         const FreqCell* cell = static_cast<const SparseMap<FreqCell>*>(this)->get(c);
         return cell != nullptr && prob(*cell) > occ_thresh;
     }
+    bool is_unknown(const Vec3u& c) const   // :141-147
+    {
+        const FreqCell* cell = static_cast<const SparseMap<FreqCell>*>(this)->get(c);
+        return cell == nullptr || cell->visited == 0;
+    }
+    double get_probability(const Vec3u& c) const  // :166-172
+    {
+        const FreqCell* cell = static_cast<const SparseMap<FreqCell>*>(this)->get(c);
+        return cell == nullptr ? occ_thresh : prob(*cell);
+    }
     uint64_t ray_cells = 0;  // work counter C (cells visited by ray casts incl. hit cells)
 };
 
@@ -567,6 +577,17 @@ public:
     {
         const ProbCell* cell = static_cast<const SparseMap<ProbCell>*>(this)->get(c);
         return cell != nullptr && cell->prob > occ_thresh_;
+    }
+    bool is_unknown(const Vec3u& c) const   // :156-162
+    {
+        const ProbCell* cell = static_cast<const SparseMap<ProbCell>*>(this)->get(c);
+        return cell == nullptr || cell->prob == occ_thresh_;
+    }
+    static float prob_of(const float& logods) { return 1.0 - 1.0 / (1.0 + std::exp(logods)); }  // :38-41
+    double get_probability(const Vec3u& c) const  // :169-175
+    {
+        const ProbCell* cell = static_cast<const SparseMap<ProbCell>*>(this)->get(c);
+        return cell == nullptr ? prob_of(occ_thresh_) : prob_of(cell->prob);
     }
     uint64_t ray_cells = 0;
 };

@@ -66,6 +66,17 @@ void export_occ(const FrequencyOccupancyMap& occ, uint32_t x0, uint32_t y0, int 
 }
 }  // namespace
 
+// OccupancyMap::{getProbability, isFree, isOccupied, isUnknown}(Vector3ui) for n cells; flags bit 0 free, 1 occupied, 2 unknown
+template <class M>
+static void occ_query(const M& m, const uint32_t* cells, int n, double* prob, uint8_t* flags)
+{
+    for (int i = 0; i < n; ++i) {
+        const Vec3u c{cells[2 * i], cells[2 * i + 1], 0};
+        prob[i]  = m.get_probability(c);
+        flags[i] = (uint8_t)((m.is_free(c) ? 1 : 0) | (m.is_occupied(c) ? 2 : 0) | (m.is_unknown(c) ? 4 : 0));
+    }
+}
+
 extern "C" {
 
 // ---- Lie / pose algebra ----------------------------------------------------------------------
@@ -457,5 +468,9 @@ void orc_lo_counters(void* h, uint64_t* out)
 void* orc_lo_occ_handle(void* h) { return &((LidarOdometry2D*)h)->occ; }
 void* orc_lo_dm_handle(void* h) { return &((LidarOdometry2D*)h)->dm; }
 uint64_t orc_slam_removed_patches(void* h) { return ((Slam2D*)h)->removed_patches; }
+
+
+void orc_freq_query(void* d, const uint32_t* cells, int n, double* prob, uint8_t* flags) { occ_query(*(FrequencyOccupancyMap*)d, cells, n, prob, flags); }
+void orc_prob_query(void* d, const uint32_t* cells, int n, double* prob, uint8_t* flags) { occ_query(*(ProbabilisticOccupancyMap*)d, cells, n, prob, flags); }
 
 }  // extern "C"

@@ -616,3 +616,13 @@ def map_image(kind, handle):
     if out.size:
         fn(_hv(handle), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size), dims)
     return out
+
+
+def occ_query(kind, handle, cells):
+    """kind 'freq' | 'prob': (getProbability, flags) of OccupancyMap for n cells; flags bit 0 isFree, 1 isOccupied, 2 isUnknown"""
+    c = np.ascontiguousarray(cells, np.uint32).reshape(-1, 2)
+    prob = np.zeros(len(c))
+    flags = np.zeros(len(c), np.uint8)
+    getattr(lib(), "orc_%s_query" % kind)(_hv(handle), c.ctypes.data_as(C.c_void_p), C.c_int(len(c)), prob.ctypes.data_as(C.c_void_p),
+                                          flags.ctypes.data_as(C.c_void_p))
+    return prob, flags

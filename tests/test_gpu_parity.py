@@ -419,3 +419,23 @@ def test_errors_are_reported_not_swallowed(gpu_api, synth):
     g.update(ds.scans[0], ds.odom[0])
     with pytest.raises(gpu_api.LamaError):
         g.update(np.zeros((400, 3)), ds.odom[1])
+
+
+def test_occupancy_grid_queries(gpu_api, po, synth):
+    """OccupancyMap::{getProbability,isFree,isOccupied,isUnknown} on device maps (occupancy_map.h:57-76), both map kinds"""
+    ds = synth.make_dataset("room", 10, n_beams=360)
+    rng = np.random.default_rng(2)
+    for occupancy in (0, 1):
+        kw = dict(trans_thresh=0.05, rot_thresh=0.05)
+        g = gpu_api.Slam2D(gpu_api.Slam2D.Options(occupancy=occupancy, **kw))
+        o = (po.Slam2DProb if occupancy else po.Slam2D)(po.SlamOptions.defaults(**kw))
+        g.setPose(*ds.truth[0]); o.set_pose(*ds.truth[0])
+        for t in range(10):
+            g.update(ds.scans[t], ds.odom[t]); o.update(ds.scans[t], ds.odom[t])
+        pts = np.c_[rng.uniform(-12, 12, (4000, 2)), np.zeros(4000)]          # inside, on and outside the mapped area
+        cells = gpu_api.w2m(0.05, pts)
+        assert (cells[:50] == np.array([po.w2m(p)[:2] for p in pts[:50]], np.uint32)).all()                 # Map::w2m
+        pg, fg = g.occupancyQuery(cells)
+        pr, fr = po.occ_query("prob" if occupancy else "freq", po.map_handle("slamp_occ" if occupancy else "slam_occ", o), cells)
+        assert (fg == fr).all() and (pg == pr).all()
+        assert (fr & 1).any() and (fr & 2).any() and (fr & 4).any()            # free, occupied and unknown cells all occur
