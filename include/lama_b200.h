@@ -116,6 +116,9 @@ int lama_pf_write_map(lama_pf* h, int particle, int kind, const char* path);
  * frequency_occupancy_map.cpp:110-172) of getOccupancyMap(particle) for n cells: prob[i] = getProbability, flags[i] bit 0 isFree,
  * bit 1 isOccupied, bit 2 isUnknown.  The Vector3d overloads are lama_w2m (Map::w2m, map.h:125-126) followed by this call. */
 int lama_pf_occupancy_query(lama_pf* h, int particle, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags);
+/* getDistanceMap(particle)->distance(Vector3d, Vector3d* gradient) for n points (distance_map.h:66, dynamic_distance_map.cpp:66-92):
+ * dist[n], grad[n][3] (grad may be NULL) */
+int lama_pf_distance(lama_pf* h, int particle, const double* pts_xyz, int n, double* dist, double* grad);
 int lama_w2m(double resolution, const double* pts_xyz, int n, uint32_t* cells_xy);
 /* the grey image sdm::export_to_png encodes (src/sdm/export.cpp:46-96; PFSlam2D::saveOccImage / saveDistImage use it):
  * dims = {width, height} = the map's bounds in cells, pixel (u, v) at pixels[u + v * width]; pixels == NULL only sizes. */
@@ -182,6 +185,7 @@ int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2],
 int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known);
 /* occupancy == 1 only: dense window of ProbabilisticOccupancyMap cells (float log-odds, prob_tag) + Container known bit */
 int lama_slam_occupancy_query(lama_slam* h, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags);   /* as lama_pf_occupancy_query */
+int lama_slam_distance(lama_slam* h, const double* pts_xyz, int n, double* dist, double* grad);                  /* as lama_pf_distance */
 int lama_slam_write_map(lama_slam* h, int kind, const char* path);                                     /* as lama_pf_write_map */
 int lama_slam_export_image(lama_slam* h, int kind, uint8_t* pixels, size_t cap, int dims[2]);           /* as lama_pf_export_image */
 int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known);

@@ -71,7 +71,7 @@ EXPORTED_SYMBOLS = [
     "lama_slam_export_occupancy", "lama_slam_export_distance", "lama_slam_export_logodds",
     "lama_loc_options_default", "lama_loc_create", "lama_loc_destroy", "lama_loc_distance_map", "lama_loc_set_pose", "lama_loc_update",
     "lama_loc_get_pose", "lama_loc_get_state", "lama_loc_get_covar", "lama_loc_get_rmse", "lama_loc_get_solve_stats",
-    "lama_pf_occupancy_query", "lama_slam_occupancy_query", "lama_w2m", "lama_slam_get_map_stats", "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
+    "lama_pf_distance", "lama_slam_distance", "lama_pf_occupancy_query", "lama_slam_occupancy_query", "lama_w2m", "lama_slam_get_map_stats", "lama_pf_write_map", "lama_pf_export_image", "lama_slam_write_map", "lama_slam_export_image", "lama_dm_write", "lama_dm_read",
     "lama_dm_export_image", "lama_loc_occupancy_read",
     "lama_loc_occupancy_set", "lama_loc_set_seed", "lama_loc_trigger_global_localization", "lama_loc_global_localization_active",
     "lama_dm_create", "lama_dm_destroy", "lama_dm_max_sqdist", "lama_dm_add_obstacles", "lama_dm_remove_obstacles", "lama_dm_update",
@@ -303,6 +303,15 @@ class PFSlam2D:
         _chk(lib().lama_pf_export_distance(self.h, C.c_int(particle), C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
 
+    def distance(self, particle, pts, grad=True):
+        """getDistanceMap(particle)->distance(point, &gradient) for n world points"""
+        p, pp = _d(pts)
+        n = p.size // 3
+        d = np.zeros(n)
+        g = np.zeros((n, 3)) if grad else None
+        _chk(lib().lama_pf_distance(self.h, C.c_int(particle), pp, C.c_int(n), d.ctypes.data_as(c_dp), g.ctypes.data_as(c_dp) if grad else None))
+        return (d, g) if grad else d
+
     def occupancyQuery(self, particle, cells):
         """(getProbability, flags) of getOccupancyMap(particle) for n cells; flags bit 0 isFree, bit 1 isOccupied, bit 2 isUnknown"""
         c, cp = _u32(cells)
@@ -447,6 +456,14 @@ class Slam2D:
         o = _dm_arrays(w, h)
         _chk(lib().lama_slam_export_distance(self.h, C.c_uint32(x0), C.c_uint32(y0), C.c_int(w), C.c_int(h), *_dm_args(o)))
         return o
+
+    def distance(self, pts, grad=True):
+        p, pp = _d(pts)
+        n = p.size // 3
+        d = np.zeros(n)
+        g = np.zeros((n, 3)) if grad else None
+        _chk(lib().lama_slam_distance(self.h, pp, C.c_int(n), d.ctypes.data_as(c_dp), g.ctypes.data_as(c_dp) if grad else None))
+        return (d, g) if grad else d
 
     def occupancyQuery(self, cells):
         c, cp = _u32(cells)

@@ -414,6 +414,14 @@ int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0,
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     return export_occ(h->p->engine(), pf_local(h, particle), x0, y0, w, hgt, occupied, visited, known);
 }
+int lama_pf_distance(lama_pf* h, int particle, const double* pts, int n, double* dist, double* grad)
+{
+    if (!h || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
+    Engine* e = h->p->engine();
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    int rc = e->dm_distance(pf_local(h, particle), pts, n, dist, grad);
+    return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
+}
 int lama_pf_occupancy_query(lama_pf* h, int particle, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
@@ -584,6 +592,14 @@ int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, in
 {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
+}
+int lama_slam_distance(lama_slam* h, const double* pts, int n, double* dist, double* grad)
+{
+    if (!h || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
+    Engine* e = h->s->engine();
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    int rc = e->dm_distance(0, pts, n, dist, grad);
+    return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
 int lama_slam_occupancy_query(lama_slam* h, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
 {

@@ -135,10 +135,9 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         if (r == cudaSuccess) d->allocs.push_back(*p);
         return r;
     };
-    CU_NEW(dalloc((void**)&v.pool, (size_t)v.n_slots * kPatchBytes));
-    if (((uintptr_t)v.pool & (kPatchBytes - 1)) != 0) {  // k_raycast ORs cell offsets into patch base addresses
-        return bail("patch pool is not 4 KiB aligned");
-    }
+    // k_raycast ORs cell offsets into patch base addresses: the pool starts on a 4 KiB boundary (cudaMalloc only promises 256 B)
+    CU_NEW(dalloc((void**)&v.pool, ((size_t)v.n_slots + 1) * kPatchBytes));
+    v.pool = reinterpret_cast<uint32_t*>(((uintptr_t)v.pool + (kPatchBytes - 1)) & ~(uintptr_t)(kPatchBytes - 1));
     CU_NEW(dalloc((void**)&v.fbits, (size_t)v.n_slots * 128));
     if (cfg.occupancy_kind == 1) CU_NEW(dalloc((void**)&v.kbits, (size_t)v.n_slots * 128));
     CU_NEW(dalloc((void**)&v.refcount, (size_t)v.n_slots * 4));

@@ -435,6 +435,9 @@ def test_occupancy_grid_queries(gpu_api, po, synth):
         pts = np.c_[rng.uniform(-12, 12, (4000, 2)), np.zeros(4000)]          # inside, on and outside the mapped area
         cells = gpu_api.w2m(0.05, pts)
         assert (cells[:50] == np.array([po.w2m(p)[:2] for p in pts[:50]], np.uint32)).all()                 # Map::w2m
+        dg, gg = g.distance(pts)                                               # getDistanceMap()->distance(point, &gradient)
+        dr, gr = po.DDM(handle=po.map_handle("slamp_dm" if occupancy else "slam_dm", o).value, owner=o).distance(pts)
+        assert (dg == dr).all() and (gg == gr).all()
         pg, fg = g.occupancyQuery(cells)
         pr, fr = po.occ_query("prob" if occupancy else "freq", po.map_handle("slamp_occ" if occupancy else "slam_occ", o), cells)
         assert (fg == fr).all() and (pg == pr).all()
