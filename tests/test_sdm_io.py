@@ -62,6 +62,53 @@ def test_oracle_sdm_layout_and_round_trip(po, tmp_path):
     assert img[int(cells[0][1]) - mn[1], int(cells[0][0]) - mn[0]] == 0 and img.max() == 255 and (img == 127).any()
 
 
+def test_product_sdm_writer_reader_and_images_on_the_host(po, synth, tmp_path):
+    """the product's .sdm / image code (csrc/sdm_io.cpp, pure host code) fed with the oracle's cell planes: its files must equal
+    the oracle's byte for byte, its reader must return the planes, its images must equal the oracle's"""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.check_call(["make", "-C", os.path.join(here, "emu"), "-s"])
+    L = C.CDLL(os.path.join(here, "emu", "_build", "libsdm_hooks.so"))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    ds = synth.make_dataset("room", 6, n_beams=180)
+    o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
+    o.set_pose(*ds.truth[0])
+    for t in range(6):
+        o.update(ds.scans[t], ds.odom[t])
+    # distance map
+    n, mn, mx = o.dm_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    d = o.export_dm(mn[0], mn[1], w, h)
+    a, b = tmp_path / "product.sdm", tmp_path / "oracle.sdm"
+    assert L.sdmtest_write_distance(str(a).encode(), C.c_float(0.05), C.c_uint32(100), C.c_uint32(int(mn[0])), C.c_uint32(int(mn[1])), C.c_int(w), C.c_int(h),
+                                    vp(d["sqdist"]), vp(d["valid"]), vp(d["known"]), vp(d["ox"]), vp(d["oy"]), vp(d["queued"])) == 1
+    hd = po.map_handle("slam_dm", o)
+    assert po.map_write("ddm", hd, b)
+    _same_files(a, b)
+    win = np.zeros(4, np.uint32); msq = np.zeros(1, np.uint32)
+    assert L.sdmtest_read_distance(str(b).encode(), vp(win), vp(msq), None, None, None, None, None, None) == 1
+    assert win.tolist() == [int(mn[0]), int(mn[1]), w, h] and msq[0] == 100
+    r = {k: np.zeros_like(v) for k, v in d.items()}
+    assert L.sdmtest_read_distance(str(b).encode(), vp(win), vp(msq), vp(r["sqdist"]), vp(r["valid"]), vp(r["known"]), vp(r["ox"]), vp(r["oy"]), vp(r["queued"])) == 1
+    for k in d:
+        assert (r[k] == d[k]).all(), k
+    img = np.zeros((h, w), np.uint8)
+    L.sdmtest_distance_image(C.c_uint32(int(mn[0])), C.c_uint32(int(mn[1])), C.c_int(w), C.c_int(h), vp(d["sqdist"]), vp(d["valid"]), vp(d["known"]), C.c_uint32(100),
+                             C.c_double(0.05), vp(img))
+    assert (img == po.map_image("ddm", hd)).all()
+    # frequency occupancy map
+    n, mn, mx = o.occ_bounds(); w, h = int(mx[0] - mn[0]), int(mx[1] - mn[1])
+    e = o.export_occ(mn[0], mn[1], w, h)
+    assert L.sdmtest_write_frequency(str(a).encode(), C.c_float(0.05), C.c_uint32(int(mn[0])), C.c_uint32(int(mn[1])), C.c_int(w), C.c_int(h), vp(e["occupied"]),
+                                     vp(e["visited"]), vp(e["known"])) == 1
+    ho = po.map_handle("slam_occ", o)
+    assert po.map_write("freq", ho, b)
+    _same_files(a, b)
+    img = np.zeros((h, w), np.uint8)
+    L.sdmtest_frequency_image(C.c_uint32(int(mn[0])), C.c_uint32(int(mn[1])), C.c_int(w), C.c_int(h), vp(e["occupied"]), vp(e["visited"]), vp(e["known"]), vp(img))
+    assert (img == po.map_image("freq", ho)).all()
+
+
 def test_png_writer_round_trip(tmp_path):
     import struct
     import zlib
