@@ -596,8 +596,10 @@ int Engine::dm_apply(int particle, const uint32_t* cells_xy, const uint8_t* is_a
     const int cap = d_->ray.event_cap;
     std::vector<uint64_t> ev;
     int done = 0;
-    do {  // event lists longer than the per-particle buffer are applied in chunks; the brushfire runs after each
-          // chunk, which matches the reference only when the whole list fits.  TODO(next): grow the buffer instead.
+    do {  // One brushfire over the whole list reproduces the reference (all cells queued, then ONE update()).  Lists longer than the
+          // per-particle event buffer (2 048 cells: the waves they start already fill most of the 8 192-entry heap in shared
+          // memory) are applied in pieces with a brushfire after each, which gives a valid distance map but not necessarily the
+          // reference's tie order -- big maps are loaded with lama_dm_read / lama_dm_import instead.
         int m = std::min(cap, n - done);
         ev.resize((size_t)std::max(m, 1));
         for (int i = 0; i < m; ++i) {
