@@ -92,10 +92,22 @@ def golden_loc():
     np.savez_compressed(os.path.join(HERE, "loc_room.npz"), states=np.array(states), covs=np.array(covs), rmse=np.array(rmses), pops=np.array([pops]))
 
 
+def golden_sdm():
+    """a small distance map in the reference's on-disk format (Map::write, map.cpp:490-529): pins the byte layout"""
+    d = po.DDM(0.05, 32, 0.5)
+    cells = np.array([(O + 5, O + 7), (O + 6, O + 7), (O + 40, O - 3), (O - 20, O + 30)], np.uint32)
+    d.add(cells)
+    d.update()
+    d.remove(cells[1:2])
+    d.update()
+    assert po.map_write("ddm", d, os.path.join(HERE, "ddm_small.sdm"))
+
+
 if __name__ == "__main__":
     golden_slam()
     golden_pf()
     golden_loc()
+    golden_sdm()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -62,6 +62,21 @@ def test_oracle_sdm_layout_and_round_trip(po, tmp_path):
     assert img[int(cells[0][1]) - mn[1], int(cells[0][0]) - mn[0]] == 0 and img.max() == 255 and (img == 127).any()
 
 
+def test_golden_sdm_file(po, tmp_path):
+    """tests/golden/ddm_small.sdm (written by make_golden.py): the oracle still writes the same bytes, the host mirror reads them"""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddm_small.sdm")
+    d = po.DDM(0.05, 32, 0.5)
+    cells = np.array([(O + 5, O + 7), (O + 6, O + 7), (O + 40, O - 3), (O - 20, O + 30)], np.uint32)
+    d.add(cells); d.update(); d.remove(cells[1:2]); d.update()
+    p = tmp_path / "now.sdm"
+    assert po.map_write("ddm", d, p)
+    f = _same_files(p, gold)
+    assert len(f["patches"]) == 7 and os.path.getsize(gold) == 36 + 7 * (8 + 10240 + 128)
+    c, m = f["patches"][(int(O + 5) >> 5) * sdm.UNIVERSAL_CONSTANT + (int(O + 7) >> 5)]
+    assert c[5 | (7 << 5)]["valid"] == 1 and c[5 | (7 << 5)]["sqdist"] == 0           # still an obstacle
+    assert c[6 | (7 << 5)]["sqdist"] == 1 and c[6 | (7 << 5)]["ox"] == -1             # removed: now 1 cell from its neighbour
+
+
 def test_product_sdm_writer_reader_and_images_on_the_host(po, synth, tmp_path):
     """the product's .sdm / image code (csrc/sdm_io.cpp, pure host code) fed with the oracle's cell planes: its files must equal
     the oracle's byte for byte, its reader must return the planes, its images must equal the oracle's"""
