@@ -68,3 +68,15 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".h", ".cuh", ".cu", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in text and "lama_oracle" not in text and "oracle/" not in text, os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lama_b200.h is a C header (extern "C" only under __cplusplus): a C99 translation unit compiles, links and runs"""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "lama_b200.h"\nint main(void){ lama_pf_options o; return lama_pf_options_default(&o) == LAMA_OK && o.particles == 1 ? 0 : 1; }\n')
+    exe = tmp_path / "c_abi"
+    lib_dir = os.path.join(ROOT, "iris_lama_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
+                           "-llama_b200", f"-Wl,-rpath,{lib_dir}"])
+    assert subprocess.call([str(exe)]) == 0
