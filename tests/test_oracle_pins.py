@@ -288,3 +288,104 @@ def test_slam2d_tracks_truth(po, synth):
     assert math.hypot(st[2] - ds.truth[-1, 0], st[3] - ds.truth[-1, 1]) < 0.05
     # gating: a scan without motion does not update
     assert s.update(ds.scans[-1], ds.odom[-1]) is False
+
+
+# ---- independent pins of the "next" rows restated in round 1 ----------------------------------------
+O_ = 1321122 * 32
+
+
+def _wall_cells(segments):
+    cells = set()
+    for x1, y1, x2, y2 in segments:
+        n = int(max(abs(x2 - x1), abs(y2 - y1)) / 0.05) + 1
+        for k in range(n + 1):
+            cells.add((int((x1 + (x2 - x1) * k / n) * 20 + O_ + 0.5), int((y1 + (y2 - y1) * k / n) * 20 + O_ + 0.5)))
+    return np.array(sorted(cells), np.uint32)
+
+
+def test_global_localization_finds_a_pose_that_explains_the_scan(po, synth):
+    """Loc2D::globalLocalization (loc2d.cpp:249-286): from a wrong prior, the localiser must end at a pose whose scan lies on the
+    mapped walls (the square room is symmetric, so the pose itself may be any of its four images)"""
+    ds = synth.make_dataset("loc_room", 4)
+    loc = po.Loc2D(po.LocOptions.defaults(trans_thresh=0.01, rot_thresh=0.01, gloc_particles=2000))
+    cells = _wall_cells(ds.segments)
+    d = loc.dm(); d.add(cells); d.update()
+    xs = np.arange(int(-9.9 * 20), int(9.9 * 20), 2)
+    loc.occ_set(np.array([(x + O_, y + O_) for x in xs for y in xs], np.uint32), -1)
+    loc.set_seed(123)
+    loc.set_pose(4.0, -3.0, 2.0)                       # far from the truth
+    loc.trigger_global_localization()
+    for t in range(4):
+        loc.update(ds.scans[t], ds.odom[t], force=(t == 0))
+    state, cov, rmse, _ = loc.get()
+    assert rmse < 0.05 and not loc.gloc_active()
+    c, s, tx, ty = state
+    pts = ds.scans[3]
+    wx, wy = c * pts[:, 0] - s * pts[:, 1] + tx, s * pts[:, 0] + c * pts[:, 1] + ty
+    dist = np.minimum(np.minimum(np.abs(wx - 10), np.abs(wx + 10)), np.minimum(np.abs(wy - 10), np.abs(wy + 10)))   # 20 m square room
+    assert np.median(dist) < 0.05
+
+
+def test_sampling_covariance_is_a_covariance(po, synth):
+    """Loc2D::addSamplingCovariance (loc2d.cpp:199-247) with cov_blend = 1: the xy block becomes the likelihood-weighted sample
+    covariance of the 161 offset poses: symmetric, positive semi-definite, no wider than the sampled square (1 m)"""
+    ds = synth.make_dataset("loc_room", 2)
+    loc = po.Loc2D(po.LocOptions.defaults(trans_thresh=0.01, rot_thresh=0.01, cov_blend=1.0))
+    d = loc.dm(); d.add(_wall_cells(ds.segments)); d.update()
+    loc.set_pose(*ds.truth[0])
+    loc.update(ds.scans[0], ds.odom[0], force=True)
+    cov = loc.get()[1].reshape(3, 3)
+    xy = cov[:2, :2]
+    assert abs(xy[0, 1] - xy[1, 0]) < 1e-15 and (np.linalg.eigvalsh(xy) > -1e-12).all()
+    assert 0 < xy[0, 0] < 1.0 and 0 < xy[1, 1] < 1.0
+    # (an offset along a wall leaves the beams on that wall where they are, so the sum of per-beam likelihoods falls off slowly:
+    #  the blended covariance is broad by construction, ~0.4 m here)
+
+
+def test_lidar_odometry_tracks_and_keeps_a_local_map(po, synth):
+    """LidarOdometry2D (lidar_odometry_2d.cpp:59-181): follows the motion without odometry; the transient map keeps only patches
+    that meet the (pose-centred, 2 * maxDistance grown) AABB of the last mapped scan -- recomputed here independently"""
+    ds = synth.make_dataset("room", 40, n_beams=1080)
+    lo = po.LidarOdometry2D()
+    for t in range(40):
+        lo.update(ds.scans[t])
+    c, s, tx, ty = lo.state()
+    travelled = float(np.hypot(ds.truth[39][0] - ds.truth[0][0], ds.truth[39][1] - ds.truth[0][1]))
+    assert abs(np.hypot(tx, ty) - travelled) < 0.05 * travelled and abs(np.arctan2(s, c)) < 0.02
+    ds = synth.make_dataset("corridor", 60, n_beams=720)
+    lo = po.LidarOdometry2D()
+    near = lambda sc: np.ascontiguousarray(sc[np.hypot(sc[:, 0], sc[:, 1]) < 3.0])
+    for t in range(60):
+        lo.update(near(ds.scans[t]))
+    assert lo.counters()["removed_patches"] > 0
+    n, mn, mx = po._bounds(po.lib().orc_ddm_bounds, (po.map_handle("lo_dm", lo),))
+    c, s, tx, ty = lo.state()
+    # every surviving patch lies within (half scan extent <= 3 m) + 2 * maxDistance (2 m) + one patch (1.6 m) of the last mapped pose,
+    # which is at most 0.1 m behind the current one
+    lo_w, hi_w = (mn.astype(float) - O_) * 0.05, (mx.astype(float) - O_) * 0.05
+    assert lo_w[0] > tx - 0.1 - 3.0 - 2.0 - 1.6 - 0.2 and hi_w[0] < tx + 0.1 + 3.0 + 2.0 + 1.6 + 0.2
+
+
+def test_sdm_file_parsed_independently_equals_the_exported_planes(po, synth, tmp_path):
+    """Map::write (map.cpp:490-529) read back with the numpy mirror (iris_lama_b200/sdm.py): cell for cell the exported map"""
+    from iris_lama_b200 import sdm
+    ds = synth.make_dataset("room", 5, n_beams=180)
+    o = po.Slam2DProb(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
+    o.set_pose(*ds.truth[0])
+    for t in range(5):
+        o.update(ds.scans[t], ds.odom[t])
+    p = tmp_path / "occ.sdm"
+    assert po.map_write("prob", po.map_handle("slamp_occ", o), p)
+    f = sdm.read_sdm(p)
+    assert f["header"]["cell_size"] == 4 and f["params"] == b""
+    n, mn, mx = o.occ_bounds()
+    e = o.export_occ(mn[0], mn[1], int(mx[0] - mn[0]), int(mx[1] - mn[1]))
+    seen = 0
+    for pid, (cells, mask) in f["patches"].items():
+        x0, y0 = sdm.patch_origin(pid)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little").reshape(32, 32).astype(bool)     # bit i = cell (i & 31, i >> 5)
+        sub = (slice(y0 - int(mn[1]), y0 - int(mn[1]) + 32), slice(x0 - int(mn[0]), x0 - int(mn[0]) + 32))
+        assert (bits == e["known"][sub].astype(bool)).all()
+        assert (cells.view("<f4").reshape(32, 32)[bits] == e["prob"][sub][bits]).all()
+        seen += int(bits.sum())
+    assert seen == int(e["known"].sum()) and len(f["patches"]) == n
