@@ -255,50 +255,6 @@ struct BeamEnds {      // 16 bytes; WINDOW-RELATIVE cell coordinates (< 2^16)
 };
 constexpr uint32_t kBeamFlag = 0x80000000u;
 
-// Map::computeRay for a planar beam, started at any step.  The major axis (delta == n) moves on every step: its
-// error term returns to 0 each time (err += n; 2 err >= n; err -= n), so only the minor axis carries state:
-//   e += d;  if (2 e >= n) { minor coordinate moves; e -= n; }          [2 e >= n  <=>  e >= (n + 1) >> 1]
-// (dx == dy: both axes move on every step, which the same update yields with d == n.)
-// The cell is kept PACKED, P = yr << 16 | xr (window-relative coordinates, each < 2^13): a step is one addition of a packed
-// step vector (sy * 65536 + sx as a signed number; no borrow crosses the halves because all cells of a beam lie inside the
-// bounding box of its end cells, which is inside the window), and P is also the key of the ordered-path log.
-struct SegWalk {
-    int e, d, n, half, i, iend;
-    int M, N;            // packed major / minor step vectors
-    uint32_t P;
-    __device__ __forceinline__ void init(const BeamEnds& b, int i0, int steps)
-    {
-        const uint32_t fx = b.fx & ~kBeamFlag, fy = b.fy & ~kBeamFlag;
-        const int ddx = (int)(b.tx - fx), ddy = (int)(b.ty - fy);
-        const int sx = ddx < 0 ? -1 : 1, sy = ddy < 0 ? -1 : 1;
-        const int dx = ddx < 0 ? -ddx : ddx, dy = ddy < 0 ? -ddy : ddy;
-        const bool xmajor = dx >= dy;
-        n = xmajor ? dx : dy;
-        d = xmajor ? dy : dx;
-        M = xmajor ? sx : sy * 65536;
-        N = xmajor ? sy * 65536 : sx;
-        half = (n + 1) >> 1;
-        i    = i0;
-        iend = min(i0 + steps, n - 1);
-        uint32_t k = 0;
-        e = 0;
-        if (i0 != 0 && n != 0) {  // closed form of the state after i0 steps
-            k = (2u * (uint32_t)i0 * (uint32_t)d + (uint32_t)n) / (2u * (uint32_t)n);
-            e = i0 * d - (int)k * n;
-        }
-        P = (fx | (fy << 16)) + (uint32_t)(M * i0 + N * (int)k);
-    }
-    __device__ __forceinline__ bool next()
-    {
-        if (i >= iend) return false;
-        ++i;
-        e += d;
-        P += (uint32_t)M;
-        if (e >= half) { P += (uint32_t)N; e -= n; }
-        return true;
-    }
-};
-
 constexpr uint32_t kCandNone = 0xFF, kCandOverflow = 0xFE;
 constexpr uint32_t kInfoSlotMask = 0x00FFFFFFu;   // slot field of a patch-info word; all ones = not writable in this pass
 
@@ -427,7 +383,7 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
         const int b = g * 32 + lane;
         const BeamEnds be = beams[b];   // the cache is padded to whole groups (padding lanes are flagged non-planar)
         SegWalk w;
-        w.init(be, seg * kSegSteps, (be.fy & kBeamFlag) ? 0 : kSegSteps);
+        w.init(be.fx & ~kBeamFlag, be.fy & ~kBeamFlag, be.tx, be.ty, seg * kSegSteps, (be.fy & kBeamFlag) ? 0 : kSegSteps);
         if (seg == 0) {
             // Lanes walk angularly adjacent beams in lock step, so close to the sensor neighbouring lanes sit on the
             // same cell: runs of equal cells are merged into ONE reduction carrying the run length (counter additions

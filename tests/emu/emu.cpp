@@ -217,6 +217,42 @@ int emu_heap_check(uint32_t seed, int n_ops, int prio_range)
     return bad;
 }
 
+// SegWalk (the ray-cast kernel's planar walk: packed cell, major/minor state, closed-form start at any step) against the
+// reference's iterative walk (RayWalk = Map::computeRay, itself checked against the oracle by the SLAM emulation).  The beam is
+// cut into segments of `seg` steps like the kernel's work items; every beam from the centre to every cell of a (2 r + 1)^2
+// square when r > 0, else `count` random beams inside a window of `side` cells.  Returns the number of beams that differ.
+int emu_segwalk_check(int r, uint32_t seed, int count, int side, int seg)
+{
+    int bad = 0;
+    auto one = [&](uint32_t fx, uint32_t fy, uint32_t tx, uint32_t ty) {
+        BeamCells bc;
+        bc.from[0] = fx; bc.from[1] = fy; bc.from[2] = 7u;
+        bc.to[0] = tx; bc.to[1] = ty; bc.to[2] = 7u;
+        bc.mark_hit = true;
+        RayWalk ref(bc);
+        const int n = ref.n;
+        bool ok = true;
+        int i = 0;
+        for (int s0 = 0; s0 == 0 || s0 < n - 1; s0 += seg) {
+            SegWalk w;
+            w.init(fx, fy, tx, ty, s0, seg);
+            while (w.next()) {
+                ok = ok && ref.next() && w.i == ++i && (w.P & 0xFFFFu) == ref.x && (w.P >> 16) == ref.y;
+            }
+        }
+        if (ref.next()) ok = false;   // the segments must cover every interior cell
+        if (!ok) ++bad;
+    };
+    if (r > 0) {
+        for (int ty = -r; ty <= r; ++ty)
+            for (int tx = -r; tx <= r; ++tx) one(2000u, 2000u, (uint32_t)(2000 + tx), (uint32_t)(2000 + ty));
+    } else {
+        std::mt19937 g(seed);
+        for (int c = 0; c < count; ++c) one(g() % side, g() % side, g() % side, g() % side);
+    }
+    return bad;
+}
+
 void* emu_create(double resolution, double l2_max, double cx, double cy, int dir_dim, double trans_thresh, double rot_thresh, uint32_t max_iter, int strategy)
 {
     Emu* e = new Emu();

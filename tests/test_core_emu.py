@@ -48,6 +48,15 @@ def test_heap_is_bit_faithful_to_std_priority_queue(emu):
         assert emu.emu_heap_check(C.c_uint32(seed), C.c_int(n), C.c_int(rng)) == 0
 
 
+def test_kernel_segment_walk_equals_iterative_bresenham(emu):
+    """ray_core.h SegWalk (what k_raycast's lanes execute: packed cell, major/minor state, closed-form start of a 64-step segment)
+    against Map::computeRay's iterative walk (map.cpp:198-227)"""
+    assert emu.emu_segwalk_check(C.c_int(150), C.c_uint32(0), C.c_int(0), C.c_int(0), C.c_int(64)) == 0      # all 301^2 beams incl. n = 0, 1, diagonals
+    assert emu.emu_segwalk_check(C.c_int(40), C.c_uint32(0), C.c_int(0), C.c_int(0), C.c_int(7)) == 0        # odd segment length: every start offset
+    assert emu.emu_segwalk_check(C.c_int(0), C.c_uint32(3), C.c_int(20000), C.c_int(2048), C.c_int(64)) == 0  # dir_dim 64 windows
+    assert emu.emu_segwalk_check(C.c_int(0), C.c_uint32(4), C.c_int(20000), C.c_int(4096), C.c_int(64)) == 0  # the largest window (dir_dim 128)
+
+
 def test_se2_host_math_equals_oracle_bitwise(emu, po):
     rng = np.random.default_rng(0)
     out = np.zeros(4)
