@@ -302,7 +302,7 @@ struct RayCtx {
     bool mark;                 // first pass: note the patches that are not writable yet
     int last_di;               // kProb
 
-    __device__ __forceinline__ uint32_t dir_of_cell(uint32_t P) const { return ((P >> 21) << log2dim) | ((P >> kPatchLog2) & 0xFFu); }
+    __device__ __forceinline__ uint32_t dir_of_cell(uint32_t P) const { return packed_dir_index(P, log2dim); }
 
     // One touch of packed cell P whose patch-info word is `info` (directory entry `di`).  `run` > 0: this lane adds the misses of
     // `run` adjacent lanes that touch the same cell (see raycast_pass); `run` == 0: another lane carries this lane's count, only
@@ -319,7 +319,7 @@ struct RayCtx {
             atomicOr(&touched[di >> 5], 1u << (di & 31));
             last_di = (int)di;
         }
-        const uint32_t off = ((P << 2) & 0x7Cu) | ((P >> 9) & 0xF80u);   // byte offset of the cell in its patch: (x & 31) * 4 + (y & 31) * 128
+        const uint32_t off = packed_cell_offset(P);   // byte offset of the cell in its patch
         if (run) {
             // the pool is 4 KiB aligned (checked at creation): patch base = pool + slot * 4096, the cell offset is OR-ed in
             uint64_t addr;

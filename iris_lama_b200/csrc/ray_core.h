@@ -124,6 +124,12 @@ struct RayWalk {
     }
 };
 
+// ---- packed cells: P = yr << 16 | xr, window-relative coordinates (each < 2^13) -------------------------------------------
+// directory index of the patch of P in a window of (1 << log2dim)^2 patches
+LAMA_HD uint32_t packed_dir_index(uint32_t P, int log2dim) { return ((P >> 21) << log2dim) | ((P >> kPatchLog2) & 0xFFu); }
+// byte offset of the cell inside its 4 KiB patch: (x & 31) * 4 + (y & 31) * 128  ==  4 * cell_index(x, y)
+LAMA_HD uint32_t packed_cell_offset(uint32_t P) { return ((P << 2) & 0x7Cu) | ((P >> 9) & 0xF80u); }
+
 // ---- the planar walk of the ray-cast kernel ---------------------------------------------------------------------------
 // Map::computeRay (map.cpp:198-227) for a planar beam (from.z == to.z: the z axis never moves), started at any step.  The major axis (delta == n) moves on every step: its
 // error term returns to 0 each time (err += n; 2 err >= n; err -= n), so only the minor axis carries state:

@@ -217,6 +217,21 @@ int emu_heap_check(uint32_t seed, int n_ops, int prio_range)
     return bad;
 }
 
+// packed-cell helpers of the ray-cast kernel against the plain addressing functions, for every cell of a dim x dim window
+int emu_packed_cell_check(int log2dim)
+{
+    DirWindow w;
+    w.dim = 1 << log2dim; w.base_px = 1000; w.base_py = 2000;
+    int bad = 0;
+    const uint32_t side = (uint32_t)w.dim << kPatchLog2;
+    for (uint32_t y = 0; y < side; ++y)
+        for (uint32_t x = 0; x < side; ++x) {
+            const uint32_t P = (y << 16) | x, ax = x + ((uint32_t)w.base_px << kPatchLog2), ay = y + ((uint32_t)w.base_py << kPatchLog2);
+            if ((int)packed_dir_index(P, log2dim) != dir_index(w, ax, ay) || packed_cell_offset(P) != 4u * cell_index(ax, ay) || P != cell_key(w, ax, ay)) ++bad;
+        }
+    return bad;
+}
+
 // SegWalk (the ray-cast kernel's planar walk: packed cell, major/minor state, closed-form start at any step) against the
 // reference's iterative walk (RayWalk = Map::computeRay, itself checked against the oracle by the SLAM emulation).  The beam is
 // cut into segments of `seg` steps like the kernel's work items; every beam from the centre to every cell of a (2 r + 1)^2

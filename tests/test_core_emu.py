@@ -57,6 +57,12 @@ def test_kernel_segment_walk_equals_iterative_bresenham(emu):
     assert emu.emu_segwalk_check(C.c_int(0), C.c_uint32(4), C.c_int(20000), C.c_int(4096), C.c_int(64)) == 0  # the largest window (dir_dim 128)
 
 
+def test_packed_cell_addressing(emu):
+    """k_raycast's packed-cell shortcuts (directory index, byte offset in the patch, log key) == dir_index / cell_index / cell_key"""
+    for log2dim in (3, 6, 7):
+        assert emu.emu_packed_cell_check(C.c_int(log2dim)) == 0
+
+
 def test_se2_host_math_equals_oracle_bitwise(emu, po):
     rng = np.random.default_rng(0)
     out = np.zeros(4)
