@@ -12,6 +12,7 @@
 #include "../../iris_lama_b200/csrc/ddm_core.h"
 #include "../../iris_lama_b200/csrc/match_core.h"
 #include "../../iris_lama_b200/csrc/ray_core.h"
+#include "../../iris_lama_b200/csrc/ray_pull.h"
 
 using namespace lama_b200;
 
@@ -62,6 +63,8 @@ struct Emu {
     uint32_t max_iter = 100;
     int strategy = 0;
     uint32_t last_pops = 0, last_cells = 0, last_events = 0, last_log = 0, last_evals = 0, last_iters = 0;
+    bool pull = false;   // map updates through the pull form of the ray cast (ray_pull.h) instead of the per-beam walk
+    uint32_t pull_fallbacks = 0;
 };
 
 double cell_dist(const Emu& e, uint32_t x, uint32_t y)
@@ -103,9 +106,16 @@ void solve(Emu& e, const ScanParams& sp, const double* pts, SE2& state, const So
     e.last_iters = ctl.iter;
 }
 
+void run_brushfire(Emu& e, std::vector<uint64_t>& events, uint32_t cells, uint32_t log_size);
+bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2& pose);
+
 // k_raycast + k_brushfire; beams are processed in a shuffled order to prove order independence of the design
 void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pose, uint32_t shuffle_seed)
 {
+    if (e.pull) {
+        if (update_maps_pull(e, sp, pts, pose)) return;
+        ++e.pull_fallbacks;
+    }
     const DirWindow win = e.occ.window;
     Affine tf = compose_tf(pose, sp.moving);
     std::vector<int> order(sp.n_beams);
@@ -156,6 +166,12 @@ void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pos
         fb = replay_cell(log.data(), (int)i, (int)j, *c, fb != 0, [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
         i = j;
     }
+    run_brushfire(e, events, cells, (uint32_t)log.size());
+}
+
+void run_brushfire(Emu& e, std::vector<uint64_t>& events, uint32_t cells, uint32_t log_size)
+{
+    const DirWindow win = e.occ.window;
     std::sort(events.begin(), events.end());
     // k_brushfire
     e.heap_l.assign(1 << 16, 0);
@@ -169,7 +185,128 @@ void update_maps(Emu& e, const ScanParams& sp, const double* pts, const SE2& pos
     e.last_pops   = bf.update();
     e.last_cells  = cells;
     e.last_events = (uint32_t)events.size();
-    e.last_log    = (uint32_t)log.size();
+    e.last_log    = log_size;
+}
+
+
+// ---- the pull form of the ray cast (ray_pull.h), laid out like k_ray_setup + k_ray_pull --------------------------------------
+struct PullScan {
+    uint32_t ox = 0, oy = 0;                 // window-relative origin cell
+    std::vector<uint32_t> list;              // class lists: n | d << 16, sorted by (class, slope, beam)
+    std::vector<uint16_t> beam_of;
+    int prefix[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<uint64_t> hits;              // pull_hit_key, sorted
+    std::vector<uint8_t> marked;             // per directory entry
+    uint32_t cells = 0;
+};
+
+// k_ray_setup: from the window-relative end cells of the beams (all starting in (ox, oy))
+void pull_setup(PullScan& ps, uint32_t ox, uint32_t oy, const std::vector<uint32_t>& tx, const std::vector<uint32_t>& ty, const std::vector<uint8_t>& mark_hit, int dim)
+{
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= dim) ++log2dim;
+    ps.ox = ox; ps.oy = oy;
+    ps.marked.assign((size_t)dim * dim, 0);
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> nd_of_beam(tx.size(), 0u);
+    for (size_t b = 0; b < tx.size(); ++b) {
+        const int ex = (int)tx[b] - (int)ox, ey = (int)ty[b] - (int)oy;
+        const PullBeam pb = pull_classify(ex, ey);
+        if (mark_hit[b]) {
+            const uint32_t di = ((ty[b] >> kPatchLog2) << log2dim) | (tx[b] >> kPatchLog2);
+            ps.hits.push_back(pull_hit_key(di, cell_index(tx[b], ty[b]), (uint32_t)b));
+            ps.marked[di] = 1;
+            ps.cells += 1;
+        }
+        if (pb.n >= 2) {
+            ps.cells += pb.n - 1;
+            keys.push_back(pull_sort_key(pb.cls, pb.n, pb.d, (uint32_t)b));
+            nd_of_beam[b] = pull_pack(pb.n, pb.d);
+            pull_mark_beam(ox, oy, ex, ey, [&](int px, int py) { ps.marked[((size_t)py << log2dim) | (size_t)px] = 1; });
+        }
+    }
+    std::sort(keys.begin(), keys.end());
+    std::sort(ps.hits.begin(), ps.hits.end());
+    int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t k : keys) {
+        ps.list.push_back(nd_of_beam[pull_key_beam(k)]);
+        ps.beam_of.push_back((uint16_t)pull_key_beam(k));
+        ++count[pull_key_class(k)];
+    }
+    for (int c = 0; c < 8; ++c) ps.prefix[c + 1] = ps.prefix[c] + count[c];
+}
+
+// the count tile of one patch: both axis passes, lane by lane (a warp runs the 32 lanes in lock step)
+void pull_patch_counts(const PullScan& ps, int px, int py, uint32_t tile[kPatchLen][kPatchLen])
+{
+    for (int r = 0; r < kPatchLen; ++r)
+        for (int c = 0; c < kPatchLen; ++c) tile[r][c] = 0;
+    const int cx0 = px * kPatchLen - (int)ps.ox, cy0 = py * kPatchLen - (int)ps.oy;
+    for (int lane = 0; lane < kPatchLen; ++lane) {
+        pull_lane_pass(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile[line][lane] += c; });   // X pass: lane = column
+        pull_lane_pass(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile[lane][line] += c; });   // Y pass: lane = row
+    }
+}
+
+bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2& pose)
+{
+    const DirWindow win = e.occ.window;
+    const uint32_t bx0 = (uint32_t)win.base_px << kPatchLog2, by0 = (uint32_t)win.base_py << kPatchLog2, side = (uint32_t)win.dim << kPatchLog2;
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= win.dim) ++log2dim;
+    Affine tf = compose_tf(pose, sp.moving);
+    std::vector<uint32_t> tx(sp.n_beams), ty(sp.n_beams);
+    std::vector<uint8_t> mh(sp.n_beams);
+    uint32_t ox = 0, oy = 0;
+    for (int b = 0; b < sp.n_beams; ++b) {
+        const BeamCells bc = beam_cells(tf, sp, pts + 3 * b);
+        const uint32_t fx = bc.from[0] - bx0, fy = bc.from[1] - by0;
+        tx[b] = bc.to[0] - bx0; ty[b] = bc.to[1] - by0;
+        mh[b] = bc.mark_hit;
+        if (bc.from[2] != bc.to[2] || (fx | fy | tx[b] | ty[b]) >= side) return false;   // not planar / outside the window: the per-beam walk handles it
+        if (b == 0) { ox = fx; oy = fy; }
+        else if (fx != ox || fy != oy) return false;                                      // no common origin (truncated rays)
+    }
+    PullScan ps;
+    pull_setup(ps, ox, oy, tx, ty, mh, win.dim);
+    std::vector<uint64_t> events;
+    uint32_t n_cand_touch = 0;
+    static uint32_t tile[kPatchLen][kPatchLen];
+    for (int py = 0; py < win.dim; ++py)
+        for (int px = 0; px < win.dim; ++px) {
+            const uint32_t di = ((uint32_t)py << log2dim) | (uint32_t)px;
+            if (!ps.marked[di]) continue;
+            pull_patch_counts(ps, px, py, tile);
+            const int h_lo = pull_hit_lower_bound(ps.hits.data(), (int)ps.hits.size(), pull_hit_key(di, 0, 0));
+            const int h_hi = pull_hit_lower_bound(ps.hits.data(), (int)ps.hits.size(), pull_hit_key(di + 1, 0, 0));
+            for (int r = 0; r < kPatchLen; ++r)
+                for (int c = 0; c < kPatchLen; ++c) {
+                    const uint32_t x = bx0 + (uint32_t)(px * kPatchLen + c), y = by0 + (uint32_t)(py * kPatchLen + r);
+                    const uint32_t ci = cell_index(x, y);
+                    const int c_lo = h_lo + pull_hit_lower_bound(ps.hits.data() + h_lo, h_hi - h_lo, pull_hit_key(di, ci, 0));
+                    const int c_hi = h_lo + pull_hit_lower_bound(ps.hits.data() + h_lo, h_hi - h_lo, pull_hit_key(di, ci + 1, 0));
+                    const uint32_t cnt = tile[r][c];
+                    if (cnt == 0 && c_hi == c_lo) continue;   // untouched: the patch is not even allocated for it
+                    uint32_t* cell = e.occ.raw(x, y, true);
+                    uint8_t& fb = e.occ.fbit[cell - e.occ.cells.data()];
+                    if (!fb && c_hi == c_lo) {   // plain cell: counter additions commute
+                        *cell += cnt * kOccMissInc;
+                        continue;
+                    }
+                    const PullRuns runs = pull_cell_runs(ps.list.data(), ps.prefix, px * kPatchLen + c - (int)ps.ox, py * kPatchLen + r - (int)ps.oy);
+                    bool obstacle = fb != 0;
+                    const uint32_t key = cell_key(win, x, y);
+                    const uint32_t before = *cell;
+                    *cell = pull_replay_cell(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), c_lo, c_hi, before, obstacle,
+                                             [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
+                    // the replay must have consumed exactly the counted crossings and the hits
+                    if (*cell != before + cnt * kOccMissInc + (uint32_t)(c_hi - c_lo) * kOccHitInc) e.occ.err |= 0x100u;
+                    fb = obstacle;
+                    n_cand_touch += cnt + (uint32_t)(c_hi - c_lo);
+                }
+        }
+    run_brushfire(e, events, ps.cells, n_cand_touch);
+    return true;
 }
 
 ScanParams scan_params(const Emu& e, int n)
@@ -267,6 +404,99 @@ int emu_segwalk_check(int r, uint32_t seed, int count, int side, int seg)
     }
     return bad;
 }
+
+// ray_pull.h against the iterative walk: random beam sets from one origin inside a window of dim x dim patches.
+//   mode 0: scan-like fan (even angles, noisy ranges)   1: random end cells   2: short beams (n = 0, 1, 2, ...)   3: axes / diagonals
+// Checks (a) the marked patches cover every touched cell, (b) the chained counts of every cell of every marked patch, (c) for
+// every touched cell the runs enumerate exactly the crossing beams with their step index, in beam order through pull_next_touch.
+// Returns the number of mismatches.
+int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
+{
+    std::mt19937 g(seed);
+    const int side = dim * kPatchLen;
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= dim) ++log2dim;
+    const uint32_t ox = (uint32_t)(side / 4 + (int)(g() % (uint32_t)(side / 2))), oy = (uint32_t)(side / 4 + (int)(g() % (uint32_t)(side / 2)));
+    std::vector<uint32_t> tx(n_beams), ty(n_beams);
+    std::vector<uint8_t> mh(n_beams, 1);
+    auto clampc = [&](int v) { return (uint32_t)std::min(std::max(v, 0), side - 1); };
+    for (int b = 0; b < n_beams; ++b) {
+        int x, y;
+        if (mode == 0) {
+            const double ang = -2.356 + 4.712 * b / std::max(1, n_beams - 1) + 1e-3 * (double)(g() % 100);
+            const double r = 4.0 + (double)(g() % (uint32_t)(side / 2));
+            x = (int)ox + (int)std::lround(r * std::cos(ang)); y = (int)oy + (int)std::lround(r * std::sin(ang));
+        } else if (mode == 1) {
+            x = (int)(g() % (uint32_t)side); y = (int)(g() % (uint32_t)side);
+        } else if (mode == 2) {
+            x = (int)ox + (int)(g() % 9) - 4; y = (int)oy + (int)(g() % 9) - 4;
+        } else {
+            const int r = (int)(g() % (uint32_t)(side / 3)), k = (int)(g() % 8);
+            const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+            x = (int)ox + r * dx[k] + ((g() % 4) == 0 ? (int)(g() % 3) - 1 : 0); y = (int)oy + r * dy[k] + ((g() % 4) == 0 ? (int)(g() % 3) - 1 : 0);
+        }
+        tx[b] = clampc(x); ty[b] = clampc(y);
+        mh[b] = (g() % 8) != 0;
+    }
+    // brute force
+    std::vector<uint32_t> ref((size_t)side * side, 0u);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> who((size_t)side * side);   // (beam, step)
+    uint32_t ref_cells = 0;
+    for (int b = 0; b < n_beams; ++b) {
+        BeamCells bc;
+        bc.from[0] = ox; bc.from[1] = oy; bc.from[2] = 5u; bc.to[0] = tx[b]; bc.to[1] = ty[b]; bc.to[2] = 5u; bc.mark_hit = mh[b];
+        RayWalk w(bc);
+        uint32_t step = 0;
+        ref_cells += mh[b] ? 1u : 0u;
+        while (w.next()) {
+            ++step; ++ref_cells;
+            ++ref[(size_t)w.y * side + w.x];
+            who[(size_t)w.y * side + w.x].push_back({(uint32_t)b, step});
+        }
+    }
+    PullScan ps;
+    pull_setup(ps, ox, oy, tx, ty, mh, dim);
+    int bad = 0;
+    if (ps.cells != ref_cells) ++bad;
+    // slope order inside the classes must be the exact rational order
+    for (int c = 0; c < 8; ++c)
+        for (int i = ps.prefix[c] + 1; i < ps.prefix[c + 1]; ++i) {
+            const uint64_t n0 = ps.list[i - 1] & 0xFFFFu, d0 = ps.list[i - 1] >> 16, n1 = ps.list[i] & 0xFFFFu, d1 = ps.list[i] >> 16;
+            if (d0 * n1 > d1 * n0) ++bad;
+        }
+    static uint32_t tile[kPatchLen][kPatchLen];
+    for (int py = 0; py < dim; ++py)
+        for (int px = 0; px < dim; ++px) {
+            const bool marked = ps.marked[((size_t)py << log2dim) | (size_t)px] != 0;
+            if (marked) pull_patch_counts(ps, px, py, tile);
+            for (int r = 0; r < kPatchLen; ++r)
+                for (int c = 0; c < kPatchLen; ++c) {
+                    const int x = px * kPatchLen + c, y = py * kPatchLen + r;
+                    const uint32_t want = ref[(size_t)y * side + x];
+                    if (!marked) {
+                        if (want) ++bad;
+                        continue;
+                    }
+                    if (tile[r][c] != want) ++bad;
+                    if (!want) continue;
+                    const PullRuns runs = pull_cell_runs(ps.list.data(), ps.prefix, x - (int)ox, y - (int)oy);
+                    std::vector<std::pair<uint32_t, uint32_t>> got;
+                    int after = -1;
+                    for (;;) {
+                        const PullTouch t = pull_next_touch(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), 0, 0, after);
+                        if (!t.valid) break;
+                        got.push_back({t.beam, t.pos});
+                        after = (int)t.beam;
+                    }
+                    auto w = who[(size_t)y * side + x];
+                    std::sort(w.begin(), w.end());
+                    if (got != w) ++bad;
+                }
+        }
+    return bad;
+}
+void emu_set_pull(void* h, int on) { ((Emu*)h)->pull = on != 0; }
+uint32_t emu_pull_fallbacks(void* h) { return ((Emu*)h)->pull_fallbacks; }
 
 void* emu_create(double resolution, double l2_max, double cx, double cy, int dir_dim, double trans_thresh, double rot_thresh, uint32_t max_iter, int strategy)
 {

@@ -19,7 +19,8 @@ def emu():
     L.emu_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_uint32, C.c_int]
     L.emu_dm_apply.restype = C.c_uint32
     L.emu_prob_replay.restype = C.c_float
-    for f in ("emu_destroy", "emu_set_pose", "emu_get_state", "emu_counters", "emu_slam_update", "emu_export_dm", "emu_export_occ", "emu_dm_apply"):
+    for f in ("emu_destroy", "emu_set_pose", "emu_get_state", "emu_counters", "emu_slam_update", "emu_export_dm", "emu_export_occ", "emu_dm_apply", "emu_set_pull",
+              "emu_pull_fallbacks"):
         getattr(L, f).argtypes = None
     return L
 
@@ -55,6 +56,15 @@ def test_kernel_segment_walk_equals_iterative_bresenham(emu):
     assert emu.emu_segwalk_check(C.c_int(40), C.c_uint32(0), C.c_int(0), C.c_int(0), C.c_int(7)) == 0        # odd segment length: every start offset
     assert emu.emu_segwalk_check(C.c_int(0), C.c_uint32(3), C.c_int(20000), C.c_int(2048), C.c_int(64)) == 0  # dir_dim 64 windows
     assert emu.emu_segwalk_check(C.c_int(0), C.c_uint32(4), C.c_int(20000), C.c_int(4096), C.c_int(64)) == 0  # the largest window (dir_dim 128)
+
+
+def test_pull_raycast_counts_equal_iterative_bresenham(emu):
+    """ray_pull.h (what k_ray_setup / k_ray_pull execute): class lists sorted by exact slope, patch marking, chained per-cell crossing counts
+    and the per-cell runs with their step indices, against Map::computeRay's iterative walk (map.cpp:198-227) for every cell of the window"""
+    emu.emu_pull_check.restype = C.c_int
+    for mode in range(4):   # scan-like fans, random end cells, very short beams (n = 0, 1, 2), axes and diagonals
+        for seed, n, dim in ((1, 1080, 16), (2, 360, 8), (3, 2000, 32), (4, 50, 8), (5, 1080, 64), (6, 720, 128)):
+            assert emu.emu_pull_check(C.c_uint32(seed * 7 + mode), C.c_int(n), C.c_int(mode), C.c_int(dim)) == 0, (mode, seed)
 
 
 def test_packed_cell_addressing(emu):
@@ -113,7 +123,8 @@ def test_brushfire_core_equals_oracle_on_add_remove_stress(emu, po, l2):
     emu.emu_destroy(C.c_void_p(h))
 
 
-@pytest.mark.parametrize("name,beams,T,shuffle", [("room", 360, 25, 0), ("room", 360, 25, 12345), ("corridor", 240, 20, 99)])
+@pytest.mark.parametrize("name,beams,T,shuffle", [("room", 360, 25, 0), ("room", 360, 25, 12345), ("corridor", 240, 20, 99), ("room", 360, 25, "pull"),
+                                                  ("corridor", 240, 20, "pull"), ("loop", 1080, 12, "pull")])
 def test_emulated_slam_equals_oracle(emu, po, synth, name, beams, T, shuffle):
     """Packed atomics in a SHUFFLED beam order + ordered replay + sequential brushfire == the reference's
     strictly sequential update (cells bit-exact), and the fused one-evaluation-per-iteration solver == Solver::solve."""
@@ -121,6 +132,10 @@ def test_emulated_slam_equals_oracle(emu, po, synth, name, beams, T, shuffle):
     t0 = ds.truth[0]
     h = emu.emu_create(0.05, 0.5, t0[0], t0[1], 64, 0.05, 0.05, 100, 0)
     emu.emu_set_pose(C.c_void_p(h), C.c_double(t0[0]), C.c_double(t0[1]), C.c_double(t0[2]))
+    pull = shuffle == "pull"   # the pull form of the ray cast (ray_pull.h) instead of per-beam walks
+    if pull:
+        emu.emu_set_pull(C.c_void_p(h), C.c_int(1))
+        shuffle = 0
     o = po.Slam2D(po.SlamOptions.defaults(trans_thresh=0.05, rot_thresh=0.05))
     o.set_pose(*t0)
     st = np.zeros(4)
@@ -146,6 +161,9 @@ def test_emulated_slam_equals_oracle(emu, po, synth, name, beams, T, shuffle):
     # the obstacle mirror bit of the occupancy word equals "distance cell is an obstacle"
     d = _export_dm(emu, h, int(mn[0]), int(mn[1]), w, hh)
     assert (a["obstacle"].astype(bool) == ((d["valid"] == 1) & (d["sqdist"] == 0))).all()
+    if pull:
+        emu.emu_pull_fallbacks.restype = C.c_uint32
+        assert emu.emu_pull_fallbacks(C.c_void_p(h)) == 0   # every scan went through the pull path
     emu.emu_destroy(C.c_void_p(h))
 
 
