@@ -23,6 +23,7 @@ struct StoreView {
     int32_t* freed_count;
     uint32_t* status;     // sticky error bits (lama_core.h)
     uint64_t* counters;   // [0] patches allocated, [1] patches detached (COW copies), [2] patches freed
+    int32_t* ray_ctrl;    // task counters of the pull ray cast (kernels.cuh RayPullView::ctrl), reset by k_merge_free
     int32_t n_slots;
     int32_t* dirs;        // [set][particle][kind][dim*dim]
     int32_t n_particles;

@@ -42,12 +42,43 @@ struct Engine::Impl {
     int state_cap = 0;
     RayParams ray{};
     BrushParams brush{};
+    int n_sms = 148;
+    bool scan_flat = false;     // the current scan has z == 0 everywhere and a sensor that keeps z planes: every beam is planar
+    bool staged_flat = false;   // the same for the staged scans
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // scratch for import/export/distance
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     std::vector<void*> allocs;
 };
+
+
+constexpr int kPullMaxBeams = 4096;   // k_ray_setup sorts the beams of a scan in shared memory
+
+static bool points_flat(const double* pts, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+        if (pts[3 * i + 2] != 0.0) return false;
+    return true;
+}
+
+// The occupancy ray cast of `count` particles.  Scans whose beams all start in the same cell (no per-beam ray truncation) go through
+// the pull form (k_ray_setup + k_ray_pull); k_raycast, the per-beam walk, takes everything else: LidarOdometry2D's and truncated rays,
+// and -- decided per particle on the device -- scans of a tilted sensor (`flat` false: the beams may leave the z plane).
+static int launch_ray_stage(Engine::Impl* d, RayParams rp, const SE2* states, int count)   // returns the number of kernels launched
+{
+    static const bool no_pull = std::getenv("LAMA_NO_PULL") != nullptr;   // developer switch: always use the per-beam walk
+    const ScanParams& sp = rp.scan;
+    const bool flat = d->scan_flat && sp.moving.l[6] == 0.0 && sp.moving.l[7] == 0.0;
+    rp.pull_fallback = 0;
+    if (!no_pull && !sp.lo_ray && sp.truncated_ray == 0.0 && sp.n_beams <= kPullMaxBeams) {
+        launch_raycast_pull(d->view, rp, states, d->d_events, d->d_stats, count, d->n_sms, d->stream);
+        if (flat) return 2;   // hit.z == start.z exactly for every beam: k_ray_setup takes every particle
+        rp.pull_fallback = 1;
+    }
+    launch_raycast(d->view, rp, states, d->d_events, d->d_stats, count, d->stream);
+    return rp.pull_fallback ? 3 : 1;
+}
 
 int cuda_device_count()
 {
@@ -169,6 +200,26 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     d->brush.raise_cap = 2048;
     d->brush.max_sqdist = e->max_sqdist_;
     CU_NEW(dalloc((void**)&d->d_events, (size_t)cfg.particles * d->ray.event_cap * 8));
+    {   // scratch of the pull ray cast (k_ray_setup -> k_ray_pull)
+        RayPullView& pv = d->ray.pull;
+        pv.stride = (std::min(cfg.max_beams, kPullMaxBeams) + 31) & ~31;
+        if (pv.stride < 32) pv.stride = 32;
+        int npad = 32;
+        while (npad < pv.stride) npad <<= 1;
+        pv.stride = npad;   // k_ray_setup writes whole sorted arrays of next_pow2(beams) entries
+        CU_NEW(dalloc((void**)&pv.hdr, (size_t)cfg.particles * sizeof(RayPullHeader)));
+        CU_NEW(dalloc((void**)&pv.list, (size_t)cfg.particles * pv.stride * 4));
+        CU_NEW(dalloc((void**)&pv.beam_of, (size_t)cfg.particles * pv.stride * 2));
+        CU_NEW(dalloc((void**)&pv.hits, (size_t)cfg.particles * pv.stride * 8));
+        CU_NEW(dalloc((void**)&pv.tasks, (size_t)cfg.particles * dim2 * 4));
+        CU_NEW(dalloc((void**)&pv.ctrl, 64));
+        CU_NEW(cudaMemset(pv.ctrl, 0, 64));
+        CU_NEW(cudaMemset(pv.hdr, 0, (size_t)cfg.particles * sizeof(RayPullHeader)));
+        v.ray_ctrl = pv.ctrl;
+        int sms = 0;
+        CU_NEW(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device));
+        d->n_sms = sms > 0 ? sms : 148;
+    }
     CU_NEW(dalloc((void**)&d->d_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
     const size_t idx_ints = std::max((size_t)cfg.particles, (size_t)cfg.dir_dim * cfg.dir_dim);   // resample indices / directory entries to delete
     CU_NEW(dalloc((void**)&d->d_idx, idx_ints * 4));
@@ -251,6 +302,7 @@ int Engine::set_scan(const double* pts, int n, const double origin[3], const dou
     CU_TRY(cudaSetDevice(cfg_.device));
     set_moving(origin, quat, truncated_ray, truncated_range, n);
     d_->d_points = d_->d_scan_buf;
+    d_->scan_flat = points_flat(pts, (size_t)n);
     // pageable host memory: cudaMemcpyAsync stages through the driver; the copy is small (N * 24 B)
     CU_TRY(cudaMemcpyAsync(d_->d_points, pts, (size_t)n * 3 * 8, cudaMemcpyHostToDevice, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));  // `pts` may be released by the caller after return
@@ -269,6 +321,7 @@ int Engine::stage_scans(const double* pts, int n_scans, int n)
     CU_TRY(cudaStreamSynchronize(d_->stream));
     d_->staged_scans = n_scans;
     d_->staged_beams = n;
+    d_->staged_flat  = points_flat(pts, (size_t)n_scans * n);
     return LAMA_OK;
 }
 
@@ -277,6 +330,7 @@ int Engine::select_staged(int index, const double origin[3], const double quat[4
     if (!d_->d_staged || index < 0 || index >= d_->staged_scans) return fail("select_staged: no such staged scan", LAMA_ERR_ARG);
     set_moving(origin, quat, truncated_ray, truncated_range, d_->staged_beams);
     d_->d_points = d_->d_staged + (size_t)index * d_->staged_beams * 3;
+    d_->scan_flat = d_->staged_flat;
     return LAMA_OK;
 }
 
@@ -400,14 +454,14 @@ int Engine::update_maps_async(const SE2* states, int first_particle, int count)
     bp.particle_offset = first_particle;
     bp.event_cap = rp.event_cap;
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
-    launch_raycast(d_->view, rp, d_->d_states, d_->d_events, d_->d_stats, count, d_->stream);
+    const int ray_kernels = launch_ray_stage(d_, rp, d_->d_states, count);
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
     launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[2], d_->stream));
     launch_merge_free(d_->view, d_->stream);
     CU_TRY(cudaGetLastError());
     { int rc = enqueue_report(count); if (rc != LAMA_OK) return rc; }
-    times_.raycast_launches += 1;
+    times_.raycast_launches += ray_kernels;
     times_.brushfire_launches += 1;
     times_.misc_launches += 1;
     h2d_bytes_ += (uint64_t)count * sizeof(SE2);
@@ -443,6 +497,7 @@ int Engine::step_async(const double* pts, int n, const double origin[3], const d
         set_moving(origin, quat, truncated_ray, truncated_range, n);
         std::memcpy(d_->h_scan, pts, (size_t)n * 24);   // free again: the previous call returned after its match, which follows its upload
         d_->d_points = d_->d_scan_buf;
+        d_->scan_flat = points_flat(pts, (size_t)n);
         CU_TRY(cudaMemcpyAsync(d_->d_points, d_->h_scan, (size_t)n * 24, cudaMemcpyHostToDevice, d_->stream));
         h2d_bytes_ += (uint64_t)n * 24;
     }
@@ -478,13 +533,13 @@ int Engine::step_async(const double* pts, int n, const double origin[3], const d
     bp.set = cur_set_;
     bp.particle_offset = 0;
     bp.event_cap = rp.event_cap;
-    launch_raycast(d_->view, rp, reinterpret_cast<const SE2*>(d_->d_results), d_->d_events, d_->d_stats, count, d_->stream);
+    const int ray_kernels = launch_ray_stage(d_, rp, reinterpret_cast<const SE2*>(d_->d_results), count);
     launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
     launch_merge_free(d_->view, d_->stream);
     CU_TRY(cudaGetLastError());
     { int rc = enqueue_report(count); if (rc != LAMA_OK) return rc; }
     times_.match_launches += 1;
-    times_.raycast_launches += 1;
+    times_.raycast_launches += ray_kernels;
     times_.brushfire_launches += 1;
     times_.misc_launches += 1;
     h2d_bytes_ += (uint64_t)count * sizeof(SE2);

@@ -462,6 +462,7 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     uint32_t* touched = reinterpret_cast<uint32_t*>(dir_s + dim2);                                                                  // kProb only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (rp.pull_fallback && rp.pull.hdr[blockIdx.x].ok) return;   // k_ray_setup / k_ray_pull took this particle's scan
     const int particle = rp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, rp.set, particle, kMapOcc);
     int32_t* gdir_s    = kProb ? dir_of(s, rp.set, particle, kMapScratch) : nullptr;
@@ -759,8 +760,302 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
     }
 }
 
+
+// ==================================================================================================
+// pull form of the ray cast (ray_pull.h): k_ray_setup + k_ray_pull
+// ==================================================================================================
+// k_ray_setup, one CTA per particle: beam end cells -> 8 slope-sorted class lists, sorted hit records and the list of patches the
+// scan can touch, appended to one global task list.  A particle whose beams are not all planar with one common origin inside the
+// window is left to k_raycast (header.ok = 0).
+struct RaySetupShared {
+    Affine tf;
+    uint32_t ox, oy, bad, cells;
+    int n_list, n_hits, task_base, pad;
+    int prefix[9];
+};
+constexpr int kSetupThreads = 256;
+
+__global__ void __launch_bounds__(kSetupThreads)
+k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdateStats* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = rp.scan.n_beams, npad = next_pow2(n < 32 ? 32 : n);
+    const int dim = s.window.dim, dim2 = dim * dim, nwords = (dim2 + 31) / 32;
+    uint64_t* keys   = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* hkeys  = keys + npad;
+    uint32_t* ndb    = reinterpret_cast<uint32_t*>(hkeys + npad);   // n | d << 16 of beam b
+    uint32_t* marks  = ndb + npad;
+    RaySetupShared& sh = *reinterpret_cast<RaySetupShared*>(marks + ((nwords + 1) & ~1));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const RayPullView& pv = rp.pull;
+    RayPullHeader* hdr = pv.hdr + blockIdx.x;
+    const uint32_t bx0 = (uint32_t)s.window.base_px << kPatchLog2, by0 = (uint32_t)s.window.base_py << kPatchLog2;
+    const uint32_t side = (uint32_t)dim << kPatchLog2;
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= dim) ++log2dim;
+
+    if (tid == 0) {
+        sh.tf = compose_tf(*reinterpret_cast<const SE2*>(reinterpret_cast<const char*>(states) + (size_t)blockIdx.x * (size_t)rp.state_stride), rp.scan.moving);
+        // the common ray start: tf.translation (pf_slam2d.cpp:449), not moved by any truncation in this mode
+        sh.ox = w2m(sh.tf.t[0], rp.scan.scale) - bx0;
+        sh.oy = w2m(sh.tf.t[1], rp.scan.scale) - by0;
+        sh.bad = (sh.ox | sh.oy) >= side ? 1u : 0u;
+        sh.cells = 0;
+        sh.n_list = sh.n_hits = 0;
+        for (int c = 0; c < 9; ++c) sh.prefix[c] = 0;
+    }
+    for (int i = tid; i < nwords; i += blockDim.x) marks[i] = 0u;
+    __syncthreads();
+    const Affine tf = sh.tf;
+    const uint32_t ox = sh.ox, oy = sh.oy;
+    uint32_t my_cells = 0, my_bad = 0;
+    for (int b = tid; b < npad; b += blockDim.x) {
+        uint64_t key = ~0ull, hk = ~0ull;
+        uint32_t nd = 0;
+        if (b < n) {
+            const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
+            const BeamCells bc = beam_cells(tf, rp.scan, pt);
+            const uint32_t fx = bc.from[0] - bx0, fy = bc.from[1] - by0, tx = bc.to[0] - bx0, ty = bc.to[1] - by0;
+            if (bc.from[2] != bc.to[2] || fx != ox || fy != oy || (tx | ty) >= side) {
+                my_bad |= (tx | ty) >= side ? 3u : 1u;   // bit 1: the beam leaves the directory window (reported, loud)
+            } else {
+                const int ex = (int)tx - (int)ox, ey = (int)ty - (int)oy;
+                const PullBeam pb = pull_classify(ex, ey);
+                if (bc.mark_hit) {
+                    const uint32_t di = ((ty >> kPatchLog2) << log2dim) | (tx >> kPatchLog2);
+                    hk = pull_hit_key(di, cell_index(tx, ty), (uint32_t)b);
+                    atomicOr(&marks[di >> 5], 1u << (di & 31));
+                    my_cells += 1;
+                }
+                if (pb.n >= 2) {
+                    my_cells += pb.n - 1;
+                    key = pull_sort_key(pb.cls, pb.n, pb.d, (uint32_t)b);
+                    nd  = pull_pack(pb.n, pb.d);
+                    pull_mark_beam(ox, oy, ex, ey, [&](int px, int py) {
+                        const uint32_t di = ((uint32_t)py << log2dim) | (uint32_t)px;
+                        atomicOr(&marks[di >> 5], 1u << (di & 31));
+                    });
+                }
+            }
+        }
+        keys[b]  = key;
+        hkeys[b] = hk;
+        ndb[b]   = nd;
+    }
+    my_cells = __reduce_add_sync(0xffffffffu, my_cells);
+    my_bad   = __reduce_or_sync(0xffffffffu, my_bad);
+    if (lane == 0) {
+        if (my_cells) atomicAdd(&sh.cells, my_cells);
+        if (my_bad) atomicOr(&sh.bad, my_bad);
+    }
+    __syncthreads();
+    if (sh.bad) {   // not for this path: k_raycast takes the particle
+        if (tid == 0) {
+            hdr->ok = 0;
+            if ((sh.bad & 2u) || (sh.ox | sh.oy) >= side) atomicOr(s.status, kErrWindow);
+        }
+        return;
+    }
+    block_bitonic_sort(keys, npad);
+    block_bitonic_sort(hkeys, npad);
+    uint32_t* glist  = pv.list + (size_t)blockIdx.x * pv.stride;
+    uint16_t* gbeam  = pv.beam_of + (size_t)blockIdx.x * pv.stride;
+    uint64_t* ghits  = pv.hits + (size_t)blockIdx.x * pv.stride;
+    for (int i = tid; i < npad; i += blockDim.x) {
+        const uint64_t k = keys[i];
+        if (k != ~0ull) {
+            const uint32_t beam = pull_key_beam(k);
+            glist[i] = ndb[beam];
+            gbeam[i] = (uint16_t)beam;
+            const int cls = pull_key_class(k), prev = i ? pull_key_class(keys[i - 1]) : -1;
+            for (int c = prev + 1; c <= cls; ++c) sh.prefix[c] = i;
+            if (i == npad - 1 || keys[i + 1] == ~0ull) {
+                sh.n_list = i + 1;
+                for (int c = cls + 1; c <= 8; ++c) sh.prefix[c] = i + 1;
+            }
+        }
+        const uint64_t h = hkeys[i];
+        if (h != ~0ull) {
+            ghits[i] = h;
+            if (i == npad - 1 || hkeys[i + 1] == ~0ull) sh.n_hits = i + 1;
+        }
+    }
+    // the patches to visit: one task each, appended to the global list (tasks of a particle stay together)
+    if (warp == 0) {
+        int total = 0;
+        for (int w0 = lane; w0 < nwords; w0 += 32) total += __popc(marks[w0]);
+        total = __reduce_add_sync(0xffffffffu, total);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(pv.ctrl, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t bits = wi < nwords ? marks[wi] : 0u;
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int k = base + incl - cnt;
+            while (bits) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                pv.tasks[k++] = ((uint32_t)blockIdx.x << 16) | (uint32_t)(wi * 32 + bit);
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        hdr->ox = (int32_t)ox;
+        hdr->oy = (int32_t)oy;
+        for (int c = 0; c < 9; ++c) hdr->prefix[c] = sh.prefix[c];
+        hdr->n_hits = sh.n_hits;
+        hdr->ok     = 1;
+        MapUpdateStats& st = stats[blockIdx.x];
+        st.ray_cells   = sh.cells;
+        st.log_records = 0;
+        st.events      = 0;   // k_ray_pull appends the obstacle events of this particle and counts them here
+        st.dm_pops     = 0;
+    }
+}
+
+// k_ray_pull: persistent warps take (particle, patch) tasks from the global list.  Per task: the two axis passes fill the count
+// tile, plain cells get `visited += count` (log-odds maps: `count` misses) with row-coalesced read-modify-writes of the patch the
+// particle owns exclusively, candidate cells (hit in this scan, or distance-map obstacles) are compacted and replayed in beam order,
+// one lane per cell.  A patch without any touched cell is neither allocated nor detached (the reference would not have created it).
+constexpr int kPullWarps = 8;
+struct PullWarpShared {
+    uint32_t tile[kPatchLen * 33];   // crossing count of every cell; row stride 33: column- and row-wise accesses are conflict free
+    uint32_t hitbits[kPatchLen];     // cells of the patch that are hit cells of this scan
+    uint16_t cand[kPatchCells];      // compacted candidate cells
+};
+
+template <bool kProb>
+__global__ void __launch_bounds__(kPullWarps * 32, 4)
+k_ray_pull(StoreView s, RayParams rp, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PullWarpShared& w = reinterpret_cast<PullWarpShared*>(smem_raw)[warp];
+    const RayPullView& pv = rp.pull;
+    const int dim = s.window.dim;
+    int log2dim = 0;
+    while ((1 << (log2dim + 1)) <= dim) ++log2dim;
+    const int total = __ldcg(pv.ctrl);
+    uint32_t err = 0;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(pv.ctrl + 1, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total) break;
+        const uint32_t task = __ldg(pv.tasks + t);
+        const int pl = (int)(task >> 16), di = (int)(task & 0xFFFFu);
+        const RayPullHeader* hdr = pv.hdr + pl;
+        const uint32_t* list    = pv.list + (size_t)pl * pv.stride;
+        const uint16_t* beam_of = pv.beam_of + (size_t)pl * pv.stride;
+        const uint64_t* hits    = pv.hits + (size_t)pl * pv.stride;
+        const int px = di & (dim - 1), py = di >> log2dim;
+        const int cx0 = px * kPatchLen - hdr->ox, cy0 = py * kPatchLen - hdr->oy;
+        for (int i = lane; i < kPatchLen * 33; i += 32) w.tile[i] = 0u;
+        w.hitbits[lane] = 0u;
+        __syncwarp();
+        uint32_t touched = 0;
+        pull_lane_pass(list, hdr->prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { w.tile[line * 33 + lane] = c; touched |= c; });   // lane = column
+        __syncwarp();
+        pull_lane_pass(list, hdr->prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { w.tile[lane * 33 + line] += c; touched |= c; });  // lane = row
+        const int n_hits = hdr->n_hits;
+        const int h_lo = pull_hit_lower_bound(hits, n_hits, pull_hit_key((uint32_t)di, 0u, 0u));
+        const int h_hi = h_lo + pull_hit_lower_bound(hits + h_lo, n_hits - h_lo, pull_hit_key((uint32_t)di + 1u, 0u, 0u));
+        for (int i = h_lo + lane; i < h_hi; i += 32) {
+            const uint32_t cell = (uint32_t)(hits[i] >> 16) & (kPatchCells - 1);
+            atomicOr(&w.hitbits[cell >> 5], 1u << (cell & 31));
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, touched != 0u) && h_hi == h_lo) continue;   // nothing of this scan lands in the patch
+
+        // Map::get (mutable): allocate on first touch, detach a shared patch (map.cpp:400-408, cow_ptr.h:104-114)
+        int32_t* gdir = dir_of(s, rp.set, rp.particle_offset + pl, kMapOcc);
+        const int e0 = gdir[di];
+        const bool hot = e0 >= 0 && (e0 & kDirHot);
+        const int slot = warp_make_exclusive(s, gdir, gdir, di, lane);
+        if (slot < 0) {
+            err |= kErrPoolEmpty;
+            continue;
+        }
+        uint32_t* patch = patch_ptr(s, slot);
+        const uint32_t hitrow  = w.hitbits[lane];                                            // lane = row
+        const uint32_t candrow = hitrow | (hot ? __ldcg(fbits_ptr(s, slot) + lane) : 0u);   // | cells that are distance-map obstacles
+        int ncand = 0;
+#pragma unroll 4
+        for (int r = 0; r < kPatchLen; ++r) {
+            const uint32_t cnt = w.tile[r * 33 + lane];
+            const uint32_t cw = __shfl_sync(0xffffffffu, candrow, r), hw = __shfl_sync(0xffffffffu, hitrow, r);
+            const bool iscand = (cw >> lane) & 1u, ishit = (hw >> lane) & 1u;
+            const bool touch = cnt != 0u || ishit;
+            const bool plain = touch && !iscand;   // misses only, never an obstacle: counter additions commute
+            if (plain) {
+                uint32_t* cell = patch + r * kPatchLen + lane;
+                if (!kProb) {
+                    *cell += cnt << 16;   // visited += cnt (wraps like the reference's uint16)
+                } else {
+                    float p = __uint_as_float(*cell);
+                    for (uint32_t k = cnt; k > 0; --k) p = prob_miss(p, rp.prob);
+                    *cell = __float_as_uint(p);
+                }
+            }
+            if (kProb) {
+                const uint32_t known = __ballot_sync(0xffffffffu, plain);
+                if (lane == 0 && known) kbits_ptr(s, slot)[r] |= known;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, touch && iscand);
+            if (touch && iscand) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * kPatchLen + lane);
+            ncand += __popc(m);
+        }
+        __syncwarp();
+        bool newhot = false;
+        for (int k = lane; k < ncand; k += 32) {
+            const uint32_t ci = w.cand[k];
+            const int r = (int)(ci >> kPatchLog2), c = (int)(ci & (kPatchLen - 1));
+            const PullRuns runs = pull_cell_runs(list, hdr->prefix, cx0 + c, cy0 + r);
+            const int c_lo = h_lo + pull_hit_lower_bound(hits + h_lo, h_hi - h_lo, pull_hit_key((uint32_t)di, ci, 0u));
+            const int c_hi = c_lo + pull_hit_lower_bound(hits + c_lo, h_hi - c_lo, pull_hit_key((uint32_t)di, ci + 1u, 0u));
+            uint32_t* fword = fbits_ptr(s, slot) + r;
+            const bool before = (__ldcg(fword) >> c) & 1u;
+            bool obstacle = before;
+            const uint32_t key = ((uint32_t)(py * kPatchLen + r) << 16) | (uint32_t)(px * kPatchLen + c);   // window-relative cell
+            auto emit = [&](bool add, uint32_t seq) {
+                const uint32_t idx = atomicAdd(&stats[pl].events, 1u);
+                if (idx < (uint32_t)rp.event_cap) events_out[(size_t)pl * rp.event_cap + idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
+            };
+            uint32_t* cell = patch + ci;
+            if (!kProb) {
+                *cell = pull_replay_cell(list, beam_of, runs, hits, c_lo, c_hi, *cell, obstacle, emit);
+            } else {
+                *cell = __float_as_uint(pull_replay_cell_prob(list, beam_of, runs, hits, c_lo, c_hi, __uint_as_float(*cell), obstacle, rp.prob, emit));
+                atomicOr(kbits_ptr(s, slot) + r, 1u << c);
+            }
+            if (obstacle != before) {
+                if (obstacle) {
+                    atomicOr(fword, 1u << c);
+                    newhot = true;
+                } else {
+                    atomicAnd(fword, ~(1u << c));
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, newhot) && !hot && lane == 0) gdir[di] |= kDirHot;   // from now on the patch may hold obstacle bits
+        __syncwarp();
+    }
+    err = __reduce_or_sync(0xffffffffu, err);
+    if (lane == 0 && err) atomicOr(s.status, err);
+}
+
 // One warp per particle (see brushfire_warp.cuh for the schedule and why it is exact).
-__global__ void __launch_bounds__(32)
+constexpr int kBrushThreads = 128;   // four warps sort the events and warm the L1; then warp 0 alone runs the sequential brushfire
+__global__ void __launch_bounds__(kBrushThreads)
 k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -768,21 +1063,30 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
     int32_t* dir      = reinterpret_cast<int32_t*>(smem_raw);
     uint64_t* lower_h = reinterpret_cast<uint64_t*>(smem_raw + (size_t)dim2 * 4);   // 16-byte aligned: dim2 * 4 is a multiple of 16
     uint64_t* raise_h = lower_h + bp.lower_cap + 2;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(raise_h + bp.raise_cap + 2);
+    uint64_t* ev      = raise_h + bp.raise_cap + 2;                                 // the events of this particle, sorted here
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(ev + bp.event_cap);
     uint64_t* bar     = reinterpret_cast<uint64_t*>(scratch + 32);
-    const int lane    = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int particle = bp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, bp.set, particle, kMapDm);
 
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    // The obstacle events arrive in any order (k_ray_pull appends them cell by cell): sorting by their (beam, step) stamp restores
+    // the reference's addObstacle / removeObstacle call sequence (ray_core.h).
+    uint32_t nev = stats[blockIdx.x].events;
+    uint32_t my_err = 0;
+    if (nev > (uint32_t)bp.event_cap) {
+        my_err |= kErrPushOverflow;
+        nev = (uint32_t)bp.event_cap;
+    }
+    const uint64_t* gev = events + (size_t)blockIdx.x * bp.event_cap;
+    const int evpad = next_pow2((int)nev);
+    for (int i = tid; i < evpad; i += blockDim.x) ev[i] = i < (int)nev ? gev[i] : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(ev, evpad);
     block_stage_tma(dir, gdir, (uint32_t)dim2 * 4u, bar, 0);
-    __syncwarp();
 
-    WarpBrushfire bf(s, dir, gdir, scratch, lane, SmemHeap{lower_h, 0u, (uint32_t)bp.lower_cap}, SmemHeap{raise_h, 0u, (uint32_t)bp.raise_cap},
-                     bp.max_sqdist);
-    const uint32_t nev = stats[blockIdx.x].events;
-    const uint64_t* ev = events + (size_t)blockIdx.x * bp.event_cap;
     // The L1 is cold at every launch and the waves started by the events stay within `reach` cells of them: pull the patch of
     // every event (32 rows = 32 lines, one per lane) and the neighbouring patches a wave can reach into L1 before the sequential
     // part starts, so that its dependent loads hit (ncu: 24 % of the loads missed L1, 21 % of the stall samples waited for them).
@@ -790,7 +1094,7 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
         int reach = 0;
         while ((uint32_t)(reach * reach) < bp.max_sqdist) ++reach;
         const int dim = s.window.dim;
-        for (uint32_t i = 0; i < nev; ++i) {
+        for (uint32_t i = warp; i < nev; i += nwarps) {
             const uint32_t key = (uint32_t)ev[i];
             const int x = (int)(key & 0xFFFFu), y = (int)(key >> 16);
             const int px = x >> kPatchLog2, py = y >> kPatchLog2, cx = x & (kPatchLen - 1), cy = y & (kPatchLen - 1);
@@ -806,6 +1110,11 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
                 }
         }
     }
+    if (warp != 0) return;
+
+    WarpBrushfire bf(s, dir, gdir, scratch, lane, SmemHeap{lower_h, 0u, (uint32_t)bp.lower_cap}, SmemHeap{raise_h, 0u, (uint32_t)bp.raise_cap},
+                     bp.max_sqdist);
+    bf.err |= my_err;
     for (uint32_t i = 0; i < nev; ++i) {
         const uint64_t e   = ev[i];
         const uint32_t key = (uint32_t)e;  // window-relative cell
@@ -882,6 +1191,7 @@ __global__ void k_merge_free(StoreView s)
     if (threadIdx.x == 0) {
         *s.free_count  = base + n;
         *s.freed_count = 0;
+        s.ray_ctrl[0] = s.ray_ctrl[1] = 0;   // task list of the pull ray cast: empty for the next scan
     }
 }
 __global__ void k_init_store(StoreView s, int n_sets)
@@ -1096,7 +1406,7 @@ size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
 size_t brushfire_smem_bytes(int dir_dim, const BrushParams& bp)
 {
     const int dim2 = dir_dim * dir_dim;
-    return (size_t)dim2 * 4 + (size_t)(bp.lower_cap + bp.raise_cap + 4) * 8 + 32 * 4 + 16 + 16;
+    return (size_t)dim2 * 4 + (size_t)(bp.lower_cap + bp.raise_cap + 4 + bp.event_cap) * 8 + 32 * 4 + 16 + 16;
 }
 
 cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayParams& rp, const BrushParams& bp)
@@ -1108,6 +1418,12 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
     else e = cudaFuncSetAttribute(k_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raycast_smem_bytes(dir_dim, rp));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_brushfire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brushfire_smem_bytes(dir_dim, bp));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_setup_smem_bytes(dir_dim, rp.scan.n_beams > 4096 ? 4096 : rp.scan.n_beams));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPullWarps * sizeof(PullWarpShared)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPullWarps * sizeof(PullWarpShared)));
     return e;
 }
 
@@ -1127,10 +1443,26 @@ void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states
     if (rp.prob_mode) k_raycast<true><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
     else k_raycast<false><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
 }
+size_t ray_setup_smem_bytes(int dir_dim, int n_beams)
+{
+    int npad = 32;
+    while (npad < n_beams) npad <<= 1;
+    const int nwords = (dir_dim * dir_dim + 31) / 32;
+    return (size_t)npad * (8 + 8 + 4) + (size_t)((nwords + 1) & ~1) * 4 + sizeof(RaySetupShared) + 16;
+}
+void launch_raycast_pull(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
+                         cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_ray_setup<<<count, kSetupThreads, ray_setup_smem_bytes(s.window.dim, rp.scan.n_beams), st>>>(s, rp, d_states, d_stats);
+    const int grid = n_sms * 4;   // persistent: four CTAs of eight warps per SM
+    if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, kPullWarps * sizeof(PullWarpShared), st>>>(s, rp, d_events, d_stats);
+    else k_ray_pull<false><<<grid, kPullWarps * 32, kPullWarps * sizeof(PullWarpShared), st>>>(s, rp, d_events, d_stats);
+}
 void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
 {
     if (count <= 0) return;
-    k_brushfire<<<count, 32, brushfire_smem_bytes(s.window.dim, bp), st>>>(s, bp, d_events, d_stats);
+    k_brushfire<<<count, kBrushThreads, brushfire_smem_bytes(s.window.dim, bp), st>>>(s, bp, d_events, d_stats);
 }
 void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_t* d_idx, int dst_first, int count, cudaStream_t st)
 {

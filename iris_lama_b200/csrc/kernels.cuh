@@ -6,6 +6,7 @@
 #include "device_store.cuh"
 #include "match_core.h"
 #include "ray_core.h"
+#include "ray_pull.h"
 
 namespace lama_b200 {
 
@@ -31,6 +32,24 @@ struct MatchParams {
     int mode;              // 0 = solve + final evaluation, 1 = single evaluation at the input state
 };
 
+// per-particle output of k_ray_setup, input of k_ray_pull (the pull form of the ray cast, ray_pull.h)
+struct RayPullHeader {   // 64 bytes
+    int32_t ox, oy;       // window-relative origin cell of the scan
+    int32_t prefix[9];    // class c of the slope-sorted beam list = [prefix[c], prefix[c + 1])
+    int32_t n_hits;
+    int32_t ok;           // 1: this particle's scan goes through k_ray_pull; 0: k_raycast handles it (tilted sensor, truncated rays)
+    int32_t pad[3];
+};
+struct RayPullView {
+    RayPullHeader* hdr;   // [particles]
+    uint32_t* list;       // [particles][stride]  n | d << 16, sorted by (class, slope, beam)
+    uint16_t* beam_of;    // [particles][stride]  beam of every list entry
+    uint64_t* hits;       // [particles][stride]  pull_hit_key records, sorted
+    uint32_t* tasks;      // [particles * dir_dim^2]  particle << 16 | directory index of a patch the scan may touch
+    int32_t* ctrl;        // [0] tasks appended by k_ray_setup, [1] tasks taken by k_ray_pull (both reset by k_merge_free)
+    int32_t stride;
+};
+
 struct RayParams {
     const double* points;
     ScanParams scan;
@@ -41,7 +60,9 @@ struct RayParams {
     int cand_cap;            // candidate bitmaps (patches with hit cells or distance-map obstacles), <= 253
     int debug;               // developer experiments (LAMA_RAY_DEBUG, only honoured by LAMA_PHASE_TIMING builds): 1 no RED, 2 no LDS
     int prob_mode;           // 1: log-odds occupancy (ProbabilisticOccupancyMap), counts go to the scratch map first
+    int pull_fallback;       // 1: k_raycast only handles the particles k_ray_setup left to it (RayPullHeader::ok == 0)
     ProbParams prob;
+    RayPullView pull;
 };
 
 struct BrushParams {
@@ -68,6 +89,11 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
 void launch_match(const StoreView& s, const MatchParams& mp, const SE2* d_states, MatchResult* d_results, int count, cudaStream_t st);
 void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count,
                     cudaStream_t st);
+// the pull form (every beam planar and starting in the same cell): k_ray_setup + k_ray_pull; particles it cannot take are left to
+// launch_raycast with rp.pull_fallback = 1
+size_t ray_setup_smem_bytes(int dir_dim, int n_beams);
+void launch_raycast_pull(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
+                         cudaStream_t st);
 void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st);
 // dst_set[dst_first + k] = src_set[idx[k]] for k in [0, count); bumps reference counts (COW share)
 void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_t* d_idx, int dst_first, int count, cudaStream_t st);

@@ -130,39 +130,31 @@ LAMA_HD void pull_lane_pass(const uint32_t* list, const int* prefix, int a_signe
 }
 
 // ---- the runs of ONE cell (ordered replay of candidate cells) -----------------------------------------------------------------
-// Up to four runs [lo, hi) of the sorted list hold the beams whose slope passes through cell (cx, cy) (offsets from O); a
-// beam of run r really crosses the cell iff its major length exceeds a[r], and it does so at step a[r] of its walk.
+// Four runs [lo, hi) of the sorted list (x-major / y-major beams, positive / negative minor side; empty when not applicable)
+// hold the beams whose slope passes through cell (cx, cy) (offsets from O); a beam of run r really crosses the cell iff its
+// major length exceeds a[r], and it does so at step a[r] of its walk.  (Fixed slots: the loops over them unroll into registers.)
 struct PullRuns {
     int lo[4], hi[4];
     uint32_t a[4];
-    int count;
 };
-LAMA_HD void pull_add_run(PullRuns& r, const uint32_t* list, const int* prefix, int cls, uint32_t a, uint32_t b)
+LAMA_HD void pull_set_run(PullRuns& r, int slot, bool on, const uint32_t* list, const int* prefix, int cls, uint32_t a, uint32_t b)
 {
-    const int lo = pull_lower_bound(list, prefix[cls], prefix[cls + 1], a, b);
-    const int hi = pull_lower_bound(list, lo, prefix[cls + 1], a, b + 1u);
-    if (hi > lo) {
-        r.lo[r.count] = lo;
-        r.hi[r.count] = hi;
-        r.a[r.count]  = a;
-        ++r.count;
-    }
+    r.lo[slot] = r.hi[slot] = 0;
+    r.a[slot]  = a;
+    if (!on) return;
+    r.lo[slot] = pull_lower_bound(list, prefix[cls], prefix[cls + 1], a, b);
+    r.hi[slot] = pull_lower_bound(list, r.lo[slot], prefix[cls + 1], a, b + 1u);
 }
 LAMA_HD PullRuns pull_cell_runs(const uint32_t* list, const int* prefix, int cx, int cy)
 {
     PullRuns r;
-    r.count = 0;
     const uint32_t ax = (uint32_t)(cx < 0 ? -cx : cx), ay = (uint32_t)(cy < 0 ? -cy : cy);
-    if (ax >= 1 && ay <= ax) {   // x-major beams
-        const int cm = cx < 0 ? 2 : 0;
-        if (cy >= 0) pull_add_run(r, list, prefix, cm, ax, ay);
-        if (cy <= 0) pull_add_run(r, list, prefix, cm | 1, ax, ay);
-    }
-    if (ay >= 1 && ax <= ay) {   // y-major beams
-        const int cm = 4 | (cy < 0 ? 2 : 0);
-        if (cx >= 0) pull_add_run(r, list, prefix, cm, ay, ax);
-        if (cx <= 0) pull_add_run(r, list, prefix, cm | 1, ay, ax);
-    }
+    const bool xm = ax >= 1 && ay <= ax, ym = ay >= 1 && ax <= ay;   // x-major / y-major beams can pass here
+    const int cmx = cx < 0 ? 2 : 0, cmy = 4 | (cy < 0 ? 2 : 0);
+    pull_set_run(r, 0, xm && cy >= 0, list, prefix, cmx, ax, ay);
+    pull_set_run(r, 1, xm && cy <= 0, list, prefix, cmx | 1, ax, ay);
+    pull_set_run(r, 2, ym && cx >= 0, list, prefix, cmy, ay, ax);
+    pull_set_run(r, 3, ym && cx <= 0, list, prefix, cmy | 1, ay, ax);
     return r;
 }
 
@@ -228,7 +220,10 @@ struct PullTouch {
 LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint64_t* hits, int h0, int h1, int after)
 {
     PullTouch t{0xFFFFFFFFu, 0u, false, false};
-    for (int r = 0; r < runs.count; ++r)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 4; ++r)
         for (int i = runs.lo[r]; i < runs.hi[r]; ++i) {
             if ((list[i] & 0xFFFFu) <= runs.a[r]) continue;   // too short to reach the cell
             const uint32_t b = beam_of[i];
