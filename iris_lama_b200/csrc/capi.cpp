@@ -2,6 +2,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -23,6 +25,12 @@ int set_err(const std::string& m, int code)
     g_err = m;
     return code;
 }
+// No C++ exception may cross the C boundary (a corrupt file or an allocation failure must come back as a status code, like
+// the reference's `return false`): every entry point below is a function-try-block closed by this handler.
+#define LAMA_CATCH                                                                                              \
+    catch (const std::bad_alloc&) { return set_err("out of host memory", LAMA_ERR_ARG); }                        \
+    catch (const std::exception& ex) { return set_err(std::string("exception: ") + ex.what(), LAMA_ERR_ARG); }   \
+    catch (...) { return set_err("unknown exception", LAMA_ERR_ARG); }
 DeviceOptions dev_from(const lama_device_options& d)
 {
     DeviceOptions o;
@@ -266,7 +274,7 @@ int lama_device_count(void) { return lama_b200::cuda_device_count(); }
 
 // ---- PFSlam2D -------------------------------------------------------------------------------------------
 int lama_pf_options_default(lama_pf_options* o)
-{
+try {
     if (!o) return set_err("null options", LAMA_ERR_ARG);
     std::memset(o, 0, sizeof(*o));
     o->particles = 1;
@@ -281,8 +289,9 @@ int lama_pf_options_default(lama_pf_options* o)
     dev_default(&o->dev);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_create(const lama_pf_options* o, lama_pf** out)
-{
+try {
     if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
     PFOptions p;
     p.particles = o->particles; p.srr = o->srr; p.str = o->str; p.stt = o->stt; p.srt = o->srt;
@@ -297,43 +306,49 @@ int lama_pf_create(const lama_pf_options* o, lama_pf** out)
     *out = new lama_pf{pf};
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_destroy(lama_pf* h)
-{
+try {
     if (!h) return LAMA_OK;
     delete h->p;
     delete h;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_set_prior(lama_pf* h, const double xyr[3])
-{
+try {
     if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
     h->p->set_prior(xyr[0], xyr[1], xyr[2]);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_update(lama_pf* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
-{
+try {
     if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->p->update(pts, n, origin, quat, odom, stamp, &did);
     if (did_update) *did_update = did ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_stage_scans(lama_pf* h, const double* pts, int n_scans, int n)
-{
+try {
     if (!h || !pts) return set_err("null argument", LAMA_ERR_ARG);
     int rc = h->p->stage_scans(pts, n_scans, n);
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_update_staged(lama_pf* h, int index, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
-{
+try {
     if (!h || !odom) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->p->update_staged(index, origin, quat, odom, stamp, &did);
     if (did_update) *did_update = did ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_get_traffic(lama_pf* h, uint64_t bytes[2], int reset)
-{
+try {
     if (!h || !bytes) return set_err("null argument", LAMA_ERR_ARG);
     h->p->settle_counters();
     Engine* e = h->p->engine();
@@ -342,26 +357,30 @@ int lama_pf_get_traffic(lama_pf* h, uint64_t bytes[2], int reset)
     if (e && reset) { e->reset_traffic(); e->reset_times(); }
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_pose(lama_pf* h, double xyr[3])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     xyr_of(h->p->pose((int)h->p->best_particle()), xyr);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_best_particle(lama_pf* h, int* idx)
-{
+try {
     if (!h || !idx) return set_err("null argument", LAMA_ERR_ARG);
     *idx = (int)h->p->best_particle();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_neff(lama_pf* h, double* neff)
-{
+try {
     if (!h || !neff) return set_err("null argument", LAMA_ERR_ARG);
     *neff = h->p->neff();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_particles(lama_pf* h, double* states, double* weights)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     for (uint32_t i = 0; i < h->p->particles(); ++i) {
         if (states) { const SE2& s = h->p->pose(i); states[4 * i] = s.c; states[4 * i + 1] = s.s; states[4 * i + 2] = s.tx; states[4 * i + 3] = s.ty; }
@@ -369,139 +388,159 @@ int lama_pf_get_particles(lama_pf* h, double* states, double* weights)
     }
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_trajectory(lama_pf* h, int particle, double* xyr, int cap, int* count)
-{
+try {
     if (!h || particle < 0 || particle >= (int)h->p->particles()) return set_err("bad particle", LAMA_ERR_ARG);
     std::vector<SE2> t = h->p->has_first_scan() ? h->p->trajectory(particle) : std::vector<SE2>();
     for (int i = 0; i < (int)t.size() && i < cap && xyr; ++i) xyr_of(t[i], &xyr[3 * i]);
     if (count) *count = (int)t.size();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_last_resample(lama_pf* h, int32_t* idx, int* count)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     const std::vector<int32_t>& v = h->p->last_resample();
     if (idx) std::copy(v.begin(), v.end(), idx);
     if (count) *count = (int)v.size();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     if (last) counters_out(h->p->last_counters(), last);
     if (total) counters_out(h->p->total_counters(), total);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_pf_kernel_times(lama_pf* h, double ms[4], uint64_t launches[5])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     h->p->settle_counters();
     return times_out(h->p->engine(), ms, launches);
 }
+LAMA_CATCH
 static int pf_local(lama_pf* h, int particle)
 {
     int k = particle - h->p->local_begin();
     return (k < 0 || k >= h->p->local_count()) ? -1 : k;
 }
 int lama_pf_map_bounds(lama_pf* h, int particle, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
-{
+try {
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     if (kind == 1) return bounds_dm_union(h->p->engine(), pf_local(h, particle), mn, mx, patches);
     return bounds_out(h->p->engine(), pf_local(h, particle), kind, mn, mx, patches);
 }
+LAMA_CATCH
 int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)
-{
+try {
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     return export_occ(h->p->engine(), pf_local(h, particle), x0, y0, w, hgt, occupied, visited, known);
 }
+LAMA_CATCH
 int lama_pf_distance(lama_pf* h, int particle, const double* pts, int n, double* dist, double* grad)
-{
+try {
     if (!h || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
     Engine* e = h->p->engine();
     if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
     int rc = e->dm_distance(pf_local(h, particle), pts, n, dist, grad);
     return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
+LAMA_CATCH
 int lama_pf_occupancy_query(lama_pf* h, int particle, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return occupancy_query(h->p->engine(), pf_local(h, particle), cells_xy, n, prob, flags);
 }
+LAMA_CATCH
 int lama_pf_write_map(lama_pf* h, int particle, int kind, const char* path)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return write_map(h->p->engine(), pf_local(h, particle), kind, true, path);
 }
+LAMA_CATCH
 int lama_pf_export_image(lama_pf* h, int particle, int kind, uint8_t* pixels, size_t cap, int dims[2])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_image(h->p->engine(), pf_local(h, particle), kind, true, pixels, cap, dims);
 }
+LAMA_CATCH
 int lama_pf_export_distance(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known,
                             int16_t* ox, int16_t* oy, uint8_t* queued)
-{
+try {
     if (!h || pf_local(h, particle) < 0) return set_err("particle not resident on this shard", LAMA_ERR_ARG);
     return export_dm(h->p->engine(), pf_local(h, particle), true, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
 }
+LAMA_CATCH
 int lama_pf_shard_begin(lama_pf* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp,
                         int* did_update, double* local_out)
-{
+try {
     if (!h || !pts || !odom || !local_out) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->p->shard_begin(pts, n, origin, quat, odom, stamp, &did, local_out);
     if (did_update) *did_update = did ? (h->p->last_counters().evals ? 2 : 1) : 0;  // 2 = matched, finish/map pending; 1 = first scan
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_shard_finish(lama_pf* h, const double* all_results, int* resampled, int32_t* idx)
-{
+try {
     if (!h || !all_results || !resampled || !idx) return set_err("null argument", LAMA_ERR_ARG);
     bool r = false;
     int rc = h->p->shard_finish(all_results, &r, idx);
     *resampled = r ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_shard_apply(lama_pf* h, const int32_t* idx)
-{
+try {
     // single-rank form: ancestors are the global indices themselves.  Multi-rank callers use
     // lama_pf_shard_apply_local below after staging remote ancestors with lama_pf_particle_unpack.
     if (!h || !idx) return set_err("null argument", LAMA_ERR_ARG);
     int rc = h->p->shard_apply(idx, idx + h->p->local_begin());
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_shard_apply_local(lama_pf* h, const int32_t* idx, const int32_t* local_src)
-{
+try {
     if (!h || !idx || !local_src) return set_err("null argument", LAMA_ERR_ARG);
     int rc = h->p->shard_apply(idx, local_src);
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_shard_map_update(lama_pf* h)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     int rc = h->p->shard_map_update();
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
+LAMA_CATCH
 int lama_pf_particle_pack_size(lama_pf* h, int slot, size_t* bytes)
-{
+try {
     if (!h || !bytes || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
     int rc = h->p->engine()->pack_size(slot, bytes);
     return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
 }
+LAMA_CATCH
 int lama_pf_particle_pack(lama_pf* h, int slot, void* buf, size_t cap, size_t* used)
-{
+try {
     if (!h || !buf || !used || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
     int rc = h->p->engine()->pack(slot, buf, cap, used);
     return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
 }
+LAMA_CATCH
 int lama_pf_particle_unpack(lama_pf* h, int slot, const void* buf, size_t bytes)
-{
+try {
     if (!h || !buf || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
     int rc = h->p->engine()->unpack(slot, buf, bytes);
     return rc == LAMA_OK ? rc : set_err(h->p->engine()->last_error(), rc);
 }
+LAMA_CATCH
 
 // ---- Slam2D ---------------------------------------------------------------------------------------------
 int lama_slam_options_default(lama_slam_options* o)
-{
+try {
     if (!o) return set_err("null options", LAMA_ERR_ARG);
     std::memset(o, 0, sizeof(*o));
     o->trans_thresh = 0.5; o->rot_thresh = 0.5; o->l2_max = 0.5; o->resolution = 0.05;
@@ -509,8 +548,9 @@ int lama_slam_options_default(lama_slam_options* o)
     dev_default(&o->dev);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_create(const lama_slam_options* o, lama_slam** out)
-{
+try {
     if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
     SlamOptions s;
     s.trans_thresh = o->trans_thresh; s.rot_thresh = o->rot_thresh; s.l2_max = o->l2_max; s.truncated_ray = o->truncated_ray;
@@ -523,91 +563,105 @@ int lama_slam_create(const lama_slam_options* o, lama_slam** out)
     *out = new lama_slam{sl};
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_destroy(lama_slam* h)
-{
+try {
     if (!h) return LAMA_OK;
     delete h->s;
     delete h;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_set_pose(lama_slam* h, const double xyr[3])
-{
+try {
     if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
     h->s->set_pose(xyr[0], xyr[1], xyr[2]);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_get_map_stats(lama_slam* h, uint64_t stats[2])
-{
+try {
     if (!h || !stats) return set_err("null argument", LAMA_ERR_ARG);
     stats[0] = h->s->map_updates();
     stats[1] = h->s->removed_patches();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_update(lama_slam* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int* did_update)
-{
+try {
     if (!h || !pts) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->s->update(pts, n, origin, quat, odom, stamp, &did);
     if (did_update) *did_update = did ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->s->error(), rc);
 }
+LAMA_CATCH
 int lama_slam_get_pose(lama_slam* h, double xyr[3])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     xyr_of(h->s->pose(), xyr);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_get_state(lama_slam* h, double st[4])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     const SE2& s = h->s->pose();
     st[0] = s.c; st[1] = s.s; st[2] = s.tx; st[3] = s.ty;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_get_processed_cells(lama_slam* h, uint32_t* n)
-{
+try {
     if (!h || !n) return set_err("null argument", LAMA_ERR_ARG);
     *n = h->s->processed_cells();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_get_counters(lama_slam* h, uint64_t last[6], uint64_t total[6])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     if (last) counters_out(h->s->last_counters(), last);
     if (total) counters_out(h->s->total_counters(), total);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_kernel_times(lama_slam* h, double ms[4], uint64_t launches[5])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return times_out(h->s->engine(), ms, launches);
 }
+LAMA_CATCH
 int lama_slam_map_bounds(lama_slam* h, int kind, uint32_t mn[2], uint32_t mx[2], int* patches)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     if (kind == 1) return bounds_dm_union(h->s->engine(), 0, mn, mx, patches);
     return bounds_out(h->s->engine(), 0, kind, mn, mx, patches);
 }
+LAMA_CATCH
 int lama_slam_export_occupancy(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* occupied, uint16_t* visited, uint8_t* known)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_occ(h->s->engine(), 0, x0, y0, w, hgt, occupied, visited, known);
 }
+LAMA_CATCH
 int lama_slam_distance(lama_slam* h, const double* pts, int n, double* dist, double* grad)
-{
+try {
     if (!h || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
     Engine* e = h->s->engine();
     if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
     int rc = e->dm_distance(0, pts, n, dist, grad);
     return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
+LAMA_CATCH
 int lama_slam_occupancy_query(lama_slam* h, const uint32_t* cells_xy, int n, double* prob, uint8_t* flags)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return occupancy_query(h->s->engine(), 0, cells_xy, n, prob, flags);
 }
+LAMA_CATCH
 int lama_w2m(double resolution, const double* pts_xyz, int n, uint32_t* cells_xy)
-{
+try {
     if (!(resolution > 0) || n < 0 || (n && (!pts_xyz || !cells_xy))) return set_err("bad argument", LAMA_ERR_ARG);
     const double scale = 1.0 / resolution;
     for (int i = 0; i < n; ++i) {
@@ -616,18 +670,21 @@ int lama_w2m(double resolution, const double* pts_xyz, int n, uint32_t* cells_xy
     }
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_slam_write_map(lama_slam* h, int kind, const char* path)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return write_map(h->s->engine(), 0, kind, true, path);
 }
+LAMA_CATCH
 int lama_slam_export_image(lama_slam* h, int kind, uint8_t* pixels, size_t cap, int dims[2])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_image(h->s->engine(), 0, kind, true, pixels, cap, dims);
 }
+LAMA_CATCH
 int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, float* logodds, uint8_t* known)
-{
+try {
     if (!h || !logodds) return set_err("null argument", LAMA_ERR_ARG);
     Engine* e = h->s->engine();
     if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
@@ -637,16 +694,18 @@ int lama_slam_export_logodds(lama_slam* h, uint32_t x0, uint32_t y0, int w, int 
     if (rc == LAMA_OK && known) rc = e->export_bits(0, 1, x0, y0, w, hgt, known);
     return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
+LAMA_CATCH
 int lama_slam_export_distance(lama_slam* h, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox,
                               int16_t* oy, uint8_t* queued)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     return export_dm(h->s->engine(), 0, true, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
 }
+LAMA_CATCH
 
 // ---- distance map grid interface --------------------------------------------------------------------------
 int lama_dm_create(double resolution, uint32_t patch_size, double l2_max, const double center_xy[2], const lama_device_options* dev, lama_dm** out)
-{
+try {
     if (!out) return set_err("null argument", LAMA_ERR_ARG);
     lama_device_options d;
     if (dev) d = *dev; else dev_default(&d);
@@ -656,8 +715,9 @@ int lama_dm_create(double resolution, uint32_t patch_size, double l2_max, const 
     *out = new lama_dm{m, true};
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_dm_destroy(lama_dm* dm)
-{
+try {
     if (!dm) return LAMA_OK;
     if (dm->owned) {
         delete dm->d;
@@ -665,64 +725,74 @@ int lama_dm_destroy(lama_dm* dm)
     }
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_dm_max_sqdist(lama_dm* dm, uint32_t* v)
-{
+try {
     if (!dm || !v) return set_err("null argument", LAMA_ERR_ARG);
     *v = dm->d->engine()->max_sqdist();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_dm_add_obstacles(lama_dm* dm, const uint32_t* cells, int n)
-{
+try {
     if (!dm || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
     return dm->d->add(cells, n, true);
 }
+LAMA_CATCH
 int lama_dm_remove_obstacles(lama_dm* dm, const uint32_t* cells, int n)
-{
+try {
     if (!dm || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
     return dm->d->add(cells, n, false);
 }
+LAMA_CATCH
 int lama_dm_update(lama_dm* dm, uint32_t* processed)
-{
+try {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     int rc = dm->d->update(processed);
     return rc == LAMA_OK ? rc : set_err(dm->d->error(), rc);
 }
+LAMA_CATCH
 int lama_dm_distance(lama_dm* dm, const double* pts, int n, double* dist, double* grad)
-{
+try {
     if (!dm || !pts || !dist) return set_err("null argument", LAMA_ERR_ARG);
     int rc = dm->d->flush_if_pending();
     if (rc == LAMA_OK) rc = dm->d->engine()->dm_distance(0, pts, n, dist, grad);
     return rc == LAMA_OK ? rc : set_err(dm->d->engine()->last_error(), rc);
 }
+LAMA_CATCH
 int lama_dm_bounds(lama_dm* dm, uint32_t mn[2], uint32_t mx[2], int* patches)
-{
+try {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     return bounds_out(dm->d->engine(), 0, 1, mn, mx, patches);
 }
+LAMA_CATCH
 int lama_dm_export(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid, uint8_t* known, int16_t* ox, int16_t* oy,
                    uint8_t* queued)
-{
+try {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     return export_dm(dm->d->engine(), 0, false, x0, y0, w, hgt, sqdist, valid, known, ox, oy, queued);
 }
+LAMA_CATCH
 int lama_dm_write(lama_dm* dm, const char* path)
-{
+try {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     int rc = dm->d->flush_if_pending();
     if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
     return write_map(dm->d->engine(), 0, 1, false, path);
 }
+LAMA_CATCH
 int lama_dm_export_image(lama_dm* dm, uint8_t* pixels, size_t cap, int dims[2])
-{
+try {
     if (!dm) return set_err("null handle", LAMA_ERR_ARG);
     int rc = dm->d->flush_if_pending();
     if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
     return export_image(dm->d->engine(), 0, 1, false, pixels, cap, dims);
 }
+LAMA_CATCH
 // Map::read into an EMPTY device distance map (map.cpp:531-575).  The file must have been written at this map's
 // resolution and maximum distance (the reference adopts the file's values; the device map's are fixed at creation).
 int lama_dm_read(lama_dm* dm, const char* path)
-{
+try {
     if (!dm || !path) return set_err("null argument", LAMA_ERR_ARG);
     Engine* e = dm->d->engine();
     SdmFile f;
@@ -734,15 +804,22 @@ int lama_dm_read(lama_dm* dm, const char* path)
     if (f.header.resolution != (float)e->config().resolution) return set_err("the file's resolution differs from this map's", LAMA_ERR_ARG);
     SdmWindow win;
     if (!sdm_window_of(f, win)) return LAMA_OK;
+    {   // the patch ids come from the file: the window they span must lie inside this map's directory window before it is sized
+        const DirWindow dw = e->window();
+        const int64_t px0 = (int64_t)(win.x0 >> kPatchLog2) - dw.base_px, py0 = (int64_t)(win.y0 >> kPatchLog2) - dw.base_py;
+        if (px0 < 0 || py0 < 0 || px0 + (win.w >> kPatchLog2) > dw.dim || py0 + (win.h >> kPatchLog2) > dw.dim)
+            return set_err("the file's patches lie outside this map's directory window", LAMA_ERR_WINDOW);
+    }
     DmPlanes p;
     const size_t cells = (size_t)win.w * win.h;
     p.sqdist.resize(cells); p.valid.resize(cells); p.known.resize(cells); p.queued.resize(cells); p.ox.resize(cells); p.oy.resize(cells);
     sdm_to_distance(f, win, p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(), p.queued.data());
     return lama_dm_import(dm, win.x0, win.y0, win.w, win.h, p.sqdist.data(), p.valid.data(), p.known.data(), p.ox.data(), p.oy.data(), p.queued.data());
 }
+LAMA_CATCH
 int lama_dm_import(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, const uint16_t* sqdist, const uint8_t* valid, const uint8_t* known,
                    const int16_t* ox, const int16_t* oy, const uint8_t* queued)
-{
+try {
     if (!dm || !sqdist || !valid || !known) return set_err("null argument", LAMA_ERR_ARG);
     std::vector<uint32_t> words((size_t)w * hgt);
     for (size_t i = 0; i < words.size(); ++i) {
@@ -752,9 +829,10 @@ int lama_dm_import(lama_dm* dm, uint32_t x0, uint32_t y0, int w, int hgt, const 
     int rc = dm->d->engine()->import_window(0, 1, x0, y0, w, hgt, words.data());
     return rc == LAMA_OK ? rc : set_err(dm->d->engine()->last_error(), rc);
 }
+LAMA_CATCH
 int lama_dm_match_normal_equations(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, const double* states, int count,
                                    int robust_kind, double robust_param, double meas_sigma, double* out)
-{
+try {
     if (!dm || !pts || !states || !out || count < 1) return set_err("bad argument", LAMA_ERR_ARG);
     Engine* e = dm->d->engine();
     int rc = dm->d->flush_if_pending();
@@ -771,9 +849,10 @@ int lama_dm_match_normal_equations(lama_dm* dm, const double* pts, int n, const 
     for (int i = 0; i < count; ++i) std::memcpy(out + (size_t)i * kNumSums, res[i].sums, sizeof(double) * kNumSums);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_dm_match_solve(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, double* states, int count, int strategy,
                         int robust_kind, double robust_param, uint32_t max_iter, uint32_t* stats, double* sums)
-{
+try {
     if (!dm || !pts || !states || count < 1) return set_err("bad argument", LAMA_ERR_ARG);
     Engine* e = dm->d->engine();
     int rc = dm->d->flush_if_pending();
@@ -794,10 +873,11 @@ int lama_dm_match_solve(lama_dm* dm, const double* pts, int n, const double* ori
     }
     return LAMA_OK;
 }
+LAMA_CATCH
 
 // ---- Loc2D ------------------------------------------------------------------------------------------------
 int lama_loc_options_default(lama_loc_options* o)
-{
+try {
     if (!o) return set_err("null options", LAMA_ERR_ARG);
     std::memset(o, 0, sizeof(*o));
     o->trans_thresh = 0.5; o->rot_thresh = 0.5; o->l2_max = 1.0; o->resolution = 0.05;
@@ -806,8 +886,9 @@ int lama_loc_options_default(lama_loc_options* o)
     dev_default(&o->dev);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_create(const lama_loc_options* o, lama_loc** out)
-{
+try {
     if (!o || !out) return set_err("null argument", LAMA_ERR_ARG);
     LocOptions l;
     l.trans_thresh = o->trans_thresh; l.rot_thresh = o->rot_thresh; l.l2_max = o->l2_max; l.resolution = o->resolution;
@@ -820,72 +901,84 @@ int lama_loc_create(const lama_loc_options* o, lama_loc** out)
     *out = new lama_loc{loc, lama_dm{loc->distance_map(), false}};
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_destroy(lama_loc* h)
-{
+try {
     if (!h) return LAMA_OK;
     delete h->l;
     delete h;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_distance_map(lama_loc* h, lama_dm** dm)
-{
+try {
     if (!h || !dm) return set_err("null argument", LAMA_ERR_ARG);
     *dm = &h->dm;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_set_pose(lama_loc* h, const double xyr[3])
-{
+try {
     if (!h || !xyr) return set_err("null argument", LAMA_ERR_ARG);
     h->l->set_pose(xyr[0], xyr[1], xyr[2]);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_update(lama_loc* h, const double* pts, int n, const double* origin, const double* quat, const double* odom, double stamp, int force,
                     int* did_update)
-{
+try {
     if (!h || !pts || !odom) return set_err("null argument", LAMA_ERR_ARG);
     bool did = false;
     int rc = h->l->update(pts, n, origin, quat, odom, stamp, force != 0, &did);
     if (did_update) *did_update = did ? 1 : 0;
     return rc == LAMA_OK ? rc : set_err(h->l->error(), rc);
 }
+LAMA_CATCH
 int lama_loc_get_pose(lama_loc* h, double xyr[3])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     xyr_of(h->l->pose(), xyr);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_get_state(lama_loc* h, double st[4])
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     const SE2& s = h->l->pose();
     st[0] = s.c; st[1] = s.s; st[2] = s.tx; st[3] = s.ty;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_get_covar(lama_loc* h, double cov[9])
-{
+try {
     if (!h || !cov) return set_err("null argument", LAMA_ERR_ARG);
     std::memcpy(cov, h->l->cov(), sizeof(double) * 9);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_get_rmse(lama_loc* h, double* rmse)
-{
+try {
     if (!h || !rmse) return set_err("null argument", LAMA_ERR_ARG);
     *rmse = h->l->rmse();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_occupancy_set(lama_loc* h, const uint32_t* cells, int n, int state)
-{
+try {
     if (!h || (!cells && n)) return set_err("null argument", LAMA_ERR_ARG);
     for (int i = 0; i < n; ++i) h->l->occupancy_map()->set(cells[2 * i], cells[2 * i + 1], state);
     return LAMA_OK;
 }
+LAMA_CATCH
 // SimpleOccupancyMap::read (Map::read, map.cpp:531-575; int8 cells: -1 free, 0 unknown, 1 occupied)
 int lama_loc_occupancy_read(lama_loc* h, const char* path)
-{
+try {
     if (!h || !path) return set_err("null argument", LAMA_ERR_ARG);
     SdmFile f;
     std::string err;
     if (!sdm_read(path, 1, 0, f, err)) return set_err(err, LAMA_ERR_ARG);
+    // Map::read adopts the file's resolution (map.cpp:549-558); this map's scale is fixed at Init, so a different one is refused
+    if (f.header.resolution != (float)h->l->occupancy_map()->resolution()) return set_err("the file's resolution differs from this map's", LAMA_ERR_ARG);
     for (size_t i = 0; i < f.ids.size(); ++i) {
         const uint32_t ax = (uint32_t)(f.ids[i] / 2642244ull) << kPatchLog2, ay = (uint32_t)(f.ids[i] % 2642244ull) << kPatchLog2;
         const int8_t* c = reinterpret_cast<const int8_t*>(f.cells.data() + i * (size_t)kPatchCells);
@@ -895,30 +988,35 @@ int lama_loc_occupancy_read(lama_loc* h, const char* path)
     }
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_set_seed(lama_loc* h, uint32_t seed)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     h->l->set_seed(seed);
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_trigger_global_localization(lama_loc* h)
-{
+try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);
     h->l->trigger_global_localization();
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_global_localization_active(lama_loc* h, int* active)
-{
+try {
     if (!h || !active) return set_err("null argument", LAMA_ERR_ARG);
     *active = h->l->global_localization_active() ? 1 : 0;
     return LAMA_OK;
 }
+LAMA_CATCH
 int lama_loc_get_solve_stats(lama_loc* h, uint32_t stats[2])
-{
+try {
     if (!h || !stats) return set_err("null argument", LAMA_ERR_ARG);
     stats[0] = h->l->iterations();
     stats[1] = h->l->evals();
     return LAMA_OK;
 }
+LAMA_CATCH
 
 }  // extern "C"

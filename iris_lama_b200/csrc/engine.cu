@@ -125,7 +125,15 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     Engine* e = new Engine();
     e->cfg_ = cfg;
     e->max_sqdist_ = radius * radius;
-    if (e->cfg_.pool_slots <= 0) e->cfg_.pool_slots = cfg.particles * 768 + 1024;
+    if (e->cfg_.pool_slots <= 0) {
+        const long long want = (long long)cfg.particles * 768 + 1024;
+        e->cfg_.pool_slots = want >= (long long)kDirSlotMask ? kDirSlotMask - 1 : (int)want;
+    }
+    if (e->cfg_.pool_slots >= kDirSlotMask) {   // directory entries keep the slot in 24 bits, all ones = "not writable"
+        err = "pool_slots must be below 2^24 - 1 (the slot field of a directory entry)";
+        delete e;
+        return nullptr;
+    }
     Impl* d = e->d_ = new Impl();
     auto bail = [&](const std::string& m) {
         err = m;
@@ -210,8 +218,8 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         CU_NEW(dalloc((void**)&pv.hdr, (size_t)cfg.particles * sizeof(RayPullHeader)));
         CU_NEW(dalloc((void**)&pv.list, (size_t)cfg.particles * pv.stride * 4));
         CU_NEW(dalloc((void**)&pv.beam_of, (size_t)cfg.particles * pv.stride * 2));
-        CU_NEW(dalloc((void**)&pv.hits, (size_t)cfg.particles * pv.stride * 8));
-        CU_NEW(dalloc((void**)&pv.tasks, (size_t)cfg.particles * dim2 * 4));
+        CU_NEW(dalloc((void**)&pv.hits, (size_t)cfg.particles * pv.stride * 4));
+        CU_NEW(dalloc((void**)&pv.tasks, (size_t)cfg.particles * dim2 * 8));
         CU_NEW(dalloc((void**)&pv.ctrl, 64));
         CU_NEW(cudaMemset(pv.ctrl, 0, 64));
         CU_NEW(cudaMemset(pv.hdr, 0, (size_t)cfg.particles * sizeof(RayPullHeader)));
@@ -834,7 +842,9 @@ int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
     const size_t n = slots.size(), need = 16 + n * 4 + n * (size_t)(kPatchBytes + 128);
     if (need > cap) return fail("pack: buffer too small", LAMA_ERR_ARG);
     uint32_t* hdr = (uint32_t*)buf;
-    hdr[0] = kPackMagic; hdr[1] = (uint32_t)cfg_.dir_dim; hdr[2] = n_kind[0]; hdr[3] = n_kind[1];
+    // the directory indices in the buffer only mean the same cells on a device with the same window: dim and base travel along
+    hdr[0] = kPackMagic; hdr[1] = (uint32_t)cfg_.dir_dim | ((uint32_t)(window_.base_px & 0xFFF) << 8) | ((uint32_t)(window_.base_py & 0xFFF) << 20);
+    hdr[2] = n_kind[0]; hdr[3] = n_kind[1];
     std::memcpy(hdr + 4, entries.data(), n * 4);
     if (n) {
         if (ensure_scratch(d_, n * 4 + n * (size_t)(kPatchBytes + 128))) return fail("pack: out of device memory", LAMA_ERR_CUDA);
@@ -858,7 +868,8 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles || bytes < 16) return fail("unpack: bad arguments", LAMA_ERR_ARG);
     const uint32_t* hdr = (const uint32_t*)buf;
-    if (hdr[0] != kPackMagic || hdr[1] != (uint32_t)cfg_.dir_dim) return fail("unpack: incompatible buffer", LAMA_ERR_ARG);
+    if (hdr[0] != kPackMagic || hdr[1] != ((uint32_t)cfg_.dir_dim | ((uint32_t)(window_.base_px & 0xFFF) << 8) | ((uint32_t)(window_.base_py & 0xFFF) << 20)))
+        return fail("unpack: incompatible buffer (directory window differs)", LAMA_ERR_ARG);
     const size_t n_occ = hdr[2], n_dm = hdr[3], n = n_occ + n_dm;
     if (bytes < 16 + n * 4 + n * (size_t)(kPatchBytes + 128)) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));

@@ -52,6 +52,12 @@ PFSlam2D* PFSlam2D::create(const PFOptions& o, std::string& err)
         err = "PFSlam2D: particles must divide evenly over shard_count";
         return nullptr;
     }
+    if (o.shard_count > 1 && o.seed == 0) {
+        // seed 0 means "take one from random_device" (pf_slam2d.cpp:131-132): every rank would draw its own, the ranks' odometry
+        // noise and resampling indices would differ and the map migration would pair up the wrong particles
+        err = "PFSlam2D: sharded operation needs an explicit (non-zero) seed shared by all ranks";
+        return nullptr;
+    }
     if (cuda_device_count() < 1) { err = "no CUDA device available: the lama_b200 hot path has no CPU fallback"; return nullptr; }
     PFSlam2D* p = new PFSlam2D();
     p->opt_ = o;

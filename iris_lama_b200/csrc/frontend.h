@@ -187,6 +187,7 @@ private:
 class SimpleOccupancyHost {
 public:
     explicit SimpleOccupancyHost(double resolution) : resolution_(resolution), scale_(1.0 / resolution) {}
+    double resolution() const { return resolution_; }
     void set(uint32_t x, uint32_t y, int state);   // -1 setFree, 0 setUnknown, 1 setOccupied
     bool is_free_world(double wx, double wy) const;
     bool bounds_world(double mn[2], double mx[2]) const;  // Map::bounds, patch granular (map.cpp:119-138)

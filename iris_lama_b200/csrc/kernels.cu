@@ -764,29 +764,94 @@ k_raycast(StoreView s, RayParams rp, const SE2* __restrict__ states, uint64_t* _
 // ==================================================================================================
 // pull form of the ray cast (ray_pull.h): k_ray_setup + k_ray_pull
 // ==================================================================================================
-// k_ray_setup, one CTA per particle: beam end cells -> 8 slope-sorted class lists, sorted hit records and the list of patches the
-// scan can touch, appended to one global task list.  A particle whose beams are not all planar with one common origin inside the
-// window is left to k_raycast (header.ok = 0).
+// k_ray_setup, one CTA per particle: beam end cells -> 8 slope-sorted class lists, the hit records grouped by patch and one task per
+// patch the scan can touch, appended to one global task list.  A particle whose beams are not all planar with one common origin
+// inside the window is left to k_raycast (header.ok = 0).
+// Sorting: a counting sort on (class, top 8 bits of the slope) puts every beam within a few places of its final position (beams
+// of a sweep are ~1 bucket apart); odd-even transposition passes then run until one changes nothing, which makes the order exact
+// for ANY input (a pathological point cloud just needs more passes).
+constexpr int kSetupThreads = 512;
+constexpr int kSlopeBuckets = 8 * 256;
 struct RaySetupShared {
     Affine tf;
     uint32_t ox, oy, bad, cells;
-    int n_list, n_hits, task_base, pad;
+    int n_list, n_hits, n_hpatch, n_tasks, task_base, swapped;
     int prefix[9];
+    uint32_t scan[kSetupThreads / 32];
+    uint32_t scan_total;
 };
-constexpr int kSetupThreads = 256;
+
+// exclusive prefix sum of one value per thread over the block (two barriers); *total = sum over the block
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_sums, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nwarps ? warp_sums[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < nwarps) warp_sums[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return warp_sums[warp] + incl - v;
+}
+
+struct RaySetupLayout {
+    size_t keys, sorted, ndb, hrec, marks, hmarks, wpfx, hwpfx, bucket, bfill, hcnt, hfill, sh, total;
+    __host__ __device__ RaySetupLayout(int n_beams, int dim2)
+    {
+        const size_t npad = ((size_t)n_beams + 31) & ~(size_t)31, nwords = ((size_t)dim2 + 31) / 32, nw2 = (nwords + 1) & ~(size_t)1;
+        size_t o = 0;
+        keys = o;   o += npad * 8;
+        sorted = o; o += (npad + 2) * 8;
+        ndb = o;    o += npad * 4;
+        hrec = o;   o += npad * 4;
+        marks = o;  o += nw2 * 4;
+        hmarks = o; o += nw2 * 4;
+        wpfx = o;   o += nw2 * 4;
+        hwpfx = o;  o += nw2 * 4;
+        bucket = o; o += (size_t)(kSlopeBuckets + 2) * 4;
+        bfill = o;  o += (size_t)kSlopeBuckets * 4;
+        hcnt = o;   o += (npad + 2) * 4;
+        hfill = o;  o += npad * 4;
+        o = (o + 15) & ~(size_t)15;
+        sh = o;     o += sizeof(RaySetupShared);
+        total = o + 16;
+    }
+};
 
 __global__ void __launch_bounds__(kSetupThreads)
 k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = rp.scan.n_beams, npad = next_pow2(n < 32 ? 32 : n);
+    const int n = rp.scan.n_beams, npad = (n + 31) & ~31;
     const int dim = s.window.dim, dim2 = dim * dim, nwords = (dim2 + 31) / 32;
-    uint64_t* keys   = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* hkeys  = keys + npad;
-    uint32_t* ndb    = reinterpret_cast<uint32_t*>(hkeys + npad);   // n | d << 16 of beam b
-    uint32_t* marks  = ndb + npad;
-    RaySetupShared& sh = *reinterpret_cast<RaySetupShared*>(marks + ((nwords + 1) & ~1));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const RaySetupLayout L(n, dim2);
+    uint64_t* keys   = reinterpret_cast<uint64_t*>(smem_raw + L.keys);     // sort key of beam b (~0: no interior cells)
+    uint64_t* sorted = reinterpret_cast<uint64_t*>(smem_raw + L.sorted);
+    uint32_t* ndb    = reinterpret_cast<uint32_t*>(smem_raw + L.ndb);      // n | d << 16 of beam b
+    uint32_t* hrec   = reinterpret_cast<uint32_t*>(smem_raw + L.hrec);     // directory index << 10 | cell of beam b's hit (~0: none)
+    uint32_t* marks  = reinterpret_cast<uint32_t*>(smem_raw + L.marks);    // patches the scan may touch
+    uint32_t* hmarks = reinterpret_cast<uint32_t*>(smem_raw + L.hmarks);   // patches holding hit cells
+    uint32_t* wpfx   = reinterpret_cast<uint32_t*>(smem_raw + L.wpfx);     // marked patches before word w
+    uint32_t* hwpfx  = reinterpret_cast<uint32_t*>(smem_raw + L.hwpfx);
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(smem_raw + L.bucket);   // counting sort: counts, then start offsets
+    uint32_t* bfill  = reinterpret_cast<uint32_t*>(smem_raw + L.bfill);
+    uint32_t* hcnt   = reinterpret_cast<uint32_t*>(smem_raw + L.hcnt);     // hits per hit patch, then start offsets
+    uint32_t* hfill  = reinterpret_cast<uint32_t*>(smem_raw + L.hfill);
+    RaySetupShared& sh = *reinterpret_cast<RaySetupShared*>(smem_raw + L.sh);
+    const int tid = threadIdx.x, lane = tid & 31;
     const RayPullView& pv = rp.pull;
     RayPullHeader* hdr = pv.hdr + blockIdx.x;
     const uint32_t bx0 = (uint32_t)s.window.base_px << kPatchLog2, by0 = (uint32_t)s.window.base_py << kPatchLog2;
@@ -799,20 +864,23 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
         // the common ray start: tf.translation (pf_slam2d.cpp:449), not moved by any truncation in this mode
         sh.ox = w2m(sh.tf.t[0], rp.scan.scale) - bx0;
         sh.oy = w2m(sh.tf.t[1], rp.scan.scale) - by0;
-        sh.bad = (sh.ox | sh.oy) >= side ? 1u : 0u;
+        sh.bad = (sh.ox | sh.oy) >= side ? 3u : 0u;
         sh.cells = 0;
         sh.n_list = sh.n_hits = 0;
         for (int c = 0; c < 9; ++c) sh.prefix[c] = 0;
     }
-    for (int i = tid; i < nwords; i += blockDim.x) marks[i] = 0u;
+    for (int i = tid; i < nwords; i += blockDim.x) marks[i] = hmarks[i] = 0u;
+    for (int i = tid; i < kSlopeBuckets; i += blockDim.x) bucket[i] = 0u;
+    for (int i = tid; i < npad + 2; i += blockDim.x) hcnt[i] = 0u;
+    for (int i = tid; i < npad; i += blockDim.x) hfill[i] = 0u;
     __syncthreads();
     const Affine tf = sh.tf;
     const uint32_t ox = sh.ox, oy = sh.oy;
     uint32_t my_cells = 0, my_bad = 0;
     for (int b = tid; b < npad; b += blockDim.x) {
-        uint64_t key = ~0ull, hk = ~0ull;
-        uint32_t nd = 0;
-        if (b < n) {
+        uint64_t key = ~0ull;
+        uint32_t nd = 0, hr = ~0u;
+        if (b < n && !sh.bad) {
             const double pt[3] = {__ldg(rp.points + 3 * (size_t)b), __ldg(rp.points + 3 * (size_t)b + 1), __ldg(rp.points + 3 * (size_t)b + 2)};
             const BeamCells bc = beam_cells(tf, rp.scan, pt);
             const uint32_t fx = bc.from[0] - bx0, fy = bc.from[1] - by0, tx = bc.to[0] - bx0, ty = bc.to[1] - by0;
@@ -823,14 +891,18 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
                 const PullBeam pb = pull_classify(ex, ey);
                 if (bc.mark_hit) {
                     const uint32_t di = ((ty >> kPatchLog2) << log2dim) | (tx >> kPatchLog2);
-                    hk = pull_hit_key(di, cell_index(tx, ty), (uint32_t)b);
+                    hr = (di << 10) | cell_index(tx, ty);
                     atomicOr(&marks[di >> 5], 1u << (di & 31));
+                    atomicOr(&hmarks[di >> 5], 1u << (di & 31));
                     my_cells += 1;
                 }
                 if (pb.n >= 2) {
                     my_cells += pb.n - 1;
                     key = pull_sort_key(pb.cls, pb.n, pb.d, (uint32_t)b);
                     nd  = pull_pack(pb.n, pb.d);
+                    uint32_t sb = (uint32_t)((key >> 16) >> 31) & 0x1FFu;   // top bits of the 2^39-scaled slope
+                    sb = sb > 255u ? 255u : sb;
+                    atomicAdd(&bucket[pb.cls * 256 + (int)sb], 1u);
                     pull_mark_beam(ox, oy, ex, ey, [&](int px, int py) {
                         const uint32_t di = ((uint32_t)py << log2dim) | (uint32_t)px;
                         atomicOr(&marks[di >> 5], 1u << (di & 31));
@@ -838,9 +910,9 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
                 }
             }
         }
-        keys[b]  = key;
-        hkeys[b] = hk;
-        ndb[b]   = nd;
+        keys[b] = key;
+        ndb[b]  = nd;
+        hrec[b] = hr;
     }
     my_cells = __reduce_add_sync(0xffffffffu, my_cells);
     my_bad   = __reduce_or_sync(0xffffffffu, my_bad);
@@ -852,59 +924,126 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
     if (sh.bad) {   // not for this path: k_raycast takes the particle
         if (tid == 0) {
             hdr->ok = 0;
-            if ((sh.bad & 2u) || (sh.ox | sh.oy) >= side) atomicOr(s.status, kErrWindow);
+            if (sh.bad & 2u) atomicOr(s.status, kErrWindow);
         }
         return;
     }
-    block_bitonic_sort(keys, npad);
-    block_bitonic_sort(hkeys, npad);
-    uint32_t* glist  = pv.list + (size_t)blockIdx.x * pv.stride;
-    uint16_t* gbeam  = pv.beam_of + (size_t)blockIdx.x * pv.stride;
-    uint64_t* ghits  = pv.hits + (size_t)blockIdx.x * pv.stride;
-    for (int i = tid; i < npad; i += blockDim.x) {
-        const uint64_t k = keys[i];
-        if (k != ~0ull) {
-            const uint32_t beam = pull_key_beam(k);
-            glist[i] = ndb[beam];
-            gbeam[i] = (uint16_t)beam;
-            const int cls = pull_key_class(k), prev = i ? pull_key_class(keys[i - 1]) : -1;
-            for (int c = prev + 1; c <= cls; ++c) sh.prefix[c] = i;
-            if (i == npad - 1 || keys[i + 1] == ~0ull) {
-                sh.n_list = i + 1;
-                for (int c = cls + 1; c <= 8; ++c) sh.prefix[c] = i + 1;
-            }
+    // ---- bucket starts; number the marked patches (tasks) and the hit patches ------------------------------------
+    {
+        constexpr int per = kSlopeBuckets / kSetupThreads;
+        uint32_t c[per], sum = 0;
+#pragma unroll
+        for (int k = 0; k < per; ++k) { c[k] = bucket[tid * per + k]; sum += c[k]; }
+        uint32_t base = block_scan_excl(sum, sh.scan, &sh.scan_total);
+#pragma unroll
+        for (int k = 0; k < per; ++k) { bucket[tid * per + k] = base; bfill[tid * per + k] = base; base += c[k]; }
+        if (tid == 0) sh.n_list = (int)sh.scan_total;
+        __syncthreads();
+        const uint32_t m0 = tid < nwords ? (uint32_t)__popc(marks[tid]) : 0u;   // nwords <= 512 (dir_dim <= 128)
+        const uint32_t p0 = block_scan_excl(m0, sh.scan, &sh.scan_total);
+        if (tid < nwords) wpfx[tid] = p0;
+        if (tid == 0) {
+            sh.n_tasks   = (int)sh.scan_total;
+            sh.task_base = atomicAdd(pv.ctrl, (int)sh.scan_total);
         }
-        const uint64_t h = hkeys[i];
-        if (h != ~0ull) {
-            ghits[i] = h;
-            if (i == npad - 1 || hkeys[i + 1] == ~0ull) sh.n_hits = i + 1;
+        __syncthreads();
+        const uint32_t m1 = tid < nwords ? (uint32_t)__popc(hmarks[tid]) : 0u;
+        const uint32_t p1 = block_scan_excl(m1, sh.scan, &sh.scan_total);
+        if (tid < nwords) hwpfx[tid] = p1;
+        if (tid == 0) sh.n_hpatch = (int)sh.scan_total;
+        __syncthreads();
+    }
+    // ---- scatter the beams into their buckets; count the hits of every hit patch -------------------------------------
+    for (int b = tid; b < n; b += blockDim.x) {
+        const uint64_t key = keys[b];
+        if (key != ~0ull) {
+            uint32_t sb = (uint32_t)((key >> 16) >> 31) & 0x1FFu;
+            sb = sb > 255u ? 255u : sb;
+            sorted[atomicAdd(&bfill[pull_key_class(key) * 256 + (int)sb], 1u)] = key;
+        }
+        const uint32_t hr = hrec[b];
+        if (hr != ~0u) {
+            const uint32_t di = hr >> 10;
+            const uint32_t ho = hwpfx[di >> 5] + (uint32_t)__popc(hmarks[di >> 5] & ((1u << (di & 31)) - 1u));
+            atomicAdd(&hcnt[ho], 1u);
         }
     }
-    // the patches to visit: one task each, appended to the global list (tasks of a particle stay together)
-    if (warp == 0) {
-        int total = 0;
-        for (int w0 = lane; w0 < nwords; w0 += 32) total += __popc(marks[w0]);
-        total = __reduce_add_sync(0xffffffffu, total);
-        int base = 0;
-        if (lane == 0) base = atomicAdd(pv.ctrl, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
-            const int wi = w0 + lane;
-            uint32_t bits = wi < nwords ? marks[wi] : 0u;
-            const int cnt = __popc(bits);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+    __syncthreads();
+    const int n_list = sh.n_list;
+    // ---- exact order: odd-even transposition until a full round changes nothing ------------------------------------
+    for (;;) {
+        if (tid == 0) sh.swapped = 0;
+        __syncthreads();
+        bool sw = false;
+        for (int i = 2 * tid; i + 1 < n_list; i += 2 * blockDim.x) {
+            const uint64_t x = sorted[i], y = sorted[i + 1];
+            if (x > y) { sorted[i] = y; sorted[i + 1] = x; sw = true; }
+        }
+        __syncthreads();
+        for (int i = 2 * tid + 1; i + 1 < n_list; i += 2 * blockDim.x) {
+            const uint64_t x = sorted[i], y = sorted[i + 1];
+            if (x > y) { sorted[i] = y; sorted[i + 1] = x; sw = true; }
+        }
+        if (sw) sh.swapped = 1;
+        __syncthreads();
+        const bool again = sh.swapped != 0;
+        __syncthreads();
+        if (!again) break;
+    }
+    // ---- class lists to global memory ------------------------------------------------------------------------------------
+    uint32_t* glist = pv.list + (size_t)blockIdx.x * pv.stride;
+    uint16_t* gbeam = pv.beam_of + (size_t)blockIdx.x * pv.stride;
+    uint32_t* ghits = pv.hits + (size_t)blockIdx.x * pv.stride;
+    for (int i = tid; i < n_list; i += blockDim.x) {
+        const uint64_t k = sorted[i];
+        const uint32_t beam = pull_key_beam(k);
+        glist[i] = ndb[beam];
+        gbeam[i] = (uint16_t)beam;
+        const int cls = pull_key_class(k), prev = i ? pull_key_class(sorted[i - 1]) : -1;
+        for (int c = prev + 1; c <= cls; ++c) sh.prefix[c] = i;
+        if (i == n_list - 1)
+            for (int c = cls + 1; c <= 8; ++c) sh.prefix[c] = n_list;
+    }
+    // ---- hit records grouped by hit patch ---------------------------------------------------------------------------------
+    {
+        const int nhp = sh.n_hpatch, per = (nhp + (int)blockDim.x - 1) / (int)blockDim.x;
+        uint32_t sum = 0;
+        for (int k = 0; k < per; ++k) {
+            const int i = tid * per + k;
+            if (i < nhp) sum += hcnt[i];
+        }
+        uint32_t base = block_scan_excl(sum, sh.scan, &sh.scan_total);
+        for (int k = 0; k < per; ++k) {
+            const int i = tid * per + k;
+            if (i < nhp) { const uint32_t c = hcnt[i]; hcnt[i] = base; base += c; }
+        }
+        if (tid == 0) {
+            sh.n_hits = (int)sh.scan_total;
+            hcnt[nhp] = sh.scan_total;
+        }
+        __syncthreads();
+    }
+    for (int b = tid; b < n; b += blockDim.x) {
+        const uint32_t hr = hrec[b];
+        if (hr == ~0u) continue;
+        const uint32_t di = hr >> 10;
+        const uint32_t ho = hwpfx[di >> 5] + (uint32_t)__popc(hmarks[di >> 5] & ((1u << (di & 31)) - 1u));
+        ghits[hcnt[ho] + atomicAdd(&hfill[ho], 1u)] = pull_hit_record(hr & (kPatchCells - 1), (uint32_t)b);
+    }
+    // ---- one task per marked patch (the tasks of a particle stay together) ---------------------------------------------------
+    for (int w = tid; w < nwords; w += blockDim.x) {
+        uint32_t bits = marks[w];
+        uint32_t k = (uint32_t)sh.task_base + wpfx[w];
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t di = (uint32_t)(w * 32 + bit);
+            uint32_t hw = 0;
+            if ((hmarks[w] >> bit) & 1u) {
+                const uint32_t ho = hwpfx[w] + (uint32_t)__popc(hmarks[w] & ((1u << bit) - 1u));
+                hw = (hcnt[ho] << 16) | (hcnt[ho + 1] - hcnt[ho]);
             }
-            int k = base + incl - cnt;
-            while (bits) {
-                const int bit = __ffs(bits) - 1;
-                bits &= bits - 1;
-                pv.tasks[k++] = ((uint32_t)blockIdx.x << 16) | (uint32_t)(wi * 32 + bit);
-            }
-            base += __shfl_sync(0xffffffffu, incl, 31);
+            pv.tasks[k++] = make_uint2(((uint32_t)blockIdx.x << 16) | di, hw);
         }
     }
     __syncthreads();
@@ -912,8 +1051,10 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
         hdr->ox = (int32_t)ox;
         hdr->oy = (int32_t)oy;
         for (int c = 0; c < 9; ++c) hdr->prefix[c] = sh.prefix[c];
-        hdr->n_hits = sh.n_hits;
-        hdr->ok     = 1;
+        hdr->n_hits    = sh.n_hits;
+        hdr->ok        = 1;
+        hdr->task_base = sh.task_base;
+        hdr->n_tasks   = sh.n_tasks;
         MapUpdateStats& st = stats[blockIdx.x];
         st.ray_cells   = sh.cells;
         st.log_records = 0;
@@ -922,132 +1063,196 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
     }
 }
 
-// k_ray_pull: persistent warps take (particle, patch) tasks from the global list.  Per task: the two axis passes fill the count
-// tile, plain cells get `visited += count` (log-odds maps: `count` misses) with row-coalesced read-modify-writes of the patch the
-// particle owns exclusively, candidate cells (hit in this scan, or distance-map obstacles) are compacted and replayed in beam order,
-// one lane per cell.  A patch without any touched cell is neither allocated nor detached (the reference would not have created it).
+// k_ray_pull: persistent CTAs take work units (particle, every splits-th patch of it), stage the particle's class lists and hit
+// records in shared memory with TMA bulk copies, and their warps then take patches one by one.  Per patch: the axis passes fill
+// the count tile, plain cells get `visited += count` (log-odds maps: `count` misses) with row-coalesced read-modify-writes of the
+// patch the particle owns exclusively, candidate cells (hit in this scan, or distance-map obstacles) are compacted and replayed in
+// beam order, one lane per cell.  A patch without any touched cell is neither allocated nor detached (the reference would not have
+// created it).
 constexpr int kPullWarps = 8;
+constexpr int kPullCandCap = 512;
 struct PullWarpShared {
-    uint32_t tile[kPatchLen * 33];   // crossing count of every cell; row stride 33: column- and row-wise accesses are conflict free
+    uint16_t tile[kPatchCells];      // crossing count of cell (r, c) at [r * 32 + (c ^ r)]: rows and columns are both conflict free
     uint32_t hitbits[kPatchLen];     // cells of the patch that are hit cells of this scan
-    uint16_t cand[kPatchCells];      // compacted candidate cells
+    uint16_t cand[kPullCandCap];     // compacted candidate cells
+};
+struct PullCtaShared {
+    RayPullHeader hdr;
+    uint64_t bar;
+    int unit, next;
+};
+struct RayPullLayout {
+    size_t list, beam_of, hits, warps, total;
+    __host__ __device__ explicit RayPullLayout(int stride)
+    {
+        size_t o = (sizeof(PullCtaShared) + 15) & ~(size_t)15;
+        list = o;    o += (size_t)stride * 4;
+        beam_of = o; o += (size_t)stride * 2;
+        hits = o;    o += (size_t)stride * 4;
+        warps = o;   o += (size_t)kPullWarps * sizeof(PullWarpShared);
+        total = o;
+    }
 };
 
 template <bool kProb>
 __global__ void __launch_bounds__(kPullWarps * 32, 4)
-k_ray_pull(StoreView s, RayParams rp, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
+k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PullWarpShared& w = reinterpret_cast<PullWarpShared*>(smem_raw)[warp];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const RayPullView& pv = rp.pull;
-    const int dim = s.window.dim;
+    const RayPullLayout L(pv.stride);
+    PullCtaShared& sh   = *reinterpret_cast<PullCtaShared*>(smem_raw);
+    uint32_t* list      = reinterpret_cast<uint32_t*>(smem_raw + L.list);
+    uint16_t* beam_of   = reinterpret_cast<uint16_t*>(smem_raw + L.beam_of);
+    uint32_t* hits      = reinterpret_cast<uint32_t*>(smem_raw + L.hits);
+    PullWarpShared& w   = reinterpret_cast<PullWarpShared*>(smem_raw + L.warps)[warp];
+    const RayPullHeader* hdr = &sh.hdr;
+    const int dim = s.window.dim, S = pv.splits;
     int log2dim = 0;
     while ((1 << (log2dim + 1)) <= dim) ++log2dim;
-    const int total = __ldcg(pv.ctrl);
-    uint32_t err = 0;
+    if (tid == 0) mbar_init(&sh.bar, 1);
+    uint32_t err = 0, parity = 0;
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(pv.ctrl + 1, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= total) break;
-        const uint32_t task = __ldg(pv.tasks + t);
-        const int pl = (int)(task >> 16), di = (int)(task & 0xFFFFu);
-        const RayPullHeader* hdr = pv.hdr + pl;
-        const uint32_t* list    = pv.list + (size_t)pl * pv.stride;
-        const uint16_t* beam_of = pv.beam_of + (size_t)pl * pv.stride;
-        const uint64_t* hits    = pv.hits + (size_t)pl * pv.stride;
-        const int px = di & (dim - 1), py = di >> log2dim;
-        const int cx0 = px * kPatchLen - hdr->ox, cy0 = py * kPatchLen - hdr->oy;
-        for (int i = lane; i < kPatchLen * 33; i += 32) w.tile[i] = 0u;
-        w.hitbits[lane] = 0u;
-        __syncwarp();
-        uint32_t touched = 0;
-        pull_lane_pass(list, hdr->prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { w.tile[line * 33 + lane] = c; touched |= c; });   // lane = column
-        __syncwarp();
-        pull_lane_pass(list, hdr->prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { w.tile[lane * 33 + line] += c; touched |= c; });  // lane = row
-        const int n_hits = hdr->n_hits;
-        const int h_lo = pull_hit_lower_bound(hits, n_hits, pull_hit_key((uint32_t)di, 0u, 0u));
-        const int h_hi = h_lo + pull_hit_lower_bound(hits + h_lo, n_hits - h_lo, pull_hit_key((uint32_t)di + 1u, 0u, 0u));
-        for (int i = h_lo + lane; i < h_hi; i += 32) {
-            const uint32_t cell = (uint32_t)(hits[i] >> 16) & (kPatchCells - 1);
-            atomicOr(&w.hitbits[cell >> 5], 1u << (cell & 31));
+        __syncthreads();   // every warp is done with the staged data of the previous unit
+        if (tid == 0) sh.unit = atomicAdd(pv.ctrl + 1, 1);
+        __syncthreads();
+        const int unit = sh.unit;
+        if (unit >= count * S) break;
+        const int pl = unit / S, split = unit - pl * S;
+        if (!__ldcg(&pv.hdr[pl].ok)) continue;   // k_raycast handles this particle
+        if (tid == 0) {
+            sh.hdr  = pv.hdr[pl];
+            sh.next = 0;
+            const uint32_t nl = (uint32_t)sh.hdr.prefix[8], nh = (uint32_t)sh.hdr.n_hits;
+            const uint32_t b0 = (nl * 4u + 15u) & ~15u, b1 = (nl * 2u + 15u) & ~15u, b2 = (nh * 4u + 15u) & ~15u;
+            mbar_expect_tx(&sh.bar, b0 + b1 + b2);
+            if (b0) tma_load_1d(list, pv.list + (size_t)pl * pv.stride, b0, &sh.bar);
+            if (b1) tma_load_1d(beam_of, pv.beam_of + (size_t)pl * pv.stride, b1, &sh.bar);
+            if (b2) tma_load_1d(hits, pv.hits + (size_t)pl * pv.stride, b2, &sh.bar);
         }
-        __syncwarp();
-        if (!__any_sync(0xffffffffu, touched != 0u) && h_hi == h_lo) continue;   // nothing of this scan lands in the patch
-
-        // Map::get (mutable): allocate on first touch, detach a shared patch (map.cpp:400-408, cow_ptr.h:104-114)
+        mbar_wait(&sh.bar, parity);
+        parity ^= 1u;
+        __syncthreads();   // sh.hdr / sh.next written by thread 0
+        const int n_tasks = hdr->n_tasks, ox = hdr->ox, oy = hdr->oy;
         int32_t* gdir = dir_of(s, rp.set, rp.particle_offset + pl, kMapOcc);
-        const int e0 = gdir[di];
-        const bool hot = e0 >= 0 && (e0 & kDirHot);
-        const int slot = warp_make_exclusive(s, gdir, gdir, di, lane);
-        if (slot < 0) {
-            err |= kErrPoolEmpty;
-            continue;
-        }
-        uint32_t* patch = patch_ptr(s, slot);
-        const uint32_t hitrow  = w.hitbits[lane];                                            // lane = row
-        const uint32_t candrow = hitrow | (hot ? __ldcg(fbits_ptr(s, slot) + lane) : 0u);   // | cells that are distance-map obstacles
-        int ncand = 0;
-#pragma unroll 4
-        for (int r = 0; r < kPatchLen; ++r) {
-            const uint32_t cnt = w.tile[r * 33 + lane];
-            const uint32_t cw = __shfl_sync(0xffffffffu, candrow, r), hw = __shfl_sync(0xffffffffu, hitrow, r);
-            const bool iscand = (cw >> lane) & 1u, ishit = (hw >> lane) & 1u;
-            const bool touch = cnt != 0u || ishit;
-            const bool plain = touch && !iscand;   // misses only, never an obstacle: counter additions commute
-            if (plain) {
-                uint32_t* cell = patch + r * kPatchLen + lane;
-                if (!kProb) {
-                    *cell += cnt << 16;   // visited += cnt (wraps like the reference's uint16)
-                } else {
-                    float p = __uint_as_float(*cell);
-                    for (uint32_t k = cnt; k > 0; --k) p = prob_miss(p, rp.prob);
-                    *cell = __float_as_uint(p);
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&sh.next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const int ti = split + t * S;
+            if (ti >= n_tasks) break;
+            const uint2 task = __ldg(pv.tasks + hdr->task_base + ti);
+            const int di = (int)(task.x & 0xFFFFu), h_lo = (int)(task.y >> 16), h_hi = h_lo + (int)(task.y & 0xFFFFu);
+            const int px = di & (dim - 1), py = di >> log2dim;
+            const int cx0 = px * kPatchLen - ox, cy0 = py * kPatchLen - oy;
+            {   // zero the tile (2 KiB: four 16-byte stores per lane)
+                uint4* tz = reinterpret_cast<uint4*>(w.tile);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            w.hitbits[lane] = 0u;
+            __syncwarp();
+            uint32_t touched = 0;
+            // X pass: x-major beams, lane = column.  Y pass: y-major beams, lane = row.  (pull_lane_pass_flat returns at once for
+            // lanes behind the diagonal, so a patch far from one of the axes costs only one of the two passes.)
+            pull_lane_pass_flat(list, hdr->prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { w.tile[line * kPatchLen + (lane ^ line)] = (uint16_t)c; touched |= c; });
+            __syncwarp();
+            pull_lane_pass_flat(list, hdr->prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { w.tile[lane * kPatchLen + (line ^ lane)] += (uint16_t)c; touched |= c; });
+            for (int i = h_lo + lane; i < h_hi; i += 32) {
+                const uint32_t cell = pull_hit_cell(hits[i]);
+                atomicOr(&w.hitbits[cell >> 5], 1u << (cell & 31));
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, touched != 0u) && h_hi == h_lo) continue;   // nothing of this scan lands in the patch
+
+            // Map::get (mutable): allocate on first touch, detach a shared patch (map.cpp:400-408, cow_ptr.h:104-114)
+            const int e0 = gdir[di];
+            const bool hot = e0 >= 0 && (e0 & kDirHot);
+            const int slot = warp_make_exclusive(s, gdir, gdir, di, lane);
+            if (slot < 0) {
+                err |= kErrPoolEmpty;
+                continue;
+            }
+            uint32_t* patch = patch_ptr(s, slot);
+            const uint32_t hitrow  = w.hitbits[lane];                                            // lane = row
+            const uint32_t candrow = hitrow | (hot ? __ldcg(fbits_ptr(s, slot) + lane) : 0u);   // | cells that are distance-map obstacles
+            int ncand = 0;
+            bool newhot = false;
+            auto replay_candidates = [&]() {
+                for (int k = lane; k < ncand; k += 32) {
+                    const uint32_t ci = w.cand[k];
+                    const int r = (int)(ci >> kPatchLog2), c = (int)(ci & (kPatchLen - 1));
+                    const PullRuns runs = pull_cell_runs(list, hdr->prefix, cx0 + c, cy0 + r);
+                    uint32_t* fword = fbits_ptr(s, slot) + r;
+                    const bool before = (__ldcg(fword) >> c) & 1u;
+                    bool obstacle = before;
+                    const uint32_t key = ((uint32_t)(py * kPatchLen + r) << 16) | (uint32_t)(px * kPatchLen + c);   // window-relative cell
+                    auto emit = [&](bool add, uint32_t seq) {
+                        const uint32_t idx = atomicAdd(&stats[pl].events, 1u);
+                        if (idx < (uint32_t)rp.event_cap) events_out[(size_t)pl * rp.event_cap + idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
+                    };
+                    uint32_t* cell = patch + ci;
+                    if (!kProb) {
+                        *cell = pull_replay_cell(list, beam_of, runs, hits, h_lo, h_hi, ci, *cell, obstacle, emit);
+                    } else {
+                        *cell = __float_as_uint(pull_replay_cell_prob(list, beam_of, runs, hits, h_lo, h_hi, ci, __uint_as_float(*cell), obstacle, rp.prob, emit));
+                        atomicOr(kbits_ptr(s, slot) + r, 1u << c);
+                    }
+                    if (obstacle != before) {
+                        if (obstacle) {
+                            atomicOr(fword, 1u << c);
+                            newhot = true;
+                        } else {
+                            atomicAnd(fword, ~(1u << c));
+                        }
+                    }
                 }
-            }
-            if (kProb) {
-                const uint32_t known = __ballot_sync(0xffffffffu, plain);
-                if (lane == 0 && known) kbits_ptr(s, slot)[r] |= known;
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, touch && iscand);
-            if (touch && iscand) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * kPatchLen + lane);
-            ncand += __popc(m);
-        }
-        __syncwarp();
-        bool newhot = false;
-        for (int k = lane; k < ncand; k += 32) {
-            const uint32_t ci = w.cand[k];
-            const int r = (int)(ci >> kPatchLog2), c = (int)(ci & (kPatchLen - 1));
-            const PullRuns runs = pull_cell_runs(list, hdr->prefix, cx0 + c, cy0 + r);
-            const int c_lo = h_lo + pull_hit_lower_bound(hits + h_lo, h_hi - h_lo, pull_hit_key((uint32_t)di, ci, 0u));
-            const int c_hi = c_lo + pull_hit_lower_bound(hits + c_lo, h_hi - c_lo, pull_hit_key((uint32_t)di, ci + 1u, 0u));
-            uint32_t* fword = fbits_ptr(s, slot) + r;
-            const bool before = (__ldcg(fword) >> c) & 1u;
-            bool obstacle = before;
-            const uint32_t key = ((uint32_t)(py * kPatchLen + r) << 16) | (uint32_t)(px * kPatchLen + c);   // window-relative cell
-            auto emit = [&](bool add, uint32_t seq) {
-                const uint32_t idx = atomicAdd(&stats[pl].events, 1u);
-                if (idx < (uint32_t)rp.event_cap) events_out[(size_t)pl * rp.event_cap + idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
+                __syncwarp();
+                ncand = 0;
             };
-            uint32_t* cell = patch + ci;
-            if (!kProb) {
-                *cell = pull_replay_cell(list, beam_of, runs, hits, c_lo, c_hi, *cell, obstacle, emit);
-            } else {
-                *cell = __float_as_uint(pull_replay_cell_prob(list, beam_of, runs, hits, c_lo, c_hi, __uint_as_float(*cell), obstacle, rp.prob, emit));
-                atomicOr(kbits_ptr(s, slot) + r, 1u << c);
-            }
-            if (obstacle != before) {
-                if (obstacle) {
-                    atomicOr(fword, 1u << c);
-                    newhot = true;
-                } else {
-                    atomicAnd(fword, ~(1u << c));
+            for (int r0 = 0; r0 < kPatchLen; r0 += 8) {
+                uint32_t v[8];   // eight rows of the patch in flight at once
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldcg(patch + (r0 + k) * kPatchLen + lane);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = r0 + k;
+                    const uint32_t cnt = w.tile[r * kPatchLen + (lane ^ r)];
+                    const uint32_t cw = __shfl_sync(0xffffffffu, candrow, r);
+                    bool plain = cnt != 0u;   // misses only, never an obstacle: counter additions commute
+                    if (cw != 0u) {           // (rare) the row holds candidate cells
+                        const uint32_t hw = __shfl_sync(0xffffffffu, hitrow, r);
+                        const bool iscand = (cw >> lane) & 1u, touch = cnt != 0u || ((hw >> lane) & 1u);
+                        plain = touch && !iscand;
+                        const uint32_t m = __ballot_sync(0xffffffffu, touch && iscand);
+                        if (m) {
+                            if (ncand + 32 > kPullCandCap) replay_candidates();
+                            if (touch && iscand) w.cand[ncand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(r * kPatchLen + lane);
+                            ncand += __popc(m);
+                        }
+                    }
+                    if (plain) {
+                        uint32_t* cell = patch + r * kPatchLen + lane;
+                        if (!kProb) {
+                            *cell = v[k] + (cnt << 16);   // visited += cnt (wraps like the reference's uint16)
+                        } else {
+                            float p = __uint_as_float(v[k]);
+                            for (uint32_t q = cnt; q > 0; --q) p = prob_miss(p, rp.prob);
+                            *cell = __float_as_uint(p);
+                        }
+                    }
+                    if (kProb) {
+                        const uint32_t known = __ballot_sync(0xffffffffu, plain);
+                        if (lane == 0 && known) kbits_ptr(s, slot)[r] |= known;
+                    }
                 }
             }
+            __syncwarp();
+            if (ncand) replay_candidates();
+            if (__any_sync(0xffffffffu, newhot) && !hot && lane == 0) gdir[di] |= kDirHot;   // from now on the patch may hold obstacle bits
+            __syncwarp();
         }
-        if (__any_sync(0xffffffffu, newhot) && !hot && lane == 0) gdir[di] |= kDirHot;   // from now on the patch may hold obstacle bits
-        __syncwarp();
     }
     err = __reduce_or_sync(0xffffffffu, err);
     if (lane == 0 && err) atomicOr(s.status, err);
@@ -1421,9 +1626,9 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ray_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_setup_smem_bytes(dir_dim, rp.scan.n_beams > 4096 ? 4096 : rp.scan.n_beams));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ray_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPullWarps * sizeof(PullWarpShared)));
+    e = cudaFuncSetAttribute(k_ray_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.pull.stride));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ray_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPullWarps * sizeof(PullWarpShared)));
+    e = cudaFuncSetAttribute(k_ray_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.pull.stride));
     return e;
 }
 
@@ -1443,21 +1648,22 @@ void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states
     if (rp.prob_mode) k_raycast<true><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
     else k_raycast<false><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
 }
-size_t ray_setup_smem_bytes(int dir_dim, int n_beams)
-{
-    int npad = 32;
-    while (npad < n_beams) npad <<= 1;
-    const int nwords = (dir_dim * dir_dim + 31) / 32;
-    return (size_t)npad * (8 + 8 + 4) + (size_t)((nwords + 1) & ~1) * 4 + sizeof(RaySetupShared) + 16;
-}
-void launch_raycast_pull(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
+size_t ray_setup_smem_bytes(int dir_dim, int n_beams) { return RaySetupLayout(n_beams, dir_dim * dir_dim).total; }
+size_t ray_pull_smem_bytes(int stride) { return RayPullLayout(stride).total; }
+void launch_raycast_pull(const StoreView& s, const RayParams& rp_in, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
                          cudaStream_t st)
 {
     if (count <= 0) return;
+    RayParams rp = rp_in;
+    // work units: enough of them to fill the machine several times over whatever the number of particles on this device
+    int splits = (6 * n_sms + count - 1) / count;
+    rp.pull.splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
     k_ray_setup<<<count, kSetupThreads, ray_setup_smem_bytes(s.window.dim, rp.scan.n_beams), st>>>(s, rp, d_states, d_stats);
-    const int grid = n_sms * 4;   // persistent: four CTAs of eight warps per SM
-    if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, kPullWarps * sizeof(PullWarpShared), st>>>(s, rp, d_events, d_stats);
-    else k_ray_pull<false><<<grid, kPullWarps * 32, kPullWarps * sizeof(PullWarpShared), st>>>(s, rp, d_events, d_stats);
+    const int units = count * rp.pull.splits;
+    const int grid = units < n_sms * 4 ? units : n_sms * 4;   // persistent: up to four CTAs of eight warps per SM
+    const size_t smem = ray_pull_smem_bytes(rp.pull.stride);
+    if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
+    else k_ray_pull<false><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
 }
 void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
 {

@@ -129,6 +129,62 @@ LAMA_HD void pull_lane_pass(const uint32_t* list, const int* prefix, int a_signe
     }
 }
 
+// The same pass as ONE loop per lane (what the kernel runs): every iteration either consumes a beam of the class list or closes a
+// cell and moves to the next line, so the lanes of a warp -- whose columns hold different numbers of beams per cell -- do not wait
+// for each other at every line, only at the end of the pass.  `emit(b, count)` closes cell b.
+template <typename EmitCell>
+LAMA_HD void pull_lane_chain(const uint32_t* list, int ptr, int end, uint32_t a, uint32_t b, uint32_t b_last, EmitCell&& emit)
+{
+    const uint32_t a2 = 2u * a;
+    uint32_t bb = 2u * (b + 1u), count = 0;
+    uint32_t n = 1u, d = 0xFFFFu;   // past the end of the list: a beam steeper than every cell bound
+    if (ptr < end) { n = list[ptr] & 0xFFFFu; d = list[ptr] >> 16; }
+    for (;;) {
+        if (a2 * d + n < bb * n) {   // the beam's slope is below the upper bound of cell b: it belongs to this cell's run
+            count += n > a ? 1u : 0u;
+            ++ptr;
+            n = 1u; d = 0xFFFFu;
+            if (ptr < end) { n = list[ptr] & 0xFFFFu; d = list[ptr] >> 16; }
+        } else {
+            emit(b, count);
+            if (b == b_last) break;
+            count = 0;
+            ++b;
+            bb += 2u;
+        }
+    }
+}
+template <typename Out>
+LAMA_HD void pull_lane_pass_flat(const uint32_t* list, const int* prefix, int a_signed, int t0, int base, Out&& out)
+{
+    const uint32_t a = (uint32_t)(a_signed < 0 ? -a_signed : a_signed);
+    if (a == 0) return;
+    const int t1 = t0 + kPatchLen - 1;
+    const uint32_t bmin = (t0 <= 0 && t1 >= 0) ? 0u : (uint32_t)(t0 > 0 ? t0 : -t1);
+    if (bmin > a) return;
+    const int cm = base | (a_signed < 0 ? 2 : 0);
+    uint32_t c0neg = 0;
+    if (t0 <= 0) {   // negative minor side (class cm | 1), away from the axis; with the axis line in the patch the chain starts at b = 0
+        const int lo = prefix[cm | 1], hi = prefix[(cm | 1) + 1];
+        const uint32_t b0 = t1 >= 0 ? 0u : (uint32_t)(-t1);
+        uint32_t b1 = (uint32_t)(-t0);
+        if (b1 > a) b1 = a;
+        const int ptr = b0 == 0 ? lo : pull_lower_bound(list, lo, hi, a, b0);
+        pull_lane_chain(list, ptr, hi, a, b0, b1, [&](uint32_t b, uint32_t c) {
+            if (b == 0) c0neg = c;   // kept for the axis cell, which the positive side emits
+            else out(-(int)b - t0, c);
+        });
+    }
+    if (t1 >= 0) {
+        const int lo = prefix[cm], hi = prefix[cm + 1];
+        const uint32_t b0 = t0 > 0 ? (uint32_t)t0 : 0u;
+        uint32_t b1 = (uint32_t)t1;
+        if (b1 > a) b1 = a;
+        const int ptr = b0 == 0 ? lo : pull_lower_bound(list, lo, hi, a, b0);
+        pull_lane_chain(list, ptr, hi, a, b0, b1, [&](uint32_t b, uint32_t c) { out((int)b - t0, b == 0 ? c + c0neg : c); });
+    }
+}
+
 // ---- the runs of ONE cell (ordered replay of candidate cells) -----------------------------------------------------------------
 // Four runs [lo, hi) of the sorted list (x-major / y-major beams, positive / negative minor side; empty when not applicable)
 // hold the beams whose slope passes through cell (cx, cy) (offsets from O); a beam of run r really crosses the cell iff its
@@ -192,24 +248,14 @@ LAMA_HD void pull_mark_beam(uint32_t ox, uint32_t oy, int ex, int ey, Mark&& mar
 }
 
 // ---- hit records ----------------------------------------------------------------------------------------------------------------
-// [directory index : 12][cell index in the patch : 10][beam : 16], sorted: the hits of a patch, and inside it of a cell, are
-// contiguous and in beam order.
-// (sums, not ORs: `cell` == 1024 is used as the end bound of a patch's last cell and carries into the directory index)
-LAMA_HD uint64_t pull_hit_key(uint32_t di, uint32_t cell, uint32_t beam) { return ((uint64_t)di << 26) + ((uint64_t)cell << 16) + (beam & 0xFFFFu); }
-LAMA_HD int pull_hit_lower_bound(const uint64_t* hits, int n, uint64_t key)
-{
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (hits[mid] >= key) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo;
-}
+// [cell index in the patch : 10 (bits 16..25)][beam : 16]; k_ray_setup groups them by patch (each task names its range), in no
+// particular order inside a patch: the replay picks a cell's hits out of the patch's few records by their cell index.
+LAMA_HD uint32_t pull_hit_record(uint32_t cell, uint32_t beam) { return (cell << 16) | (beam & 0xFFFFu); }
+LAMA_HD uint32_t pull_hit_cell(uint32_t rec) { return rec >> 16; }
 
 // ---- ordered replay of one candidate cell ---------------------------------------------------------------------------------------
-// Touches = the crossing beams of the runs (misses) and the hit records hits[h0, h1) of the cell; a beam touches a cell at
-// most once.  They are visited in beam order by repeated minimum selection (the lists are short), starting from the cell's
+// Touches = the crossing beams of the runs (misses) and those of the patch's hit records hits[h0, h1) that name cell `ci`; a beam
+// touches a cell at most once.  They are visited in beam order by repeated minimum selection (the lists are short), starting from the cell's
 // counters BEFORE the scan; returns the counters after the scan and the new obstacle-mirror bit, and emits the obstacle events
 // exactly like replay_cell (ray_core.h).
 //   setFree  frequency_occupancy_map.cpp:65-74   setOccupied :81-91   addObstacle / removeObstacle dynamic_distance_map.cpp:212-242
@@ -217,7 +263,7 @@ struct PullTouch {
     uint32_t beam, pos;
     bool hit, valid;
 };
-LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint64_t* hits, int h0, int h1, int after)
+LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, int after)
 {
     PullTouch t{0xFFFFFFFFu, 0u, false, false};
 #if defined(__CUDA_ARCH__)
@@ -232,7 +278,8 @@ LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of,
             }
         }
     for (int i = h0; i < h1; ++i) {
-        const uint32_t b = (uint32_t)hits[i] & 0xFFFFu;
+        if (pull_hit_cell(hits[i]) != ci) continue;
+        const uint32_t b = hits[i] & 0xFFFFu;
         if ((int)b > after && b < t.beam) {
             t.beam = b; t.pos = 0u; t.hit = true; t.valid = true;
         }
@@ -240,13 +287,13 @@ LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of,
     return t;
 }
 template <typename Emit>
-LAMA_HD uint32_t pull_replay_cell(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint64_t* hits, int h0, int h1, uint32_t word,
+LAMA_HD uint32_t pull_replay_cell(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, uint32_t word,
                                   bool& obstacle, Emit&& emit)
 {
     uint32_t occupied = occ_occupied(word), visited = occ_visited(word);
     int after = -1;
     for (;;) {
-        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, after);
+        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, ci, after);
         if (!t.valid) break;
         after = (int)t.beam;
         const uint32_t seq = (t.beam << 15) | (t.pos & 0x7FFFu);   // == log_seq(log_record(., beam, pos, hit))
@@ -271,12 +318,12 @@ LAMA_HD uint32_t pull_replay_cell(const uint32_t* list, const uint16_t* beam_of,
 }
 // log-odds cells (ProbabilisticOccupancyMap, probabilistic_occupancy_map.cpp:82-107)
 template <typename Emit>
-LAMA_HD float pull_replay_cell_prob(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint64_t* hits, int h0, int h1, float prob,
+LAMA_HD float pull_replay_cell_prob(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, float prob,
                                     bool& obstacle, const ProbParams& pp, Emit&& emit)
 {
     int after = -1;
     for (;;) {
-        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, after);
+        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, ci, after);
         if (!t.valid) break;
         after = (int)t.beam;
         const uint32_t seq = (t.beam << 15) | (t.pos & 0x7FFFu);

@@ -78,6 +78,14 @@ bool sdm_read(const std::string& path, uint32_t expect_cell_size, size_t n_param
     f.params.resize(n_params);
     if (n_params && std::fread(f.params.data(), n_params, 1, fp.f) != 1) { err = "truncated parameters in " + path; return false; }
     const size_t patch_bytes = (size_t)kPatchCells * f.header.cell_size, n = (size_t)f.header.num_patches;
+    {   // num_patches comes from an untrusted file: it must fit what is left of it before anything is sized from it
+        const long here = std::ftell(fp.f);
+        if (here < 0 || std::fseek(fp.f, 0, SEEK_END) != 0) { err = "cannot size " + path; return false; }
+        const long end = std::ftell(fp.f);
+        if (end < here || std::fseek(fp.f, here, SEEK_SET) != 0) { err = "cannot size " + path; return false; }
+        const size_t per_patch = 8 + patch_bytes + 8 * (size_t)kMaskWords;
+        if (f.header.num_patches > (uint64_t)(end - here) / per_patch) { err = "truncated patch list in " + path; return false; }  // map.cpp:567
+    }
     f.ids.resize(n);
     f.cells.resize(n * patch_bytes);
     f.masks.resize(n * kMaskWords);

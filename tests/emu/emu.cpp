@@ -195,7 +195,8 @@ struct PullScan {
     std::vector<uint32_t> list;              // class lists: n | d << 16, sorted by (class, slope, beam)
     std::vector<uint16_t> beam_of;
     int prefix[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    std::vector<uint64_t> hits;              // pull_hit_key, sorted
+    std::vector<uint32_t> hits;              // pull_hit_record, grouped by patch (hit_lo / hit_n per directory entry), unordered inside
+    std::vector<int> hit_lo, hit_n;
     std::vector<uint8_t> marked;             // per directory entry
     uint32_t cells = 0;
 };
@@ -207,6 +208,9 @@ void pull_setup(PullScan& ps, uint32_t ox, uint32_t oy, const std::vector<uint32
     while ((1 << (log2dim + 1)) <= dim) ++log2dim;
     ps.ox = ox; ps.oy = oy;
     ps.marked.assign((size_t)dim * dim, 0);
+    ps.hit_lo.assign((size_t)dim * dim, 0);
+    ps.hit_n.assign((size_t)dim * dim, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> hit_of;   // (directory entry, record)
     std::vector<uint64_t> keys;
     std::vector<uint32_t> nd_of_beam(tx.size(), 0u);
     for (size_t b = 0; b < tx.size(); ++b) {
@@ -214,7 +218,7 @@ void pull_setup(PullScan& ps, uint32_t ox, uint32_t oy, const std::vector<uint32
         const PullBeam pb = pull_classify(ex, ey);
         if (mark_hit[b]) {
             const uint32_t di = ((ty[b] >> kPatchLog2) << log2dim) | (tx[b] >> kPatchLog2);
-            ps.hits.push_back(pull_hit_key(di, cell_index(tx[b], ty[b]), (uint32_t)b));
+            hit_of.push_back({di, pull_hit_record(cell_index(tx[b], ty[b]), (uint32_t)b)});
             ps.marked[di] = 1;
             ps.cells += 1;
         }
@@ -226,7 +230,14 @@ void pull_setup(PullScan& ps, uint32_t ox, uint32_t oy, const std::vector<uint32
         }
     }
     std::sort(keys.begin(), keys.end());
-    std::sort(ps.hits.begin(), ps.hits.end());
+    // counting sort by patch; the order inside a patch is whatever the scatter's atomics produce on the device: scramble it here
+    std::mt19937 g(12345u + (uint32_t)tx.size());
+    std::shuffle(hit_of.begin(), hit_of.end(), g);
+    std::stable_sort(hit_of.begin(), hit_of.end(), [](const std::pair<uint32_t, uint32_t>& l, const std::pair<uint32_t, uint32_t>& r) { return l.first < r.first; });
+    for (size_t i = 0; i < hit_of.size(); ++i) {
+        if (ps.hit_n[hit_of[i].first]++ == 0) ps.hit_lo[hit_of[i].first] = (int)i;
+        ps.hits.push_back(hit_of[i].second);
+    }
     int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (uint64_t k : keys) {
         ps.list.push_back(nd_of_beam[pull_key_beam(k)]);
@@ -243,8 +254,8 @@ void pull_patch_counts(const PullScan& ps, int px, int py, uint32_t tile[kPatchL
         for (int c = 0; c < kPatchLen; ++c) tile[r][c] = 0;
     const int cx0 = px * kPatchLen - (int)ps.ox, cy0 = py * kPatchLen - (int)ps.oy;
     for (int lane = 0; lane < kPatchLen; ++lane) {
-        pull_lane_pass(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile[line][lane] += c; });   // X pass: lane = column
-        pull_lane_pass(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile[lane][line] += c; });   // Y pass: lane = row
+        pull_lane_pass_flat(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile[line][lane] += c; });   // X pass: lane = column
+        pull_lane_pass_flat(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile[lane][line] += c; });   // Y pass: lane = row
     }
 }
 
@@ -277,19 +288,18 @@ bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2
             const uint32_t di = ((uint32_t)py << log2dim) | (uint32_t)px;
             if (!ps.marked[di]) continue;
             pull_patch_counts(ps, px, py, tile);
-            const int h_lo = pull_hit_lower_bound(ps.hits.data(), (int)ps.hits.size(), pull_hit_key(di, 0, 0));
-            const int h_hi = pull_hit_lower_bound(ps.hits.data(), (int)ps.hits.size(), pull_hit_key(di + 1, 0, 0));
+            const int h_lo = ps.hit_lo[di], h_hi = h_lo + ps.hit_n[di];
             for (int r = 0; r < kPatchLen; ++r)
                 for (int c = 0; c < kPatchLen; ++c) {
                     const uint32_t x = bx0 + (uint32_t)(px * kPatchLen + c), y = by0 + (uint32_t)(py * kPatchLen + r);
                     const uint32_t ci = cell_index(x, y);
-                    const int c_lo = h_lo + pull_hit_lower_bound(ps.hits.data() + h_lo, h_hi - h_lo, pull_hit_key(di, ci, 0));
-                    const int c_hi = h_lo + pull_hit_lower_bound(ps.hits.data() + h_lo, h_hi - h_lo, pull_hit_key(di, ci + 1, 0));
+                    int n_hit = 0;
+                    for (int i = h_lo; i < h_hi; ++i) n_hit += pull_hit_cell(ps.hits[i]) == ci;
                     const uint32_t cnt = tile[r][c];
-                    if (cnt == 0 && c_hi == c_lo) continue;   // untouched: the patch is not even allocated for it
+                    if (cnt == 0 && n_hit == 0) continue;   // untouched: the patch is not even allocated for it
                     uint32_t* cell = e.occ.raw(x, y, true);
                     uint8_t& fb = e.occ.fbit[cell - e.occ.cells.data()];
-                    if (!fb && c_hi == c_lo) {   // plain cell: counter additions commute
+                    if (!fb && n_hit == 0) {   // plain cell: counter additions commute
                         *cell += cnt * kOccMissInc;
                         continue;
                     }
@@ -297,12 +307,12 @@ bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2
                     bool obstacle = fb != 0;
                     const uint32_t key = cell_key(win, x, y);
                     const uint32_t before = *cell;
-                    *cell = pull_replay_cell(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), c_lo, c_hi, before, obstacle,
+                    *cell = pull_replay_cell(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), h_lo, h_hi, ci, before, obstacle,
                                              [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
                     // the replay must have consumed exactly the counted crossings and the hits
-                    if (*cell != before + cnt * kOccMissInc + (uint32_t)(c_hi - c_lo) * kOccHitInc) e.occ.err |= 0x100u;
+                    if (*cell != before + cnt * kOccMissInc + (uint32_t)n_hit * kOccHitInc) e.occ.err |= 0x100u;
                     fb = obstacle;
-                    n_cand_touch += cnt + (uint32_t)(c_hi - c_lo);
+                    n_cand_touch += cnt + (uint32_t)n_hit;
                 }
         }
     run_brushfire(e, events, ps.cells, n_cand_touch);
@@ -468,7 +478,21 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
     for (int py = 0; py < dim; ++py)
         for (int px = 0; px < dim; ++px) {
             const bool marked = ps.marked[((size_t)py << log2dim) | (size_t)px] != 0;
-            if (marked) pull_patch_counts(ps, px, py, tile);
+            if (marked) {
+                pull_patch_counts(ps, px, py, tile);
+                // the line-by-line form of the pass (pull_lane_pass) must produce the same tile as the single-loop form the kernel runs
+                static uint32_t tile2[kPatchLen][kPatchLen];
+                for (int r = 0; r < kPatchLen; ++r)
+                    for (int c = 0; c < kPatchLen; ++c) tile2[r][c] = 0;
+                const int cx0 = px * kPatchLen - (int)ox, cy0 = py * kPatchLen - (int)oy;
+                for (int lane = 0; lane < kPatchLen; ++lane) {
+                    pull_lane_pass(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile2[line][lane] += c; });
+                    pull_lane_pass(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile2[lane][line] += c; });
+                }
+                for (int r = 0; r < kPatchLen; ++r)
+                    for (int c = 0; c < kPatchLen; ++c)
+                        if (tile[r][c] != tile2[r][c]) ++bad;
+            }
             for (int r = 0; r < kPatchLen; ++r)
                 for (int c = 0; c < kPatchLen; ++c) {
                     const int x = px * kPatchLen + c, y = py * kPatchLen + r;
@@ -483,7 +507,7 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
                     std::vector<std::pair<uint32_t, uint32_t>> got;
                     int after = -1;
                     for (;;) {
-                        const PullTouch t = pull_next_touch(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), 0, 0, after);
+                        const PullTouch t = pull_next_touch(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), 0, 0, 0u, after);
                         if (!t.valid) break;
                         got.push_back({t.beam, t.pos});
                         after = (int)t.beam;

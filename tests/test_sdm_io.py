@@ -124,6 +124,33 @@ def test_product_sdm_writer_reader_and_images_on_the_host(po, synth, tmp_path):
     assert (img == po.map_image("freq", ho)).all()
 
 
+def test_corrupt_sdm_files_are_refused_not_thrown(tmp_path):
+    """Map::read returns false on a short file (map.cpp:565-568); the product's reader must do the same for a truncated patch list and
+    for a header whose 64-bit num_patches promises more than the file holds (no allocation sized from it, no exception)"""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.check_call(["make", "-C", os.path.join(here, "emu"), "-s"])
+    L = C.CDLL(os.path.join(here, "emu", "_build", "libsdm_hooks.so"))
+    gold = os.path.join(here, "golden", "ddm_small.sdm")
+    raw = open(gold, "rb").read()
+    win, msq = (C.c_uint32 * 4)(), C.c_uint32()
+
+    def reads(data):
+        p = tmp_path / "x.sdm"
+        p.write_bytes(data)
+        return L.sdmtest_read_distance(str(p).encode(), win, C.byref(msq), None, None, None, None, None, None)
+
+    assert reads(raw) == 1
+    assert reads(raw[:-100]) == 0                                   # last patch cut short
+    assert reads(raw[:36]) == 0                                     # header + parameters only, 7 patches announced
+    hdr = sdm.read_sdm(gold)["header"]
+    off = hdr.dtype.fields["num_patches"][1]
+    huge = bytearray(raw)
+    huge[off:off + 8] = (2 ** 62).to_bytes(8, "little")             # would be a 4 EiB resize
+    assert reads(bytes(huge)) == 0
+
+
 def test_png_writer_round_trip(tmp_path):
     import struct
     import zlib
