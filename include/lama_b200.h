@@ -101,6 +101,13 @@ int lama_pf_get_particles(lama_pf* h, double* states, double* weights);
 int lama_pf_get_trajectory(lama_pf* h, int particle, double* xyr, int cap, int* count);
 /* indices drawn by the last PFSlam2D::resample (pf_slam2d.cpp:537-574); *count = 0 when the last update did not resample */
 int lama_pf_get_last_resample(lama_pf* h, int32_t* idx, int* count);
+/* The whole resampling history in 16 bytes: out[0] = resamplings so far (Summary::resample count, pf_slam2d.h:88-129), out[1] = FNV-1a
+ * hash over (accepted-scan number, the P ancestor indices) of each of them, bytes little endian (src/pf_slam2d.cpp:537-553). */
+int lama_pf_get_resample_digest(lama_pf* h, uint64_t out[2]);
+/* PFSlam2D::Summary time buckets (include/lama/pf_slam2d.h:88-129, filled at src/pf_slam2d.cpp:251-311) as host wall-clock sums in ms:
+ * {sampling (drawFromMotion), solve (scan matching: enqueue + wait), normalise, resample}; the map bucket is the device time of
+ * lama_pf_kernel_times (the map update runs asynchronously behind the next scan's sampling). */
+int lama_pf_get_summary(lama_pf* h, double ms[4]);
 /* work counters of the last update and totals: {residual evals (as the reference would count), ray cells,
    distance-map pops, patches detached, GN iterations, resampled} */
 int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6]);

@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "lama_last_error", "lama_version", "lama_device_count",
     "lama_pf_options_default", "lama_pf_create", "lama_pf_destroy", "lama_pf_set_prior", "lama_pf_update", "lama_pf_get_pose",
     "lama_pf_stage_scans", "lama_pf_update_staged", "lama_pf_get_traffic",
-    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample",
+    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary",
     "lama_pf_get_counters", "lama_pf_kernel_times", "lama_pf_map_bounds", "lama_pf_export_occupancy", "lama_pf_export_distance",
     "lama_pf_shard_begin", "lama_pf_shard_finish", "lama_pf_shard_apply", "lama_pf_shard_apply_local", "lama_pf_shard_map_update",
     "lama_pf_particle_pack_size", "lama_pf_particle_pack", "lama_pf_particle_unpack",
@@ -282,6 +282,18 @@ class PFSlam2D:
         n = C.c_int(0)
         _chk(lib().lama_pf_get_last_resample(self.h, idx.ctypes.data_as(c_i32p), C.byref(n)))
         return idx[:n.value].copy()
+
+    def resampleDigest(self):
+        """(number of resamplings so far, FNV-1a hash of the whole resampling history)"""
+        d = np.zeros(2, np.uint64)
+        _chk(lib().lama_pf_get_resample_digest(self.h, _vp(d)))
+        return int(d[0]), int(d[1])
+
+    def summary(self):
+        """PFSlam2D::Summary buckets (pf_slam2d.h:88-129) as host wall-clock sums in ms"""
+        t = np.zeros(4)
+        _chk(lib().lama_pf_get_summary(self.h, t.ctypes.data_as(c_dp)))
+        return dict(zip(("sampling", "solve", "normalize", "resample"), t.tolist()))
 
     def counters(self):
         return _counters(lib().lama_pf_get_counters, self.h)

@@ -407,6 +407,20 @@ try {
     return LAMA_OK;
 }
 LAMA_CATCH
+int lama_pf_get_resample_digest(lama_pf* h, uint64_t out[2])
+try {
+    if (!h || !out) return set_err("null argument", LAMA_ERR_ARG);
+    h->p->resample_digest(out);
+    return LAMA_OK;
+}
+LAMA_CATCH
+int lama_pf_get_summary(lama_pf* h, double ms[4])
+try {
+    if (!h || !ms) return set_err("null argument", LAMA_ERR_ARG);
+    h->p->summary_ms(ms);
+    return LAMA_OK;
+}
+LAMA_CATCH
 int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6])
 try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);

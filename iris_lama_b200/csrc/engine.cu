@@ -43,6 +43,7 @@ struct Engine::Impl {
     RayParams ray{};
     BrushParams brush{};
     int n_sms = 148;
+    int pull_max_particles = 48;
     bool scan_flat = false;     // the current scan has z == 0 everywhere and a sensor that keeps z planes: every beam is planar
     bool staged_flat = false;   // the same for the staged scans
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -67,8 +68,11 @@ static bool points_flat(const double* pts, size_t n)
 // and -- decided per particle on the device -- scans of a tilted sensor (`flat` false: the beams may leave the z plane).
 static int launch_ray_stage(Engine::Impl* d, RayParams rp, const SE2* states, int count)   // returns the number of kernels launched
 {
-    static const bool no_pull = std::getenv("LAMA_NO_PULL") != nullptr;   // developer switch: always use the per-beam walk
     const ScanParams& sp = rp.scan;
+    // Which form is faster depends on how many particles this device holds: the walk runs one CTA per particle (0.31 ms at 256
+    // particles, but still 0.19 ms at 32: most SMs idle), the pull form spreads the patches of all particles over every SM (0.47 ms
+    // at 256, 0.17 ms at 32).  LAMA_PULL_MAX_PARTICLES overrides the crossover (0 = never pull; read when the engine is created).
+    const bool no_pull = count > d->pull_max_particles;
     const bool flat = d->scan_flat && sp.moving.l[6] == 0.0 && sp.moving.l[7] == 0.0;
     rp.pull_fallback = 0;
     if (!no_pull && !sp.lo_ray && sp.truncated_ray == 0.0 && sp.n_beams <= kPullMaxBeams) {
@@ -192,6 +196,10 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
 
     d->ray.log_cap   = next_pow2_host(std::max(4096, 3 * cfg.max_beams));
     d->ray.cand_cap  = 192;
+    if (const char* cc = std::getenv("LAMA_RAY_CAND_CAP")) {   // test hook: force the candidate-overflow path of k_raycast
+        const int v = std::atoi(cc);
+        d->ray.cand_cap = v < 1 ? 1 : (v > 253 ? 253 : v);
+    }
     d->ray.prob_mode = cfg.occupancy_kind == 1 ? 1 : 0;
     {   // ProbabilisticOccupancyMap's constructor (probabilistic_occupancy_map.cpp:43-60): float logods(), stored as doubles
         auto logods = [](float prob) -> float { return (float)std::log(prob / (1.0 - prob)); };
@@ -216,8 +224,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         while (npad < pv.stride) npad <<= 1;
         pv.stride = npad;   // k_ray_setup writes whole sorted arrays of next_pow2(beams) entries
         CU_NEW(dalloc((void**)&pv.hdr, (size_t)cfg.particles * sizeof(RayPullHeader)));
-        CU_NEW(dalloc((void**)&pv.list, (size_t)cfg.particles * pv.stride * 4));
-        CU_NEW(dalloc((void**)&pv.beam_of, (size_t)cfg.particles * pv.stride * 2));
+        CU_NEW(dalloc((void**)&pv.list, (size_t)cfg.particles * pv.stride * sizeof(PullEntry)));
         CU_NEW(dalloc((void**)&pv.hits, (size_t)cfg.particles * pv.stride * 4));
         CU_NEW(dalloc((void**)&pv.tasks, (size_t)cfg.particles * dim2 * 8));
         CU_NEW(dalloc((void**)&pv.ctrl, 64));
@@ -227,6 +234,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
         int sms = 0;
         CU_NEW(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device));
         d->n_sms = sms > 0 ? sms : 148;
+        if (const char* pm = std::getenv("LAMA_PULL_MAX_PARTICLES")) d->pull_max_particles = std::atoi(pm);
     }
     CU_NEW(dalloc((void**)&d->d_stats, (size_t)cfg.particles * sizeof(MapUpdateStats)));
     const size_t idx_ints = std::max((size_t)cfg.particles, (size_t)cfg.dir_dim * cfg.dir_dim);   // resample indices / directory entries to delete

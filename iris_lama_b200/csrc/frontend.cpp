@@ -2,6 +2,7 @@
 #include "frontend.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -162,6 +163,7 @@ int PFSlam2D::match_local(double* local_out)
 
 void PFSlam2D::absorb_results(const double* all)
 {
+    ++scans_seen_;
     for (uint32_t i = 0; i < P_; ++i) {
         pose_[i] = SE2{all[5 * i], all[5 * i + 1], all[5 * i + 2], all[5 * i + 3]};
         nodes_.push_back(Node{pose_[i], node_of_[i]});  // particle->poses.push_back(pose)
@@ -210,8 +212,19 @@ bool PFSlam2D::compute_resample(std::vector<int32_t>& idx)
     return true;
 }
 
+void PFSlam2D::note_resample(const std::vector<int32_t>& idx)
+{
+    auto mix = [this](uint64_t v) {
+        for (int k = 0; k < 8; ++k) { resample_hash_ ^= (v >> (8 * k)) & 0xFFu; resample_hash_ *= 1099511628211ull; }
+    };
+    ++resample_count_;
+    mix(scans_seen_);
+    for (int32_t i : idx) mix((uint64_t)(uint32_t)i);
+}
+
 void PFSlam2D::apply_resample_host(const std::vector<int32_t>& idx)
 {
+    note_resample(idx);
     std::vector<SE2> np(P_);
     std::vector<double> nw(P_), nn(P_), ns(P_);
     std::vector<int> nnode(P_);
@@ -309,14 +322,24 @@ int PFSlam2D::pipelined_begin(const double* pts, int n, const double* origin, co
 // (every copy of an ancestor would apply the same scan at the same pose).  The host only waits for the match results.
 int PFSlam2D::update_pipelined(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update)
 {
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
     const bool moved = predict_and_gate(odom_xyr);
+    const auto t1 = clk::now();
+    t_sample_ += ms(t0, t1);
     std::vector<double> all((size_t)P_ * 5);
     int rc = pipelined_begin(pts, n, origin, quat, moved, did_update, all.data());
+    const auto t2 = clk::now();
+    t_solve_ += ms(t1, t2);
     if (rc != LAMA_OK || !moved) return rc;
     absorb_results(all.data());
     normalize();
+    const auto t3 = clk::now();
+    t_norm_ += ms(t2, t3);
     std::vector<int32_t> v;
     counters_pending_ = true;
+    struct Stop { clk::time_point t; double& acc; ~Stop() { acc += std::chrono::duration<double, std::milli>(clk::now() - t).count(); } } stop{t3, t_resample_};
     if (compute_resample(v)) {
         apply_resample_host(v);
         last_idx_ = v;

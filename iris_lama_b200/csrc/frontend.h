@@ -74,6 +74,11 @@ public:
     void weights(int i, double w[3]) const { w[0] = weight_[i]; w[1] = nweight_[i]; w[2] = wsum_[i]; }
     std::vector<SE2> trajectory(int particle) const;
     const std::vector<int32_t>& last_resample() const { return last_idx_; }
+    // {number of resamplings so far, FNV-1a hash over (scan number, indices) of every one of them}: the resampling history in 16 bytes
+    void resample_digest(uint64_t out[2]) const { out[0] = resample_count_; out[1] = resample_hash_; }
+    // PFSlam2D::Summary buckets (include/lama/pf_slam2d.h:88-129) as host wall-clock sums in ms since creation:
+    // {sampling (drawFromMotion), solve (enqueue + wait for the match results), normalise, resample (decision + device copies)}
+    void summary_ms(double out[4]) const { out[0] = t_sample_; out[1] = t_solve_; out[2] = t_norm_; out[3] = t_resample_; }
     const Counters& last_counters() { settle_counters(); return last_; }
     const Counters& total_counters() { settle_counters(); return total_; }
     Engine* engine() { return eng_.get(); }
@@ -101,6 +106,9 @@ private:
     bool has_first_ = false;
     double acc_trans_ = 0, acc_rot_ = 0, neff_ = 0;
     std::vector<int32_t> last_idx_;
+    uint64_t resample_count_ = 0, resample_hash_ = 1469598103934665603ull, scans_seen_ = 0;
+    double t_sample_ = 0, t_solve_ = 0, t_norm_ = 0, t_resample_ = 0;
+    void note_resample(const std::vector<int32_t>& idx);
     Counters last_, total_;
     uint64_t detached_seen_ = 0;
     std::string err_;

@@ -991,14 +991,12 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
         if (!again) break;
     }
     // ---- class lists to global memory ------------------------------------------------------------------------------------
-    uint32_t* glist = pv.list + (size_t)blockIdx.x * pv.stride;
-    uint16_t* gbeam = pv.beam_of + (size_t)blockIdx.x * pv.stride;
-    uint32_t* ghits = pv.hits + (size_t)blockIdx.x * pv.stride;
+    PullEntry* glist = pv.list + (size_t)blockIdx.x * pv.stride;
+    uint32_t* ghits  = pv.hits + (size_t)blockIdx.x * pv.stride;
     for (int i = tid; i < n_list; i += blockDim.x) {
         const uint64_t k = sorted[i];
         const uint32_t beam = pull_key_beam(k);
-        glist[i] = ndb[beam];
-        gbeam[i] = (uint16_t)beam;
+        glist[i] = PullEntry{ndb[beam], beam, pull_magic(ndb[beam] & 0xFFFFu)};
         const int cls = pull_key_class(k), prev = i ? pull_key_class(sorted[i - 1]) : -1;
         for (int c = prev + 1; c <= cls; ++c) sh.prefix[c] = i;
         if (i == n_list - 1)
@@ -1071,10 +1069,11 @@ k_ray_setup(StoreView s, RayParams rp, const SE2* __restrict__ states, MapUpdate
 // created it).
 constexpr int kPullWarps = 8;
 constexpr int kPullCandCap = 512;
+constexpr int kTileStride = kPatchLen + 2;   // uint16 counters, rows 34 apart: column-wise and row-wise accesses are both conflict free
 struct PullWarpShared {
-    uint16_t tile[kPatchCells];      // crossing count of cell (r, c) at [r * 32 + (c ^ r)]: rows and columns are both conflict free
-    uint32_t hitbits[kPatchLen];     // cells of the patch that are hit cells of this scan
-    uint16_t cand[kPullCandCap];     // compacted candidate cells
+    uint16_t tile[kPatchLen * kTileStride];   // crossing count of cell (r, c) at [r * 34 + c]
+    uint32_t hitbits[kPatchLen];              // cells of the patch that are hit cells of this scan
+    uint16_t cand[kPullCandCap];              // compacted candidate cells
 };
 struct PullCtaShared {
     RayPullHeader hdr;
@@ -1082,17 +1081,58 @@ struct PullCtaShared {
     int unit, next;
 };
 struct RayPullLayout {
-    size_t list, beam_of, hits, warps, total;
-    __host__ __device__ explicit RayPullLayout(int stride)
+    size_t list, hits, warps, total;
+    __host__ __device__ explicit RayPullLayout(int n_beams)
     {
+        const size_t cap = ((size_t)n_beams + 31) & ~(size_t)31;
         size_t o = (sizeof(PullCtaShared) + 15) & ~(size_t)15;
-        list = o;    o += (size_t)stride * 4;
-        beam_of = o; o += (size_t)stride * 2;
-        hits = o;    o += (size_t)stride * 4;
-        warps = o;   o += (size_t)kPullWarps * sizeof(PullWarpShared);
+        list = o;  o += cap * sizeof(PullEntry);
+        hits = o;  o += cap * 4;
+        warps = o; o += (size_t)kPullWarps * sizeof(PullWarpShared);
         total = o;
     }
 };
+
+// Ordered replay of the compacted candidate cells of one patch, one lane per cell (kept out of line: it is the rare path and
+// would otherwise be inlined twice into k_ray_pull, whose hot loops then fall out of the instruction cache).  Returns true when a
+// cell became a distance-map obstacle.
+template <bool kProb>
+static __device__ __noinline__ bool pull_replay_patch(const StoreView& s, const RayParams& rp, const PullEntry* list, const int* prefix, const uint32_t* hits, int h_lo, int h_hi,
+                                                      const uint16_t* cand, int ncand, uint32_t* patch, int slot, int cx0, int cy0, int px, int py,
+                                                      MapUpdateStats* st, uint64_t* events, int lane)
+{
+    bool newhot = false;
+    for (int k = lane; k < ncand; k += 32) {
+        const uint32_t ci = cand[k];
+        const int r = (int)(ci >> kPatchLog2), c = (int)(ci & (kPatchLen - 1));
+        const PullRuns runs = pull_cell_runs(list, prefix, cx0 + c, cy0 + r);
+        uint32_t* fword = fbits_ptr(s, slot) + r;
+        const bool before = (__ldcg(fword) >> c) & 1u;
+        bool obstacle = before;
+        const uint32_t key = ((uint32_t)(py * kPatchLen + r) << 16) | (uint32_t)(px * kPatchLen + c);   // window-relative cell
+        auto emit = [&](bool add, uint32_t seq) {
+            const uint32_t idx = atomicAdd(&st->events, 1u);
+            if (idx < (uint32_t)rp.event_cap) events[idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
+        };
+        uint32_t* cell = patch + ci;
+        if (!kProb) {
+            *cell = pull_replay_cell(list, runs, hits, h_lo, h_hi, ci, *cell, obstacle, emit);
+        } else {
+            *cell = __float_as_uint(pull_replay_cell_prob(list, runs, hits, h_lo, h_hi, ci, __uint_as_float(*cell), obstacle, rp.prob, emit));
+            atomicOr(kbits_ptr(s, slot) + r, 1u << c);
+        }
+        if (obstacle != before) {
+            if (obstacle) {
+                atomicOr(fword, 1u << c);
+                newhot = true;
+            } else {
+                atomicAnd(fword, ~(1u << c));
+            }
+        }
+    }
+    __syncwarp();
+    return newhot;
+}
 
 template <bool kProb>
 __global__ void __launch_bounds__(kPullWarps * 32, 4)
@@ -1101,10 +1141,9 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const RayPullView& pv = rp.pull;
-    const RayPullLayout L(pv.stride);
+    const RayPullLayout L(rp.scan.n_beams);
     PullCtaShared& sh   = *reinterpret_cast<PullCtaShared*>(smem_raw);
-    uint32_t* list      = reinterpret_cast<uint32_t*>(smem_raw + L.list);
-    uint16_t* beam_of   = reinterpret_cast<uint16_t*>(smem_raw + L.beam_of);
+    PullEntry* list     = reinterpret_cast<PullEntry*>(smem_raw + L.list);
     uint32_t* hits      = reinterpret_cast<uint32_t*>(smem_raw + L.hits);
     PullWarpShared& w   = reinterpret_cast<PullWarpShared*>(smem_raw + L.warps)[warp];
     const RayPullHeader* hdr = &sh.hdr;
@@ -1124,12 +1163,10 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
         if (tid == 0) {
             sh.hdr  = pv.hdr[pl];
             sh.next = 0;
-            const uint32_t nl = (uint32_t)sh.hdr.prefix[8], nh = (uint32_t)sh.hdr.n_hits;
-            const uint32_t b0 = (nl * 4u + 15u) & ~15u, b1 = (nl * 2u + 15u) & ~15u, b2 = (nh * 4u + 15u) & ~15u;
-            mbar_expect_tx(&sh.bar, b0 + b1 + b2);
+            const uint32_t b0 = (uint32_t)sh.hdr.prefix[8] * (uint32_t)sizeof(PullEntry), b1 = ((uint32_t)sh.hdr.n_hits * 4u + 15u) & ~15u;
+            mbar_expect_tx(&sh.bar, b0 + b1);
             if (b0) tma_load_1d(list, pv.list + (size_t)pl * pv.stride, b0, &sh.bar);
-            if (b1) tma_load_1d(beam_of, pv.beam_of + (size_t)pl * pv.stride, b1, &sh.bar);
-            if (b2) tma_load_1d(hits, pv.hits + (size_t)pl * pv.stride, b2, &sh.bar);
+            if (b1) tma_load_1d(hits, pv.hits + (size_t)pl * pv.stride, b1, &sh.bar);
         }
         mbar_wait(&sh.bar, parity);
         parity ^= 1u;
@@ -1146,25 +1183,49 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
             const int di = (int)(task.x & 0xFFFFu), h_lo = (int)(task.y >> 16), h_hi = h_lo + (int)(task.y & 0xFFFFu);
             const int px = di & (dim - 1), py = di >> log2dim;
             const int cx0 = px * kPatchLen - ox, cy0 = py * kPatchLen - oy;
-            {   // zero the tile (2 KiB: four 16-byte stores per lane)
-                uint4* tz = reinterpret_cast<uint4*>(w.tile);
+            {   // zero the count tile (2 176 bytes)
+                uint32_t* tz = reinterpret_cast<uint32_t*>(w.tile);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < kPatchLen * kTileStride / 2 / 32; ++i) tz[i * 32 + lane] = 0u;
             }
             w.hitbits[lane] = 0u;
             __syncwarp();
-            uint32_t touched = 0;
-            // X pass: x-major beams, lane = column.  Y pass: y-major beams, lane = row.  (pull_lane_pass_flat returns at once for
-            // lanes behind the diagonal, so a patch far from one of the axes costs only one of the two passes.)
-            pull_lane_pass_flat(list, hdr->prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { w.tile[line * kPatchLen + (lane ^ line)] = (uint16_t)c; touched |= c; });
+            bool touched = false;
+            {   // x-major classes: lane = column.  All lanes run over the same beams; each beam lands in one row of the lane's column.
+                const int m = cx0 + lane;
+                const uint32_t a = (uint32_t)(m < 0 ? -m : m);
+                pull_patch_classes(list, hdr->prefix, 0, cx0, cy0, [&](int, bool mneg, bool tneg, int lo, int hi) {
+                    if (m == 0 || (m < 0) != mneg) return;
+                    for (int i = lo; i < hi; ++i) {
+                        const int pos = pull_land(list[i], a, tneg, cy0);
+                        if (pos >= 0) {
+                            ++w.tile[pos * kTileStride + lane];
+                            touched = true;
+                        }
+                    }
+                });
+            }
             __syncwarp();
-            pull_lane_pass_flat(list, hdr->prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { w.tile[lane * kPatchLen + (line ^ lane)] += (uint16_t)c; touched |= c; });
+            {   // y-major classes: lane = row
+                const int m = cy0 + lane;
+                const uint32_t a = (uint32_t)(m < 0 ? -m : m);
+                pull_patch_classes(list, hdr->prefix, 4, cy0, cx0, [&](int, bool mneg, bool tneg, int lo, int hi) {
+                    if (m == 0 || (m < 0) != mneg) return;
+                    for (int i = lo; i < hi; ++i) {
+                        const int pos = pull_land(list[i], a, tneg, cx0);
+                        if (pos >= 0) {
+                            ++w.tile[lane * kTileStride + pos];
+                            touched = true;
+                        }
+                    }
+                });
+            }
             for (int i = h_lo + lane; i < h_hi; i += 32) {
                 const uint32_t cell = pull_hit_cell(hits[i]);
                 atomicOr(&w.hitbits[cell >> 5], 1u << (cell & 31));
             }
             __syncwarp();
-            if (!__any_sync(0xffffffffu, touched != 0u) && h_hi == h_lo) continue;   // nothing of this scan lands in the patch
+            if (!__any_sync(0xffffffffu, touched) && h_hi == h_lo) continue;   // nothing of this scan lands in the patch
 
             // Map::get (mutable): allocate on first touch, detach a shared patch (map.cpp:400-408, cow_ptr.h:104-114)
             const int e0 = gdir[di];
@@ -1180,35 +1241,8 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
             int ncand = 0;
             bool newhot = false;
             auto replay_candidates = [&]() {
-                for (int k = lane; k < ncand; k += 32) {
-                    const uint32_t ci = w.cand[k];
-                    const int r = (int)(ci >> kPatchLog2), c = (int)(ci & (kPatchLen - 1));
-                    const PullRuns runs = pull_cell_runs(list, hdr->prefix, cx0 + c, cy0 + r);
-                    uint32_t* fword = fbits_ptr(s, slot) + r;
-                    const bool before = (__ldcg(fword) >> c) & 1u;
-                    bool obstacle = before;
-                    const uint32_t key = ((uint32_t)(py * kPatchLen + r) << 16) | (uint32_t)(px * kPatchLen + c);   // window-relative cell
-                    auto emit = [&](bool add, uint32_t seq) {
-                        const uint32_t idx = atomicAdd(&stats[pl].events, 1u);
-                        if (idx < (uint32_t)rp.event_cap) events_out[(size_t)pl * rp.event_cap + idx] = push_record((seq << 1) | (add ? 1u : 0u), key);
-                    };
-                    uint32_t* cell = patch + ci;
-                    if (!kProb) {
-                        *cell = pull_replay_cell(list, beam_of, runs, hits, h_lo, h_hi, ci, *cell, obstacle, emit);
-                    } else {
-                        *cell = __float_as_uint(pull_replay_cell_prob(list, beam_of, runs, hits, h_lo, h_hi, ci, __uint_as_float(*cell), obstacle, rp.prob, emit));
-                        atomicOr(kbits_ptr(s, slot) + r, 1u << c);
-                    }
-                    if (obstacle != before) {
-                        if (obstacle) {
-                            atomicOr(fword, 1u << c);
-                            newhot = true;
-                        } else {
-                            atomicAnd(fword, ~(1u << c));
-                        }
-                    }
-                }
-                __syncwarp();
+                newhot |= pull_replay_patch<kProb>(s, rp, list, hdr->prefix, hits, h_lo, h_hi, w.cand, ncand, patch, slot, cx0, cy0, px, py, stats + pl,
+                                                   events_out + (size_t)pl * rp.event_cap, lane);
                 ncand = 0;
             };
             for (int r0 = 0; r0 < kPatchLen; r0 += 8) {
@@ -1218,7 +1252,7 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int r = r0 + k;
-                    const uint32_t cnt = w.tile[r * kPatchLen + (lane ^ r)];
+                    const uint32_t cnt = w.tile[r * kTileStride + lane];
                     const uint32_t cw = __shfl_sync(0xffffffffu, candrow, r);
                     bool plain = cnt != 0u;   // misses only, never an obstacle: counter additions commute
                     if (cw != 0u) {           // (rare) the row holds candidate cells
@@ -1258,7 +1292,6 @@ k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_o
     if (lane == 0 && err) atomicOr(s.status, err);
 }
 
-// One warp per particle (see brushfire_warp.cuh for the schedule and why it is exact).
 constexpr int kBrushThreads = 128;   // four warps sort the events and warm the L1; then warp 0 alone runs the sequential brushfire
 __global__ void __launch_bounds__(kBrushThreads)
 k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, MapUpdateStats* __restrict__ stats)
@@ -1626,9 +1659,9 @@ cudaError_t configure_kernels(int dir_dim, uint32_t max_sqdist_limit, const RayP
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ray_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_setup_smem_bytes(dir_dim, rp.scan.n_beams > 4096 ? 4096 : rp.scan.n_beams));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ray_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.pull.stride));
+    e = cudaFuncSetAttribute(k_ray_pull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.scan.n_beams > 4096 ? 4096 : rp.scan.n_beams));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ray_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.pull.stride));
+    e = cudaFuncSetAttribute(k_ray_pull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ray_pull_smem_bytes(rp.scan.n_beams > 4096 ? 4096 : rp.scan.n_beams));
     return e;
 }
 
@@ -1649,7 +1682,7 @@ void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states
     else k_raycast<false><<<count, kRayThreads, raycast_smem_bytes(s.window.dim, rp), st>>>(s, rp, d_states, d_events, d_stats);
 }
 size_t ray_setup_smem_bytes(int dir_dim, int n_beams) { return RaySetupLayout(n_beams, dir_dim * dir_dim).total; }
-size_t ray_pull_smem_bytes(int stride) { return RayPullLayout(stride).total; }
+size_t ray_pull_smem_bytes(int n_beams) { return RayPullLayout(n_beams).total; }
 void launch_raycast_pull(const StoreView& s, const RayParams& rp_in, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
                          cudaStream_t st)
 {
@@ -1661,7 +1694,7 @@ void launch_raycast_pull(const StoreView& s, const RayParams& rp_in, const SE2* 
     k_ray_setup<<<count, kSetupThreads, ray_setup_smem_bytes(s.window.dim, rp.scan.n_beams), st>>>(s, rp, d_states, d_stats);
     const int units = count * rp.pull.splits;
     const int grid = units < n_sms * 4 ? units : n_sms * 4;   // persistent: up to four CTAs of eight warps per SM
-    const size_t smem = ray_pull_smem_bytes(rp.pull.stride);
+    const size_t smem = ray_pull_smem_bytes(rp.scan.n_beams);
     if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
     else k_ray_pull<false><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
 }

@@ -43,8 +43,7 @@ struct RayPullHeader {   // 64 bytes
 };
 struct RayPullView {
     RayPullHeader* hdr;   // [particles]
-    uint32_t* list;       // [particles][stride]  n | d << 16, sorted by (class, slope, beam)
-    uint16_t* beam_of;    // [particles][stride]  beam of every list entry
+    PullEntry* list;      // [particles][stride]  class lists sorted by (class, slope, beam)
     uint32_t* hits;       // [particles][stride]  pull_hit_record, grouped by patch
     uint2* tasks;         // [particles * dir_dim^2]  {particle << 16 | directory index, first hit record << 16 | number of hit records}
     int32_t* ctrl;        // [0] tasks appended by k_ray_setup, [1] work units taken by k_ray_pull (both reset by k_merge_free)
@@ -94,7 +93,7 @@ void launch_raycast(const StoreView& s, const RayParams& rp, const SE2* d_states
 // the pull form (every beam planar and starting in the same cell): k_ray_setup + k_ray_pull; particles it cannot take are left to
 // launch_raycast with rp.pull_fallback = 1
 size_t ray_setup_smem_bytes(int dir_dim, int n_beams);
-size_t ray_pull_smem_bytes(int stride);
+size_t ray_pull_smem_bytes(int n_beams);
 void launch_raycast_pull(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
                          cudaStream_t st);
 void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st);

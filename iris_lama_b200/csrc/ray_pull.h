@@ -8,16 +8,18 @@
 // Exactness.  All beams of a 2-D scan start in the same cell O (the sensor origin; Options::truncated_ray == 0) and are
 // planar.  For a beam with end offset (ex, ey) from O let n = max(|ex|, |ey|) be its major length and d = min(..) its minor
 // length (|ex| == |ey| counts as x-major, like computeRay's `if 2 err >= n` on both axes).  After i steps (1 <= i <= n - 1)
-// the walk sits at major offset i and minor offset k = floor((2 i d + n) / (2 n))  (closed form of the error accumulator,
+// the walk sits at major offset i and minor offset k(i) = floor((2 i d + n) / (2 n))  (closed form of the error accumulator,
 // ray_core.h SegWalk).  Hence the beam crosses the cell at major offset a, minor offset b  iff
-//        1 <= a <= n - 1   and   2 b n <= 2 a d + n < 2 (b + 1) n,
+//        1 <= a <= n - 1   and   k(a) == b      <=>      2 b n <= 2 a d + n < 2 (b + 1) n,
 // i.e. iff its slope d / n lies in [(2 b - 1) / (2 a), (2 b + 1) / (2 a)) and it is long enough.  Beams are split into 8
 // classes (major axis, sign along the major axis, sign along the minor axis; a zero minor extent has sign +) and sorted by
-// slope inside each class; the beams that cross a cell then form ONE contiguous run of a class list (two runs when the cell
-// lies on an axis through O), and the runs of the cells of one grid line abut: walking a line of the patch in the direction
-// of growing b consumes the class list front to back ("chain"), one comparison per crossing beam.
-// Counter additions commute (ray_core.h), so `visited += count` replaces `count` atomics; cells that need the ordered replay
-// (hit cells of this scan, distance-map obstacles) enumerate their runs and replay their touches in beam order.
+// slope inside each class, so the beams that can cross a RECTANGLE of cells form one contiguous range of a class list.
+// A warp owns a 32 x 32 patch: for an x-major class every lane takes one COLUMN (major offset a) and all lanes run over the
+// same range of beams; beam i lands in row k_i(a) of the lane's column -- computed directly, the division being an exact
+// multiplication by a per-beam reciprocal -- and the lane adds 1 to its own counter of that row: no atomics, no conflicts
+// (y-major classes: lane = row).  Counter additions commute (ray_core.h), so `visited += count` replaces `count` atomics; cells
+// that need the ordered replay (hit cells of this scan, distance-map obstacles) look up the runs of the class lists that cross
+// them and replay their touches in beam order.
 #pragma once
 
 #include "ray_core.h"
@@ -40,8 +42,24 @@ LAMA_HD PullBeam pull_classify(int ex, int ey)
     b.cls = (xmajor ? 0 : 4) | ((xmajor ? ex < 0 : ey < 0) ? 2 : 0) | ((xmajor ? ey < 0 : ex < 0) ? 1 : 0);
     return b;
 }
-// entry of a class list: n | d << 16 (cell offsets inside a directory window are < 2^13)
+// entry of a class list (cell offsets inside a directory window are < 2^12, so n, d < 4096)
+struct PullEntry {
+    uint32_t nd;      // n | d << 16
+    uint32_t beam;
+    uint64_t magic;   // floor(x / (2 n)) == (x * magic) >> 38  for every x < 2^25
+};
 LAMA_HD uint32_t pull_pack(uint32_t n, uint32_t d) { return n | (d << 16); }
+// Division by the invariant 2 n as multiplication (Granlund & Montgomery): with D = 2 n <= 2^13 and magic = floor(2^38 / D) + 1,
+// x * magic / 2^38 = x / D + x e / (D 2^38) with 0 < e <= D, and x e < 2^25 2^13 = 2^38 keeps the excess below 1 / D: the floor is
+// exact for all x < 2^25 (x = 2 a d + n <= 2 * 4095 * 4095 + 4095 < 2^25; the product stays below 2^62).  Checked exhaustively on
+// the host for every n (tests/emu).
+LAMA_HD uint64_t pull_magic(uint32_t n) { return n ? ((1ull << 38) / (2ull * n) + 1ull) : 0ull; }
+// k(a): minor offset of the beam (n, d) after a steps
+LAMA_HD uint32_t pull_minor_at(uint32_t nd, uint64_t magic, uint32_t a)
+{
+    const uint32_t n = nd & 0xFFFFu, d = nd >> 16;
+    return (uint32_t)(((uint64_t)(2u * a * d + n) * magic) >> 38);
+}
 // Sort key: class, then slope, then beam.  Two different slopes d1/n1 != d2/n2 with n < 2^13 differ by more than 2^-26, so
 // floor(d 2^39 / n) orders them strictly; equal slopes get equal fixed-point values (and are then ordered by beam).
 LAMA_HD uint64_t pull_sort_key(int cls, uint32_t n, uint32_t d, uint32_t beam)
@@ -64,124 +82,62 @@ LAMA_HD bool pull_at_least_lower(uint32_t nd, uint32_t a, uint32_t b)   // slope
     return 2u * a * d + n >= 2u * b * n;
 }
 // first entry of list[lo, hi) whose slope is >= the lower bound of cell (a, b)
-LAMA_HD int pull_lower_bound(const uint32_t* list, int lo, int hi, uint32_t a, uint32_t b)
+LAMA_HD int pull_lower_bound(const PullEntry* list, int lo, int hi, uint32_t a, uint32_t b)
 {
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (pull_at_least_lower(list[mid], a, b)) hi = mid;
+        if (pull_at_least_lower(list[mid].nd, a, b)) hi = mid;
         else lo = mid + 1;
     }
     return lo;
 }
-// One chain step: `ptr` stands on the first entry whose slope is >= the lower bound of cell (a, b); consumes the run of the
-// cell and returns how many of its beams are long enough to reach it.  Afterwards `ptr` stands at the lower bound of (a, b+1).
-LAMA_HD uint32_t pull_step(const uint32_t* list, int& ptr, int end, uint32_t a, uint32_t b)
+// ---- the count tile of a patch, one class at a time -----------------------------------------------------------------------
+// The beams of class `cls` that can cross the rectangle [a_lo, a_hi] x [b_lo, b_hi] (major x minor offsets, all >= 0, a_lo >= 1):
+// every such beam has a slope in [(2 b_lo - 1) / (2 a_hi), (2 b_hi + 1) / (2 a_lo)).
+LAMA_HD void pull_class_range(const PullEntry* list, const int* prefix, int cls, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, int& lo, int& hi)
 {
-    uint32_t count = 0;
-    while (ptr < end) {
-        const uint32_t nd = list[ptr];
-        if (!pull_below_upper(nd, a, b)) break;
-        count += (nd & 0xFFFFu) > a ? 1u : 0u;
-        ++ptr;
-    }
-    return count;
+    lo = pull_lower_bound(list, prefix[cls], prefix[cls + 1], a_hi, b_lo);
+    hi = pull_lower_bound(list, lo, prefix[cls + 1], a_lo, b_hi + 1u);
 }
-
-// ---- one lane's share of an axis pass over a 32 x 32 patch ------------------------------------------------------------------
-// The X pass counts the crossings of x-major beams: a lane owns a COLUMN (major offset a_signed = cx) and walks the 32 rows
-// of the patch (minor offsets t0 .. t0 + 31 = cy); the Y pass swaps the roles (lane = row, lines = columns) for the y-major
-// beams.  `prefix[c] .. prefix[c + 1]` delimit class c in `list`; `base` is 0 (X pass) or 4 (Y pass).
-// `out(line, count)` is called for the lines this lane has anything to say about (count may be 0); other lines are untouched.
-template <typename Out>
-LAMA_HD void pull_lane_pass(const uint32_t* list, const int* prefix, int a_signed, int t0, int base, Out&& out)
+// Where one beam of a class with minor sign `minor_negative` lands on the lane's grid line: the lane sits at major offset a (>= 1)
+// and its line covers the signed minor offsets t0 .. t0 + 31; returns the position 0 .. 31 on the line, or -1 when the beam does
+// not touch it (too short, or its cell lies outside the patch).
+LAMA_HD int pull_land(const PullEntry& e, uint32_t a, bool minor_negative, int t0)
 {
-    const uint32_t a = (uint32_t)(a_signed < 0 ? -a_signed : a_signed);
-    if (a == 0) return;   // the walk never visits major offset 0 (the origin's own line)
-    const int t1 = t0 + kPatchLen - 1;
-    // smallest |t| of the patch: beyond the diagonal (b > a) no beam of this major axis passes
-    const uint32_t bmin = (t0 <= 0 && t1 >= 0) ? 0u : (uint32_t)(t0 > 0 ? t0 : -t1);
-    if (bmin > a) return;
-    const int cm = base | (a_signed < 0 ? 2 : 0);
-    uint32_t c0neg = 0;
-    if (t0 <= 0) {   // lines on the negative minor side: class cm | 1, walked away from the axis (b = -t grows)
-        const int lo = prefix[cm | 1], hi = prefix[(cm | 1) + 1];
-        const int tstart = t1 < -1 ? t1 : -1;
-        uint32_t b = (uint32_t)(-tstart);
-        int ptr;
-        if (t1 >= 0) {   // the patch holds the axis line t = 0: its cell also collects the negative-side beams with b = 0
-            ptr   = lo;
-            c0neg = pull_step(list, ptr, hi, a, 0u);
-        } else {
-            ptr = pull_lower_bound(list, lo, hi, a, b);
-        }
-        for (int t = tstart; t >= t0 && b <= a; --t, ++b) out(t - t0, pull_step(list, ptr, hi, a, b));
-    }
-    if (t1 >= 0) {
-        const int lo = prefix[cm], hi = prefix[cm + 1];
-        const int tstart = t0 > 0 ? t0 : 0;
-        uint32_t b = (uint32_t)tstart;
-        int ptr = b == 0 ? lo : pull_lower_bound(list, lo, hi, a, b);
-        for (int t = tstart; t <= t1 && b <= a; ++t, ++b) {
-            uint32_t c = pull_step(list, ptr, hi, a, b);
-            if (t == 0) c += c0neg;
-            out(t - t0, c);
-        }
-    }
+    if ((e.nd & 0xFFFFu) <= a) return -1;
+    const int k = (int)pull_minor_at(e.nd, e.magic, a);
+    const int pos = (minor_negative ? -k : k) - t0;
+    return (unsigned)pos < (unsigned)kPatchLen ? pos : -1;
 }
-
-// The same pass as ONE loop per lane (what the kernel runs): every iteration either consumes a beam of the class list or closes a
-// cell and moves to the next line, so the lanes of a warp -- whose columns hold different numbers of beams per cell -- do not wait
-// for each other at every line, only at the end of the pass.  `emit(b, count)` closes cell b.
-template <typename EmitCell>
-LAMA_HD void pull_lane_chain(const uint32_t* list, int ptr, int end, uint32_t a, uint32_t b, uint32_t b_last, EmitCell&& emit)
+// The four classes of one major axis on a patch whose lanes sit at the signed major offsets m0 .. m0 + 31 and whose lines cover the
+// signed minor offsets t0 .. t0 + 31: calls visit(cls, major_negative, minor_negative, lo, hi) for every class with a non-empty
+// beam range.  (Lanes on the other side of the origin along the major axis, and the lane at major offset 0, sit a class out.)
+template <typename Visit>
+LAMA_HD void pull_patch_classes(const PullEntry* list, const int* prefix, int base, int m0, int t0, Visit&& visit)
 {
-    const uint32_t a2 = 2u * a;
-    uint32_t bb = 2u * (b + 1u), count = 0;
-    uint32_t n = 1u, d = 0xFFFFu;   // past the end of the list: a beam steeper than every cell bound
-    if (ptr < end) { n = list[ptr] & 0xFFFFu; d = list[ptr] >> 16; }
-    for (;;) {
-        if (a2 * d + n < bb * n) {   // the beam's slope is below the upper bound of cell b: it belongs to this cell's run
-            count += n > a ? 1u : 0u;
-            ++ptr;
-            n = 1u; d = 0xFFFFu;
-            if (ptr < end) { n = list[ptr] & 0xFFFFu; d = list[ptr] >> 16; }
-        } else {
-            emit(b, count);
-            if (b == b_last) break;
-            count = 0;
-            ++b;
-            bb += 2u;
+    const int m1 = m0 + kPatchLen - 1, t1 = t0 + kPatchLen - 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1   // one copy of the visitor's beam loop in the kernel, not four
+#endif
+    for (int mneg = 0; mneg < 2; ++mneg) {
+        // major offsets a >= 1 of the lanes on this side of the origin
+        int a_lo, a_hi;
+        if (!mneg) { a_lo = m0 > 1 ? m0 : 1; a_hi = m1; }
+        else { a_lo = m1 < -1 ? -m1 : 1; a_hi = -m0; }
+        if (a_hi < a_lo) continue;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int tneg = 0; tneg < 2; ++tneg) {
+            int b_lo, b_hi;   // |minor offsets| of the lines on this side (the axis line t = 0 belongs to both)
+            if (!tneg) { b_lo = t0 > 0 ? t0 : 0; b_hi = t1; }
+            else { b_lo = t1 < 0 ? -t1 : 0; b_hi = -t0; }
+            if (b_hi < b_lo || b_lo > a_hi) continue;   // beyond the diagonal no beam of this major axis passes
+            const int cls = base | (mneg ? 2 : 0) | (tneg ? 1 : 0);
+            int lo, hi;
+            pull_class_range(list, prefix, cls, (uint32_t)a_lo, (uint32_t)a_hi, (uint32_t)b_lo, (uint32_t)b_hi, lo, hi);
+            if (hi > lo) visit(cls, mneg != 0, tneg != 0, lo, hi);
         }
-    }
-}
-template <typename Out>
-LAMA_HD void pull_lane_pass_flat(const uint32_t* list, const int* prefix, int a_signed, int t0, int base, Out&& out)
-{
-    const uint32_t a = (uint32_t)(a_signed < 0 ? -a_signed : a_signed);
-    if (a == 0) return;
-    const int t1 = t0 + kPatchLen - 1;
-    const uint32_t bmin = (t0 <= 0 && t1 >= 0) ? 0u : (uint32_t)(t0 > 0 ? t0 : -t1);
-    if (bmin > a) return;
-    const int cm = base | (a_signed < 0 ? 2 : 0);
-    uint32_t c0neg = 0;
-    if (t0 <= 0) {   // negative minor side (class cm | 1), away from the axis; with the axis line in the patch the chain starts at b = 0
-        const int lo = prefix[cm | 1], hi = prefix[(cm | 1) + 1];
-        const uint32_t b0 = t1 >= 0 ? 0u : (uint32_t)(-t1);
-        uint32_t b1 = (uint32_t)(-t0);
-        if (b1 > a) b1 = a;
-        const int ptr = b0 == 0 ? lo : pull_lower_bound(list, lo, hi, a, b0);
-        pull_lane_chain(list, ptr, hi, a, b0, b1, [&](uint32_t b, uint32_t c) {
-            if (b == 0) c0neg = c;   // kept for the axis cell, which the positive side emits
-            else out(-(int)b - t0, c);
-        });
-    }
-    if (t1 >= 0) {
-        const int lo = prefix[cm], hi = prefix[cm + 1];
-        const uint32_t b0 = t0 > 0 ? (uint32_t)t0 : 0u;
-        uint32_t b1 = (uint32_t)t1;
-        if (b1 > a) b1 = a;
-        const int ptr = b0 == 0 ? lo : pull_lower_bound(list, lo, hi, a, b0);
-        pull_lane_chain(list, ptr, hi, a, b0, b1, [&](uint32_t b, uint32_t c) { out((int)b - t0, b == 0 ? c + c0neg : c); });
     }
 }
 
@@ -193,7 +149,7 @@ struct PullRuns {
     int lo[4], hi[4];
     uint32_t a[4];
 };
-LAMA_HD void pull_set_run(PullRuns& r, int slot, bool on, const uint32_t* list, const int* prefix, int cls, uint32_t a, uint32_t b)
+LAMA_HD void pull_set_run(PullRuns& r, int slot, bool on, const PullEntry* list, const int* prefix, int cls, uint32_t a, uint32_t b)
 {
     r.lo[slot] = r.hi[slot] = 0;
     r.a[slot]  = a;
@@ -201,7 +157,7 @@ LAMA_HD void pull_set_run(PullRuns& r, int slot, bool on, const uint32_t* list, 
     r.lo[slot] = pull_lower_bound(list, prefix[cls], prefix[cls + 1], a, b);
     r.hi[slot] = pull_lower_bound(list, r.lo[slot], prefix[cls + 1], a, b + 1u);
 }
-LAMA_HD PullRuns pull_cell_runs(const uint32_t* list, const int* prefix, int cx, int cy)
+LAMA_HD PullRuns pull_cell_runs(const PullEntry* list, const int* prefix, int cx, int cy)
 {
     PullRuns r;
     const uint32_t ax = (uint32_t)(cx < 0 ? -cx : cx), ay = (uint32_t)(cy < 0 ? -cy : cy);
@@ -263,7 +219,31 @@ struct PullTouch {
     uint32_t beam, pos;
     bool hit, valid;
 };
-LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, int after)
+// the hit records of one cell, picked out of its patch's records once (a cell rarely holds more than a few hits; beyond kMax the
+// replay falls back to scanning the patch's records every time)
+struct PullCellHits {
+    static constexpr int kMax = 4;
+    uint32_t beam[kMax];
+    int n;   // > kMax: too many for the registers
+};
+LAMA_HD PullCellHits pull_cell_hits(const uint32_t* hits, int h0, int h1, uint32_t ci)
+{
+    PullCellHits c;
+    c.n = 0;
+    for (int k = 0; k < PullCellHits::kMax; ++k) c.beam[k] = 0xFFFFFFFFu;
+    for (int i = h0; i < h1; ++i) {
+        if (pull_hit_cell(hits[i]) != ci) continue;
+        const uint32_t b = hits[i] & 0xFFFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < PullCellHits::kMax; ++k)
+            if (c.n == k) c.beam[k] = b;
+        ++c.n;
+    }
+    return c;
+}
+LAMA_HD PullTouch pull_next_touch(const PullEntry* list, const PullRuns& runs, const PullCellHits& ch, const uint32_t* hits, int h0, int h1, uint32_t ci, int after)
 {
     PullTouch t{0xFFFFFFFFu, 0u, false, false};
 #if defined(__CUDA_ARCH__)
@@ -271,12 +251,24 @@ LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of,
 #endif
     for (int r = 0; r < 4; ++r)
         for (int i = runs.lo[r]; i < runs.hi[r]; ++i) {
-            if ((list[i] & 0xFFFFu) <= runs.a[r]) continue;   // too short to reach the cell
-            const uint32_t b = beam_of[i];
+            if ((list[i].nd & 0xFFFFu) <= runs.a[r]) continue;   // too short to reach the cell
+            const uint32_t b = list[i].beam;
             if ((int)b > after && b < t.beam) {
                 t.beam = b; t.pos = runs.a[r]; t.hit = false; t.valid = true;
             }
         }
+    if (ch.n <= PullCellHits::kMax) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < PullCellHits::kMax; ++k) {
+            const uint32_t b = ch.beam[k];
+            if (k < ch.n && (int)b > after && b < t.beam) {
+                t.beam = b; t.pos = 0u; t.hit = true; t.valid = true;
+            }
+        }
+        return t;
+    }
     for (int i = h0; i < h1; ++i) {
         if (pull_hit_cell(hits[i]) != ci) continue;
         const uint32_t b = hits[i] & 0xFFFFu;
@@ -287,13 +279,14 @@ LAMA_HD PullTouch pull_next_touch(const uint32_t* list, const uint16_t* beam_of,
     return t;
 }
 template <typename Emit>
-LAMA_HD uint32_t pull_replay_cell(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, uint32_t word,
+LAMA_HD uint32_t pull_replay_cell(const PullEntry* list, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, uint32_t word,
                                   bool& obstacle, Emit&& emit)
 {
     uint32_t occupied = occ_occupied(word), visited = occ_visited(word);
+    const PullCellHits ch = pull_cell_hits(hits, h0, h1, ci);
     int after = -1;
     for (;;) {
-        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, ci, after);
+        const PullTouch t = pull_next_touch(list, runs, ch, hits, h0, h1, ci, after);
         if (!t.valid) break;
         after = (int)t.beam;
         const uint32_t seq = (t.beam << 15) | (t.pos & 0x7FFFu);   // == log_seq(log_record(., beam, pos, hit))
@@ -318,12 +311,13 @@ LAMA_HD uint32_t pull_replay_cell(const uint32_t* list, const uint16_t* beam_of,
 }
 // log-odds cells (ProbabilisticOccupancyMap, probabilistic_occupancy_map.cpp:82-107)
 template <typename Emit>
-LAMA_HD float pull_replay_cell_prob(const uint32_t* list, const uint16_t* beam_of, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, float prob,
+LAMA_HD float pull_replay_cell_prob(const PullEntry* list, const PullRuns& runs, const uint32_t* hits, int h0, int h1, uint32_t ci, float prob,
                                     bool& obstacle, const ProbParams& pp, Emit&& emit)
 {
+    const PullCellHits ch = pull_cell_hits(hits, h0, h1, ci);
     int after = -1;
     for (;;) {
-        const PullTouch t = pull_next_touch(list, beam_of, runs, hits, h0, h1, ci, after);
+        const PullTouch t = pull_next_touch(list, runs, ch, hits, h0, h1, ci, after);
         if (!t.valid) break;
         after = (int)t.beam;
         const uint32_t seq = (t.beam << 15) | (t.pos & 0x7FFFu);

@@ -125,3 +125,50 @@ class ShardedPFSlam2D:
             self.pf.unpackParticle(self.per + k, t.cpu().numpy())
             self.migrated_bytes += t.numel()
         self.pf.shardApply(idx, local_sources(idx, self.rank, self.world, need[self.rank]))
+
+
+class LocalShards:
+    """G logical ranks in ONE process (all handles on the same device): the orchestration of ShardedPFSlam2D with the exchange done
+    by plain copies instead of collectives.  It drives exactly the calls a rank makes (shardBegin / shardFinish / packParticle /
+    unpackParticle / shardApply with local sources / shardMapUpdate), so that the sharded code path can be checked against the
+    single-process oracle where only one GPU (or none: any object with the shard* calls works) is available."""
+
+    def __init__(self, handles, particles: int):
+        self.h = list(handles)
+        self.G = len(self.h)
+        self.P = particles
+        self.per = particles // self.G
+        self.migrated_bytes = 0
+        self.last_idx = np.zeros(0, np.int32)
+
+    def update(self, pts, odom, timestamp=0.0) -> bool:
+        begun = [h.shardBegin(pts, odom, timestamp) for h in self.h]
+        dids = {d for d, _ in begun}
+        assert len(dids) == 1, "the ranks disagree about the motion gate"
+        did = dids.pop()
+        self.last_idx = np.zeros(0, np.int32)
+        if did != 2:
+            return did != 0
+        all_results = np.concatenate([loc for _, loc in begun], axis=0).reshape(self.P, 5)   # the all-gather
+        fin = [h.shardFinish(all_results) for h in self.h]
+        resampled = {r for r, _ in fin}
+        assert len(resampled) == 1, "the ranks disagree about resampling"
+        if resampled.pop():
+            idx = fin[0][1]
+            for r, i in fin[1:]:
+                assert (i == idx).all(), "the ranks drew different resampling indices"
+            self.last_idx = idx.copy()
+            need, serve = migration_plan(idx, self.G)
+            packed = {}
+            for r in range(self.G):   # every rank packs what it serves ...
+                for dst, gid in serve[r]:
+                    packed[(dst, gid)] = self.h[r].packParticle(gid - r * self.per)
+            for r in range(self.G):   # ... and unpacks what it needs into its staging slots
+                for k, a in enumerate(need[r]):
+                    buf = packed[(r, a)]
+                    self.h[r].unpackParticle(self.per + k, buf)
+                    self.migrated_bytes += buf.size
+                self.h[r].shardApply(idx, local_sources(idx, r, self.G, need[r]))
+        for h in self.h:
+            h.shardMapUpdate()
+        return True

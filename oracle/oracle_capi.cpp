@@ -218,6 +218,13 @@ void* orc_pf_create(const orc_pf_options* o)
 }
 void orc_pf_destroy(void* h) { delete (PFSlam2D*)h; }
 void orc_pf_set_prior(void* h, double x, double y, double r) { ((PFSlam2D*)h)->set_prior(Pose2D(x, y, r)); }
+// bench only: change the size of the thread pool of a running filter (the reference fixes it in the constructor, pf_slam2d.cpp:123-128)
+void orc_pf_set_threads(void* h, int32_t n)
+{
+    auto* pf = (PFSlam2D*)h;
+    pf->opt.threads = n;
+    pf->pool.reset(n > 1 ? new ThreadPool((size_t)n) : nullptr);
+}
 void orc_pf_set_shuffle(void* h, uint32_t s) { ((PFSlam2D*)h)->shuffle_ties = s; }
 int orc_pf_update(void* h, const double* pts, int n, const double* origin, const double* quat, const double* odom_xyr)
 {

@@ -368,6 +368,9 @@ class PFSlam2D:
         keys = ("evals", "ray_cells", "dm_pops", "detached", "gn_iters", "resampled")
         return dict(zip(keys, last.tolist())), dict(zip(keys, tot.tolist()))
 
+    def set_threads(self, n):
+        lib().orc_pf_set_threads(self.h, C.c_int32(n))
+
     def times(self):
         t = np.zeros(4)
         lib().orc_pf_times(self.h, t.ctypes.data_as(c_dp))

@@ -192,8 +192,7 @@ void run_brushfire(Emu& e, std::vector<uint64_t>& events, uint32_t cells, uint32
 // ---- the pull form of the ray cast (ray_pull.h), laid out like k_ray_setup + k_ray_pull --------------------------------------
 struct PullScan {
     uint32_t ox = 0, oy = 0;                 // window-relative origin cell
-    std::vector<uint32_t> list;              // class lists: n | d << 16, sorted by (class, slope, beam)
-    std::vector<uint16_t> beam_of;
+    std::vector<PullEntry> list;             // class lists sorted by (class, slope, beam)
     int prefix[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> hits;              // pull_hit_record, grouped by patch (hit_lo / hit_n per directory entry), unordered inside
     std::vector<int> hit_lo, hit_n;
@@ -240,23 +239,40 @@ void pull_setup(PullScan& ps, uint32_t ox, uint32_t oy, const std::vector<uint32
     }
     int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (uint64_t k : keys) {
-        ps.list.push_back(nd_of_beam[pull_key_beam(k)]);
-        ps.beam_of.push_back((uint16_t)pull_key_beam(k));
+        const uint32_t nd = nd_of_beam[pull_key_beam(k)];
+        ps.list.push_back(PullEntry{nd, pull_key_beam(k), pull_magic(nd & 0xFFFFu)});
         ++count[pull_key_class(k)];
     }
     for (int c = 0; c < 8; ++c) ps.prefix[c + 1] = ps.prefix[c] + count[c];
 }
 
-// the count tile of one patch: both axis passes, lane by lane (a warp runs the 32 lanes in lock step)
+// the count tile of one patch the way a warp of k_ray_pull fills it: per class every lane runs over the same beam range and drops
+// each beam into the counter of the cell where it crosses the lane's column (x-major classes) / row (y-major classes)
 void pull_patch_counts(const PullScan& ps, int px, int py, uint32_t tile[kPatchLen][kPatchLen])
 {
     for (int r = 0; r < kPatchLen; ++r)
         for (int c = 0; c < kPatchLen; ++c) tile[r][c] = 0;
     const int cx0 = px * kPatchLen - (int)ps.ox, cy0 = py * kPatchLen - (int)ps.oy;
-    for (int lane = 0; lane < kPatchLen; ++lane) {
-        pull_lane_pass_flat(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile[line][lane] += c; });   // X pass: lane = column
-        pull_lane_pass_flat(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile[lane][line] += c; });   // Y pass: lane = row
-    }
+    pull_patch_classes(ps.list.data(), ps.prefix, 0, cx0, cy0, [&](int, bool mneg, bool tneg, int lo, int hi) {   // lane = column
+        for (int lane = 0; lane < kPatchLen; ++lane) {
+            const int m = cx0 + lane;
+            if (m == 0 || (m < 0) != mneg) continue;
+            for (int i = lo; i < hi; ++i) {
+                const int pos = pull_land(ps.list[i], (uint32_t)(m < 0 ? -m : m), tneg, cy0);
+                if (pos >= 0) ++tile[pos][lane];
+            }
+        }
+    });
+    pull_patch_classes(ps.list.data(), ps.prefix, 4, cy0, cx0, [&](int, bool mneg, bool tneg, int lo, int hi) {   // lane = row
+        for (int lane = 0; lane < kPatchLen; ++lane) {
+            const int m = cy0 + lane;
+            if (m == 0 || (m < 0) != mneg) continue;
+            for (int i = lo; i < hi; ++i) {
+                const int pos = pull_land(ps.list[i], (uint32_t)(m < 0 ? -m : m), tneg, cx0);
+                if (pos >= 0) ++tile[lane][pos];
+            }
+        }
+    });
 }
 
 bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2& pose)
@@ -307,7 +323,7 @@ bool update_maps_pull(Emu& e, const ScanParams& sp, const double* pts, const SE2
                     bool obstacle = fb != 0;
                     const uint32_t key = cell_key(win, x, y);
                     const uint32_t before = *cell;
-                    *cell = pull_replay_cell(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), h_lo, h_hi, ci, before, obstacle,
+                    *cell = pull_replay_cell(ps.list.data(), runs, ps.hits.data(), h_lo, h_hi, ci, before, obstacle,
                                              [&](bool add, uint32_t seq) { events.push_back(push_record((seq << 1) | (add ? 1u : 0u), key)); });
                     // the replay must have consumed exactly the counted crossings and the hits
                     if (*cell != before + cnt * kOccMissInc + (uint32_t)n_hit * kOccHitInc) e.occ.err |= 0x100u;
@@ -471,7 +487,7 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
     // slope order inside the classes must be the exact rational order
     for (int c = 0; c < 8; ++c)
         for (int i = ps.prefix[c] + 1; i < ps.prefix[c + 1]; ++i) {
-            const uint64_t n0 = ps.list[i - 1] & 0xFFFFu, d0 = ps.list[i - 1] >> 16, n1 = ps.list[i] & 0xFFFFu, d1 = ps.list[i] >> 16;
+            const uint64_t n0 = ps.list[i - 1].nd & 0xFFFFu, d0 = ps.list[i - 1].nd >> 16, n1 = ps.list[i].nd & 0xFFFFu, d1 = ps.list[i].nd >> 16;
             if (d0 * n1 > d1 * n0) ++bad;
         }
     static uint32_t tile[kPatchLen][kPatchLen];
@@ -480,18 +496,6 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
             const bool marked = ps.marked[((size_t)py << log2dim) | (size_t)px] != 0;
             if (marked) {
                 pull_patch_counts(ps, px, py, tile);
-                // the line-by-line form of the pass (pull_lane_pass) must produce the same tile as the single-loop form the kernel runs
-                static uint32_t tile2[kPatchLen][kPatchLen];
-                for (int r = 0; r < kPatchLen; ++r)
-                    for (int c = 0; c < kPatchLen; ++c) tile2[r][c] = 0;
-                const int cx0 = px * kPatchLen - (int)ox, cy0 = py * kPatchLen - (int)oy;
-                for (int lane = 0; lane < kPatchLen; ++lane) {
-                    pull_lane_pass(ps.list.data(), ps.prefix, cx0 + lane, cy0, 0, [&](int line, uint32_t c) { tile2[line][lane] += c; });
-                    pull_lane_pass(ps.list.data(), ps.prefix, cy0 + lane, cx0, 4, [&](int line, uint32_t c) { tile2[lane][line] += c; });
-                }
-                for (int r = 0; r < kPatchLen; ++r)
-                    for (int c = 0; c < kPatchLen; ++c)
-                        if (tile[r][c] != tile2[r][c]) ++bad;
             }
             for (int r = 0; r < kPatchLen; ++r)
                 for (int c = 0; c < kPatchLen; ++c) {
@@ -507,7 +511,7 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
                     std::vector<std::pair<uint32_t, uint32_t>> got;
                     int after = -1;
                     for (;;) {
-                        const PullTouch t = pull_next_touch(ps.list.data(), ps.beam_of.data(), runs, ps.hits.data(), 0, 0, 0u, after);
+                        const PullTouch t = pull_next_touch(ps.list.data(), runs, pull_cell_hits(ps.hits.data(), 0, 0, 0u), ps.hits.data(), 0, 0, 0u, after);
                         if (!t.valid) break;
                         got.push_back({t.beam, t.pos});
                         after = (int)t.beam;
@@ -517,6 +521,25 @@ int emu_pull_check(uint32_t seed, int n_beams, int mode, int dim)
                     if (got != w) ++bad;
                 }
         }
+    return bad;
+}
+// pull_minor_at (division by 2 n as a multiplication) against the plain division: every n, d <= n, and the a around every jump of k
+int emu_magic_check(int n_max)
+{
+    int bad = 0;
+    for (uint32_t n = 1; n <= (uint32_t)n_max; ++n) {
+        const uint64_t magic = pull_magic(n);
+        // all dividends x = 2 a d + n with a, d < 4096 are below 2^25: check the floor at every multiple of 2 n in that range, just below and at it
+        for (uint64_t q = 0; q * 2 * n < (1ull << 25); ++q) {
+            const uint64_t x1 = q * 2 * n, x0 = x1 ? x1 - 1 : 0, x2 = x1 + 2 * n - 1;
+            if (((x1 * magic) >> 38) != x1 / (2 * n) || ((x0 * magic) >> 38) != x0 / (2 * n)) ++bad;
+            if (x2 < (1ull << 25) && ((x2 * magic) >> 38) != x2 / (2 * n)) ++bad;
+        }
+        const uint32_t ds[4] = {0u, 1u, n / 2, n};
+        for (uint32_t d : ds)
+            for (uint32_t a = 1; a < 4096; a += (a < 64 ? 1 : 37))
+                if (pull_minor_at(pull_pack(n, d), magic, a) != (2u * a * d + n) / (2u * n)) ++bad;
+    }
     return bad;
 }
 void emu_set_pull(void* h, int on) { ((Emu*)h)->pull = on != 0; }

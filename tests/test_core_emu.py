@@ -59,9 +59,10 @@ def test_kernel_segment_walk_equals_iterative_bresenham(emu):
 
 
 def test_pull_raycast_counts_equal_iterative_bresenham(emu):
-    """ray_pull.h (what k_ray_setup / k_ray_pull execute): class lists sorted by exact slope, patch marking, chained per-cell crossing counts
+    """ray_pull.h (what k_ray_setup / k_ray_pull execute): class lists sorted by exact slope, patch marking, per-cell crossing counts (one beam range per class and patch, k(a) by exact reciprocal division)
     and the per-cell runs with their step indices, against Map::computeRay's iterative walk (map.cpp:198-227) for every cell of the window"""
     emu.emu_pull_check.restype = C.c_int
+    assert emu.emu_magic_check(C.c_int(4096)) == 0   # the exact reciprocal division behind k(a) = floor((2 a d + n) / (2 n))
     for mode in range(4):   # scan-like fans, random end cells, very short beams (n = 0, 1, 2), axes and diagonals
         for seed, n, dim in ((1, 1080, 16), (2, 360, 8), (3, 2000, 32), (4, 50, 8), (5, 1080, 64), (6, 720, 128)):
             assert emu.emu_pull_check(C.c_uint32(seed * 7 + mode), C.c_int(n), C.c_int(mode), C.c_int(dim)) == 0, (mode, seed)

@@ -119,3 +119,20 @@ def test_sharded_update_equals_single_process(world):
             want = truth[r * per + k]
             # the per-scan ids encode which global particle slot absorbed the scan: identical lineages required
             assert got == want, (r, k, got, want)
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_logical_ranks_in_one_process_equal_single_process(G):
+    """distributed.LocalShards (what the GPU suite uses for its G-logical-ranks test) drives the same shard protocol"""
+    from iris_lama_b200.distributed import LocalShards
+    P, T = 8, 10
+    hs = [StubPF(P, r, G) for r in range(G)]
+    sh = LocalShards(hs, P)
+    for t in range(T):
+        sh.update(np.zeros((4, 3)), np.zeros(3))
+    truth = _single_process_truth(P, T)
+    per = P // G
+    for r in range(G):
+        for k in range(per):
+            assert [v for _, v in hs[r].maps[k]] == truth[r * per + k], (r, k)
+    assert sh.migrated_bytes > 0
