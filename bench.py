@@ -269,7 +269,7 @@ def gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
         from iris_lama_b200.distributed import ShardedPFSlam2D
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # the bench's own plumbing: barriers, max over ranks, handing out the NCCL id
 
     steps, warmup, pre = args.steps, args.warmup, args.prebuild
     # scan 0 initialises the maps, scans 1 .. pre build them (untimed), then W warm-up and K timed scans; every pass replays the SAME scans
@@ -302,7 +302,14 @@ def gpu_arm(args):
     def timed_pass(data, t_first, k_steps, staged, timing=False, sample_clocks=False, **opts):
         """one fresh filter over scans 0 .. t_first + k_steps of `data`; the last k_steps are timed, each with its own event pair"""
         pf = new_pf(timing, **opts)
-        sh = ShardedPFSlam2D(pf, PARTICLES, device=dev) if world > 1 else None
+        sh = None
+        if world > 1 and args.sharded_impl == "python":
+            sh = ShardedPFSlam2D(pf, PARTICLES, device=dev)   # round-1 orchestration: torch.distributed collectives driven from Python
+        elif world > 1:
+            import torch.distributed as dist                   # the sharded step inside the library (NCCL from C++, shard_comm.cpp)
+            box = [api.shard_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            pf.shardConnect(box[0])
         if staged and sh is None:
             pf.stageScans(data.scans[:t_first + k_steps])
             step = lambda t: pf.updateStaged(t, data.odom[t])
@@ -369,6 +376,7 @@ def gpu_arm(args):
         by = {"k_match": d["evals"] * BEAMS * 8.0 / steps, "k_raycast": d["ray_cells"] * 8.0 / steps, "k_brushfire": d["dm_pops"] * 72.0 / steps}
         t = {"k_match": tm["match_ms"], "k_raycast": tm["raycast_ms"], "k_brushfire": tm["brushfire_ms"]}
         kernel_ms = dict(t)
+        kernel_ms["map_device"] = tm["raycast_ms"] + tm["brushfire_ms"]
         dom = max(t, key=t.get)
         ach = by[dom] / (t[dom] * 1e-3) / 1e9 if t[dom] > 0 else 0.0
         traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of that kernel (per launch)
@@ -439,7 +447,9 @@ def gpu_arm(args):
                 "config": {"workload": WORKLOAD, "particles": PARTICLES, "beams": BEAMS, "prebuild_scans": pre,
                            "parallelism": f"particles sharded over {world} GPU(s)",
                            "l2": "per-scan working set (~290 MB of touched map patches over 256 particles) exceeds the 126 MB L2; no explicit flush",
-                           "value_inputs": "scans staged in HBM" if world == 1 else "host scans (sharded path)",
+                           "value_inputs": "scans staged in HBM",
+                           "sharded_step": None if world == 1 else ("inside liblama_b200.so (NCCL all-gather + send/recv from C++)" if args.sharded_impl == "native"
+                                                                    else "torch.distributed collectives driven from Python"),
                            "updates_in_timed_region": n_upd,
                            "timer": "one CUDA event pair per step on the launching stream (a step enqueues match + map update at once; the event after "
                                     "it completes when that map update has); value = K / sum of the K steps; host wall clock of the same region: "
@@ -450,7 +460,7 @@ def gpu_arm(args):
                         "timer": "host clock around the K lama_pf_update calls with host buffers, device synchronised at both ends", "step_ms": stats_e2e},
                 "gpu_launches": gpu_launches,
                 "counters_per_step": {k: v / steps for k, v in work.items()},
-                "summary_ms_per_step": {**summary_value, "map_device": (kernel_ms["raycast_ms"] + kernel_ms["brushfire_ms"]) if kernel_ms else None,
+                "summary_ms_per_step": {**summary_value, "map_device": kernel_ms["map_device"] if kernel_ms else None,
                                         "note": "reference Summary buckets (pf_slam2d.h:88-129): host wall clock of sampling / solve (enqueue + wait for the "
                                                 "match) / normalise / resample; the map bucket runs asynchronously on the device"}}
         if roofline:
@@ -512,6 +522,7 @@ def main():
     ap.add_argument("--no-regimes", action="store_true")
     ap.add_argument("--no-full-loop", action="store_true")
     ap.add_argument("--full-loop", type=int, default=5000, help="scans of the full-loop regime (BASELINE config 4: 5 000)")
+    ap.add_argument("--sharded-impl", default="native", choices=["native", "python"])
     ap.add_argument("--prebuild", type=int, default=300, help="untimed scans that build the map before warm-up (both arms)")
     args = ap.parse_args()
     if args.warmup < 3:

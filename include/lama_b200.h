@@ -137,6 +137,17 @@ int lama_pf_export_occupancy(lama_pf* h, int particle, uint32_t x0, uint32_t y0,
 int lama_pf_export_distance(lama_pf* h, int particle, uint32_t x0, uint32_t y0, int w, int hgt, uint16_t* sqdist, uint8_t* valid,
                             uint8_t* known, int16_t* ox, int16_t* oy, uint8_t* queued);
 
+/* ---- multi-GPU behind lama_pf_update: particles shard over shard_count ranks, one host thread / process per GPU.  Rank 0 asks for an
+ * id (lama_shard_unique_id = ncclGetUniqueId), hands its 128 bytes to every rank by any means (MPI, a file, torch.distributed ...), and
+ * every rank calls lama_pf_shard_connect() on its handle (created with shard_rank / shard_count and the SAME non-zero seed).  From then
+ * on lama_pf_update() / lama_pf_update_staged() run the whole sharded step of PFSlam2D::update (src/pf_slam2d.cpp:178-312): match +
+ * map update of the local particles (:254-266, :292-302), ONE NCCL all-gather of the match results, normalize / resample (:274-287,
+ * :511-574) on identical bytes on every rank, NCCL send / recv of the maps of remote ancestors.  libnccl.so.2 is loaded at run time.
+ * lama_pf_shard_stats: {collectives issued, bytes of maps received}. */
+int lama_shard_unique_id(uint8_t id[128]);
+int lama_pf_shard_connect(lama_pf* h, const uint8_t id[128]);
+int lama_pf_shard_stats(lama_pf* h, uint64_t out[2]);
+
 /* --- sharded (multi-GPU) operation: the caller moves the small per-scan vectors between ranks ------------
  * begin : predict (every rank draws the noise of ALL particles, keeping the RNG streams identical) + gate +
  *         scan matching of the local shard; local_out = P_local x 5 doubles (state[4], log-likelihood)
@@ -267,6 +278,31 @@ int lama_dm_match_normal_equations(lama_dm* dm, const double* pts_xyz, int n, co
  * stats = count x 2 {iterations, evaluations}; sums = count x 12 at the final states (may be NULL) */
 int lama_dm_match_solve(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4], double* states,
                         int count, int strategy, int robust_kind, double robust_param, uint32_t max_iter, uint32_t* stats, double* sums);
+
+/* MatchSurface2D::error() (src/match_surface_2d.cpp:92-116): sqrt(sum d^2 / N), d = nearest-cell distance, of the cloud at `count` states */
+int lama_dm_match_error(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4], const double* states, int count,
+                        double* rmse);
+
+/* ---- GraphSlam2D's loop-closure front end on a device map (src/graph_slam2d.cpp:283-392) ----
+ * findLoopClosureCandidates (:283-313): ids of the key poses (x, y pairs) within `radius` of the query among the first
+ * n_keys - ignore_n_chain_poses, nearest first, at most max_candidates (Options::loop_max_candidates, graph_slam2d.h:75). */
+int lama_loop_closure_candidates(const double* key_xy, int n_keys, int ignore_n_chain_poses, const double query_xy[2], double radius, int max_candidates, int* ids,
+                                 int* count);
+/* correlateCandidateScan (:315-355): the candidate key pose's cloud against the distance map -- one Gauss-Newton iteration (Huber 0.15) from
+ * the candidate's pose and one from the reference position, the better start refined to convergence; between = matched pose - ref pose
+ * (Pose2D::operator-, pose2d.cpp:81-84), *rmse = MatchSurface2D::error() there.  ref / cand poses are the corrected key poses (:319-320). */
+int lama_slam_correlate_candidate_scan(lama_slam* h, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                                       const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3], double* rmse);
+int lama_dm_correlate_candidate_scan(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                                     const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3], double* rmse);
+/* coarseSearchAndCorrelateCandidateScan (:357-392): first against a coarse distance map (0.25 m cells, 2.5 m reach) built from the reference
+ * key pose's cloud alone, then against the map itself. */
+int lama_slam_coarse_correlate_candidate_scan(lama_slam* h, const double* ref_pts_xyz, int ref_n, const double ref_origin[3], const double ref_quat_xyzw[4],
+                                              const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                                              const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3], double* rmse);
+int lama_dm_coarse_correlate_candidate_scan(lama_dm* dm, const double* ref_pts_xyz, int ref_n, const double ref_origin[3], const double ref_quat_xyzw[4],
+                                            const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4],
+                                            const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3], double* rmse);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "lama_last_error", "lama_version", "lama_device_count",
     "lama_pf_options_default", "lama_pf_create", "lama_pf_destroy", "lama_pf_set_prior", "lama_pf_update", "lama_pf_get_pose",
     "lama_pf_stage_scans", "lama_pf_update_staged", "lama_pf_get_traffic",
-    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary",
+    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary", "lama_shard_unique_id", "lama_pf_shard_connect", "lama_pf_shard_stats", "lama_loop_closure_candidates", "lama_slam_correlate_candidate_scan", "lama_dm_correlate_candidate_scan", "lama_slam_coarse_correlate_candidate_scan", "lama_dm_coarse_correlate_candidate_scan", "lama_dm_match_error",
     "lama_pf_get_counters", "lama_pf_kernel_times", "lama_pf_map_bounds", "lama_pf_export_occupancy", "lama_pf_export_distance",
     "lama_pf_shard_begin", "lama_pf_shard_finish", "lama_pf_shard_apply", "lama_pf_shard_apply_local", "lama_pf_shard_map_update",
     "lama_pf_particle_pack_size", "lama_pf_particle_pack", "lama_pf_particle_unpack",
@@ -190,6 +190,36 @@ def _bounds(fn, args):
     n = C.c_int(0)
     _chk(fn(*args, mn.ctypes.data_as(c_u32p), mx.ctypes.data_as(c_u32p), C.byref(n)))
     return n.value, mn, mx
+
+
+def loop_closure_candidates(key_xy, ignore_n_chain_poses, query_xy, radius, max_candidates=5):
+    """GraphSlam2D::findLoopClosureCandidates (src/graph_slam2d.cpp:283-313): ids of the key poses near `query_xy`, nearest first"""
+    k, kp = _d(key_xy)
+    q, qp = _d(query_xy)
+    ids = np.zeros(max(1, max_candidates), np.int32)
+    n = C.c_int(0)
+    _chk(lib().lama_loop_closure_candidates(kp, C.c_int(k.size // 2), C.c_int(ignore_n_chain_poses), qp, C.c_double(radius), C.c_int(max_candidates),
+                                            ids.ctypes.data_as(c_i32p), C.byref(n)))
+    return ids[:n.value].copy()
+
+
+def _correlate(fn, h, pts, ref_xyr, cand_xyr, origin, quat, ref_pts=None):
+    p, pp = _d(pts); o, op = _d(origin); q, qp = _d(quat); r, rp = _d(ref_xyr); c, cp = _d(cand_xyr)
+    out = np.zeros(3)
+    rmse = C.c_double(0)
+    if ref_pts is None:
+        _chk(fn(h, pp, C.c_int(p.size // 3), op, qp, rp, cp, out.ctypes.data_as(c_dp), C.byref(rmse)))
+    else:
+        a, ap = _d(ref_pts)
+        _chk(fn(h, ap, C.c_int(a.size // 3), op, qp, pp, C.c_int(p.size // 3), op, qp, rp, cp, out.ctypes.data_as(c_dp), C.byref(rmse)))
+    return out, rmse.value
+
+
+def shard_unique_id() -> bytes:
+    """rank 0: the id (ncclGetUniqueId, 128 bytes) every rank passes to PFSlam2D.shardConnect"""
+    buf = (C.c_uint8 * 128)()
+    _chk(lib().lama_shard_unique_id(buf))
+    return bytes(buf)
 
 
 class PFSlam2D:
@@ -343,6 +373,18 @@ class PFSlam2D:
         """PFSlam2D::saveOccImage (pf_slam2d.cpp:338-342): the best particle's occupancy map as PNG"""
         write_png(path, self.exportImage(self.getBestParticleIdx(), 0))
 
+    # ---- multi-GPU behind update(): NCCL inside the library --------------------------------------------------
+    def shardConnect(self, unique_id: bytes):
+        """every rank: connect this handle to the others with the 128-byte id rank 0 got from shard_unique_id()"""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _chk(lib().lama_pf_shard_connect(self.h, buf))
+
+    def shardStats(self):
+        """(collectives issued, bytes of particle maps received)"""
+        s = np.zeros(2, np.uint64)
+        _chk(lib().lama_pf_shard_stats(self.h, _vp(s)))
+        return int(s[0]), int(s[1])
+
     # ---- split-phase calls used by iris_lama_b200.distributed ------------------------------------------
     def shardBegin(self, pts, odom, timestamp=0.0, origin=_ID3, quat=_IDQ):
         p, pp = _d(pts)
@@ -484,6 +526,14 @@ class Slam2D:
         _chk(lib().lama_slam_occupancy_query(self.h, cp, C.c_int(n), prob.ctypes.data_as(c_dp), _vp(flags)))
         return prob, flags
 
+    def correlateCandidateScan(self, pts, ref_xyr, cand_xyr, origin=_ID3, quat=_IDQ):
+        """GraphSlam2D::correlateCandidateScan (graph_slam2d.cpp:315-355) against this Slam2D's distance map -> (between xyr, rmse)"""
+        return _correlate(lib().lama_slam_correlate_candidate_scan, self.h, pts, ref_xyr, cand_xyr, origin, quat)
+
+    def coarseCorrelateCandidateScan(self, ref_pts, pts, ref_xyr, cand_xyr, origin=_ID3, quat=_IDQ):
+        """GraphSlam2D::coarseSearchAndCorrelateCandidateScan (graph_slam2d.cpp:357-392) -> (between xyr, rmse)"""
+        return _correlate(lib().lama_slam_coarse_correlate_candidate_scan, self.h, pts, ref_xyr, cand_xyr, origin, quat, ref_pts)
+
     def writeMap(self, kind, path):
         _chk(lib().lama_slam_write_map(self.h, C.c_int(kind), str(path).encode()))
 
@@ -587,6 +637,20 @@ class DynamicDistanceMap:
         _chk(lib().lama_dm_match_normal_equations(self.h, pp, C.c_int(p.size // 3), op, qp, sp, C.c_int(count), C.c_int(robust[0]),
                                                   C.c_double(robust[1]), C.c_double(meas_sigma), out.ctypes.data_as(c_dp)))
         return out
+
+    def matchError(self, pts, states, origin=_ID3, quat=_IDQ):
+        """MatchSurface2D::error (match_surface_2d.cpp:92-116) at `count` states"""
+        p, pp = _d(pts); o, op = _d(origin); q, qp = _d(quat); s, sp = _d(states)
+        count = s.size // 4
+        out = np.zeros(count)
+        _chk(lib().lama_dm_match_error(self.h, pp, C.c_int(p.size // 3), op, qp, sp, C.c_int(count), out.ctypes.data_as(c_dp)))
+        return out
+
+    def correlateCandidateScan(self, pts, ref_xyr, cand_xyr, origin=_ID3, quat=_IDQ):
+        return _correlate(lib().lama_dm_correlate_candidate_scan, self.h, pts, ref_xyr, cand_xyr, origin, quat)
+
+    def coarseCorrelateCandidateScan(self, ref_pts, pts, ref_xyr, cand_xyr, origin=_ID3, quat=_IDQ):
+        return _correlate(lib().lama_dm_coarse_correlate_candidate_scan, self.h, pts, ref_xyr, cand_xyr, origin, quat, ref_pts)
 
     def matchSolve(self, pts, states, strategy=0, robust=(1, 0.15), max_iter=100, origin=_ID3, quat=_IDQ):
         p, pp = _d(pts)

@@ -11,6 +11,7 @@
 // headers must come first.
 #include "frontend.h"
 #include "sdm_io.h"
+#include "shard_comm.h"
 
 #include "../../include/lama_b200.h"
 
@@ -530,6 +531,27 @@ try {
     return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
 }
 LAMA_CATCH
+int lama_shard_unique_id(uint8_t id[128])
+try {
+    if (!id) return set_err("null argument", LAMA_ERR_ARG);
+    std::string err;
+    return shard_unique_id(id, err) == 0 ? LAMA_OK : set_err(err, LAMA_ERR_CUDA);
+}
+LAMA_CATCH
+int lama_pf_shard_connect(lama_pf* h, const uint8_t id[128])
+try {
+    if (!h || !id) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = h->p->shard_connect(id);
+    return rc == LAMA_OK ? rc : set_err(h->p->error(), rc);
+}
+LAMA_CATCH
+int lama_pf_shard_stats(lama_pf* h, uint64_t out[2])
+try {
+    if (!h || !out) return set_err("null argument", LAMA_ERR_ARG);
+    h->p->shard_stats(out);
+    return LAMA_OK;
+}
+LAMA_CATCH
 int lama_pf_particle_pack_size(lama_pf* h, int slot, size_t* bytes)
 try {
     if (!h || !bytes || !h->p->engine()) return set_err("bad argument", LAMA_ERR_ARG);
@@ -886,6 +908,90 @@ try {
         if (sums) std::memcpy(sums + (size_t)i * kNumSums, res[i].sums, sizeof(double) * kNumSums);
     }
     return LAMA_OK;
+}
+LAMA_CATCH
+
+// ---- GraphSlam2D loop-closure front end (src/graph_slam2d.cpp:283-392) ---------------------------------------------------------------------
+namespace {
+int correlate_on(Engine* e, const DeviceOptions* coarse_dev, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat, const double* pts, int n,
+                 const double* origin, const double* quat, const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3], double* rmse)
+{
+    if (!e) return set_err("no map yet (update() has not been called)", LAMA_ERR_STATE);
+    if (!pts || n < 1 || !ref_xyr || !cand_xyr || !between_xyr || !rmse) return set_err("bad argument", LAMA_ERR_ARG);
+    const SE2 ref = se2_from_xyr(ref_xyr[0], ref_xyr[1], ref_xyr[2]), cand = se2_from_xyr(cand_xyr[0], cand_xyr[1], cand_xyr[2]);
+    SE2 between{1, 0, 0, 0};
+    int rc;
+    if (coarse_dev) {
+        if (!ref_pts || ref_n < 1) return set_err("bad argument", LAMA_ERR_ARG);
+        std::string err;
+        rc = coarse_correlate_candidate_scan(e, 0, *coarse_dev, ref_pts, ref_n, ref_origin, ref_quat, pts, n, origin, quat, ref, cand, &between, rmse, err);
+        if (rc != LAMA_OK) return set_err(err, rc);
+    } else {
+        rc = correlate_candidate_scan(e, 0, pts, n, origin, quat, ref, cand, &between, rmse);
+        if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    }
+    xyr_of(between, between_xyr);
+    return LAMA_OK;
+}
+}  // namespace
+int lama_loop_closure_candidates(const double* key_xy, int n_keys, int ignore_n_chain_poses, const double query_xy[2], double radius, int max_candidates, int* ids,
+                                 int* count)
+try {
+    if (!key_xy || !query_xy || !ids || !count || n_keys < 0 || max_candidates < 0) return set_err("bad argument", LAMA_ERR_ARG);
+    const std::vector<int> v = find_loop_closure_candidates(key_xy, n_keys, ignore_n_chain_poses, query_xy, radius, max_candidates);
+    std::copy(v.begin(), v.end(), ids);
+    *count = (int)v.size();
+    return LAMA_OK;
+}
+LAMA_CATCH
+int lama_slam_correlate_candidate_scan(lama_slam* h, const double* pts, int n, const double* origin, const double* quat, const double ref_xyr[3],
+                                       const double cand_xyr[3], double between_xyr[3], double* rmse)
+try {
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    return correlate_on(h->s->engine(), nullptr, nullptr, 0, nullptr, nullptr, pts, n, origin, quat, ref_xyr, cand_xyr, between_xyr, rmse);
+}
+LAMA_CATCH
+int lama_slam_coarse_correlate_candidate_scan(lama_slam* h, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat, const double* pts, int n,
+                                              const double* origin, const double* quat, const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3],
+                                              double* rmse)
+try {
+    if (!h) return set_err("null handle", LAMA_ERR_ARG);
+    const DeviceOptions dev = h->s->device_options();
+    return correlate_on(h->s->engine(), &dev, ref_pts, ref_n, ref_origin, ref_quat, pts, n, origin, quat, ref_xyr, cand_xyr, between_xyr, rmse);
+}
+LAMA_CATCH
+int lama_dm_correlate_candidate_scan(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, const double ref_xyr[3],
+                                     const double cand_xyr[3], double between_xyr[3], double* rmse)
+try {
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = dm->d->flush_if_pending();
+    if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
+    return correlate_on(dm->d->engine(), nullptr, nullptr, 0, nullptr, nullptr, pts, n, origin, quat, ref_xyr, cand_xyr, between_xyr, rmse);
+}
+LAMA_CATCH
+int lama_dm_coarse_correlate_candidate_scan(lama_dm* dm, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat, const double* pts, int n,
+                                            const double* origin, const double* quat, const double ref_xyr[3], const double cand_xyr[3], double between_xyr[3],
+                                            double* rmse)
+try {
+    if (!dm) return set_err("null handle", LAMA_ERR_ARG);
+    int rc = dm->d->flush_if_pending();
+    if (rc != LAMA_OK) return set_err(dm->d->error(), rc);
+    DeviceOptions dev;
+    dev.device = dm->d->engine()->config().device;
+    return correlate_on(dm->d->engine(), &dev, ref_pts, ref_n, ref_origin, ref_quat, pts, n, origin, quat, ref_xyr, cand_xyr, between_xyr, rmse);
+}
+LAMA_CATCH
+int lama_dm_match_error(lama_dm* dm, const double* pts, int n, const double* origin, const double* quat, const double* states, int count, double* rmse)
+try {
+    if (!dm || !pts || !states || !rmse || count < 1) return set_err("bad argument", LAMA_ERR_ARG);
+    Engine* e = dm->d->engine();
+    int rc = dm->d->flush_if_pending();
+    if (rc == LAMA_OK) rc = e->set_scan(pts, n, origin, quat, 0, 0);
+    if (rc != LAMA_OK) return set_err(e->last_error(), rc);
+    std::vector<SE2> st((size_t)count);
+    for (int i = 0; i < count; ++i) st[i] = SE2{states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+    rc = e->match_error(st.data(), count, 0, true, rmse);
+    return rc == LAMA_OK ? rc : set_err(e->last_error(), rc);
 }
 LAMA_CATCH
 

@@ -34,7 +34,7 @@ struct Engine::Impl {
     MapUpdateStats* h_stats = nullptr;  // pinned; two halves (ping-pong between consecutive map updates)
     uint64_t* h_report = nullptr;       // pinned; per half: {status, allocated, detached, freed, free slots}
     double* h_scan = nullptr;           // pinned staging of a host scan (step_async)
-    cudaEvent_t ev_match = nullptr;
+    cudaEvent_t ev_match = nullptr, ev_sync = nullptr;
     uint64_t* d_events = nullptr;
     int32_t* d_idx = nullptr;
     int32_t* h_idx = nullptr;  // pinned
@@ -50,6 +50,7 @@ struct Engine::Impl {
     // scratch for import/export/distance
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    std::vector<void*> mig_blocks;   // device arena of one migration round (pack_device / migration_alloc)
     std::vector<void*> allocs;
 };
 
@@ -244,6 +245,7 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     std::memset(d->h_report, 0, 2 * 8 * sizeof(uint64_t));
     CU_NEW(cudaMallocHost((void**)&d->h_scan, (size_t)cfg.max_beams * 24));
     CU_NEW(cudaEventCreateWithFlags(&d->ev_match, cudaEventDisableTiming));
+    CU_NEW(cudaEventCreateWithFlags(&d->ev_sync, cudaEventDisableTiming));
     CU_NEW(cudaMallocHost((void**)&d->h_idx, idx_ints * 4));
     CU_NEW(cudaMallocHost((void**)&d->h_status, 64));
 
@@ -273,6 +275,8 @@ Engine::~Engine()
     if (d_->h_report) cudaFreeHost(d_->h_report);
     if (d_->h_scan) cudaFreeHost(d_->h_scan);
     if (d_->ev_match) cudaEventDestroy(d_->ev_match);
+    if (d_->ev_sync) cudaEventDestroy(d_->ev_sync);
+    for (void* p : d_->mig_blocks) cudaFree(p);
     if (d_->h_idx) cudaFreeHost(d_->h_idx);
     if (d_->h_status) cudaFreeHost(d_->h_status);
     if (d_->d_scratch) cudaFree(d_->d_scratch);
@@ -436,6 +440,25 @@ int Engine::match(const SE2* states, int count, int first_particle, bool shared_
     return LAMA_OK;
 }
 
+int Engine::match_error(const SE2* states, int count, int first_particle, bool shared_map, double* out)
+{
+    { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
+    if (count < 1 || first_particle < 0 || (!shared_map && first_particle + count > cfg_.particles) || first_particle >= cfg_.particles)
+        return fail("match_error: particle range out of bounds", LAMA_ERR_ARG);
+    if (d_->scan.n_beams < 1) return fail("match_error: no scan uploaded", LAMA_ERR_STATE);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
+    std::memcpy(d_->h_states, states, (size_t)count * sizeof(SE2));
+    CU_TRY(cudaMemcpyAsync(d_->d_states, d_->h_states, (size_t)count * sizeof(SE2), cudaMemcpyHostToDevice, d_->stream));
+    double* d_out = reinterpret_cast<double*>(d_->d_results);   // count doubles fit in count MatchResults
+    launch_match_error(d_->view, cur_set_, first_particle, shared_map, d_->d_points, d_->scan, d_->d_states, count, cfg_.resolution, max_sqdist_, d_out, d_->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)count * 8, cudaMemcpyDeviceToHost, d_->stream));
+    CU_TRY(cudaStreamSynchronize(d_->stream));
+    times_.misc_launches += 1;
+    return LAMA_OK;
+}
+
 int Engine::update_maps(const SE2* states, int first_particle, int count, HostMapStats* out)
 {
     int rc = update_maps_async(states, first_particle, count);
@@ -500,16 +523,17 @@ int Engine::enqueue_report(int count)
     return LAMA_OK;
 }
 
-int Engine::step_async(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
-                       const SE2* predicted, int count, const SolverOptions& so, double meas_sigma, HostMatchResult* out)
+int Engine::step_enqueue(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
+                         const SE2* predicted, int count, const SolverOptions& so, double meas_sigma)
 {
-    if (count < 1 || count > cfg_.particles) return fail("step_async: particle range out of bounds", LAMA_ERR_ARG);
+    if (count < 1 || count > cfg_.particles) return fail("step_enqueue: particle range out of bounds", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     // the previous scan's map update may still be running: nothing below waits for it on the host
-    const bool had_pending = pending_maps_ != 0;
-    const int prev_count = pending_maps_, prev_buf = pending_buf_;
+    enq_had_pending_ = pending_maps_ != 0;
+    enq_prev_count_  = pending_maps_;
+    enq_prev_buf_    = pending_buf_;
     if (pts) {
-        if (n < 1 || n > cfg_.max_beams) return fail("step_async: number of beams out of range", LAMA_ERR_ARG);
+        if (n < 1 || n > cfg_.max_beams) return fail("step_enqueue: number of beams out of range", LAMA_ERR_ARG);
         set_moving(origin, quat, truncated_ray, truncated_range, n);
         std::memcpy(d_->h_scan, pts, (size_t)n * 24);   // free again: the previous call returned after its match, which follows its upload
         d_->d_points = d_->d_scan_buf;
@@ -517,7 +541,7 @@ int Engine::step_async(const double* pts, int n, const double origin[3], const d
         CU_TRY(cudaMemcpyAsync(d_->d_points, d_->h_scan, (size_t)n * 24, cudaMemcpyHostToDevice, d_->stream));
         h2d_bytes_ += (uint64_t)n * 24;
     }
-    if (d_->scan.n_beams < 1) return fail("step_async: no scan selected", LAMA_ERR_STATE);
+    if (d_->scan.n_beams < 1) return fail("step_enqueue: no scan selected", LAMA_ERR_STATE);
     { int rc = ensure_states(count); if (rc != LAMA_OK) return rc; }
     std::memcpy(d_->h_states, predicted, (size_t)count * sizeof(SE2));
     CU_TRY(cudaMemcpyAsync(d_->d_states, d_->h_states, (size_t)count * sizeof(SE2), cudaMemcpyHostToDevice, d_->stream));
@@ -560,19 +584,50 @@ int Engine::step_async(const double* pts, int n, const double origin[3], const d
     times_.misc_launches += 1;
     h2d_bytes_ += (uint64_t)count * sizeof(SE2);
     d2h_bytes_ += (uint64_t)count * sizeof(MatchResult);
+    return LAMA_OK;
+}
+
+int Engine::collect_previous()
+{
+    // everything enqueued before this scan's match has completed: collect the previous map update without waiting
+    if (!enq_had_pending_) return LAMA_OK;
+    enq_had_pending_ = false;
+    const int cur_count = pending_maps_, cur_buf = pending_buf_;
+    pending_maps_ = enq_prev_count_;
+    pending_buf_  = enq_prev_buf_;
+    const int rc = settle(nullptr, true);
+    pending_maps_ = cur_count;
+    pending_buf_  = cur_buf;
+    return rc;
+}
+
+int Engine::step_async(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
+                       const SE2* predicted, int count, const SolverOptions& so, double meas_sigma, HostMatchResult* out)
+{
+    { int rc = step_enqueue(pts, n, origin, quat, truncated_ray, truncated_range, predicted, count, so, meas_sigma); if (rc != LAMA_OK) return rc; }
     CU_TRY(cudaEventSynchronize(d_->ev_match));
     static_assert(sizeof(HostMatchResult) == sizeof(MatchResult), "layout");
     std::memcpy(out, d_->h_results, (size_t)count * sizeof(MatchResult));
-    // everything enqueued before this scan's match has completed: collect the previous map update without waiting
-    if (had_pending) {
-        const int cur_count = pending_maps_, cur_buf = pending_buf_;
-        pending_maps_ = prev_count;
-        pending_buf_  = prev_buf;
-        const int rc = settle(nullptr, true);
-        pending_maps_ = cur_count;
-        pending_buf_  = cur_buf;
-        if (rc != LAMA_OK) return rc;
-    }
+    return collect_previous();
+}
+
+void* Engine::stream_handle() const { return d_->stream; }
+
+int Engine::wait_for_stream(void* other_stream)
+{
+    CU_TRY(cudaSetDevice(cfg_.device));
+    CU_TRY(cudaEventRecord(d_->ev_sync, d_->stream));
+    CU_TRY(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(other_stream), d_->ev_sync, 0));
+    return LAMA_OK;
+}
+
+int Engine::pack_results(int count, double digest, double* d_out, void* stream)
+{
+    CU_TRY(cudaSetDevice(cfg_.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CU_TRY(cudaStreamWaitEvent(st, d_->ev_match, 0));
+    launch_pack_results(d_->d_results, count, digest, d_out, st);
+    CU_TRY(cudaGetLastError());
     return LAMA_OK;
 }
 
@@ -828,7 +883,25 @@ int Engine::pack_size(int particle, size_t* bytes)
     return LAMA_OK;
 }
 
-int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
+int Engine::migration_alloc(size_t bytes, void** dptr)
+{
+    CU_TRY(cudaSetDevice(cfg_.device));
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+    d_->mig_blocks.push_back(p);
+    *dptr = p;
+    return LAMA_OK;
+}
+void Engine::migration_reset()
+{
+    cudaSetDevice(cfg_.device);
+    cudaStreamSynchronize(d_->stream);
+    for (void* p : d_->mig_blocks) cudaFree(p);
+    d_->mig_blocks.clear();
+}
+
+// blob = n x u32 directory index (occupancy entries first) + n patches (4 KiB) + n x 128 B obstacle-mirror bits, all on the device
+int Engine::pack_device(int particle, DeviceBlob* out)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     if (particle < 0 || particle >= cfg_.particles) return fail("pack: bad particle", LAMA_ERR_ARG);
@@ -847,59 +920,88 @@ int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
                 slots.push_back(dir[kind * dim2 + e]);
                 ++n_kind[kind];
             }
-    const size_t n = slots.size(), need = 16 + n * 4 + n * (size_t)(kPatchBytes + 128);
-    if (need > cap) return fail("pack: buffer too small", LAMA_ERR_ARG);
-    uint32_t* hdr = (uint32_t*)buf;
-    // the directory indices in the buffer only mean the same cells on a device with the same window: dim and base travel along
-    hdr[0] = kPackMagic; hdr[1] = (uint32_t)cfg_.dir_dim | ((uint32_t)(window_.base_px & 0xFFF) << 8) | ((uint32_t)(window_.base_py & 0xFFF) << 20);
-    hdr[2] = n_kind[0]; hdr[3] = n_kind[1];
-    std::memcpy(hdr + 4, entries.data(), n * 4);
+    const size_t n = slots.size();
+    out->n_occ = n_kind[0];
+    out->n_dm  = n_kind[1];
+    out->bytes = n * 4 + n * (size_t)(kPatchBytes + 128);
+    { int rc = migration_alloc(out->bytes + n * 4, &out->dptr); if (rc != LAMA_OK) return rc; }
     if (n) {
-        if (ensure_scratch(d_, n * 4 + n * (size_t)(kPatchBytes + 128))) return fail("pack: out of device memory", LAMA_ERR_CUDA);
-        char* base = (char*)d_->d_scratch;
-        uint32_t* d_out = (uint32_t*)base;                                     // n patches, then n x 32 obstacle-mirror words
-        uint32_t* d_fb  = (uint32_t*)(base + n * (size_t)kPatchBytes);
-        int32_t* d_slots = (int32_t*)(base + n * (size_t)(kPatchBytes + 128));
+        char* base = (char*)out->dptr;
+        uint32_t* d_out  = (uint32_t*)(base + n * 4);                                  // n patches, then n x 32 obstacle-mirror words
+        uint32_t* d_fb   = (uint32_t*)(base + n * 4 + n * (size_t)kPatchBytes);
+        int32_t* d_slots = (int32_t*)(base + out->bytes);                              // scratch behind the blob
+        CU_TRY(cudaMemcpyAsync(base, entries.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
         CU_TRY(cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
         launch_gather_patches(d_->view, d_slots, (int)n, d_out, d_fb, d_->stream);
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync((char*)buf + 16 + n * 4, d_out, n * (size_t)(kPatchBytes + 128), cudaMemcpyDeviceToHost, d_->stream));
-        CU_TRY(cudaStreamSynchronize(d_->stream));
+        CU_TRY(cudaStreamSynchronize(d_->stream));   // `entries` / `slots` are host temporaries
         times_.misc_launches += 1;
     }
-    *used = need;
     return LAMA_OK;
 }
 
-int Engine::unpack(int particle, const void* buf, size_t bytes)
+int Engine::unpack_device(int particle, const DeviceBlob& blob)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
-    if (particle < 0 || particle >= cfg_.particles || bytes < 16) return fail("unpack: bad arguments", LAMA_ERR_ARG);
-    const uint32_t* hdr = (const uint32_t*)buf;
-    if (hdr[0] != kPackMagic || hdr[1] != ((uint32_t)cfg_.dir_dim | ((uint32_t)(window_.base_px & 0xFFF) << 8) | ((uint32_t)(window_.base_py & 0xFFF) << 20)))
-        return fail("unpack: incompatible buffer (directory window differs)", LAMA_ERR_ARG);
-    const size_t n_occ = hdr[2], n_dm = hdr[3], n = n_occ + n_dm;
-    if (bytes < 16 + n * 4 + n * (size_t)(kPatchBytes + 128)) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
+    const size_t n = (size_t)blob.n_occ + blob.n_dm;
+    if (particle < 0 || particle >= cfg_.particles || blob.bytes < n * 4 + n * (size_t)(kPatchBytes + 128)) return fail("unpack: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     launch_release(d_->view, cur_set_, particle, 1, d_->stream);
     launch_merge_free(d_->view, d_->stream);
     if (n) {
-        if (ensure_scratch(d_, n * 4 + n * (size_t)(kPatchBytes + 128))) return fail("unpack: out of device memory", LAMA_ERR_CUDA);
-        char* base = (char*)d_->d_scratch;
-        uint32_t* d_in = (uint32_t*)base;
-        uint32_t* d_fb = (uint32_t*)(base + n * (size_t)kPatchBytes);
-        int32_t* d_entries = (int32_t*)(base + n * (size_t)(kPatchBytes + 128));
-        CU_TRY(cudaMemcpyAsync(d_entries, hdr + 4, n * 4, cudaMemcpyHostToDevice, d_->stream));
-        CU_TRY(cudaMemcpyAsync(d_in, (const char*)buf + 16 + n * 4, n * (size_t)(kPatchBytes + 128), cudaMemcpyHostToDevice, d_->stream));
-        launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)n_occ, d_in, d_fb, d_->stream);
-        launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + n_occ, (int)n_dm, d_in + n_occ * (size_t)kPatchCells, d_fb + n_occ * 32,
-                               d_->stream);
+        const char* base = (const char*)blob.dptr;
+        const int32_t* d_entries = (const int32_t*)base;
+        const uint32_t* d_in = (const uint32_t*)(base + n * 4);
+        const uint32_t* d_fb = (const uint32_t*)(base + n * 4 + n * (size_t)kPatchBytes);
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)blob.n_occ, d_in, d_fb, d_->stream);
+        launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + blob.n_occ, (int)blob.n_dm, d_in + blob.n_occ * (size_t)kPatchCells,
+                               d_fb + blob.n_occ * 32, d_->stream);
         times_.misc_launches += 2;
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));
     return check_device_status();
+}
+
+static uint32_t pack_window_word(int dir_dim, const DirWindow& w) { return (uint32_t)dir_dim | ((uint32_t)(w.base_px & 0xFFF) << 8) | ((uint32_t)(w.base_py & 0xFFF) << 20); }
+
+// host form: {u32 magic, u32 dim + window base, u32 n_occ, u32 n_dm} + the device blob
+int Engine::pack(int particle, void* buf, size_t cap, size_t* used)
+{
+    DeviceBlob blob;
+    { int rc = pack_device(particle, &blob); if (rc != LAMA_OK) return rc; }
+    const size_t need = 16 + blob.bytes;
+    if (need > cap) { migration_reset(); return fail("pack: buffer too small", LAMA_ERR_ARG); }
+    uint32_t* hdr = (uint32_t*)buf;
+    // the directory indices in the buffer only mean the same cells on a device with the same window: dim and base travel along
+    hdr[0] = kPackMagic; hdr[1] = pack_window_word(cfg_.dir_dim, window_); hdr[2] = blob.n_occ; hdr[3] = blob.n_dm;
+    if (blob.bytes) {
+        CU_TRY(cudaMemcpyAsync((char*)buf + 16, blob.dptr, blob.bytes, cudaMemcpyDeviceToHost, d_->stream));
+        CU_TRY(cudaStreamSynchronize(d_->stream));
+    }
+    migration_reset();
+    *used = need;
+    return LAMA_OK;
+}
+
+int Engine::unpack(int particle, const void* buf, size_t bytes)
+{
+    if (particle < 0 || particle >= cfg_.particles || bytes < 16) return fail("unpack: bad arguments", LAMA_ERR_ARG);
+    const uint32_t* hdr = (const uint32_t*)buf;
+    if (hdr[0] != kPackMagic || hdr[1] != pack_window_word(cfg_.dir_dim, window_)) return fail("unpack: incompatible buffer (directory window differs)", LAMA_ERR_ARG);
+    DeviceBlob blob;
+    blob.n_occ = hdr[2];
+    blob.n_dm  = hdr[3];
+    const size_t n = (size_t)blob.n_occ + blob.n_dm;
+    blob.bytes = n * 4 + n * (size_t)(kPatchBytes + 128);
+    if (bytes < 16 + blob.bytes) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
+    CU_TRY(cudaSetDevice(cfg_.device));
+    { int rc = migration_alloc(blob.bytes, &blob.dptr); if (rc != LAMA_OK) return rc; }
+    if (blob.bytes) CU_TRY(cudaMemcpyAsync(blob.dptr, (const char*)buf + 16, blob.bytes, cudaMemcpyHostToDevice, d_->stream));
+    const int rc = unpack_device(particle, blob);
+    migration_reset();
+    return rc;
 }
 
 double Engine::logodds_threshold() const { return d_->ray.prob.thresh; }

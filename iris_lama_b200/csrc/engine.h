@@ -69,6 +69,9 @@ public:
     int match(const SE2* states, int count, int first_particle, bool shared_map, const SolverOptions& so, double meas_sigma, int mode,
               HostMatchResult* out);
 
+    // MatchSurface2D::error() (nearest-cell RMSE of the current scan) at `count` states, maps chosen like match().
+    int match_error(const SE2* states, int count, int first_particle, bool shared_map, double* out);
+
     // Ray-cast + distance-map update of particles [first, first+count) at the given poses.
     int update_maps(const SE2* states, int first_particle, int count, HostMapStats* out);
     // Same, but returns right after the launches; the work is collected by settle(), which every later entry point
@@ -82,6 +85,14 @@ public:
     // update keeps running and is collected by the next settle().  `pts` != nullptr: upload that scan first (no synchronisation).
     int step_async(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
                    const SE2* predicted, int count, const SolverOptions& so, double meas_sigma, HostMatchResult* out);
+    // The same without waiting for anything (sharded ranks): the match results stay on the device, where pack_results() turns them into
+    // the exchange payload on another stream once the match has finished; collect_previous() then books the previous scan's map update.
+    int step_enqueue(const double* pts, int n, const double origin[3], const double quat[4], double truncated_ray, double truncated_range,
+                     const SE2* predicted, int count, const SolverOptions& so, double meas_sigma);
+    int pack_results(int count, double digest, double* d_out, void* stream);   // `stream` (cudaStream_t) first waits for the match
+    int collect_previous();                                                     // call after the match is known to have completed
+    void* stream_handle() const;                                                // cudaStream_t of the engine
+    int wait_for_stream(void* other_stream);                                    // `other_stream` waits for everything enqueued on the engine's stream so far
     bool map_update_pending() const { return pending_maps_ != 0; }
     const uint64_t* settled_store_counters() const { return settled_counters_; }   // {allocated, detached, freed, free slots} at the last settle
     const std::vector<HostMapStats>& last_map_stats() const { return last_map_stats_; }
@@ -93,6 +104,13 @@ public:
     int resample(const int32_t* idx);
     // Serialise / restore the two maps of one resident slot (particle migration between GPUs).
     // Layout: {u32 magic, u32 dim, u32 n_occ, u32 n_dm} + n x u32 directory index + n patches (4 KiB) + n x 128 B obstacle-mirror bits.
+    // Device-side form (NCCL send / recv between GPUs): the blob = n x u32 directory index + n patches + n x 128 B mirror bits stays in a
+    // device arena owned by the engine (valid until migration_reset()); counts = {occupancy patches, distance patches}.
+    struct DeviceBlob { void* dptr = nullptr; size_t bytes = 0; uint32_t n_occ = 0, n_dm = 0; };
+    int pack_device(int particle, DeviceBlob* out);
+    int migration_alloc(size_t bytes, void** dptr);           // receive buffer in the same arena
+    int unpack_device(int particle, const DeviceBlob& blob);
+    void migration_reset();
     int pack_size(int particle, size_t* bytes);
     int pack(int particle, void* buf, size_t cap, size_t* used);
     int unpack(int particle, const void* buf, size_t bytes);
@@ -148,6 +166,8 @@ private:
     int pending_buf_ = 0;                 // which half of the ping-pong host buffers the pending map update reports into
     uint64_t settled_counters_[4] = {0, 0, 0, 0};
     std::vector<HostMapStats> last_map_stats_;
+    bool enq_had_pending_ = false;        // step_enqueue: the previous scan's map update still has to be booked (collect_previous)
+    int enq_prev_count_ = 0, enq_prev_buf_ = 0;
     void set_moving(const double origin[3], const double quat[4], double truncated_ray, double truncated_range, int n);
     int enqueue_report(int count);
     int fail(const std::string& what, int code);

@@ -1,6 +1,10 @@
 // frontend.cpp -- host orchestration of PFSlam2D / Slam2D / Loc2D over the device Engine.
 #include "frontend.h"
 
+#include <cuda_runtime.h>
+
+#include "shard_comm.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -75,7 +79,17 @@ PFSlam2D* PFSlam2D::create(const PFOptions& o, std::string& err)
     p->node_of_.assign(p->P_, -1);
     return p;
 }
-PFSlam2D::~PFSlam2D() = default;
+PFSlam2D::~PFSlam2D()
+{
+    if (comm_) {
+        shard_comm_destroy(comm_);
+        cudaFree(d_send_);
+        cudaFree(d_recv_);
+        cudaFree(d_tab_);
+        cudaFreeHost(h_recv_);
+        cudaFreeHost(h_tab_);
+    }
+}
 
 double PFSlam2D::rng_normal(double sigma)  // random::normal, src/random.cpp:69-73
 {
@@ -366,9 +380,197 @@ void PFSlam2D::collect_map_stats(Counters& c)
     detached_seen_ = sc[1];
 }
 
+// ---- sharded update over NCCL ---------------------------------------------------------------------------------------------------
+constexpr int kShardF = 7;   // kernels.cuh kShardFields: state (4), likelihood, reference evaluations, iterations
+
+int PFSlam2D::shard_connect(const uint8_t id[128])
+{
+    if (opt_.shard_count < 2) return fail("shard_connect: the handle was created with shard_count 1", LAMA_ERR_STATE);
+    if (comm_) return fail("shard_connect: already connected", LAMA_ERR_STATE);
+    std::string e;
+    comm_ = shard_comm_create(id, (int)opt_.shard_rank, (int)opt_.shard_count, opt_.dev.device, e);
+    if (!comm_) return fail(e, LAMA_ERR_CUDA);
+    const size_t per = (size_t)(hi_ - lo_), payload = per * kShardF + 1;
+    bool ok = cudaMalloc((void**)&d_send_, payload * 8) == cudaSuccess && cudaMalloc((void**)&d_recv_, payload * 8 * opt_.shard_count) == cudaSuccess &&
+              cudaMallocHost((void**)&h_recv_, payload * 8 * opt_.shard_count) == cudaSuccess && cudaMalloc((void**)&d_tab_, (size_t)P_ * 3 * 8 * 2) == cudaSuccess &&
+              cudaMallocHost((void**)&h_tab_, (size_t)P_ * 3 * 8 * 2) == cudaSuccess;
+    if (!ok) return fail("shard_connect: out of memory", LAMA_ERR_CUDA);
+    return LAMA_OK;
+}
+
+// One sharded step, the same on every rank (src/pf_slam2d.cpp:178-312 with the two fan-outs :254-266,:292-302 running on this rank's
+// particles only).  Every rank draws the odometry noise of ALL particles (identical generators), enqueues match + map update of its
+// shard, and all-gathers {state, likelihood, counts} of the local particles plus a digest of its previous resampling decision -- one
+// collective per scan.  Normalise / resample then run on identical bytes with identical generator states on every rank.
+int PFSlam2D::update_sharded(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update)
+{
+    *did_update = false;
+    if (!has_first_) {   // first scan: every rank builds its own copy from the prior, nothing to exchange (pf_slam2d.cpp:185-228)
+        std::vector<double> dummy((size_t)(hi_ - lo_) * 5);
+        return shard_begin(pts, n, origin, quat, odom_xyr, 0.0, did_update, dummy.data());
+    }
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
+    const bool moved = predict_and_gate(odom_xyr);
+    const auto t1 = clk::now();
+    t_sample_ += ms(t0, t1);
+    if (!moved) {
+        int rcs = settle_counters();
+        last_ = Counters();
+        last_idx_.clear();
+        staged_index_ = -1;
+        return rcs;
+    }
+    *did_update = true;
+    Counters prev = last_;
+    const bool prev_pending = counters_pending_;
+    counters_pending_ = false;
+    last_ = Counters();
+    last_idx_.clear();
+    const int staged = staged_index_;
+    staged_index_ = -1;
+    int rc = LAMA_OK;
+    if (staged >= 0) {
+        rc = eng_->select_staged(staged, origin, quat, opt_.truncated_ray, opt_.truncated_range);
+        if (rc != LAMA_OK) return engine_fail(rc);
+    }
+    const int nl = hi_ - lo_, G = (int)opt_.shard_count;
+    rc = eng_->step_enqueue(staged >= 0 ? nullptr : pts, n, origin, quat, opt_.truncated_ray, opt_.truncated_range, &pose_[lo_], nl, make_solver(0, opt_.max_iter),
+                            opt_.meas_sigma);
+    if (rc != LAMA_OK) return engine_fail(rc);
+    const size_t payload = (size_t)nl * kShardF + 1;
+    rc = eng_->pack_results(nl, digest_, d_send_, shard_stream(comm_));   // waits for the match on the communicator's stream
+    if (rc != LAMA_OK) return engine_fail(rc);
+    if (shard_allgather(comm_, d_send_, d_recv_, payload * 8) != 0) return fail(shard_error(comm_), LAMA_ERR_CUDA);
+    if (cudaMemcpyAsync(h_recv_, d_recv_, payload * 8 * G, cudaMemcpyDeviceToHost, (cudaStream_t)shard_stream(comm_)) != cudaSuccess)
+        return fail("update_sharded: copy of the gathered results failed", LAMA_ERR_CUDA);
+    if (shard_sync(comm_) != 0) return fail(shard_error(comm_), LAMA_ERR_CUDA);
+    ++shard_collectives_;
+    rc = eng_->collect_previous();   // the previous scan's map update precedes this scan's match in the engine's stream
+    if (prev_pending) {
+        collect_map_stats(prev);
+        total_.add(prev);
+    }
+    if (rc != LAMA_OK) return engine_fail(rc);
+    const auto t2 = clk::now();
+    t_solve_ += ms(t1, t2);
+    std::vector<double> all((size_t)P_ * 5);
+    for (int r = 0; r < G; ++r) {
+        const double* src = h_recv_ + (size_t)r * payload;
+        if (src[(size_t)nl * kShardF] != h_recv_[(size_t)nl * kShardF]) return fail("the resampling decision diverged between ranks", LAMA_ERR_STATE);
+        for (int k = 0; k < nl; ++k) {
+            const double* f = src + (size_t)k * kShardF;
+            double* dst = &all[((size_t)r * nl + k) * 5];
+            dst[0] = f[0]; dst[1] = f[1]; dst[2] = f[2]; dst[3] = f[3]; dst[4] = f[4];
+            last_.evals += (uint64_t)f[5] + 1;   // + the likelihood pass
+            last_.gn_iters += (uint64_t)f[6];
+        }
+    }
+    absorb_results(all.data());
+    normalize();
+    const auto t3 = clk::now();
+    t_norm_ += ms(t2, t3);
+    std::vector<int32_t> v;
+    const bool res = compute_resample(v);
+    digest_ = 0.0;
+    if (res) {
+        uint64_t acc = 1;
+        for (uint32_t i = 0; i < P_; ++i) acc = (acc + (uint64_t)(uint32_t)v[i] * (uint64_t)(i + 1)) % 9007199254740881ull;
+        digest_ = (double)acc;
+        rc = migrate_and_apply(v);
+        if (rc != LAMA_OK) return rc;
+        last_.resampled = 1;
+    }
+    t_resample_ += ms(t3, clk::now());
+    counters_pending_ = !res;   // this scan's map update is still running; after a resampling it has been waited for and booked already
+    return LAMA_OK;
+}
+
+// Resampling across ranks: the offspring of a remote ancestor need its (already updated) maps.  Who needs what follows from the
+// indices alone, which every rank holds; only the blob sizes are exchanged first (one small all-gather), then all blobs move in one
+// grouped NCCL send / recv between device arenas.
+int PFSlam2D::migrate_and_apply(const std::vector<int32_t>& idx)
+{
+    const int G = (int)opt_.shard_count, per = hi_ - lo_, me = (int)opt_.shard_rank;
+    // need[r]: sorted unique remote ancestors of rank r's new particles; serve: (destination, ancestor) pairs this rank sends
+    std::vector<std::vector<int>> need((size_t)G);
+    for (int r = 0; r < G; ++r) {
+        std::vector<int> a(idx.begin() + (size_t)r * per, idx.begin() + (size_t)(r + 1) * per);
+        std::sort(a.begin(), a.end());
+        a.erase(std::unique(a.begin(), a.end()), a.end());
+        for (int g : a)
+            if (g / per != r) need[(size_t)r].push_back(g);
+    }
+    std::vector<std::pair<int, int>> serve;
+    for (int r = 0; r < G; ++r)
+        for (int g : need[(size_t)r])
+            if (g / per == me) serve.push_back({r, g});
+    // pack every local particle somebody needs (once), after this scan's map update has finished (pack_device settles)
+    std::vector<Engine::DeviceBlob> blob((size_t)per);
+    std::vector<int64_t> mine((size_t)per * 3, 0);
+    for (const auto& sv : serve) {
+        const int k = sv.second - lo_;
+        if (blob[(size_t)k].dptr) continue;
+        int rc = eng_->pack_device(k, &blob[(size_t)k]);
+        if (rc != LAMA_OK) return engine_fail(rc);
+        mine[(size_t)k * 3] = (int64_t)blob[(size_t)k].bytes; mine[(size_t)k * 3 + 1] = blob[(size_t)k].n_occ; mine[(size_t)k * 3 + 2] = blob[(size_t)k].n_dm;
+    }
+    cudaStream_t cs = (cudaStream_t)shard_stream(comm_);
+    std::memcpy(h_tab_, mine.data(), mine.size() * 8);
+    int64_t* d_all = d_tab_ + (size_t)P_ * 3;
+    int64_t* h_all = h_tab_ + (size_t)P_ * 3;
+    if (cudaMemcpyAsync(d_tab_, h_tab_, mine.size() * 8, cudaMemcpyHostToDevice, cs) != cudaSuccess) return fail("migrate: size table upload failed", LAMA_ERR_CUDA);
+    if (shard_allgather(comm_, d_tab_, d_all, mine.size() * 8) != 0) return fail(shard_error(comm_), LAMA_ERR_CUDA);
+    if (cudaMemcpyAsync(h_all, d_all, (size_t)P_ * 3 * 8, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail("migrate: size table download failed", LAMA_ERR_CUDA);
+    if (shard_sync(comm_) != 0) return fail(shard_error(comm_), LAMA_ERR_CUDA);
+    ++shard_collectives_;
+    std::vector<ShardXfer> sends, recvs;
+    for (const auto& sv : serve) {
+        const Engine::DeviceBlob& b = blob[(size_t)(sv.second - lo_)];
+        if (b.bytes) sends.push_back({sv.first, b.dptr, b.bytes});
+    }
+    std::vector<Engine::DeviceBlob> in(need[(size_t)me].size());
+    for (size_t k = 0; k < in.size(); ++k) {
+        const int g = need[(size_t)me][k];
+        in[k].bytes = (size_t)h_all[(size_t)g * 3]; in[k].n_occ = (uint32_t)h_all[(size_t)g * 3 + 1]; in[k].n_dm = (uint32_t)h_all[(size_t)g * 3 + 2];
+        int rc = eng_->migration_alloc(in[k].bytes, &in[k].dptr);
+        if (rc != LAMA_OK) return engine_fail(rc);
+        if (in[k].bytes) recvs.push_back({g / per, in[k].dptr, in[k].bytes});
+        shard_migrated_bytes_ += in[k].bytes;
+    }
+    if (shard_exchange(comm_, sends, recvs) != 0 || shard_sync(comm_) != 0) return fail(shard_error(comm_), LAMA_ERR_CUDA);
+    if (!sends.empty() || !recvs.empty()) ++shard_collectives_;
+    std::vector<int32_t> local_src((size_t)per);
+    for (size_t k = 0; k < in.size(); ++k) {
+        int rc = eng_->unpack_device(per + (int)k, in[k]);   // staging slots behind the local particles
+        if (rc != LAMA_OK) return engine_fail(rc);
+    }
+    for (int k = 0; k < per; ++k) {
+        const int g = idx[(size_t)lo_ + k];
+        if (g / per == me) local_src[(size_t)k] = g - lo_;
+        else local_src[(size_t)k] = per + (int)(std::lower_bound(need[(size_t)me].begin(), need[(size_t)me].end(), g) - need[(size_t)me].begin());
+    }
+    eng_->migration_reset();
+    pending_maps_ = true;   // shard_apply's precondition
+    int rc = shard_apply(idx.data(), local_src.data());
+    pending_maps_ = false;
+    if (rc != LAMA_OK) return rc;
+    // resample() waited for the map update and collected it
+    collect_map_stats(last_);
+    total_.add(last_);
+    return LAMA_OK;
+}
+
 int PFSlam2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update)
 {
-    if (opt_.shard_count != 1) return fail("PFSlam2D::update on a sharded handle: use the shard_* calls", LAMA_ERR_STATE);
+    if (opt_.shard_count != 1) {
+        if (!comm_) return fail("PFSlam2D::update on a sharded handle: connect the ranks first (lama_pf_shard_connect) or use the split-phase shard_* calls", LAMA_ERR_STATE);
+        bool did = false;
+        int rc = update_sharded(pts, n, origin, quat, odom_xyr, &did);
+        if (did_update) *did_update = did;
+        return rc;
+    }
     if (has_first_ && eng_ && opt_.dev.timing == 0) {
         bool did = false;
         int rc = update_pipelined(pts, n, origin, quat, odom_xyr, &did);
@@ -542,6 +744,97 @@ std::vector<SE2> PFSlam2D::trajectory(int particle) const
     for (int n = node_of_[particle]; n >= 0; n = nodes_[n].parent) out.push_back(nodes_[n].pose);
     std::reverse(out.begin(), out.end());
     return out;
+}
+
+// =====================================================================================================
+// GraphSlam2D loop-closure front end (src/graph_slam2d.cpp:283-392)
+// =====================================================================================================
+std::vector<int> find_loop_closure_candidates(const double* key_xy, int n_keys, int ignore_n, const double query[2], double radius, int max_candidates)
+{
+    std::vector<std::pair<double, int>> hits;
+    const int n = n_keys - ignore_n;   // KeyPosesNanoFlannAdaptor::kdtree_get_point_count (:73)
+    for (int i = 0; i < n; ++i) {
+        const double dx = key_xy[2 * i] - query[0], dy = key_xy[2 * i + 1] - query[1];
+        const double d2 = dx * dx + dy * dy;   // L2_Simple_Adaptor: squared distance; radiusSearch keeps d2 < radius^2 (:296)
+        if (d2 < radius * radius) hits.push_back({d2, i});
+    }
+    std::sort(hits.begin(), hits.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });   // IndexDist_Sorter
+    if ((int)hits.size() > max_candidates) hits.resize((size_t)max_candidates);                                                               // :298-301
+    std::vector<int> out;
+    for (const auto& h : hits) out.push_back(h.second);
+    return out;
+}
+
+static SolverOptions huber_solver(uint32_t max_iter)
+{
+    SolverOptions so = make_solver(0, max_iter);   // GaussNewton (:324)
+    so.robust_kind  = kRobustHuber;                // HuberWeight(0.15) (:325)
+    so.robust_param = 0.15;
+    return so;
+}
+
+int correlate_candidate_scan(Engine* e, int particle, const double* pts, int n, const double* origin, const double* quat, const SE2& ref_pose, const SE2& cand_pose,
+                             SE2* between, double* rmse)
+{
+    int rc = e->set_scan(pts, n, origin, quat, 0, 0);
+    if (rc != LAMA_OK) return rc;
+    // the two starts (:328-329): the candidate's own pose, and the reference position with the candidate's heading
+    SE2 st[2] = {cand_pose, se2_from_xyr(ref_pose.tx, ref_pose.ty, se2_rotation(cand_pose))};
+    HostMatchResult res[2];
+    rc = e->match(st, 2, particle, true, huber_solver(1), 0.05, 0, res);   // one iteration each (:326, :334-339)
+    if (rc != LAMA_OK) return rc;
+    SE2 after[2] = {res[0].state, res[1].state};
+    double err2[2];
+    rc = e->match_error(after, 2, particle, true, err2);
+    if (rc != LAMA_OK) return rc;
+    const int pick = err2[0] < err2[1] ? 0 : 1;                            // :342-345
+    HostMatchResult fin;
+    rc = e->match(&after[pick], 1, particle, true, huber_solver(100), 0.05, 0, &fin);   // :348-349
+    if (rc != LAMA_OK) return rc;
+    rc = e->match_error(&fin.state, 1, particle, true, rmse);
+    if (rc != LAMA_OK) return rc;
+    *between = se2_mul(se2_inv(fin.state), ref_pose);                      // Pose2D(state) - ref_pose (:351, pose2d.cpp:81-84)
+    return LAMA_OK;
+}
+
+int coarse_correlate_candidate_scan(Engine* e, int particle, const DeviceOptions& dev, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat,
+                                    const double* pts, int n, const double* origin, const double* quat, const SE2& ref_pose, const SE2& cand_pose, SE2* between,
+                                    double* rmse, std::string& err)
+{
+    // a coarse distance map of the reference cloud alone (:377-381): resolution 0.25 m, reach 2.5 m
+    std::unique_ptr<DistanceMapDev> coarse(DistanceMapDev::create(0.25, 32, 2.5, ref_pose.tx, ref_pose.ty, dev, err));
+    if (!coarse) return LAMA_ERR_CUDA;
+    {
+        ScanParams sp{};
+        sp.n_beams = ref_n;
+        sp.scale   = 1.0 / 0.25;
+        Engine* ce = coarse->engine();
+        int rc = ce->set_scan(ref_pts, ref_n, ref_origin, ref_quat, 0, 0);   // only to build the sensor transform exactly like the kernels do
+        if (rc != LAMA_OK) { err = ce->last_error(); return rc; }
+        const Affine tf = compose_tf(ref_pose, ce->scan_params().moving);
+        std::vector<uint32_t> cells((size_t)ref_n * 2);
+        for (int i = 0; i < ref_n; ++i) {
+            double hit[3];
+            apply_tf(tf, ref_pts[3 * i], ref_pts[3 * i + 1], ref_pts[3 * i + 2], hit);
+            cells[2 * i]     = w2m(hit[0], sp.scale);
+            cells[2 * i + 1] = w2m(hit[1], sp.scale);
+        }
+        rc = coarse->add(cells.data(), ref_n, true);
+        uint32_t processed = 0;
+        if (rc == LAMA_OK) rc = coarse->update(&processed);
+        if (rc != LAMA_OK) { err = coarse->error(); return rc; }
+        rc = ce->set_scan(pts, n, origin, quat, 0, 0);
+        HostMatchResult r0;
+        if (rc == LAMA_OK) rc = ce->match(&cand_pose, 1, 0, true, huber_solver(100), 0.05, 0, &r0);   // :383-384
+        if (rc != LAMA_OK) { err = ce->last_error(); return rc; }
+        int rc2 = e->set_scan(pts, n, origin, quat, 0, 0);
+        HostMatchResult r1;
+        if (rc2 == LAMA_OK) rc2 = e->match(&r0.state, 1, particle, true, huber_solver(100), 0.05, 0, &r1);   // :386-387
+        if (rc2 == LAMA_OK) rc2 = e->match_error(&r1.state, 1, particle, true, rmse);
+        if (rc2 != LAMA_OK) { err = e->last_error(); return rc2; }
+        *between = se2_mul(se2_inv(r1.state), ref_pose);   // :389
+    }
+    return LAMA_OK;
 }
 
 // =====================================================================================================

@@ -15,6 +15,8 @@
 
 namespace lama_b200 {
 
+struct ShardComm;
+
 struct DeviceOptions {
     int device = 0, dir_dim = 64, pool_slots = 0, max_beams = 2048, timing = 0;
     uint64_t stream = 0;
@@ -65,6 +67,11 @@ public:
     int shard_apply(const int32_t* idx, const int32_t* local_src);
     int shard_map_update();
 
+    // Sharded operation behind update(): after shard_connect() every rank's update() runs the whole sharded step (shard_comm.h) --
+    // match + map update of the local particles, ONE all-gather of the match results, the identical resampling decision on every rank,
+    // NCCL send / recv of the maps of remote ancestors.
+    int shard_connect(const uint8_t id[128]);
+    void shard_stats(uint64_t out[2]) const { out[0] = shard_collectives_; out[1] = shard_migrated_bytes_; }
     size_t best_particle() const;                 // pf_slam2d.cpp:314-330
     double neff() const { return neff_; }
     uint32_t particles() const { return P_; }
@@ -113,6 +120,16 @@ private:
     uint64_t detached_seen_ = 0;
     std::string err_;
     bool pending_maps_ = false, counters_pending_ = false;
+    struct ShardComm* comm_ = nullptr;
+    double* d_send_ = nullptr;      // device: local payload (per x kShardFields + 1 digest)
+    double* d_recv_ = nullptr;      // device: gathered payloads
+    double* h_recv_ = nullptr;      // pinned host copy
+    int64_t* d_tab_ = nullptr;      // device: blob sizes of the particles this rank serves / of all particles
+    int64_t* h_tab_ = nullptr;      // pinned
+    double digest_ = 0.0;           // of the previous scan's resampling decision, compared across ranks one scan later
+    uint64_t shard_collectives_ = 0, shard_migrated_bytes_ = 0;
+    int update_sharded(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], bool* did_update);
+    int migrate_and_apply(const std::vector<int32_t>& idx);
     std::vector<double> staged_host_;  // kept until the engine exists
     int staged_scans_ = 0, staged_beams_ = 0, staged_index_ = -1;
     int ensure_engine(int n);
@@ -156,6 +173,7 @@ public:
     const Counters& last_counters() const { return last_; }
     const Counters& total_counters() const { return total_; }
     Engine* engine() { return eng_.get(); }
+    const DeviceOptions& device_options() const { return opt_.dev; }
     const std::string& error() const { return err_; }
 
 private:
@@ -189,6 +207,21 @@ private:
     std::vector<uint8_t> pend_kind_;
     std::string err_;
 };
+
+// ---- GraphSlam2D's loop-closure front end (src/graph_slam2d.cpp:283-355) on a device distance map -------------------------------------
+// findLoopClosureCandidates (:283-313): the key poses within `radius` of `query` among the first n_keys - ignore_n (the tail of the chain is
+// skipped), nearest first (nanoflann's sorted radius search), at most max_candidates.
+std::vector<int> find_loop_closure_candidates(const double* key_xy, int n_keys, int ignore_n, const double query[2], double radius, int max_candidates);
+// correlateCandidateScan (:315-355): the candidate's cloud matched against the map of `particle` from its own pose and from the reference
+// position, one GN iteration each (Huber 0.15), the better one refined to convergence; between = matched - ref_pose, returns the
+// nearest-cell RMSE (MatchSurface2D::error).
+int correlate_candidate_scan(Engine* e, int particle, const double* pts, int n, const double* origin, const double* quat, const SE2& ref_pose, const SE2& cand_pose,
+                             SE2* between, double* rmse);
+// coarseSearchAndCorrelateCandidateScan (:357-392): first against a coarse (0.25 m, 2.5 m reach) distance map of the reference cloud alone, then
+// against the map of `particle`.
+int coarse_correlate_candidate_scan(Engine* e, int particle, const DeviceOptions& dev, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat,
+                                    const double* pts, int n, const double* origin, const double* quat, const SE2& ref_pose, const SE2& cand_pose, SE2* between,
+                                    double* rmse, std::string& err);
 
 // SimpleOccupancyMap (src/sdm/simple_occupancy_map.cpp:36-149): Loc2D's static tri-state map.  It is only consulted by
 // the host-side rejection sampling of globalLocalization, so it lives on the host.

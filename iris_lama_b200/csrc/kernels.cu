@@ -37,7 +37,6 @@ struct MatchShared {
     Affine tf;
     SE2 state;
     SolverControl ctl;
-    double warp_part[kMatchThreads / 32][kNumSums];
     double sums[kNumSums];
     int done;
     uint32_t evals_done;
@@ -99,6 +98,7 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
     int32_t* dir        = reinterpret_cast<int32_t*>(smem_raw);
     double* dtab        = reinterpret_cast<double*>(smem_raw + (size_t)dim2 * 4);
     MatchShared& sh     = *reinterpret_cast<MatchShared*>(smem_raw + (size_t)dim2 * 4 + (size_t)(mp.max_sqdist + 1) * 8);
+    double* part        = reinterpret_cast<double*>(smem_raw + (size_t)dim2 * 4 + (size_t)(mp.max_sqdist + 1) * 8 + ((sizeof(MatchShared) + 15) & ~(size_t)15));
     const int tid       = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int particle  = mp.shared_map ? mp.particle_offset : mp.particle_offset + blockIdx.x;
     const int32_t* gdir = dir_of(s, mp.set, particle, kMapDm);
@@ -118,7 +118,7 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
 
     const int n = mp.scan.n_beams;
     const bool single = mp.mode == 1;
-    if (tid == 0) sh.tf = compose_tf(sh.state, mp.scan.moving);
+    if (tid == 0) sh.tf = compose_tf_fast(sh.state, mp.scan.moving);
     __syncthreads();
     for (;;) {
         double acc[kNumSums];
@@ -127,21 +127,21 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
         const Affine tf = sh.tf;
         for (int b = tid; b < n; b += blockDim.x)
             eval_beam(acc, tf, mp.points + 3 * (size_t)b, mp.scan.scale, s.pool, dir, s.window, dtab, mp.max_sqdist, mp.solver, mp.meas_sigma);
+        // Block reduction through shared memory, fixed order (deterministic): every thread parks its 12 partial sums, then warp k adds
+        // up sum k over all threads (a strided pass + one warp shuffle tree) -- 12 stores per thread instead of 60 shuffles per value.
 #pragma unroll
-        for (int k = 0; k < kNumSums; ++k) {
-            double v = warp_sum(acc[k]);
-            if (lane == 0) sh.warp_part[warp][k] = v;
+        for (int k = 0; k < kNumSums; ++k) part[k * kMatchThreads + tid] = acc[k];
+        __syncthreads();
+        for (int k = warp; k < kNumSums; k += (int)(blockDim.x >> 5)) {
+            double v = 0.0;
+            for (int t = lane; t < (int)blockDim.x; t += 32) v += part[k * kMatchThreads + t];
+            v = warp_sum(v);
+            if (lane == 0) sh.sums[k] = v;
         }
         __syncthreads();
-        // Two block barriers per evaluation: warp 0 finishes the reduction (fixed order: deterministic), runs the
-        // solver control and already prepares the transform of the next evaluation.
+        // Solver control on warp 0 (one logical thread; the two transcendental calls of SE2::exp run on two lanes), which also prepares the
+        // transform of the next evaluation.
         if (warp == 0) {
-            if (lane < kNumSums) {
-                double v = 0.0;
-                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh.warp_part[w][lane];
-                sh.sums[lane] = v;
-            }
-            __syncwarp();
             if (lane == 0) {
                 ++sh.evals_done;
                 if (single || sh.done == 1) {
@@ -151,7 +151,7 @@ k_match(StoreView s, MatchParams mp, const SE2* __restrict__ states_in, MatchRes
                     // one at the final state (likelihood, covariance, rmse); otherwise do one more pass.
                     sh.done = sh.ctl.state_dirty ? 1 : 2;
                 }
-                if (sh.done != 2) sh.tf = compose_tf(sh.state, mp.scan.moving);
+                if (sh.done != 2) sh.tf = compose_tf_fast(sh.state, mp.scan.moving);
             }
         }
         __syncthreads();
@@ -1416,6 +1416,21 @@ __global__ void k_delete_patches(StoreView s, int set, int particle, const int32
     }
 }
 
+// the per-particle payload of the sharded exchange: {state (4), likelihood, reference evaluations, iterations}, then one digest word
+__global__ void k_pack_results(const MatchResult* __restrict__ res, int n, double digest, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const MatchResult& r = res[i];
+        double* o = out + (size_t)i * kShardFields;
+        o[0] = r.state.c; o[1] = r.state.s; o[2] = r.state.tx; o[3] = r.state.ty;
+        o[4] = r.sums[11];
+        o[5] = (double)r.evals_ref;
+        o[6] = (double)r.iterations;
+    }
+    if (i == 0) out[(size_t)n * kShardFields] = digest;
+}
+
 __global__ void k_merge_free(StoreView s)
 {
     __shared__ int n, base;
@@ -1596,6 +1611,38 @@ __global__ void k_sampling(StoreView s, int set, int particle, const double* __r
     }
 }
 
+// MatchSurface2D::error() (src/match_surface_2d.cpp:92-116): sqrt(sum d^2 / N) with d the NEAREST-cell distance (w2m rounding +
+// DynamicDistanceMap::distance(Vector3ui), dynamic_distance_map.cpp:140-147) of every point at the given state.  One block per state.
+__global__ void k_match_error(StoreView s, int set, int particle0, int shared_map, const double* __restrict__ points, ScanParams scan, const SE2* __restrict__ states,
+                              double resolution, uint32_t max_sqdist, double* __restrict__ out)
+{
+    __shared__ Affine tf;
+    __shared__ double part[8];
+    const int32_t* d = dir_of(s, set, shared_map ? particle0 : particle0 + blockIdx.x, kMapDm);
+    if (threadIdx.x == 0) tf = compose_tf(states[blockIdx.x], scan.moving);
+    __syncthreads();
+    const double dmax = mul_rn(sqrt((double)max_sqdist), resolution);
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < scan.n_beams; k += blockDim.x) {
+        double hit[3];
+        apply_tf(tf, points[3 * k], points[3 * k + 1], points[3 * k + 2], hit);
+        const uint32_t x = w2m(hit[0], scan.scale), y = w2m(hit[1], scan.scale);
+        const int di = dir_index(s.window, x, y);
+        const int slot = di < 0 ? -1 : d[di];
+        const uint32_t w = slot < 0 ? 0u : __ldcg(patch_ptr(s, slot & kDirSlotMask) + cell_index(x, y));
+        const double dist = (w & kDmValid) ? mul_rn(sqrt((double)dm_sqdist(w)), resolution) : dmax;
+        acc += mul_rn(dist, dist);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w];
+        out[blockIdx.x] = sqrt(v / (double)scan.n_beams);
+    }
+}
+
 __global__ void k_distance(StoreView s, int set, int particle, const double* __restrict__ pts, int n, double resolution, uint32_t max_sqdist,
                            double* __restrict__ dist, double* __restrict__ grad)
 {
@@ -1630,7 +1677,7 @@ __global__ void k_distance(StoreView s, int set, int particle, const double* __r
 // ==================================================================================================
 size_t match_smem_bytes(int dir_dim, uint32_t max_sqdist)
 {
-    return (size_t)dir_dim * dir_dim * 4 + (size_t)(max_sqdist + 1) * 8 + sizeof(MatchShared) + 16;
+    return (size_t)dir_dim * dir_dim * 4 + (size_t)(max_sqdist + 1) * 8 + ((sizeof(MatchShared) + 15) & ~(size_t)15) + (size_t)kNumSums * kMatchThreads * 8 + 16;
 }
 size_t raycast_smem_bytes(int dir_dim, const RayParams& rp)
 {
@@ -1714,6 +1761,10 @@ void launch_release(const StoreView& s, int set, int first, int count, cudaStrea
     k_release<<<dim3(count, s.n_kinds), 256, 0, st>>>(s, set, first);
 }
 void launch_merge_free(const StoreView& s, cudaStream_t st) { k_merge_free<<<1, 256, 0, st>>>(s); }
+void launch_pack_results(const MatchResult* d_results, int n, double digest, double* d_out, cudaStream_t st)
+{
+    k_pack_results<<<(n + 127) / 128, 128, 0, st>>>(d_results, n, digest, d_out);
+}
 void launch_delete_patches(const StoreView& s, int set, int particle, const int32_t* d_list, int count, cudaStream_t st)
 {
     if (count <= 0) return;
@@ -1763,6 +1814,12 @@ void launch_sampling(const StoreView& s, int set, int particle, const double* d_
 {
     if (n_offsets <= 0) return;
     k_sampling<<<n_offsets, 128, 0, st>>>(s, set, particle, d_points, scan, pose, d_offsets, stride, resolution, max_sqdist, d_out);
+}
+void launch_match_error(const StoreView& s, int set, int particle0, bool shared_map, const double* d_points, const ScanParams& scan, const SE2* d_states, int count,
+                        double resolution, uint32_t max_sqdist, double* d_out, cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_match_error<<<count, 256, 0, st>>>(s, set, particle0, shared_map ? 1 : 0, d_points, scan, d_states, resolution, max_sqdist, d_out);
 }
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st)

@@ -102,6 +102,9 @@ void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_
 // releases every patch referenced by particles [first, first+count) of `set` and clears their directories
 void launch_release(const StoreView& s, int set, int first, int count, cudaStream_t st);
 void launch_merge_free(const StoreView& s, cudaStream_t st);
+// sharded exchange: kShardFields doubles per particle out of the match results (state, likelihood, evaluation / iteration counts) + one digest
+constexpr int kShardFields = 7;
+void launch_pack_results(const MatchResult* d_results, int n, double digest, double* d_out, cudaStream_t st);
 void launch_gather_cells(const StoreView& s, int set, int particle, int kind, const uint32_t* d_cells, int n, uint32_t* d_words, uint8_t* d_flags,
                          cudaStream_t st);
 void launch_delete_patches(const StoreView& s, int set, int particle, const int32_t* d_list, int count, cudaStream_t st);
@@ -120,6 +123,9 @@ void launch_scatter_patches(const StoreView& s, int set, int particle, int kind,
 // Loc2D::addSamplingCovariance likelihoods: out[i] for offset i (offsets = n x 2 doubles)
 void launch_sampling(const StoreView& s, int set, int particle, const double* d_points, const ScanParams& scan, const SE2& pose, const double* d_offsets,
                      int n_offsets, int stride, double resolution, uint32_t max_sqdist, double* d_out, cudaStream_t st);
+// MatchSurface2D::error() of `count` states (block k on the map of particle0 + k, or all on particle0's with shared_map)
+void launch_match_error(const StoreView& s, int set, int particle0, bool shared_map, const double* d_points, const ScanParams& scan, const SE2* d_states, int count,
+                        double resolution, uint32_t max_sqdist, double* d_out, cudaStream_t st);
 // batched DistanceMap::distance(point, &grad) on one particle's distance map (SDM grid interface)
 void launch_distance(const StoreView& s, int set, int particle, const double* d_pts, int n, double resolution, uint32_t max_sqdist, double* d_dist,
                      double* d_grad, cudaStream_t st);

@@ -198,6 +198,22 @@ LAMA_HD Affine compose_tf(const SE2& pose, const MovingTf& m)
     }
     return r;
 }
+// The same transform with Rz built straight from the unit complex number of the state: cos(atan2(s, c)) and c differ by a few
+// 1e-16, so this is the transform of compose_tf up to the last bits -- good for the residual evaluations of the scan matcher (sums
+// reduced in another order than the reference's anyway), NOT for the map update, where a last-bit difference can move a hit cell.
+LAMA_HD Affine compose_tf_fast(const SE2& pose, const MovingTf& m)
+{
+    const double s = pose.s, c = pose.c;
+    const double f[9] = {c, -s, 0, s, c, 0, 0, 0, 1.0};
+    const double ft[3] = {pose.tx, pose.ty, 0.0};
+    Affine r;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            r.l[i * 3 + j] = add_rn(add_rn(mul_rn(f[i * 3 + 0], m.l[0 * 3 + j]), mul_rn(f[i * 3 + 1], m.l[1 * 3 + j])), mul_rn(f[i * 3 + 2], m.l[2 * 3 + j]));
+        r.t[i] = add_rn(add_rn(add_rn(mul_rn(f[i * 3 + 0], m.t[0]), mul_rn(f[i * 3 + 1], m.t[1])), mul_rn(f[i * 3 + 2], m.t[2])), ft[i]);
+    }
+    return r;
+}
 LAMA_HD void apply_tf(const Affine& a, double px, double py, double pz, double out[3])
 {
     for (int i = 0; i < 3; ++i)

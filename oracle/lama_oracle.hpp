@@ -1163,6 +1163,81 @@ inline SolveStats solve(const SolverOptions& opt, MatchSurface2D& problem, doubl
 }
 
 // ----------------------------------------------------------------------------------------------
+// GraphSlam2D's loop-closure front end (src/graph_slam2d.cpp:283-392)
+// ----------------------------------------------------------------------------------------------
+// MatchSurface2D::error (src/match_surface_2d.cpp:92-116)
+inline double match_error(const DynamicDistanceMap& dm, const PointCloud& pc, const SE2& state)
+{
+    Affine3 tf = compose(fixed_tf(state.tx, state.ty, state.r.log()), moving_tf(pc));
+    double sq = 0, hit[3];
+    for (size_t i = 0; i < pc.size(); ++i) {
+        tf.apply(&pc.pts[3 * i], hit);
+        const double d = dm.distance(dm.w2m(hit));
+        sq += d * d;
+    }
+    return std::sqrt(sq / (double)pc.size());
+}
+// findLoopClosureCandidates (:283-313): nanoflann radius search (squared L2, results sorted by distance) over the first n - ignore key poses
+inline std::vector<int> find_loop_closure_candidates(const std::vector<double>& key_xy, int ignore_n, const double query[2], double radius, size_t max_candidates)
+{
+    std::vector<std::pair<int, double>> results;
+    const int n = (int)(key_xy.size() / 2) - ignore_n;
+    for (int i = 0; i < n; ++i) {
+        const double d0 = query[0] - key_xy[2 * i], d1 = query[1] - key_xy[2 * i + 1];
+        const double d2 = d0 * d0 + d1 * d1;
+        if (d2 < radius * radius) results.push_back({i, d2});
+    }
+    std::sort(results.begin(), results.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.second < b.second; });
+    if (results.size() > max_candidates) results.erase(results.begin() + (long)max_candidates, results.end());   // :298-301
+    std::vector<int> out;
+    for (auto& c : results) out.push_back(c.first);
+    return out;
+}
+inline SolverOptions loop_solver(uint32_t max_iter)
+{
+    SolverOptions so;
+    so.max_iterations = max_iter;
+    so.strategy.kind  = Strategy::GaussNewton;   // :324
+    so.robust.kind    = RobustCost::Huber;       // :325
+    so.robust.param   = 0.15;
+    return so;
+}
+// correlateCandidateScan (:315-355)
+inline double correlate_candidate_scan(const DynamicDistanceMap& dm, const PointCloud& cloud, const Pose2D& ref_pose, const Pose2D& candidate_pose, Pose2D& between)
+{
+    MatchSurface2D ms0(&dm, &cloud, candidate_pose.state);
+    MatchSurface2D ms1(&dm, &cloud, Pose2D(ref_pose.x(), ref_pose.y(), candidate_pose.rotation()).state);
+    solve(loop_solver(1), ms0, nullptr);
+    const double rmse0 = match_error(dm, cloud, ms0.state);
+    solve(loop_solver(1), ms1, nullptr);
+    const double rmse1 = match_error(dm, cloud, ms1.state);
+    MatchSurface2D* msp = rmse0 < rmse1 ? &ms0 : &ms1;
+    solve(loop_solver(100), *msp, nullptr);
+    between = Pose2D(msp->state).minus(ref_pose);
+    return match_error(dm, cloud, msp->state);
+}
+// coarseSearchAndCorrelateCandidateScan (:357-392)
+inline double coarse_correlate_candidate_scan(const DynamicDistanceMap& map, const PointCloud& ref_cloud, const PointCloud& cloud, const Pose2D& ref_pose,
+                                              const Pose2D& candidate_pose, Pose2D& between)
+{
+    Affine3 tf = compose(fixed_tf(ref_pose.x(), ref_pose.y(), ref_pose.state.r.log()), moving_tf(ref_cloud));
+    DynamicDistanceMap dm(0.25, 32);
+    dm.set_max_distance(2.5);
+    double hit[3];
+    for (size_t i = 0; i < ref_cloud.size(); ++i) {
+        tf.apply(&ref_cloud.pts[3 * i], hit);
+        dm.add_obstacle(dm.w2m(hit));
+    }
+    dm.update();
+    MatchSurface2D ms(&dm, &cloud, candidate_pose.state);
+    solve(loop_solver(100), ms, nullptr);
+    ms.surface = &map;
+    solve(loop_solver(100), ms, nullptr);
+    between = Pose2D(ms.state).minus(ref_pose);
+    return match_error(map, cloud, ms.state);
+}
+
+// ----------------------------------------------------------------------------------------------
 // Thread pool used by the timed CPU baseline: one task per particle per phase, wait() barrier
 // (src/thread_pool.cpp:52-114, src/pf_slam2d.cpp:254-266,292-302).
 // ----------------------------------------------------------------------------------------------

@@ -199,6 +199,39 @@ void orc_match_solve(void* d, const double* pts, int n, const double* origin, co
     if (stats) { stats[0] = st.iterations; stats[1] = st.evals; }
 }
 
+// ---- GraphSlam2D loop-closure front end -------------------------------------------------------------------
+int orc_loop_closure_candidates(const double* key_xy, int n_keys, int ignore_n, const double* query, double radius, int max_candidates, int* ids)
+{
+    std::vector<double> k(key_xy, key_xy + 2 * (size_t)n_keys);
+    std::vector<int> v = find_loop_closure_candidates(k, ignore_n, query, radius, (size_t)max_candidates);
+    for (size_t i = 0; i < v.size(); ++i) ids[i] = v[i];
+    return (int)v.size();
+}
+double orc_match_error(void* d, const double* pts, int n, const double* origin, const double* quat, const double* state)
+{
+    PointCloud pc = make_cloud(pts, n, origin, quat);
+    return match_error(*(DynamicDistanceMap*)d, pc, se2_from(state));
+}
+double orc_correlate_candidate_scan(void* d, const double* pts, int n, const double* origin, const double* quat, const double* ref_xyr, const double* cand_xyr,
+                                    double* between_xyr)
+{
+    PointCloud pc = make_cloud(pts, n, origin, quat);
+    Pose2D between;
+    double rmse = correlate_candidate_scan(*(DynamicDistanceMap*)d, pc, Pose2D(ref_xyr[0], ref_xyr[1], ref_xyr[2]), Pose2D(cand_xyr[0], cand_xyr[1], cand_xyr[2]), between);
+    between_xyr[0] = between.x(); between_xyr[1] = between.y(); between_xyr[2] = between.rotation();
+    return rmse;
+}
+double orc_coarse_correlate_candidate_scan(void* d, const double* ref_pts, int ref_n, const double* ref_origin, const double* ref_quat, const double* pts, int n,
+                                           const double* origin, const double* quat, const double* ref_xyr, const double* cand_xyr, double* between_xyr)
+{
+    PointCloud rc = make_cloud(ref_pts, ref_n, ref_origin, ref_quat), pc = make_cloud(pts, n, origin, quat);
+    Pose2D between;
+    double rmse = coarse_correlate_candidate_scan(*(DynamicDistanceMap*)d, rc, pc, Pose2D(ref_xyr[0], ref_xyr[1], ref_xyr[2]), Pose2D(cand_xyr[0], cand_xyr[1], cand_xyr[2]),
+                                                  between);
+    between_xyr[0] = between.x(); between_xyr[1] = between.y(); between_xyr[2] = between.rotation();
+    return rmse;
+}
+
 // ---- PFSlam2D --------------------------------------------------------------------------------------------
 struct orc_pf_options {
     uint32_t particles;

@@ -303,6 +303,28 @@ class DDM:
         lib().orc_match_normal_eq(self.h, pp, C.c_int(p.size // 3), op, qp, sp, C.c_int(robust[0]), C.c_double(robust[1]), out.ctypes.data_as(c_dp))
         return out
 
+    def match_error(self, pts, state, origin=(0, 0, 0), quat=(0, 0, 0, 1)):
+        """MatchSurface2D::error (match_surface_2d.cpp:92-116)"""
+        p, pp = _d(pts); o, op = _d(origin); q, qp = _d(quat); s, sp = _d(state)
+        lib().orc_match_error.restype = C.c_double
+        return lib().orc_match_error(self.h, pp, C.c_int(p.size // 3), op, qp, sp)
+
+    def correlate_candidate_scan(self, pts, ref_xyr, cand_xyr, origin=(0, 0, 0), quat=(0, 0, 0, 1)):
+        """GraphSlam2D::correlateCandidateScan (graph_slam2d.cpp:315-355) against this map -> (between xyr, rmse)"""
+        p, pp = _d(pts); o, op = _d(origin); q, qp = _d(quat); r, rp = _d(ref_xyr); c, cp = _d(cand_xyr)
+        out = np.zeros(3)
+        lib().orc_correlate_candidate_scan.restype = C.c_double
+        rmse = lib().orc_correlate_candidate_scan(self.h, pp, C.c_int(p.size // 3), op, qp, rp, cp, out.ctypes.data_as(c_dp))
+        return out, rmse
+
+    def coarse_correlate_candidate_scan(self, ref_pts, pts, ref_xyr, cand_xyr):
+        """GraphSlam2D::coarseSearchAndCorrelateCandidateScan (graph_slam2d.cpp:357-392) -> (between xyr, rmse)"""
+        a, ap = _d(ref_pts); p, pp = _d(pts); o, op = _d(_ID3); q, qp = _d(_IDQ); r, rp = _d(ref_xyr); c, cp = _d(cand_xyr)
+        out = np.zeros(3)
+        lib().orc_coarse_correlate_candidate_scan.restype = C.c_double
+        rmse = lib().orc_coarse_correlate_candidate_scan(self.h, ap, C.c_int(a.size // 3), op, qp, pp, C.c_int(p.size // 3), op, qp, rp, cp, out.ctypes.data_as(c_dp))
+        return out, rmse
+
     def match_solve(self, pts, state, strategy=0, robust=(1, 0.15), max_iter=100, want_cov=False, origin=(0, 0, 0), quat=(0, 0, 0, 1)):
         p, pp = _d(pts)
         o, op = _d(origin)
@@ -318,6 +340,15 @@ class DDM:
 
 _ID3 = np.zeros(3)
 _IDQ = np.array([0.0, 0, 0, 1])
+
+
+def loop_closure_candidates(key_xy, ignore_n, query, radius, max_candidates):
+    """GraphSlam2D::findLoopClosureCandidates (graph_slam2d.cpp:283-313)"""
+    k, kp = _d(key_xy); qq, qp = _d(query)
+    ids = np.zeros(max(1, max_candidates), np.int32)
+    n = lib().orc_loop_closure_candidates(kp, C.c_int(k.size // 2), C.c_int(ignore_n), qp, C.c_double(radius), C.c_int(max_candidates),
+                                          ids.ctypes.data_as(C.POINTER(C.c_int32)))
+    return ids[:n].copy()
 
 
 class PFSlam2D:

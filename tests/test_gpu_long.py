@@ -131,12 +131,13 @@ def test_map_update_with_a_tilted_sensor(gpu_api, po, synth, monkeypatch, pull_m
 
 
 def test_more_candidate_patches_than_bitmaps(gpu_api, po, synth, monkeypatch):
-    """LAMA_RAY_CAND_CAP = 4: almost every patch with hit cells or obstacles overflows the walk kernel's candidate bitmaps and
-    falls back to logging every touch (kCandOverflow); the result must not change"""
+    """LAMA_RAY_CAND_CAP = 2: every patch with hit cells or obstacles but two overflows the walk kernel's candidate bitmaps and
+    falls back to logging every touch (kCandOverflow); the result must not change.  (Few beams: the log has to hold every touch
+    of those patches; with a full scan the same setting ends in the loud LAMA_ERR_OVERFLOW instead, checked last.)"""
     monkeypatch.setenv("LAMA_PULL_MAX_PARTICLES", "0")
-    monkeypatch.setenv("LAMA_RAY_CAND_CAP", "4")
+    monkeypatch.setenv("LAMA_RAY_CAND_CAP", "2")
     Pn, T = 4, 10
-    ds = synth.make_dataset("room", T, n_beams=360)
+    ds = synth.make_dataset("room", T, n_beams=24)
     opts = dict(trans_thresh=0.05, rot_thresh=0.05, seed=11)
     g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(Pn, **opts))
     o = po.PFSlam2D(po.PFOptions.defaults(Pn, threads=4, **opts))
@@ -146,3 +147,11 @@ def test_more_candidate_patches_than_bitmaps(gpu_api, po, synth, monkeypatch):
         cg, _ = g.counters(); co, _ = o.counters()
         assert (cg["ray_cells"], cg["dm_pops"]) == (co["ray_cells"], co["dm_pops"]), t
     _cells_equal(g, o, range(Pn))
+    dense = synth.make_dataset("room", 3, n_beams=720)
+    g2 = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(Pn, **opts))
+    g2.setPrior(*dense.truth[0])
+    with pytest.raises(gpu_api.LamaError) as e:      # the touch log cannot hold a dense scan's touches of the overflowing patches: loud, never silent
+        for t in range(3):
+            g2.update(dense.scans[t], dense.odom[t])
+        g2.getPose(); g2.counters()
+    assert e.value.code == -6

@@ -442,3 +442,31 @@ def test_occupancy_grid_queries(gpu_api, po, synth):
         pr, fr = po.occ_query("prob" if occupancy else "freq", po.map_handle("slamp_occ" if occupancy else "slam_occ", o), cells)
         assert (fg == fr).all() and (pg == pr).all()
         assert (fr & 1).any() and (fr & 2).any() and (fr & 4).any()            # free, occupied and unknown cells all occur
+
+
+# ---- SURVEY 8(f) row 4 (second half): GraphSlam2D's loop-closure scan correlation -----------------------------------------------------
+def test_loop_closure_scan_correlation(gpu_api, po, synth):
+    """correlateCandidateScan / coarseSearchAndCorrelateCandidateScan (src/graph_slam2d.cpp:315-392) and MatchSurface2D::error
+    (match_surface_2d.cpp:92-116) on a device distance map against the oracle: same `between` pose, same RMSE, for candidates that
+    are close to, and far from, the reference key pose"""
+    ds = synth.make_dataset("loc_room", 6)
+    cells = _room_cells(ds.segments)
+    g, o = gpu_api.DynamicDistanceMap(l2_max=0.5), po.DDM(l2_max=0.5)
+    g.addObstacle(cells); o.add(cells); g.update(); o.update()
+    rng = np.random.default_rng(8)
+    for t in range(6):
+        truth = ds.truth[t]
+        st = po.se2_from_xyr(*(truth + rng.normal(0, [0.03, 0.03, 0.01])))
+        assert abs(g.matchError(ds.scans[t], [st])[0] - o.match_error(ds.scans[t], st)) < 1e-12
+        for dpose in ([0.05, -0.04, 0.02], [0.6, 0.3, -0.05], [-1.5, 0.8, 0.3]):
+            cand = truth + np.array(dpose)                         # where the pose graph believes the candidate key pose is
+            ref = ds.truth[(t + 2) % 6] + np.array([0.02, 0.01, -0.01])
+            bg, eg = g.correlateCandidateScan(ds.scans[t], ref, cand)
+            bo, eo = o.correlate_candidate_scan(ds.scans[t], ref, cand)
+            assert np.abs(bg - bo).max() < POSE_TOL and abs(eg - eo) < 1e-9, (t, dpose)
+            bg, eg = g.coarseCorrelateCandidateScan(ds.scans[(t + 2) % 6], ds.scans[t], ref, cand)
+            bo, eo = o.coarse_correlate_candidate_scan(ds.scans[(t + 2) % 6], ds.scans[t], ref, cand)
+            assert np.abs(bg - bo).max() < POSE_TOL and abs(eg - eo) < 1e-9, (t, dpose, "coarse")
+    # a well-placed candidate ends on the walls: RMSE of the order of the range noise
+    bg, eg = g.correlateCandidateScan(ds.scans[0], ds.truth[1], ds.truth[0] + np.array([0.08, -0.05, 0.03]))
+    assert eg < 0.05

@@ -389,3 +389,22 @@ def test_sdm_file_parsed_independently_equals_the_exported_planes(po, synth, tmp
         assert (cells.view("<f4").reshape(32, 32)[bits] == e["prob"][sub][bits]).all()
         seen += int(bits.sum())
     assert seen == int(e["known"].sum()) and len(f["patches"]) == n
+
+
+def test_loop_closure_candidates_product_oracle_and_brute_force(po):
+    """GraphSlam2D::findLoopClosureCandidates (graph_slam2d.cpp:283-313): the product's host function (no GPU needed), the oracle's restatement and a numpy
+    brute force agree: first n - ignore key poses only, strictly inside the radius, nearest first, capped"""
+    from iris_lama_b200 import api
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        n = int(rng.integers(1, 200))
+        keys = rng.uniform(-20, 20, size=(n, 2))
+        q = rng.uniform(-20, 20, 2)
+        radius = float(rng.uniform(0.5, 15))
+        ignore = int(rng.integers(0, min(n, 25) + 1))
+        cap = int(rng.integers(1, 8))
+        d2 = ((keys[:n - ignore] - q) ** 2).sum(1)
+        order = np.argsort(d2, kind="stable")
+        want = [int(i) for i in order if d2[i] < radius * radius][:cap]
+        assert api.loop_closure_candidates(keys, ignore, q, radius, cap).tolist() == want
+        assert po.loop_closure_candidates(keys, ignore, q, radius, cap).tolist() == want
