@@ -879,7 +879,7 @@ int Engine::pack_size(int particle, size_t* bytes)
     CU_TRY(cudaStreamSynchronize(d_->stream));
     size_t n = 0;
     for (int32_t v : dir) n += v >= 0;
-    *bytes = 16 + n * 4 + n * (size_t)(kPatchBytes + 128);
+    *bytes = 16 + ((n * 4 + 15) & ~(size_t)15) + n * (size_t)(kPatchBytes + 128);
     return LAMA_OK;
 }
 
@@ -900,7 +900,10 @@ void Engine::migration_reset()
     d_->mig_blocks.clear();
 }
 
-// blob = n x u32 directory index (occupancy entries first) + n patches (4 KiB) + n x 128 B obstacle-mirror bits, all on the device
+// the directory indices at the head of a blob, padded so that the patches behind them stay 16-byte aligned (they are copied as uint4)
+static size_t blob_entry_bytes(size_t n) { return (n * 4 + 15) & ~(size_t)15; }
+
+// blob = n x u32 directory index (occupancy entries first, padded to 16 bytes) + n patches (4 KiB) + n x 128 B obstacle-mirror bits, all on the device
 int Engine::pack_device(int particle, DeviceBlob* out)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
@@ -920,15 +923,15 @@ int Engine::pack_device(int particle, DeviceBlob* out)
                 slots.push_back(dir[kind * dim2 + e]);
                 ++n_kind[kind];
             }
-    const size_t n = slots.size();
+    const size_t n = slots.size(), ne = blob_entry_bytes(n);
     out->n_occ = n_kind[0];
     out->n_dm  = n_kind[1];
-    out->bytes = n * 4 + n * (size_t)(kPatchBytes + 128);
+    out->bytes = ne + n * (size_t)(kPatchBytes + 128);
     { int rc = migration_alloc(out->bytes + n * 4, &out->dptr); if (rc != LAMA_OK) return rc; }
     if (n) {
         char* base = (char*)out->dptr;
-        uint32_t* d_out  = (uint32_t*)(base + n * 4);                                  // n patches, then n x 32 obstacle-mirror words
-        uint32_t* d_fb   = (uint32_t*)(base + n * 4 + n * (size_t)kPatchBytes);
+        uint32_t* d_out  = (uint32_t*)(base + ne);                                     // n patches, then n x 32 obstacle-mirror words
+        uint32_t* d_fb   = (uint32_t*)(base + ne + n * (size_t)kPatchBytes);
         int32_t* d_slots = (int32_t*)(base + out->bytes);                              // scratch behind the blob
         CU_TRY(cudaMemcpyAsync(base, entries.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
         CU_TRY(cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
@@ -943,16 +946,16 @@ int Engine::pack_device(int particle, DeviceBlob* out)
 int Engine::unpack_device(int particle, const DeviceBlob& blob)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
-    const size_t n = (size_t)blob.n_occ + blob.n_dm;
-    if (particle < 0 || particle >= cfg_.particles || blob.bytes < n * 4 + n * (size_t)(kPatchBytes + 128)) return fail("unpack: bad arguments", LAMA_ERR_ARG);
+    const size_t n = (size_t)blob.n_occ + blob.n_dm, ne = blob_entry_bytes(n);
+    if (particle < 0 || particle >= cfg_.particles || blob.bytes < ne + n * (size_t)(kPatchBytes + 128)) return fail("unpack: bad arguments", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     launch_release(d_->view, cur_set_, particle, 1, d_->stream);
     launch_merge_free(d_->view, d_->stream);
     if (n) {
         const char* base = (const char*)blob.dptr;
         const int32_t* d_entries = (const int32_t*)base;
-        const uint32_t* d_in = (const uint32_t*)(base + n * 4);
-        const uint32_t* d_fb = (const uint32_t*)(base + n * 4 + n * (size_t)kPatchBytes);
+        const uint32_t* d_in = (const uint32_t*)(base + ne);
+        const uint32_t* d_fb = (const uint32_t*)(base + ne + n * (size_t)kPatchBytes);
         launch_scatter_patches(d_->view, cur_set_, particle, kMapOcc, d_entries, (int)blob.n_occ, d_in, d_fb, d_->stream);
         launch_scatter_patches(d_->view, cur_set_, particle, kMapDm, d_entries + blob.n_occ, (int)blob.n_dm, d_in + blob.n_occ * (size_t)kPatchCells,
                                d_fb + blob.n_occ * 32, d_->stream);
@@ -994,7 +997,7 @@ int Engine::unpack(int particle, const void* buf, size_t bytes)
     blob.n_occ = hdr[2];
     blob.n_dm  = hdr[3];
     const size_t n = (size_t)blob.n_occ + blob.n_dm;
-    blob.bytes = n * 4 + n * (size_t)(kPatchBytes + 128);
+    blob.bytes = blob_entry_bytes(n) + n * (size_t)(kPatchBytes + 128);
     if (bytes < 16 + blob.bytes) return fail("unpack: truncated buffer", LAMA_ERR_ARG);
     CU_TRY(cudaSetDevice(cfg_.device));
     { int rc = migration_alloc(blob.bytes, &blob.dptr); if (rc != LAMA_OK) return rc; }

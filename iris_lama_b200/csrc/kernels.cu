@@ -1745,7 +1745,7 @@ void launch_raycast_pull(const StoreView& s, const RayParams& rp_in, const SE2* 
     if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
     else k_ray_pull<false><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
 }
-void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
+void launch_brushfire(const StoreView& s, const BrushParams& bp, uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st)
 {
     if (count <= 0) return;
     k_brushfire<<<count, kBrushThreads, brushfire_smem_bytes(s.window.dim, bp), st>>>(s, bp, d_events, d_stats);

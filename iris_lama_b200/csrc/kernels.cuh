@@ -96,7 +96,7 @@ size_t ray_setup_smem_bytes(int dir_dim, int n_beams);
 size_t ray_pull_smem_bytes(int n_beams);
 void launch_raycast_pull(const StoreView& s, const RayParams& rp, const SE2* d_states, uint64_t* d_events, MapUpdateStats* d_stats, int count, int n_sms,
                          cudaStream_t st);
-void launch_brushfire(const StoreView& s, const BrushParams& bp, const uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st);
+void launch_brushfire(const StoreView& s, const BrushParams& bp, uint64_t* d_events, MapUpdateStats* d_stats, int count, cudaStream_t st);
 // dst_set[dst_first + k] = src_set[idx[k]] for k in [0, count); bumps reference counts (COW share)
 void launch_copy_dirs(const StoreView& s, int src_set, int dst_set, const int32_t* d_idx, int dst_first, int count, cudaStream_t st);
 // releases every patch referenced by particles [first, first+count) of `set` and clears their directories

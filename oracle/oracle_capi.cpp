@@ -514,3 +514,14 @@ void orc_freq_query(void* d, const uint32_t* cells, int n, double* prob, uint8_t
 void orc_prob_query(void* d, const uint32_t* cells, int n, double* prob, uint8_t* flags) { occ_query(*(ProbabilisticOccupancyMap*)d, cells, n, prob, flags); }
 
 }  // extern "C"
+extern "C" {
+// instrumentation: the largest brushfire heap any particle's distance map has held so far
+uint64_t orc_pf_peak_queue(void* h)
+{
+    auto* pf = (PFSlam2D*)h;
+    uint64_t m = 0;
+    for (auto& p : pf->particles[pf->cur])
+        if (p.dm) m = std::max<uint64_t>(m, p.dm->peak_queue);
+    return m;
+}
+}
