@@ -283,6 +283,16 @@ int lama_dm_match_solve(lama_dm* dm, const double* pts_xyz, int n, const double 
 int lama_dm_match_error(lama_dm* dm, const double* pts_xyz, int n, const double sensor_origin[3], const double sensor_quat_xyzw[4], const double* states, int count,
                         double* rmse);
 
+/* ---- lama::SimplePGO::optimize (include/lama/simple_pgo.h:43-57, src/simple_pgo.cpp:48-105): pose-graph optimisation on the device ----
+ * nodes_xyr = node_list (n_nodes x {x, y, rotation}), edges = edge_list (from, to pairs + measured relative poses), fixed = fixed_list.
+ * The factor graph is the reference's: a prior on node 0 (sigmas 1) or on every fixed node (sigmas 0.1), BetweenFactor<SE2> on consecutive
+ * nodes (measured = node[i]^-1 node[i+1]) and on the edges, sigmas (0.5, 0.5, 0.1), miniSAM Levenberg-Marquardt with diagonal damping
+ * (vendor/minisam/minisam/nonlinear/LevenbergMarquardtOptimizer.cpp:56-332).  *status = miniSAM's NonlinearOptimizationStatus (0 SUCCESS,
+ * 1 MAX_ITERATION, 2 ERROR_INCREASE, 3 RANK_DEFICIENCY, 4 INVALID); like the reference, nodes_xyr is only updated on SUCCESS.
+ * report = {LM iterations, lambda tries, CG iterations, initial error, final error, device ms}. */
+int lama_pgo_optimize(int device, double* nodes_xyr, int n_nodes, const int* edges_from_to, const double* edges_xyr, int n_edges, const int* fixed_nodes,
+                      const double* fixed_xyr, int n_fixed, int* status, double report[6]);
+
 /* ---- GraphSlam2D's loop-closure front end on a device map (src/graph_slam2d.cpp:283-392) ----
  * findLoopClosureCandidates (:283-313): ids of the key poses (x, y pairs) within `radius` of the query among the first
  * n_keys - ignore_n_chain_poses, nearest first, at most max_candidates (Options::loop_max_candidates, graph_slam2d.h:75). */

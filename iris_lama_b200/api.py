@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "lama_last_error", "lama_version", "lama_device_count",
     "lama_pf_options_default", "lama_pf_create", "lama_pf_destroy", "lama_pf_set_prior", "lama_pf_update", "lama_pf_get_pose",
     "lama_pf_stage_scans", "lama_pf_update_staged", "lama_pf_get_traffic",
-    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary", "lama_shard_unique_id", "lama_pf_shard_connect", "lama_pf_shard_stats", "lama_loop_closure_candidates", "lama_slam_correlate_candidate_scan", "lama_dm_correlate_candidate_scan", "lama_slam_coarse_correlate_candidate_scan", "lama_dm_coarse_correlate_candidate_scan", "lama_dm_match_error",
+    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary", "lama_shard_unique_id", "lama_pf_shard_connect", "lama_pf_shard_stats", "lama_pgo_optimize", "lama_loop_closure_candidates", "lama_slam_correlate_candidate_scan", "lama_dm_correlate_candidate_scan", "lama_slam_coarse_correlate_candidate_scan", "lama_dm_coarse_correlate_candidate_scan", "lama_dm_match_error",
     "lama_pf_get_counters", "lama_pf_kernel_times", "lama_pf_map_bounds", "lama_pf_export_occupancy", "lama_pf_export_distance",
     "lama_pf_shard_begin", "lama_pf_shard_finish", "lama_pf_shard_apply", "lama_pf_shard_apply_local", "lama_pf_shard_map_update",
     "lama_pf_particle_pack_size", "lama_pf_particle_pack", "lama_pf_particle_unpack",
@@ -190,6 +190,33 @@ def _bounds(fn, args):
     n = C.c_int(0)
     _chk(fn(*args, mn.ctypes.data_as(c_u32p), mx.ctypes.data_as(c_u32p), C.byref(n)))
     return n.value, mn, mx
+
+
+class SimplePGO:
+    """lama::SimplePGO (include/lama/simple_pgo.h:43-57): node_list (n x {x, y, rotation}), edge_list [(from, to, xyr)], fixed_list [(node, xyr)]"""
+
+    def __init__(self, node_list, edge_list=(), fixed_list=(), device=0):
+        self.node_list = np.array(node_list, dtype=np.float64).reshape(-1, 3).copy()
+        self.edge_list = list(edge_list)
+        self.fixed_list = list(fixed_list)
+        self.device = device
+        self.status = None
+        self.report = None
+
+    def optimize(self) -> bool:
+        """SimplePGO::optimize (src/simple_pgo.cpp:48-105): True on SUCCESS (node_list then holds the optimised poses)"""
+        ft = np.ascontiguousarray([[e[0], e[1]] for e in self.edge_list], np.int32).reshape(-1, 2)
+        ex = np.ascontiguousarray([e[2] for e in self.edge_list], np.float64).reshape(-1, 3)
+        fn = np.ascontiguousarray([f[0] for f in self.fixed_list], np.int32)
+        fx = np.ascontiguousarray([f[1] for f in self.fixed_list], np.float64).reshape(-1, 3)
+        st = C.c_int(-1)
+        rep = np.zeros(6)
+        _chk(lib().lama_pgo_optimize(C.c_int(self.device), self.node_list.ctypes.data_as(c_dp), C.c_int(len(self.node_list)), ft.ctypes.data_as(c_i32p),
+                                     ex.ctypes.data_as(c_dp), C.c_int(len(ft)), fn.ctypes.data_as(c_i32p), fx.ctypes.data_as(c_dp), C.c_int(len(fn)),
+                                     C.byref(st), rep.ctypes.data_as(c_dp)))
+        self.status = st.value
+        self.report = dict(zip(("iterations", "lambda_tries", "cg_iterations", "initial_error", "final_error", "device_ms"), rep.tolist()))
+        return st.value == 0
 
 
 def loop_closure_candidates(key_xy, ignore_n_chain_poses, query_xy, radius, max_candidates=5):

@@ -12,6 +12,7 @@
 #include "frontend.h"
 #include "sdm_io.h"
 #include "shard_comm.h"
+#include "pgo.h"
 
 #include "../../include/lama_b200.h"
 
@@ -907,6 +908,34 @@ try {
         if (stats) { stats[2 * i] = res[i].iterations; stats[2 * i + 1] = res[i].evals_ref; }
         if (sums) std::memcpy(sums + (size_t)i * kNumSums, res[i].sums, sizeof(double) * kNumSums);
     }
+    return LAMA_OK;
+}
+LAMA_CATCH
+
+// ---- SimplePGO (src/simple_pgo.cpp:48-105) -----------------------------------------------------------------------------------------------------
+int lama_pgo_optimize(int device, double* nodes_xyr, int n_nodes, const int* edges_from_to, const double* edges_xyr, int n_edges, const int* fixed_nodes,
+                      const double* fixed_xyr, int n_fixed, int* status, double report[6])
+try {
+    if (!nodes_xyr || n_nodes < 1 || n_edges < 0 || n_fixed < 0 || (n_edges && (!edges_from_to || !edges_xyr)) || (n_fixed && (!fixed_nodes || !fixed_xyr)))
+        return set_err("bad argument", LAMA_ERR_ARG);
+    std::vector<SE2> nodes((size_t)n_nodes);
+    for (int i = 0; i < n_nodes; ++i) nodes[(size_t)i] = se2_from_xyr(nodes_xyr[3 * i], nodes_xyr[3 * i + 1], nodes_xyr[3 * i + 2]);
+    std::vector<PgoEdge> edges((size_t)n_edges);
+    for (int e = 0; e < n_edges; ++e)
+        edges[(size_t)e] = PgoEdge{edges_from_to[2 * e], edges_from_to[2 * e + 1], se2_from_xyr(edges_xyr[3 * e], edges_xyr[3 * e + 1], edges_xyr[3 * e + 2])};
+    std::vector<PgoFixed> fixed((size_t)n_fixed);
+    for (int f = 0; f < n_fixed; ++f) fixed[(size_t)f] = PgoFixed{fixed_nodes[f], se2_from_xyr(fixed_xyr[3 * f], fixed_xyr[3 * f + 1], fixed_xyr[3 * f + 2])};
+    PgoReport rep;
+    std::string err;
+    const int rc = pgo_optimize(device, nodes, edges, fixed, rep, err);
+    if (rc != LAMA_OK) return set_err(err, rc);
+    if (status) *status = rep.status;
+    if (report) {
+        report[0] = rep.iterations; report[1] = rep.lambda_tries; report[2] = (double)rep.cg_iterations;
+        report[3] = rep.initial_error; report[4] = rep.final_error; report[5] = rep.device_ms;
+    }
+    if (rep.status == 0)
+        for (int i = 0; i < n_nodes; ++i) xyr_of(nodes[(size_t)i], nodes_xyr + 3 * i);
     return LAMA_OK;
 }
 LAMA_CATCH

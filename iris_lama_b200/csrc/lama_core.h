@@ -170,6 +170,25 @@ LAMA_HD SE2 se2_from_xyr(double x, double y, double theta)  // se2.hpp:648-651
     return r;
 }
 LAMA_HD double se2_rotation(const SE2& a) { return atan2(a.s, a.c); }  // so2.hpp:401-404
+// SE2::log (se2.hpp:519-542): (upsilon, theta) with upsilon = V^-1 t
+LAMA_HD void se2_log(const SE2& a, double out[3])
+{
+    const double theta = se2_rotation(a), half = 0.5 * theta;
+    const double real_minus_one = a.c - 1.0;
+    double h;
+    if (fabs(real_minus_one) < kLieEps) h = 1.0 - (1.0 / 12.0) * theta * theta;
+    else h = -(half * a.s) / real_minus_one;
+    out[0] = h * a.tx + half * a.ty;
+    out[1] = -half * a.tx + h * a.ty;
+    out[2] = theta;
+}
+// SE2::Adj (se2.hpp:125-133), row major 3 x 3
+LAMA_HD void se2_adj(const SE2& a, double m[9])
+{
+    m[0] = a.c; m[1] = -a.s; m[2] = a.ty;
+    m[3] = a.s; m[4] = a.c;  m[5] = -a.tx;
+    m[6] = 0.0; m[7] = 0.0;  m[8] = 1.0;
+}
 
 // ---- sensor -> map transform ---------------------------------------------------------------------------
 // tf = [T(x,y,0) Rz(theta)] * [T(sensor_origin) R(sensor_quat)]   (match_surface_2d.cpp:49-58,

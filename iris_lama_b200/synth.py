@@ -194,3 +194,42 @@ def make_dataset(name: str, n_scans: int, n_beams: int | None = None, range_seed
             cur = _compose(cur, d)
             odom[t] = cur
     return Dataset(name, segs, truth, odom, scans, angles, max_range)
+
+
+def make_pose_graph(n_nodes, n_loops, seed=7, step=0.1, odom_sigma=(0.02, 0.02, 0.004), loop_sigma=(0.01, 0.01, 0.002), radius=2.0):
+    """Synthetic input of SimplePGO (BASELINE.json configs[4]): a robot driving laps of a rounded figure whose size drifts slowly, so that it
+    keeps revisiting places.  Returns (truth n x 3, node_list n x 3 = odometry-integrated poses with drift, edge_list [(from, to, xyr)]):
+    the loop edges connect poses that are close in space (< radius) but far apart in time, measured with a little noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_nodes) * step
+    lap = 40.0                                     # metres per lap
+    ang = 2 * np.pi * t / lap
+    r = 5.0 + 1.5 * np.sin(0.37 * ang)             # the laps do not coincide exactly
+    x, y = r * np.cos(ang), r * np.sin(ang) * 0.8
+    th = np.arctan2(np.gradient(y), np.gradient(x))
+    truth = np.stack([x, y, th], 1)
+
+    def se2(p):
+        c, s = np.cos(p[2]), np.sin(p[2])
+        return np.array([[c, -s, p[0]], [s, c, p[1]], [0, 0, 1.0]])
+
+    def xyr(m):
+        return np.array([m[0, 2], m[1, 2], np.arctan2(m[1, 0], m[0, 0])])
+
+    T = [se2(p) for p in truth]
+    nodes = [truth[0].copy()]
+    cur = T[0]
+    for i in range(n_nodes - 1):
+        d = xyr(np.linalg.inv(T[i]) @ T[i + 1]) + rng.normal(0, odom_sigma)
+        cur = cur @ se2(d)
+        nodes.append(xyr(cur))
+    # loop closures: spatial neighbours that are not temporal neighbours
+    from scipy.spatial import cKDTree
+    tree = cKDTree(truth[:, :2])
+    pairs = [(a, b) for a, b in tree.query_pairs(radius) if abs(a - b) > 50]
+    rng.shuffle(pairs)
+    edges = []
+    for a, b in pairs[:n_loops]:
+        a, b = (a, b) if a < b else (b, a)
+        edges.append((int(a), int(b), xyr(np.linalg.inv(T[a]) @ T[b]) + rng.normal(0, loop_sigma)))
+    return truth, np.array(nodes), edges
