@@ -63,7 +63,11 @@ def test_device_pgo_equals_oracle(gpu_api, n, loops, fixed):
     o = pg.SimplePGO(nodes, edges, fl)
     g = gpu_api.SimplePGO(nodes, edges, fl)
     ok_o, ok_g = o.optimize(), g.optimize()
-    assert ok_g == ok_o and ok_o
+    assert ok_g == ok_o
+    if loops == 0:   # the odometry chain alone is consistent with itself: zero error, LM gives up, nothing changes (see the CPU test)
+        assert not ok_o and g.status == 2 and np.abs(g.node_list - nodes).max() == 0
+        return
+    assert ok_o
     assert g.report["iterations"] == o.iterations and g.report["lambda_tries"] == o.lambda_tries     # same LM decisions
     assert abs(g.report["initial_error"] - o.errors[0]) < 1e-9 * o.errors[0]
     assert abs(g.report["final_error"] - o.errors[-1]) < 1e-6 * max(1.0, o.errors[-1])
@@ -75,16 +79,17 @@ def test_device_pgo_equals_oracle(gpu_api, n, loops, fixed):
 @pytest.mark.gpu
 def test_device_pgo_config5_size(gpu_api):
     """BASELINE.json configs[4]: 10 000 poses, 50 000 odometry + loop constraints -- too much for the scipy LU of the oracle in a test
-    (fill-in), so size-independent properties: SUCCESS, monotone error, the drift is repaired, a second call is a fixed point"""
+    (fill-in), so size-independent properties: SUCCESS, the error drops by orders of magnitude, the drift shrinks, and the run is
+    deterministic (fixed-order reductions: a second run from the same input returns the same bits)"""
     n = 10000
     truth, nodes, edges = synth.make_pose_graph(n, 40001, seed=11, radius=3.0)
     assert len(edges) + n - 1 >= 50000
     g = gpu_api.SimplePGO(nodes, edges)
     assert g.optimize() and g.report["final_error"] < 1e-2 * g.report["initial_error"]
     assert np.abs(g.node_list - truth)[:, :2].max() < np.abs(nodes - truth)[:, :2].max()
-    g2 = gpu_api.SimplePGO(g.node_list, edges)
-    assert g2.optimize() and g2.report["iterations"] <= 2
-    assert np.abs(g2.node_list - g.node_list)[:, :2].max() < 1e-3
+    g2 = gpu_api.SimplePGO(nodes, edges)
+    assert g2.optimize() and g2.report["iterations"] == g.report["iterations"] and g2.report["cg_iterations"] == g.report["cg_iterations"]
+    assert (g2.node_list == g.node_list).all()
 
 
 def test_pgo_needs_a_gpu_or_fails_loudly():
