@@ -278,8 +278,8 @@ def gpu_arm(args):
     ds = make_data(n_scans)
     stream = torch.cuda.Stream(device=dev)   # the engine launches on this stream, so torch CUDA events see its kernels
 
-    def new_pf(timing=False, **opts):
-        o = api.PFSlam2D.Options(PARTICLES, device=local_rank, timing=int(timing), shard_rank=rank, shard_count=world,
+    def new_pf(timing=False, particles=PARTICLES, **opts):
+        o = api.PFSlam2D.Options(particles, device=local_rank, timing=int(timing), shard_rank=rank, shard_count=world,
                                  stream=stream.cuda_stream, **pf_options_kwargs(**opts))
         pf = api.PFSlam2D(o)
         pf.setPrior(*ds.truth[0])
@@ -299,12 +299,12 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed_pass(data, t_first, k_steps, staged, timing=False, sample_clocks=False, **opts):
+    def timed_pass(data, t_first, k_steps, staged, timing=False, sample_clocks=False, particles=PARTICLES, **opts):
         """one fresh filter over scans 0 .. t_first + k_steps of `data`; the last k_steps are timed, each with its own event pair"""
-        pf = new_pf(timing, **opts)
+        pf = new_pf(timing, particles, **opts)
         sh = None
         if world > 1 and args.sharded_impl == "python":
-            sh = ShardedPFSlam2D(pf, PARTICLES, device=dev)   # round-1 orchestration: torch.distributed collectives driven from Python
+            sh = ShardedPFSlam2D(pf, particles, device=dev)   # round-1 orchestration: torch.distributed collectives driven from Python
         elif world > 1:
             import torch.distributed as dist                   # the sharded step inside the library (NCCL from C++, shard_comm.cpp)
             box = [api.shard_unique_id() if rank == 0 else None]
@@ -364,6 +364,15 @@ def gpu_arm(args):
     h2d, d2h = r2["h2d"], r2["d2h"]
     stats_e2e = step_stats(r2["per_step"])
     del r2
+
+    # ---- weak scaling (N > 1): the filter grows with the node, 256 particles per GPU stay; same scans, same public call ------------
+    weak = None
+    if world > 1 and not args.no_weak:
+        rw = timed_pass(ds, first, steps, staged=False, particles=PARTICLES * world)
+        weak = {"particles": PARTICLES * world, "particles_per_gpu": PARTICLES, "scans_per_s": steps / rw["dt"], "e2e_scans_per_s": steps / rw["wall"],
+                "particle_scans_per_s": PARTICLES * world * steps / rw["dt"], "resamples": rw["work"]["resampled"], **step_stats(rw["per_step"]),
+                "note": "P = 256 x N: per-GPU work fixed; efficiency = scans_per_s here / the N = 1 line's value (256 particles on one GPU)"}
+        del rw
 
     # ---- pass 3: per-kernel CUDA-event durations for the roofline (timing mode adds event records and host syncs) ------------
     roofline, kernel_ms = None, None
@@ -463,6 +472,9 @@ def gpu_arm(args):
                 "summary_ms_per_step": {**summary_value, "map_device": kernel_ms["map_device"] if kernel_ms else None,
                                         "note": "reference Summary buckets (pf_slam2d.h:88-129): host wall clock of sampling / solve (enqueue + wait for the "
                                                 "match) / normalise / resample; the map bucket runs asynchronously on the device"}}
+        line["particle_scans_per_s"] = PARTICLES * value
+        if weak:
+            line["weak_scaling"] = weak
         if roofline:
             line["roofline"] = roofline
             line["kernel_ms_per_step"] = kernel_ms
@@ -521,6 +533,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-regimes", action="store_true")
     ap.add_argument("--no-full-loop", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling pass (P = 256 x N) of a multi-GPU run")
     ap.add_argument("--full-loop", type=int, default=5000, help="scans of the full-loop regime (BASELINE config 4: 5 000)")
     ap.add_argument("--sharded-impl", default="native", choices=["native", "python"])
     ap.add_argument("--prebuild", type=int, default=300, help="untimed scans that build the map before warm-up (both arms)")
