@@ -96,6 +96,14 @@ struct WarpBrushfire {
     const uint32_t max_sqdist;
     uint32_t err;
     bool dead;           // the pool ran dry: stop touching the map
+#ifdef LAMA_PHASE_TIMING
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};   // pop, current + obstacle cell, neighbour fetch, obstacle-of-neighbour check, commit (pushes + stores), pushes alone
+#define BF_CLK(v) const long long v = clock64()
+#define BF_ACC(k, a, b) cyc[k] += (b) - (a)
+#else
+#define BF_CLK(v) do { } while (0)
+#define BF_ACC(k, a, b) do { } while (0)
+#endif
 
     __device__ WarpBrushfire(const StoreView& sv, int32_t* d, int32_t* g, uint32_t* sc, int l, SmemHeap lo, SmemHeap ra, uint32_t msq)
         : s(sv), dir(d), gdir(g), scratch(sc), side((uint32_t)sv.window.dim * kPatchLen), log2dim(ilog2(sv.window.dim)), lane(l), lower_q(lo),
@@ -277,9 +285,15 @@ struct WarpBrushfire {
         const int dxi = (i == 0) - (i == 2), dyi = (i == 1) - (i == 3);
         const bool go = lane < 4 && !(dxi * cox > 0 || dyi * coy > 0);  // only update away from the obstacle (:296)
         const uint32_t nx = x + dxi, ny = y + dyi;
+        BF_CLK(c0);
         uint32_t* p = rel_lptr(cur, interior_cell(x, y), x, y, dxi, dyi, go);
         uint32_t n = 0;
         if (go) n = touch(p);
+#ifdef LAMA_PHASE_TIMING
+        n = __shfl_sync(kFullMask, n, lane);   // wait for the load, so that the split below means something
+#endif
+        BF_CLK(c1);
+        BF_ACC(2, c0, c1);
         const int rx = cox - dxi, ry = coy - dyi;
         const uint32_t new_sq = (uint32_t)(rx * rx + ry * ry);
         const uint32_t cmp_sq = (n & kDmValid) ? dm_sqdist(n) : max_sqdist;
@@ -294,15 +308,22 @@ struct WarpBrushfire {
         }
         __syncwarp();
         unsigned m = __ballot_sync(kFullMask, over) & 0xFu;
+        BF_CLK(c2);
+        BF_ACC(3, c1, c2);
         const uint32_t key = key_of(nx, ny);
         while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
+            BF_CLK(c4);
             push_lower(__shfl_sync(kFullMask, new_sq, l), __shfl_sync(kFullMask, key, l));
+            BF_CLK(c5);
+            BF_ACC(5, c4, c5);
             if (lane == l) *p = dm_pack(new_sq, rx, ry, true, true);
         }
         if (lane == 0) *cur = c & ~kDmQueued;
         __syncwarp();
+        BF_CLK(c3);
+        BF_ACC(4, c2, c3);
     }
 
     // :160-197
@@ -318,13 +339,18 @@ struct WarpBrushfire {
             raise(x, y, cur);
         }
         while (lower_q.size) {
+            BF_CLK(a0);
             const uint32_t key = heap_key(lower_q.pop());
+            BF_CLK(a1);
+            BF_ACC(0, a0, a1);
             const uint32_t x = key & 0xFFFFu, y = key >> 16;
             uint32_t* cur = uptr(x, y);
             const uint32_t c = touch(cur);
             ++processed;
             if (c & kDmValid) {
                 const uint32_t o = touch(rel_uptr(cur, x, y, dm_ox(c), dm_oy(c)));
+                BF_CLK(a2);
+                BF_ACC(1, a1, a2);
                 if (dm_sqdist(o) == 0 && (c & kDmQueued)) lower(x, y, cur, c);
             }
         }

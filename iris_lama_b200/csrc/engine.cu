@@ -466,6 +466,14 @@ int Engine::update_maps(const SE2* states, int first_particle, int count, HostMa
     return settle(out);
 }
 
+// developer builds (LAMA_PHASE_TIMING): LAMA_BF_DEBUG = ordinal of the map update whose k_brushfire prints its per-particle phase cycles
+static int brush_debug_flag()
+{
+    static int launch_no = 0;
+    const char* dbg = std::getenv("LAMA_BF_DEBUG");
+    return dbg && std::atoi(dbg) == launch_no++;
+}
+
 // Launches ray cast + brushfire and returns without waiting; settle() (called by every later entry point)
 // synchronises, collects the per-particle statistics and surfaces device errors.
 int Engine::update_maps_async(const SE2* states, int first_particle, int count)
@@ -492,6 +500,7 @@ int Engine::update_maps_async(const SE2* states, int first_particle, int count)
     bp.set = cur_set_;
     bp.particle_offset = first_particle;
     bp.event_cap = rp.event_cap;
+    bp.debug = brush_debug_flag();
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[0], d_->stream));
     const int ray_kernels = launch_ray_stage(d_, rp, d_->d_states, count);
     if (timing_) CU_TRY(cudaEventRecord(d_->ev[1], d_->stream));
@@ -573,6 +582,7 @@ int Engine::step_enqueue(const double* pts, int n, const double origin[3], const
     bp.set = cur_set_;
     bp.particle_offset = 0;
     bp.event_cap = rp.event_cap;
+    bp.debug = brush_debug_flag();
     const int ray_kernels = launch_ray_stage(d_, rp, reinterpret_cast<const SE2*>(d_->d_results), count);
     launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
     launch_merge_free(d_->view, d_->stream);

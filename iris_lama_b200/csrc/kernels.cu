@@ -1308,6 +1308,9 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
     const int particle = bp.particle_offset + blockIdx.x;
     int32_t* gdir      = dir_of(s, bp.set, particle, kMapDm);
 
+#ifdef LAMA_PHASE_TIMING
+    long long bt[5] = {clock64(), 0, 0, 0, 0};
+#endif
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     // The obstacle events arrive in any order (k_ray_pull appends them cell by cell): sorting by their (beam, step) stamp restores
@@ -1349,6 +1352,9 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
         }
     }
     if (warp != 0) return;
+#ifdef LAMA_PHASE_TIMING
+    bt[1] = clock64();
+#endif
 
     WarpBrushfire bf(s, dir, gdir, scratch, lane, SmemHeap{lower_h, 0u, (uint32_t)bp.lower_cap}, SmemHeap{raise_h, 0u, (uint32_t)bp.raise_cap},
                      bp.max_sqdist);
@@ -1359,7 +1365,16 @@ k_brushfire(StoreView s, BrushParams bp, const uint64_t* __restrict__ events, Ma
         if ((e >> 32) & 1u) bf.add_obstacle(key & 0xFFFFu, key >> 16);
         else bf.remove_obstacle(key & 0xFFFFu, key >> 16);
     }
+#ifdef LAMA_PHASE_TIMING
+    bt[2] = clock64();
+    const uint32_t q0 = bf.raise_q.size, q1 = bf.lower_q.size;
+#endif
     const uint32_t processed = bf.update();
+#ifdef LAMA_PHASE_TIMING
+    bt[3] = clock64();
+    if (lane == 0 && bp.debug) printf("bf %d: pre %lld events %lld update %lld | nev %u raise %u lower %u pops %u\n", blockIdx.x, bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], nev, q0, q1, processed);
+    if (lane == 0 && bp.debug) printf("bfc %d: pop %lld cur %lld nbr %lld chk %lld commit %lld (pushes %lld)\n", blockIdx.x, bf.cyc[0], bf.cyc[1], bf.cyc[2], bf.cyc[3], bf.cyc[4], bf.cyc[5]);
+#endif
     const uint32_t err = __reduce_or_sync(0xffffffffu, bf.err);
     if (lane == 0) {
         stats[blockIdx.x].dm_pops = processed;

@@ -72,6 +72,7 @@ struct BrushParams {
     int event_cap;         // stride of the per-particle event lists
     int lower_cap, raise_cap;
     uint32_t max_sqdist;
+    int debug;             // LAMA_PHASE_TIMING builds only: print the per-particle phase cycles of this launch
 };
 
 // per-particle outputs of the map update
