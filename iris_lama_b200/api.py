@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "lama_last_error", "lama_version", "lama_device_count",
     "lama_pf_options_default", "lama_pf_create", "lama_pf_destroy", "lama_pf_set_prior", "lama_pf_update", "lama_pf_get_pose",
     "lama_pf_stage_scans", "lama_pf_update_staged", "lama_pf_get_traffic",
-    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary", "lama_shard_unique_id", "lama_pf_shard_connect", "lama_pf_shard_stats", "lama_pgo_optimize", "lama_loop_closure_candidates", "lama_slam_correlate_candidate_scan", "lama_dm_correlate_candidate_scan", "lama_slam_coarse_correlate_candidate_scan", "lama_dm_coarse_correlate_candidate_scan", "lama_dm_match_error",
+    "lama_pf_get_best_particle", "lama_pf_get_neff", "lama_pf_get_particles", "lama_pf_get_trajectory", "lama_pf_get_last_resample", "lama_pf_get_resample_digest", "lama_pf_get_summary", "lama_pf_get_memory_usage", "lama_pf_get_timestamps", "lama_shard_unique_id", "lama_pf_shard_connect", "lama_pf_shard_stats", "lama_pgo_optimize", "lama_loop_closure_candidates", "lama_slam_correlate_candidate_scan", "lama_dm_correlate_candidate_scan", "lama_slam_coarse_correlate_candidate_scan", "lama_dm_coarse_correlate_candidate_scan", "lama_dm_match_error",
     "lama_pf_get_counters", "lama_pf_kernel_times", "lama_pf_map_bounds", "lama_pf_export_occupancy", "lama_pf_export_distance",
     "lama_pf_shard_begin", "lama_pf_shard_finish", "lama_pf_shard_apply", "lama_pf_shard_apply_local", "lama_pf_shard_map_update",
     "lama_pf_particle_pack_size", "lama_pf_particle_pack", "lama_pf_particle_unpack",
@@ -351,6 +351,18 @@ class PFSlam2D:
         t = np.zeros(4)
         _chk(lib().lama_pf_get_summary(self.h, t.ctypes.data_as(c_dp)))
         return dict(zip(("sampling", "solve", "normalize", "resample"), t.tolist()))
+
+    def getMemoryUsage(self):
+        """getMemoryUsage() and its (occmem, dmmem) overload (pf_slam2d.cpp:151-176): (total, occmem, dmmem) in bytes of the reference's containers"""
+        m = np.zeros(3, np.uint64)
+        _chk(lib().lama_pf_get_memory_usage(self.h, _vp(m)))
+        return int(m[0]), int(m[1]), int(m[2])
+
+    def getTimestamps(self):
+        n = C.c_int(0)
+        t = np.zeros(4)
+        _chk(lib().lama_pf_get_timestamps(self.h, t.ctypes.data_as(c_dp), 4, C.byref(n)))
+        return t[:min(n.value, 4)].tolist()
 
     def counters(self):
         return _counters(lib().lama_pf_get_counters, self.h)

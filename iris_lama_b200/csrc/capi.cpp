@@ -423,6 +423,22 @@ try {
     return LAMA_OK;
 }
 LAMA_CATCH
+int lama_pf_get_memory_usage(lama_pf* h, uint64_t out[3])
+try {
+    if (!h || !out) return set_err("null argument", LAMA_ERR_ARG);
+    int rc = h->p->memory_usage(out);
+    return rc == LAMA_OK ? LAMA_OK : set_err(h->p->error(), rc);
+}
+LAMA_CATCH
+int lama_pf_get_timestamps(lama_pf* h, double* stamps, int cap, int* count)
+try {
+    if (!h || !count || (cap > 0 && !stamps) || cap < 0) return set_err("null argument / negative capacity", LAMA_ERR_ARG);
+    const std::vector<double>& t = h->p->timestamps();
+    *count = (int)t.size();
+    for (int i = 0; i < cap && i < (int)t.size(); ++i) stamps[i] = t[(size_t)i];
+    return LAMA_OK;
+}
+LAMA_CATCH
 int lama_pf_get_counters(lama_pf* h, uint64_t last[6], uint64_t total[6])
 try {
     if (!h) return set_err("null handle", LAMA_ERR_ARG);

@@ -1082,4 +1082,30 @@ int Engine::bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2])
     return n;
 }
 
+int Engine::memory_usage(int kind, uint32_t cell_bytes, uint64_t* out)
+{
+    if (settle(nullptr) != LAMA_OK) return -1;
+    if (kind < 0 || kind > 1 || !out) return -1;
+    cudaSetDevice(cfg_.device);
+    const size_t dim2 = (size_t)cfg_.dir_dim * cfg_.dir_dim, stride = (size_t)d_->view.n_kinds * dim2;
+    std::vector<int32_t> dirs((size_t)cfg_.particles * stride), ref((size_t)d_->view.n_slots);
+    const int32_t* src = d_->view.dirs + (size_t)cur_set_ * cfg_.particles * stride;
+    if (cudaMemcpyAsync(dirs.data(), src, dirs.size() * 4, cudaMemcpyDeviceToHost, d_->stream) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(ref.data(), d_->view.refcount, ref.size() * 4, cudaMemcpyDeviceToHost, d_->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(d_->stream) != cudaSuccess) return -1;
+    const double container = (double)kPatchLen * kPatchLen * cell_bytes;
+    for (int p = 0; p < cfg_.particles; ++p) {
+        const int32_t* dir = dirs.data() + (size_t)p * stride + (size_t)kind * dim2;
+        double total = 0.0;
+        for (size_t e = 0; e < dim2; ++e) {
+            if (dir[e] < 0) continue;
+            const int uses = ref[(size_t)(dir[e] & kDirSlotMask)];
+            total += 72.0;
+            total += container / (double)(uses > 0 ? uses : 1);
+        }
+        out[p] = (uint64_t)total;
+    }
+    return 0;
+}
+
 }  // namespace lama_b200

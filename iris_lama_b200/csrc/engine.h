@@ -131,6 +131,9 @@ public:
     int gather_cells(int particle, int kind, const uint32_t* cells_xy, int n, uint32_t* words, uint8_t* flags);
     // bounding box (in cells) of allocated patches of one map; returns the number of patches
     int bounds(int particle, int kind, uint32_t mn[2], uint32_t mx[2]);
+    // Map::memory() (src/sdm/map.cpp:115-125) of one map kind of every particle: per patch 72 bytes of table entry (key, COWPtr = shared_ptr + mutex, pointer)
+    // plus the container's cell bytes divided by its use count; out[particle] truncated to an integer like the reference's return value
+    int memory_usage(int kind, uint32_t cell_bytes, uint64_t* out);
 
     // sticky device error bits (lama_core.h) -- reads the device word; 0 = ok
     uint32_t device_status();

@@ -562,8 +562,23 @@ int PFSlam2D::migrate_and_apply(const std::vector<int32_t>& idx)
     return LAMA_OK;
 }
 
+int PFSlam2D::memory_usage(uint64_t out[3])
+{
+    out[0] = out[1] = out[2] = 0;
+    if (!has_first_ || !eng_) return LAMA_OK;
+    const int local = eng_->config().particles;
+    std::vector<uint64_t> occ((size_t)local), dm((size_t)local);
+    // sizeof(frequency) = 4 (frequency_occupancy_map.h), sizeof(distance_t) = 10 (dynamic_distance_map.h: three int16, uint16, two bool)
+    if (eng_->memory_usage(0 /* occupancy */, 4u, occ.data()) != 0 || eng_->memory_usage(1 /* distance */, 10u, dm.data()) != 0) return engine_fail(LAMA_ERR_CUDA);
+    for (int i = 0; i < local; ++i) out[0] += occ[(size_t)i] + dm[(size_t)i];
+    out[1] = occ[0] * (uint64_t)local;
+    out[2] = dm[0] * (uint64_t)local;
+    return LAMA_OK;
+}
+
 int PFSlam2D::update(const double* pts, int n, const double* origin, const double* quat, const double odom_xyr[3], double stamp, bool* did_update)
 {
+    if (!has_first_) timestamps_.push_back(stamp);
     if (opt_.shard_count != 1) {
         if (!comm_) return fail("PFSlam2D::update on a sharded handle: connect the ranks first (lama_pf_shard_connect) or use the split-phase shard_* calls", LAMA_ERR_STATE);
         bool did = false;

@@ -85,6 +85,10 @@ public:
     void resample_digest(uint64_t out[2]) const { out[0] = resample_count_; out[1] = resample_hash_; }
     // PFSlam2D::Summary buckets (include/lama/pf_slam2d.h:88-129) as host wall-clock sums in ms since creation:
     // {sampling (drawFromMotion), solve (enqueue + wait for the match results), normalise, resample (decision + device copies)}
+    // getMemoryUsage() / getMemoryUsage(occmem, dmmem) (src/pf_slam2d.cpp:151-176): out = {total over all particles, occmem, dmmem}; the two-argument
+    // overload of the reference adds particle 0's maps P times, which is reproduced
+    int memory_usage(uint64_t out[3]);
+    const std::vector<double>& timestamps() const { return timestamps_; }   // getTimestamps(): the reference records the first scan's stamp (pf_slam2d.cpp:187)
     void summary_ms(double out[4]) const { out[0] = t_sample_; out[1] = t_solve_; out[2] = t_norm_; out[3] = t_resample_; }
     const Counters& last_counters() { settle_counters(); return last_; }
     const Counters& total_counters() { settle_counters(); return total_; }
@@ -101,6 +105,7 @@ private:
     PFSlam2D() = default;
     PFOptions opt_;
     std::unique_ptr<Engine> eng_;
+    std::vector<double> timestamps_;
     std::mt19937 gen_;  // stands in for the reference's process-global generator (src/random.cpp:38-39)
     uint32_t P_ = 0;
     int lo_ = 0, hi_ = 0;

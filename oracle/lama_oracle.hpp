@@ -279,6 +279,17 @@ public:
     {
     }
 
+    // Map::memory (map.cpp:115-125) with the reference's sizes: key 8 + sizeof(COWPtr<Container>) 56 (shared_ptr + std::mutex, cow_ptr.h:117-118) +
+    // pointer 8 per table entry, Container::memory() = volume * sizeof(cell type of the reference) shared between the owners
+    size_t memory(uint32_t ref_cell_bytes) const
+    {
+        double total = 0.0;
+        for (auto& kv : patches) {
+            total += 8 + 56 + 8;
+            total += (double)((size_t)patch_volume * ref_cell_bytes) / (double)kv.second.use_count();
+        }
+        return (size_t)total;
+    }
     // map.h:137-138 : tf_ * p with tf_ = Translation(adjust*patch_length) * Scaling(scale)
     void w2m_nocast(const double p[3], double m[3]) const
     {

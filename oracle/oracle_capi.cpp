@@ -515,6 +515,20 @@ void orc_prob_query(void* d, const uint32_t* cells, int n, double* prob, uint8_t
 
 }  // extern "C"
 extern "C" {
+// PFSlam2D::getMemoryUsage() and its (occmem, dmmem) overload, pf_slam2d.cpp:151-176 (the overload sums particle 0's maps P times)
+void orc_pf_memory_usage(void* h, uint64_t out[3])
+{
+    auto* pf = (PFSlam2D*)h;
+    out[0] = out[1] = out[2] = 0;
+    auto& ps = pf->particles[pf->cur];
+    for (size_t i = 0; i < ps.size(); ++i) {
+        if (!ps[i].dm || !ps[i].occ) continue;
+        out[0] += ps[i].dm->memory(10);
+        out[0] += ps[i].occ->memory(4);
+        out[1] += ps[0].occ->memory(4);
+        out[2] += ps[0].dm->memory(10);
+    }
+}
 // instrumentation: the largest brushfire heap any particle's distance map has held so far
 uint64_t orc_pf_peak_queue(void* h)
 {

@@ -402,6 +402,12 @@ class PFSlam2D:
     def set_threads(self, n):
         lib().orc_pf_set_threads(self.h, C.c_int32(n))
 
+    def memory_usage(self):
+        """getMemoryUsage() and its (occmem, dmmem) overload: (total, occmem, dmmem)"""
+        m = np.zeros(3, np.uint64)
+        lib().orc_pf_memory_usage(self.h, m.ctypes.data_as(C.c_void_p))
+        return int(m[0]), int(m[1]), int(m[2])
+
     def times(self):
         t = np.zeros(4)
         lib().orc_pf_times(self.h, t.ctypes.data_as(c_dp))

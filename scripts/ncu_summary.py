@@ -4,9 +4,9 @@ usage: python scripts/ncu_summary.py report.ncu-rep out.md out_traffic.json "tit
 import csv, json, subprocess, sys
 
 rep, out_md, out_json, title = sys.argv[1:5]
-KERNELS = ["k_raycast", "k_brushfire", "k_match"]
+KERNELS = ["k_raycast", "k_brushfire", "k_match", "k_ray_pull", "k_ray_setup"]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__block_size", "smsp__inst_executed.sum",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__block_size", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__thread_inst_executed.sum",
            "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
@@ -34,5 +34,7 @@ for k in KERNELS:
     src = subprocess.run([sys.executable, "scripts/ncu_lines.py", rep, k, "14"], capture_output=True, text=True).stdout
     md += ["per source line (samples, warp instructions, top stall reasons):", "```", src.rstrip(), "```", ""]
 open(out_md, "w").write("\n".join(md) + "\n")
+commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+traffic["commit"] = commit + " (HEAD when the summary was written; the library of the capture was built from it)"
 json.dump(traffic, open(out_json, "w"), indent=1)
 print(json.dumps(traffic))

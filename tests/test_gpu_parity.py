@@ -342,6 +342,28 @@ def test_pfslam2d_motion_gate_and_rng_stream(gpu_api, po, synth):
     assert 2 <= ups < T
 
 
+def test_pfslam2d_memory_usage_and_timestamps(gpu_api, po, synth):
+    """getMemoryUsage (pf_slam2d.cpp:151-176 over Map::memory, map.cpp:115-125) and getTimestamps.  Without resampling the sharing state of the patches
+    equals the reference's, so the byte counts agree (one truncation per map); after a resampling the device store shares MORE (the offspring are copied
+    after the map update), so it reports at most the reference's bytes."""
+    P, T = 8, 10
+    ds = synth.make_dataset("room", T, n_beams=180)
+    g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(P, trans_thresh=0.05, rot_thresh=0.05, seed=5))
+    o = po.PFSlam2D(po.PFOptions.defaults(P, trans_thresh=0.05, rot_thresh=0.05, seed=5))
+    g.setPrior(*ds.truth[0]); o.set_prior(*ds.truth[0])
+    assert g.getMemoryUsage() == (0, 0, 0) and g.getTimestamps() == []
+    for t in range(T):
+        g.update(ds.scans[t], ds.odom[t], timestamp=100.0 + t); o.update(ds.scans[t], ds.odom[t])
+        assert len(o.last_resample()) == 0
+        mg, mo = g.getMemoryUsage(), o.memory_usage()
+        assert all(abs(a - b) <= 2 * P for a, b in zip(mg, mo)), (t, mg, mo)
+        assert mg[0] > 0
+    assert g.getTimestamps() == [100.0]
+    g2, o2, n_res = _run_pf_pair(gpu_api, po, ds, P, T, seed=5, meas_sigma_gain=0.02)
+    assert n_res >= 2
+    assert 0 < g2.getMemoryUsage()[0] <= o2.memory_usage()[0]
+
+
 # ---- SURVEY 8(f) row 4 (front-end half): LidarOdometry2D and Slam2D's transient map ---------------------------------------
 def _near(scan, r):
     """the beams shorter than r: a short-range sensor, so that the surface AABB moves with the robot"""
