@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblama_b200.so")
+LIB_PATH = os.environ.get("LAMA_B200_LIB") or os.path.join(_HERE, "liblama_b200.so")   # the override is for developer builds of the same library
 _lib = None
 
 c_dp = C.POINTER(C.c_double)

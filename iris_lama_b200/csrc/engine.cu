@@ -1096,10 +1096,15 @@ int Engine::memory_usage(int kind, uint32_t cell_bytes, uint64_t* out)
     const double container = (double)kPatchLen * kPatchLen * cell_bytes;
     for (int p = 0; p < cfg_.particles; ++p) {
         const int32_t* dir = dirs.data() + (size_t)p * stride + (size_t)kind * dim2;
+        const int32_t* occ = dirs.data() + (size_t)p * stride;   // kind 0
         double total = 0.0;
         for (size_t e = 0; e < dim2; ++e) {
-            if (dir[e] < 0) continue;
-            const int uses = ref[(size_t)(dir[e] & kDirSlotMask)];
+            // The reference's distance map also owns a patch wherever an occupancy cell was touched (the first touch of an occupancy cell reports
+            // "changed" and calls removeObstacle, whose mutable get allocates: capi.cpp export_dm); on the device those cells live in the occupancy
+            // patch only, so such a patch is counted with the sharing state of the occupancy patch that stands in for it.
+            const int32_t ent = dir[e] >= 0 ? dir[e] : (kind == 1 ? occ[e] : -1);
+            if (ent < 0) continue;
+            const int uses = ref[(size_t)(ent & kDirSlotMask)];
             total += 72.0;
             total += container / (double)(uses > 0 ? uses : 1);
         }
