@@ -111,8 +111,9 @@ int lama_pf_get_summary(lama_pf* h, double ms[4]);
 /* uint64_t PFSlam2D::getMemoryUsage() and getMemoryUsage(occmem, dmmem) (src/pf_slam2d.cpp:151-176) from Map::memory() (src/sdm/map.cpp:115-125: per patch
  * 72 bytes of table entry + cell bytes / use count of the shared patch): out = {total over the particles, occmem, dmmem}.  The two-argument overload of the
  * reference adds particle 0's maps P times; occmem / dmmem reproduce that.  On a sharded handle the sums run over this rank's particles.
- * The reference's distance map also owns a patch wherever an occupancy cell was touched; the device counts such a patch with the use count of the
- * occupancy patch that stands in for it (an estimate of the reference's bytes once particles diverge, exact while maps are fully shared). */
+ * The reference's distance map also owns a patch wherever an occupancy cell was touched; the device counts a distance patch as shared by no more
+ * particles than the occupancy patch over the same cells (an upper estimate of the reference's bytes once particles diverge, exact while maps are
+ * fully shared). */
 int lama_pf_get_memory_usage(lama_pf* h, uint64_t out[3]);
 /* const std::deque<double>& PFSlam2D::getTimestamps() (include/lama/pf_slam2d.h:205-206; only the first scan's stamp is ever pushed, src/pf_slam2d.cpp:187) */
 int lama_pf_get_timestamps(lama_pf* h, double* stamps, int cap, int* count);

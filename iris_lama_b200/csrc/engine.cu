@@ -1100,11 +1100,18 @@ int Engine::memory_usage(int kind, uint32_t cell_bytes, uint64_t* out)
         double total = 0.0;
         for (size_t e = 0; e < dim2; ++e) {
             // The reference's distance map also owns a patch wherever an occupancy cell was touched (the first touch of an occupancy cell reports
-            // "changed" and calls removeObstacle, whose mutable get allocates: capi.cpp export_dm); on the device those cells live in the occupancy
-            // patch only, so such a patch is counted with the sharing state of the occupancy patch that stands in for it.
-            const int32_t ent = dir[e] >= 0 ? dir[e] : (kind == 1 ? occ[e] : -1);
-            if (ent < 0) continue;
-            const int uses = ref[(size_t)(ent & kDirSlotMask)];
+            // "changed" and calls removeObstacle, whose mutable get allocates -- and un-shares -- the distance patch: capi.cpp export_dm).  On the
+            // device those cells live in the occupancy patch only, so a distance patch counts as shared by no more particles than the occupancy
+            // patch over the same cells (which the ray cast un-shares on any touch, not only on first touches: an upper estimate of the bytes).
+            int uses = 0;
+            if (kind == 1) {
+                const int ud = dir[e] >= 0 ? ref[(size_t)(dir[e] & kDirSlotMask)] : 0, uo = occ[e] >= 0 ? ref[(size_t)(occ[e] & kDirSlotMask)] : 0;
+                if (ud <= 0 && uo <= 0) continue;
+                uses = ud > 0 && uo > 0 ? std::min(ud, uo) : std::max(ud, uo);
+            } else {
+                if (dir[e] < 0) continue;
+                uses = ref[(size_t)(dir[e] & kDirSlotMask)];
+            }
             total += 72.0;
             total += container / (double)(uses > 0 ? uses : 1);
         }

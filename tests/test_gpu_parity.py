@@ -346,22 +346,28 @@ def test_pfslam2d_memory_usage_and_timestamps(gpu_api, po, synth):
     """getMemoryUsage (pf_slam2d.cpp:151-176 over Map::memory, map.cpp:115-125) and getTimestamps.  The occupancy maps have the reference's patches and,
     without resampling, its sharing state: byte counts agree (one truncation per map).  The reference's distance map also owns a patch wherever an
     occupancy cell was touched; the device keeps those cells in the occupancy patch and counts such a patch with THAT patch's use count, which the ray cast
-    un-shares at other moments than the reference un-shares its distance patch: equal after the first scan (everything shared), an estimate afterwards."""
+    un-shares on any touch (the reference: on first touches): equal after the first scan (everything shared), an upper estimate afterwards."""
     P, T = 8, 10
     ds = synth.make_dataset("room", T, n_beams=180)
     g = gpu_api.PFSlam2D(gpu_api.PFSlam2D.Options(P, trans_thresh=0.05, rot_thresh=0.05, seed=5))
     o = po.PFSlam2D(po.PFOptions.defaults(P, trans_thresh=0.05, rot_thresh=0.05, seed=5))
     g.setPrior(*ds.truth[0]); o.set_prior(*ds.truth[0])
     assert g.getMemoryUsage() == (0, 0, 0) and g.getTimestamps() == []
+    resampled, checked = False, 0
     for t in range(T):
         g.update(ds.scans[t], ds.odom[t], timestamp=100.0 + t); o.update(ds.scans[t], ds.odom[t])
-        assert len(o.last_resample()) == 0
+        resampled |= len(o.last_resample()) > 0
         mg, mo = g.getMemoryUsage(), o.memory_usage()
+        if resampled:                                                          # from here on the device store shares more than the reference (DESIGN 2)
+            assert 0 < mg[0] <= 1.5 * mo[0]
+            continue
+        checked += 1
         assert abs(mg[1] - mo[1]) <= 2 * P, (t, mg, mo)                       # occmem
         if t == 0:
             assert all(abs(a - b) <= 2 * P for a, b in zip(mg, mo)), (mg, mo)
         else:
-            assert 0.67 * mo[2] <= mg[2] <= 1.5 * mo[2] and 0.67 * mo[0] <= mg[0] <= 1.5 * mo[0], (t, mg, mo)
+            assert 0.8 * mo[2] <= mg[2] <= 1.3 * mo[2] and 0.8 * mo[0] <= mg[0] <= 1.3 * mo[0], (t, mg, mo)
+    assert checked >= 2
     assert g.getTimestamps() == [100.0]
     g2, o2, n_res = _run_pf_pair(gpu_api, po, ds, P, T, seed=5, meas_sigma_gain=0.02)
     assert n_res >= 2
