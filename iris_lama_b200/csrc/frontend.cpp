@@ -1,5 +1,6 @@
 // frontend.cpp -- host orchestration of PFSlam2D / Slam2D / Loc2D over the device Engine.
 #include "frontend.h"
+#include "rng_skip.h"
 
 #include <cuda_runtime.h>
 
@@ -146,10 +147,22 @@ bool PFSlam2D::predict_and_gate(const double odom_xyr[3])
     const SE2 odometry = se2_from_xyr(odom_xyr[0], odom_xyr[1], odom_xyr[2]);
     const SE2 odelta   = se2_mul(se2_inv(odom_), odometry);  // Pose2D::operator-, pose2d.cpp:81-84
     odom_ = odometry;
-    for (uint32_t i = 0; i < P_; ++i) draw_from_motion(odelta, pose_[i]);
     acc_trans_ += xy_norm(odelta);
     acc_rot_ += std::fabs(se2_rotation(odelta));
-    if (acc_trans_ <= opt_.trans_thresh && acc_rot_ <= opt_.rot_thresh) return false;
+    const bool moved = !(acc_trans_ <= opt_.trans_thresh && acc_rot_ <= opt_.rot_thresh);   // the gate does not depend on the samples
+    // Every rank draws the noise of ALL particles, so that the random streams stay identical.  On a scan that will be matched the predicted poses of
+    // the other ranks' particles are never read (absorb_results replaces them with the gathered match results): for those only the generator is
+    // advanced (rng_skip.h) -- 1.8 k of 2 k particles at 8 ranks.  A gated scan keeps the predictions, so there every pose is computed.
+    for (uint32_t i = 0; i < P_; ++i) {
+        if (moved && ((int)i < lo_ || (int)i >= hi_)) {
+            rng_skip_normal(gen_);
+            rng_skip_normal(gen_);
+            rng_skip_normal(gen_);
+        } else {
+            draw_from_motion(odelta, pose_[i]);
+        }
+    }
+    if (!moved) return false;
     acc_trans_ = 0;
     acc_rot_   = 0;
     return true;
