@@ -3,7 +3,8 @@
 
 A "step" is one PFSlam2D::update() of one synthetic 1080-beam scan (predict -> scan matching of every particle ->
 normalise / resample -> ray-cast + distance-map update of every particle).  Synthetic data, fp64 arithmetic over
-packed u32 map cells.  N GPUs: particles shard over ranks (the SAME 256-particle filter is split, so `scaling` is "strong").
+packed u32 map cells.  N GPUs: particles shard over ranks (the SAME 256-particle filter is split, so `scaling` is "strong"); a multi-GPU line also carries
+`weak_scaling`: the same scans with 256 particles PER GPU (P = 256 x N), which is what the partitioning is for (skip with --no-weak).
 
   python bench.py --gpus 1 --steps K --warmup W            # this framework
   python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference on the host cores
