@@ -377,13 +377,14 @@ def gpu_arm(args):
 
     # ---- pass 3: per-kernel CUDA-event durations for the roofline (timing mode adds event records and host syncs) ------------
     roofline, kernel_ms = None, None
-    if world == 1:
-        r3 = timed_pass(ds, first, steps, staged=True, timing=True)
+    if world == 1 or args.sharded_impl == "native":
+        # N > 1: the sharded step records its kernel events without host synchronisation (Engine::step_enqueue); the figures are RANK 0's shard
+        r3 = timed_pass(ds, first, steps, staged=(world == 1), timing=True)
         d, tm = r3["work"], r3["kernel_ms"]
         peak, peak_kind = load_peaks()
         # algorithmic bytes: match E*N*(4 cells x 2 B); ray C*(4 B read + 4 B write); brushfire W*(5x8 B read + 4x8 B write);
-        # copy D * 2 * 1024 * 12 B
-        by = {"k_match": d["evals"] * BEAMS * 8.0 / steps, "k_raycast": d["ray_cells"] * 8.0 / steps, "k_brushfire": d["dm_pops"] * 72.0 / steps}
+        # copy D * 2 * 1024 * 12 B.  On a sharded handle the evaluations are counted over all ranks (they travel with the all-gather), cells and pops locally.
+        by = {"k_match": d["evals"] / world * BEAMS * 8.0 / steps, "k_raycast": d["ray_cells"] * 8.0 / steps, "k_brushfire": d["dm_pops"] * 72.0 / steps}
         t = {"k_match": tm["match_ms"], "k_raycast": tm["raycast_ms"], "k_brushfire": tm["brushfire_ms"]}
         kernel_ms = dict(t)
         kernel_ms["map_device"] = tm["raycast_ms"] + tm["brushfire_ms"]
@@ -391,7 +392,7 @@ def gpu_arm(args):
         ach = by[dom] / (t[dom] * 1e-3) / 1e9 if t[dom] > 0 else 0.0
         traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of that kernel (per launch)
         for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
-            if name.endswith("ncu_traffic.json"):
+            if world == 1 and name.endswith("ncu_traffic.json"):
                 with open(os.path.join(ROOT, "profiles", name)) as f:
                     tj = json.load(f)
                 if dom in tj:
@@ -402,6 +403,8 @@ def gpu_arm(args):
                     "all_kernels": {kk: {"GBps": (by[kk] / (t[kk] * 1e-3) / 1e9 if t[kk] > 0 else 0.0), "ms_per_step": t[kk], "bytes_per_step": by[kk],
                                          "frac": (by[kk] / (t[kk] * 1e-3) / 1e9 / peak if t[kk] > 0 else 0.0)} for kk in t},
                     "bytes_copy_per_step": d["detached"] * 2 * 1024 * 12.0 / steps}
+        if world > 1:
+            roofline["scope"] = "rank 0's shard: %d of %d particles (no ncu capture of a sharded run: traffic null)" % (PARTICLES // world, PARTICLES)
         del r3
 
     # ---- CPU baseline + parity (rank 0, N = 1 only): the same scans on the host cores, then GPU vs CPU state --------------------

@@ -47,6 +47,10 @@ struct Engine::Impl {
     bool scan_flat = false;     // the current scan has z == 0 everywhere and a sensor that keeps z planes: every beam is planar
     bool staged_flat = false;   // the same for the staged scans
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // timing of the pipelined step (step_enqueue): per report buffer {before match, after match, after the ray stage, after the brushfire}; read when
+    // that step is collected, so no host synchronisation is added
+    cudaEvent_t evp[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    bool evp_used[2] = {false, false};
     // scratch for import/export/distance
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -160,6 +164,8 @@ Engine* Engine::create(const EngineConfig& cfg, std::string& err)
     CU_NEW(cudaEventCreate(&d->ev[0]));
     CU_NEW(cudaEventCreate(&d->ev[1]));
     CU_NEW(cudaEventCreate(&d->ev[2]));
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 4; ++k) CU_NEW(cudaEventCreate(&d->evp[b][k]));
 
     // directory window centred on (center_x, center_y)
     const uint32_t cx = w2m(cfg.center_x, scale), cy = w2m(cfg.center_y, scale);
@@ -281,6 +287,9 @@ Engine::~Engine()
     if (d_->h_status) cudaFreeHost(d_->h_status);
     if (d_->d_scratch) cudaFree(d_->d_scratch);
     if (d_->d_staged) cudaFree(d_->d_staged);
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 4; ++k)
+            if (d_->evp[b][k]) cudaEventDestroy(d_->evp[b][k]);
     if (d_->ev[0]) cudaEventDestroy(d_->ev[0]);
     if (d_->ev[1]) cudaEventDestroy(d_->ev[1]);
     if (d_->ev[2]) cudaEventDestroy(d_->ev[2]);
@@ -565,7 +574,10 @@ int Engine::step_enqueue(const double* pts, int n, const double origin[3], const
     mp.particle_offset = 0;
     mp.shared_map = 0;
     mp.mode = 0;
+    const int tbuf = 1 - pending_buf_;   // the report buffer enqueue_report() will hand to this step
+    if (timing_) CU_TRY(cudaEventRecord(d_->evp[tbuf][0], d_->stream));
     launch_match(d_->view, mp, d_->d_states, d_->d_results, count, d_->stream);
+    if (timing_) CU_TRY(cudaEventRecord(d_->evp[tbuf][1], d_->stream));
     CU_TRY(cudaMemcpyAsync(d_->h_results, d_->d_results, (size_t)count * sizeof(MatchResult), cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaEventRecord(d_->ev_match, d_->stream));
     // map update on the matched poses, read from the match results on the device
@@ -584,7 +596,12 @@ int Engine::step_enqueue(const double* pts, int n, const double origin[3], const
     bp.event_cap = rp.event_cap;
     bp.debug = brush_debug_flag();
     const int ray_kernels = launch_ray_stage(d_, rp, reinterpret_cast<const SE2*>(d_->d_results), count);
+    if (timing_) CU_TRY(cudaEventRecord(d_->evp[tbuf][2], d_->stream));
     launch_brushfire(d_->view, bp, d_->d_events, d_->d_stats, count, d_->stream);
+    if (timing_) {
+        CU_TRY(cudaEventRecord(d_->evp[tbuf][3], d_->stream));
+        d_->evp_used[tbuf] = true;
+    }
     launch_merge_free(d_->view, d_->stream);
     CU_TRY(cudaGetLastError());
     { int rc = enqueue_report(count); if (rc != LAMA_OK) return rc; }
@@ -648,7 +665,16 @@ int Engine::settle(HostMapStats* out, bool already_complete)
     pending_maps_ = 0;
     CU_TRY(cudaSetDevice(cfg_.device));
     if (!already_complete) CU_TRY(cudaStreamSynchronize(d_->stream));
-    if (timing_ && !already_complete) {
+    if (timing_ && d_->evp_used[pending_buf_]) {   // a pipelined step: its four events have completed (the stream is past them, or was just synchronised)
+        float m = 0, a = 0, b = 0;
+        cudaEventElapsedTime(&m, d_->evp[pending_buf_][0], d_->evp[pending_buf_][1]);
+        cudaEventElapsedTime(&a, d_->evp[pending_buf_][1], d_->evp[pending_buf_][2]);
+        cudaEventElapsedTime(&b, d_->evp[pending_buf_][2], d_->evp[pending_buf_][3]);
+        times_.match_ms += m;
+        times_.raycast_ms += a;
+        times_.brushfire_ms += b;
+        d_->evp_used[pending_buf_] = false;
+    } else if (timing_ && !already_complete) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, d_->ev[0], d_->ev[1]);
         cudaEventElapsedTime(&b, d_->ev[1], d_->ev[2]);
