@@ -333,8 +333,8 @@ struct RayCtx {
 #endif
             asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(hit ? kOccHitInc : run * kOccMissInc) : "memory");
         }
+        if (info >= (kCandNone << 24)) return;   // no candidate cell in this patch (the common case): one compare on the whole word
         const uint32_t ccand = info >> 24;
-        if (ccand == kCandNone) return;
         const uint32_t ci = off >> 2;
         if (hit || ccand == kCandOverflow || ((cand[ccand * 32 + (ci >> 5)] >> (ci & 31)) & 1u)) {
             const uint32_t idx = atomicAdd(&sh.log_count, 1u);
@@ -403,17 +403,23 @@ __device__ __forceinline__ void raycast_pass(RayCtx<kProb>& c, const BeamEnds* b
             }
         } else {
             // software pipeline: the patch-info word of the NEXT cell is fetched from shared memory before the current cell is
-            // processed, so the load latency overlaps the address arithmetic and the reduction of the current cell (the kernel is
-            // latency bound: 31 % of its stall samples were waits for this load)
-            bool v = w.next();
-            uint32_t P = w.P, pos = (uint32_t)w.i, di = c.dir_of_cell(P);
-            uint32_t info = c.pinfo[di];
-            while (v) {
-                const bool vn = w.next();                     // w.P stays on the last cell when the segment is finished
-                const uint32_t Pn = w.P, din = c.dir_of_cell(Pn);
-                const uint32_t infon = c.pinfo[din];
-                c.cell(P, info, di, (uint32_t)b, pos, false, 1u);
-                P = Pn; di = din; info = infon; pos = (uint32_t)w.i; v = vn;
+            // processed, so the load latency overlaps the address arithmetic and the reduction of the current cell.  The lane counts
+            // its steps itself (no end test inside the walk); the step taken past the last cell of the segment lands on a cell of the
+            // same beam (at most its end cell), so its directory index is valid and its patch-info word is simply not used.
+            int rem = w.iend - w.i;
+            if (rem > 0) {
+                w.step();
+                uint32_t P = w.P, di = c.dir_of_cell(P);
+                uint32_t info = c.pinfo[di];
+                for (;;) {
+                    const uint32_t pos = (uint32_t)w.i;
+                    w.step();
+                    const uint32_t Pn = w.P, din = c.dir_of_cell(Pn);
+                    const uint32_t infon = c.pinfo[din];
+                    c.cell(P, info, di, (uint32_t)b, pos, false, 1u);
+                    if (--rem == 0) break;
+                    P = Pn; di = din; info = infon;
+                }
             }
         }
     }

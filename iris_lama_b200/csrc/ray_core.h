@@ -133,13 +133,14 @@ LAMA_HD uint32_t packed_cell_offset(uint32_t P) { return ((P << 2) & 0x7Cu) | ((
 // ---- the planar walk of the ray-cast kernel ---------------------------------------------------------------------------
 // Map::computeRay (map.cpp:198-227) for a planar beam (from.z == to.z: the z axis never moves), started at any step.  The major axis (delta == n) moves on every step: its
 // error term returns to 0 each time (err += n; 2 err >= n; err -= n), so only the minor axis carries state:
-//   e += d;  if (2 e >= n) { minor coordinate moves; e -= n; }          [2 e >= n  <=>  e >= (n + 1) >> 1]
+//   e += d;  if (2 e >= n) { minor coordinate moves; e -= n; }          [kept as e2 = 2 e - n: a sign test]
 // (dx == dy: both axes move on every step, which the same update yields with d == n.)
 // The cell is kept PACKED, P = yr << 16 | xr (window-relative coordinates, each < 2^13): a step is one addition of a packed
 // step vector (sy * 65536 + sx as a signed number; no borrow crosses the halves because all cells of a beam lie inside the
 // bounding box of its end cells, which is inside the window), and P is also the key of the ordered-path log.
 struct SegWalk {
-    int e, d, n, half, i, iend;
+    // the minor-axis state is kept as e2 = 2 e - n, so that the reference's test 2 e >= n is a sign test: e2 += 2 d; if (e2 >= 0) { move; e2 -= 2 n; }
+    int e2, d2, n2, i, iend;
     int M, N;            // packed major / minor step vectors
     uint32_t P;
     LAMA_HD void init(uint32_t fx, uint32_t fy, uint32_t tx, uint32_t ty, int i0, int steps)
@@ -148,28 +149,33 @@ struct SegWalk {
         const int sx = ddx < 0 ? -1 : 1, sy = ddy < 0 ? -1 : 1;
         const int dx = ddx < 0 ? -ddx : ddx, dy = ddy < 0 ? -ddy : ddy;
         const bool xmajor = dx >= dy;
-        n = xmajor ? dx : dy;
-        d = xmajor ? dy : dx;
+        const int n = xmajor ? dx : dy, d = xmajor ? dy : dx;
         M = xmajor ? sx : sy * 65536;
         N = xmajor ? sy * 65536 : sx;
-        half = (n + 1) >> 1;
+        d2   = 2 * d;
+        n2   = 2 * n;
         i    = i0;
         iend = i0 + steps < n - 1 ? i0 + steps : n - 1;
         uint32_t k = 0;
-        e = 0;
+        int e = 0;
         if (i0 != 0 && n != 0) {  // closed form of the state after i0 steps
             k = (2u * (uint32_t)i0 * (uint32_t)d + (uint32_t)n) / (2u * (uint32_t)n);
             e = i0 * d - (int)k * n;
         }
-        P = (fx | (fy << 16)) + (uint32_t)(M * i0 + N * (int)k);
+        e2 = 2 * e - n;
+        P  = (fx | (fy << 16)) + (uint32_t)(M * i0 + N * (int)k);
+    }
+    LAMA_HD void step()   // one step without the end test: callers that count the steps themselves (iend - i of them)
+    {
+        ++i;
+        e2 += d2;
+        P += (uint32_t)M;
+        if (e2 >= 0) { P += (uint32_t)N; e2 -= n2; }
     }
     LAMA_HD bool next()
     {
         if (i >= iend) return false;
-        ++i;
-        e += d;
-        P += (uint32_t)M;
-        if (e >= half) { P += (uint32_t)N; e -= n; }
+        step();
         return true;
     }
 };
