@@ -63,7 +63,77 @@ LAMA_HD void accumulate(double s[kNumSums], const BeamEval& e, int robust_kind, 
 
 // Solve A h = b, A symmetric 3x3 given by its upper triangle {A00,A01,A02,A11,A12,A22}, with an
 // LDL^T that pivots on the largest remaining diagonal entry (Eigen::LDLT's strategy).
+//
+// Written with compile-time indices only: the pivot is applied by swapping NAMED scalars inside `if (piv == ...)`, the permutation is applied with
+// selects, so that on the device every value lives in a register.  (The first version indexed M[piv][j] and b[perm[i]] at run time, which put the
+// matrices into local memory: in k_match the one warp that solves -- while 16 others wait at the barrier -- then chased local-memory loads
+// that missed the L1 half of the time.)  The floating-point operations and their order are those of ldlt_solve3_indexed below, which stays as
+// the executable specification: tests/emu compares the two bit for bit.
+LAMA_HD void ldlt_swap(double& x, double& y) { const double t = x; x = y; y = t; }
 LAMA_HD void ldlt_solve3(const double a[6], const double b[3], double h[3])
+{
+    // the full matrix: both triangles are carried, because the trailing update computes M[i][j] and M[j][i] with different operand orders and a later
+    // pivot swap can move an upper element into the lower triangle
+    double m00 = a[0], m01 = a[1], m02 = a[2], m10 = a[1], m11 = a[3], m12 = a[4], m20 = a[2], m21 = a[4], m22 = a[5];
+    int p0 = 0, p1 = 1, p2 = 2;
+    // ---- k = 0 ----
+    {
+        int piv = 0;
+        double best = fabs(m00);
+        if (fabs(m11) > best) { best = fabs(m11); piv = 1; }
+        if (fabs(m22) > best) { best = fabs(m22); piv = 2; }
+        if (piv == 1) {          // rows 0 <-> 1, then columns 0 <-> 1
+            const int t = p0; p0 = p1; p1 = t;
+            ldlt_swap(m00, m10); ldlt_swap(m01, m11); ldlt_swap(m02, m12);
+            ldlt_swap(m00, m01); ldlt_swap(m10, m11); ldlt_swap(m20, m21);
+        } else if (piv == 2) {   // rows 0 <-> 2, then columns 0 <-> 2
+            const int t = p0; p0 = p2; p2 = t;
+            ldlt_swap(m00, m20); ldlt_swap(m01, m21); ldlt_swap(m02, m22);
+            ldlt_swap(m00, m02); ldlt_swap(m10, m12); ldlt_swap(m20, m22);
+        }
+    }
+    const double d0 = m00;
+    double l10 = (d0 != 0.0) ? m10 / d0 : 0.0;
+    double l20 = (d0 != 0.0) ? m20 / d0 : 0.0;
+    m11 -= l10 * d0 * l10; m12 -= l10 * d0 * l20;
+    m21 -= l20 * d0 * l10; m22 -= l20 * d0 * l20;
+    // ---- k = 1 ----
+    {
+        if (fabs(m22) > fabs(m11)) {   // rows 1 <-> 2, columns 1 <-> 2, and the finished column of L
+            const int t = p1; p1 = p2; p2 = t;
+            ldlt_swap(m10, m20); ldlt_swap(m11, m21); ldlt_swap(m12, m22);
+            ldlt_swap(m01, m02); ldlt_swap(m11, m12); ldlt_swap(m21, m22);
+            ldlt_swap(l10, l20);
+        }
+    }
+    const double d1 = m11;
+    const double l21 = (d1 != 0.0) ? m21 / d1 : 0.0;
+    m22 -= l21 * d1 * l21;
+    // ---- k = 2 ----
+    const double d2 = m22;
+    // forward substitution on the permuted right-hand side, diagonal scaling, back substitution
+    double y0 = p0 == 0 ? b[0] : (p0 == 1 ? b[1] : b[2]);
+    double y1 = p1 == 0 ? b[0] : (p1 == 1 ? b[1] : b[2]);
+    double y2 = p2 == 0 ? b[0] : (p2 == 1 ? b[1] : b[2]);
+    y1 -= l10 * y0;
+    y2 -= l20 * y0;
+    y2 -= l21 * y1;
+    y0 = (d0 != 0.0) ? y0 / d0 : 0.0;
+    y1 = (d1 != 0.0) ? y1 / d1 : 0.0;
+    y2 = (d2 != 0.0) ? y2 / d2 : 0.0;
+    const double z2 = y2;
+    double z1 = y1;
+    z1 -= l21 * z2;
+    double z0 = y0;
+    z0 -= l10 * z1;
+    z0 -= l20 * z2;
+    h[0] = p0 == 0 ? z0 : (p1 == 0 ? z1 : z2);
+    h[1] = p0 == 1 ? z0 : (p1 == 1 ? z1 : z2);
+    h[2] = p0 == 2 ? z0 : (p1 == 2 ? z1 : z2);
+}
+
+// the same with run-time indices (the original formulation): executable specification of ldlt_solve3, used by the host tests only
+LAMA_HD void ldlt_solve3_indexed(const double a[6], const double b[3], double h[3])
 {
     double M[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
     int perm[3] = {0, 1, 2};

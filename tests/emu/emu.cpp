@@ -431,6 +431,39 @@ int emu_segwalk_check(int r, uint32_t seed, int count, int side, int seg)
     return bad;
 }
 
+// ldlt_solve3 (named scalars, compile-time indices: what k_match runs) against ldlt_solve3_indexed (the original run-time indexed formulation): the same
+// bits for random symmetric matrices of every kind the solver can meet -- positive definite, indefinite, rank deficient, equal diagonal entries (pivot ties),
+// zeros.  Returns the number of systems whose three solution components are not bit-identical.
+int emu_ldlt_check(uint32_t seed, int count)
+{
+    std::mt19937_64 g(seed);
+    std::uniform_real_distribution<double> u(-1.0, 1.0);
+    int bad = 0;
+    for (int c = 0; c < count; ++c) {
+        double a[6], b[3], h1[3], h2[3];
+        const int kind = c % 8;
+        double J[3][3];
+        for (auto& r : J) for (double& v : r) v = u(g) * (kind == 1 ? 1e3 : 1.0);
+        if (kind <= 2) {            // J^T J: positive semi-definite like the normal equations
+            if (kind == 2) for (int j = 0; j < 3; ++j) J[2][j] = J[0][j] + J[1][j];   // rank 2
+            int q = 0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = i; j < 3; ++j) { double v = 0; for (int k = 0; k < 3; ++k) v += J[k][i] * J[k][j]; a[q++] = v; }
+        } else {
+            for (double& v : a) v = u(g);
+            if (kind == 4) a[3] = a[0];                    // pivot ties on the diagonal
+            if (kind == 5) { a[3] = a[0]; a[5] = a[0]; }
+            if (kind == 6) { a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; }   // a zero row / column
+            if (kind == 7) for (double& v : a) v = 0.0;    // everything zero
+        }
+        for (double& v : b) v = u(g);
+        lama_b200::ldlt_solve3(a, b, h1);
+        lama_b200::ldlt_solve3_indexed(a, b, h2);
+        if (std::memcmp(h1, h2, sizeof(h1)) != 0) ++bad;
+    }
+    return bad;
+}
+
 // ray_pull.h against the iterative walk: random beam sets from one origin inside a window of dim x dim patches.
 //   mode 0: scan-like fan (even angles, noisy ranges)   1: random end cells   2: short beams (n = 0, 1, 2, ...)   3: axes / diagonals
 // Checks (a) the marked patches cover every touched cell, (b) the chained counts of every cell of every marked patch, (c) for

@@ -74,6 +74,11 @@ def test_packed_cell_addressing(emu):
         assert emu.emu_packed_cell_check(C.c_int(log2dim)) == 0
 
 
+def test_register_only_ldlt_equals_the_indexed_formulation(emu):
+    """match_core.h ldlt_solve3 (what k_match runs: no run-time indices, so no local memory on the device) == ldlt_solve3_indexed, bit for bit"""
+    assert emu.emu_ldlt_check(C.c_uint32(3), C.c_int(400000)) == 0
+
+
 def test_se2_host_math_equals_oracle_bitwise(emu, po):
     rng = np.random.default_rng(0)
     out = np.zeros(4)
