@@ -43,7 +43,8 @@ struct Engine::Impl {
     RayParams ray{};
     BrushParams brush{};
     int n_sms = 148;
-    int pull_max_particles = 48;
+    int pull_max_particles = 0;   // the pull form of the ray cast is used up to this many particles per device; 0 = never (since the walk's inner loop was
+                                  // slimmed it wins at every count: profiles/r02_pull_vs_walk_after_exp13.txt); LAMA_PULL_MAX_PARTICLES overrides
     bool scan_flat = false;     // the current scan has z == 0 everywhere and a sensor that keeps z planes: every beam is planar
     bool staged_flat = false;   // the same for the staged scans
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};

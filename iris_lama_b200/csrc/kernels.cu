@@ -1140,8 +1140,12 @@ static __device__ __noinline__ bool pull_replay_patch(const StoreView& s, const 
     return newhot;
 }
 
+#ifndef LAMA_PULL_MIN_CTAS
+#define LAMA_PULL_MIN_CTAS 4
+#endif
+constexpr int kPullCtasPerSm = LAMA_PULL_MIN_CTAS;   // resident CTAs per SM the register budget is sized for (4: 64 registers, 2: 128)
 template <bool kProb>
-__global__ void __launch_bounds__(kPullWarps * 32, 4)
+__global__ void __launch_bounds__(kPullWarps * 32, kPullCtasPerSm)
 k_ray_pull(StoreView s, RayParams rp, int count, uint64_t* __restrict__ events_out, MapUpdateStats* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1761,7 +1765,7 @@ void launch_raycast_pull(const StoreView& s, const RayParams& rp_in, const SE2* 
     rp.pull.splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
     k_ray_setup<<<count, kSetupThreads, ray_setup_smem_bytes(s.window.dim, rp.scan.n_beams), st>>>(s, rp, d_states, d_stats);
     const int units = count * rp.pull.splits;
-    const int grid = units < n_sms * 4 ? units : n_sms * 4;   // persistent: up to four CTAs of eight warps per SM
+    const int grid = units < n_sms * kPullCtasPerSm ? units : n_sms * kPullCtasPerSm;   // persistent: every CTA of eight warps resident
     const size_t smem = ray_pull_smem_bytes(rp.scan.n_beams);
     if (rp.prob_mode) k_ray_pull<true><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
     else k_ray_pull<false><<<grid, kPullWarps * 32, smem, st>>>(s, rp, count, d_events, d_stats);
