@@ -375,6 +375,16 @@ def gpu_arm(args):
                 "note": "P = 256 x N: per-GPU work fixed; efficiency = scans_per_s here / the N = 1 line's value (256 particles on one GPU)"}
         del rw
 
+    # ---- N > 1: a window with resampling scans, i.e. with map migration between ranks (the measurement gain is lowered like in the N = 1 regime) --------
+    shard_resample = None
+    if world > 1 and not args.no_weak and args.sharded_impl == "native":
+        kf, pf_first = 80, 60
+        rs = timed_pass(ds, pf_first, kf, staged=False, meas_sigma_gain=FORCED_GAIN)
+        st = rs["pf"].shardStats()
+        shard_resample = {"scans_per_s": kf / rs["dt"], "first_scan": pf_first, "steps": kf, **step_stats(rs["per_step"]), "meas_sigma_gain": FORCED_GAIN,
+                          "resamples": rs["work"]["resampled"], "shard_stats_rank0": st}
+        del rs
+
     # ---- pass 3: per-kernel CUDA-event durations for the roofline (timing mode adds event records and host syncs) ------------
     roofline, kernel_ms = None, None
     if world == 1 or args.sharded_impl == "native":
@@ -479,6 +489,8 @@ def gpu_arm(args):
         line["particle_scans_per_s"] = PARTICLES * value
         if weak:
             line["weak_scaling"] = weak
+        if shard_resample:
+            line["regimes"] = {"resample_forced": shard_resample}
         if roofline:
             line["roofline"] = roofline
             line["kernel_ms_per_step"] = kernel_ms
