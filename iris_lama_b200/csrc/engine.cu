@@ -55,7 +55,10 @@ struct Engine::Impl {
     // scratch for import/export/distance
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    std::vector<void*> mig_blocks;   // device arena of one migration round (pack_device / migration_alloc)
+    // device arena of a migration round (pack_device / migration_alloc): bump allocation out of chunks that are kept between rounds, so that a resampling
+    // scan costs no cudaMalloc / cudaFree once the arena has grown to its working size
+    std::vector<std::pair<char*, size_t>> mig_chunks;
+    size_t mig_chunk = 0, mig_off = 0;
     std::vector<void*> allocs;
 };
 
@@ -283,7 +286,7 @@ Engine::~Engine()
     if (d_->h_scan) cudaFreeHost(d_->h_scan);
     if (d_->ev_match) cudaEventDestroy(d_->ev_match);
     if (d_->ev_sync) cudaEventDestroy(d_->ev_sync);
-    for (void* p : d_->mig_blocks) cudaFree(p);
+    for (auto& c : d_->mig_chunks) cudaFree(c.first);
     if (d_->h_idx) cudaFreeHost(d_->h_idx);
     if (d_->h_status) cudaFreeHost(d_->h_status);
     if (d_->d_scratch) cudaFree(d_->d_scratch);
@@ -923,18 +926,28 @@ int Engine::pack_size(int particle, size_t* bytes)
 int Engine::migration_alloc(size_t bytes, void** dptr)
 {
     CU_TRY(cudaSetDevice(cfg_.device));
-    void* p = nullptr;
-    CU_TRY(cudaMalloc(&p, bytes ? bytes : 16));
-    d_->mig_blocks.push_back(p);
-    *dptr = p;
+    const size_t need = ((bytes ? bytes : 16) + 255) & ~(size_t)255;
+    while (d_->mig_chunk < d_->mig_chunks.size() && d_->mig_off + need > d_->mig_chunks[d_->mig_chunk].second) {
+        ++d_->mig_chunk;
+        d_->mig_off = 0;
+    }
+    if (d_->mig_chunk == d_->mig_chunks.size()) {
+        const size_t chunk = std::max(need, (size_t)64 << 20);
+        void* p = nullptr;
+        CU_TRY(cudaMalloc(&p, chunk));
+        d_->mig_chunks.push_back({(char*)p, chunk});
+        d_->mig_off = 0;
+    }
+    *dptr = d_->mig_chunks[d_->mig_chunk].first + d_->mig_off;
+    d_->mig_off += need;
     return LAMA_OK;
 }
 void Engine::migration_reset()
 {
     cudaSetDevice(cfg_.device);
-    cudaStreamSynchronize(d_->stream);
-    for (void* p : d_->mig_blocks) cudaFree(p);
-    d_->mig_blocks.clear();
+    cudaStreamSynchronize(d_->stream);   // nothing enqueued on the engine's stream reads the arena any more
+    d_->mig_chunk = 0;
+    d_->mig_off   = 0;
 }
 
 // the directory indices at the head of a blob, padded so that the patches behind them stay 16-byte aligned (they are copied as uint4)
@@ -973,14 +986,13 @@ int Engine::pack_device(int particle, DeviceBlob* out)
         CU_TRY(cudaMemcpyAsync(base, entries.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
         CU_TRY(cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, d_->stream));
         launch_gather_patches(d_->view, d_slots, (int)n, d_out, d_fb, d_->stream);
-        CU_TRY(cudaGetLastError());
-        CU_TRY(cudaStreamSynchronize(d_->stream));   // `entries` / `slots` are host temporaries
+        CU_TRY(cudaGetLastError());   // no synchronisation: `entries` / `slots` are pageable, the runtime has staged them when cudaMemcpyAsync returns
         times_.misc_launches += 1;
     }
     return LAMA_OK;
 }
 
-int Engine::unpack_device(int particle, const DeviceBlob& blob)
+int Engine::unpack_device(int particle, const DeviceBlob& blob, bool check)
 {
     { int rc_settle = settle(nullptr); if (rc_settle != LAMA_OK) return rc_settle; }
     const size_t n = (size_t)blob.n_occ + blob.n_dm, ne = blob_entry_bytes(n);
@@ -999,6 +1011,7 @@ int Engine::unpack_device(int particle, const DeviceBlob& blob)
         times_.misc_launches += 2;
     }
     CU_TRY(cudaGetLastError());
+    if (!check) return LAMA_OK;   // the caller unpacks several blobs and checks the device status after the last one
     CU_TRY(cudaMemcpyAsync(d_->h_status, d_->view.status, 4, cudaMemcpyDeviceToHost, d_->stream));
     CU_TRY(cudaStreamSynchronize(d_->stream));
     return check_device_status();

@@ -109,7 +109,7 @@ public:
     struct DeviceBlob { void* dptr = nullptr; size_t bytes = 0; uint32_t n_occ = 0, n_dm = 0; };
     int pack_device(int particle, DeviceBlob* out);
     int migration_alloc(size_t bytes, void** dptr);           // receive buffer in the same arena
-    int unpack_device(int particle, const DeviceBlob& blob);
+    int unpack_device(int particle, const DeviceBlob& blob, bool check = true);   // check = false: no status read-back / synchronisation (the last call of a batch checks)
     void migration_reset();
     int pack_size(int particle, size_t* bytes);
     int pack(int particle, void* buf, size_t cap, size_t* used);

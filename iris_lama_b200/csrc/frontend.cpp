@@ -530,6 +530,8 @@ int PFSlam2D::migrate_and_apply(const std::vector<int32_t>& idx)
         mine[(size_t)k * 3] = (int64_t)blob[(size_t)k].bytes; mine[(size_t)k * 3 + 1] = blob[(size_t)k].n_occ; mine[(size_t)k * 3 + 2] = blob[(size_t)k].n_dm;
     }
     cudaStream_t cs = (cudaStream_t)shard_stream(comm_);
+    // the gather kernels of the packs run on the engine's stream; everything the communicator's stream does from here on (the sends) comes after them
+    if (eng_->wait_for_stream(cs) != LAMA_OK) return engine_fail(LAMA_ERR_CUDA);
     std::memcpy(h_tab_, mine.data(), mine.size() * 8);
     int64_t* d_all = d_tab_ + (size_t)P_ * 3;
     int64_t* h_all = h_tab_ + (size_t)P_ * 3;
@@ -556,7 +558,7 @@ int PFSlam2D::migrate_and_apply(const std::vector<int32_t>& idx)
     if (!sends.empty() || !recvs.empty()) ++shard_collectives_;
     std::vector<int32_t> local_src((size_t)per);
     for (size_t k = 0; k < in.size(); ++k) {
-        int rc = eng_->unpack_device(per + (int)k, in[k]);   // staging slots behind the local particles
+        int rc = eng_->unpack_device(per + (int)k, in[k], k + 1 == in.size());   // staging slots behind the local particles; one status check for all
         if (rc != LAMA_OK) return engine_fail(rc);
     }
     for (int k = 0; k < per; ++k) {
