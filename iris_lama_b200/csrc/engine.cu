@@ -78,9 +78,10 @@ static bool points_flat(const double* pts, size_t n)
 static int launch_ray_stage(Engine::Impl* d, RayParams rp, const SE2* states, int count)   // returns the number of kernels launched
 {
     const ScanParams& sp = rp.scan;
-    // Which form is faster depends on how many particles this device holds: the walk runs one CTA per particle (0.31 ms at 256
-    // particles, but still 0.19 ms at 32: most SMs idle), the pull form spreads the patches of all particles over every SM (0.47 ms
-    // at 256, 0.17 ms at 32).  LAMA_PULL_MAX_PARTICLES overrides the crossover (0 = never pull; read when the engine is created).
+    // The walk runs one CTA per particle, the pull form spreads the patches of all particles over every SM.  Measured at the end of round 2
+    // (profiles/r02_pull_vs_walk_after_exp13.txt): walk 0.161 / 0.162 / 0.190 / 0.309 ms, pull 0.177 / 0.227 / 0.317 / 0.487 ms at 32 / 64 / 128 / 256
+    // particles -- the walk everywhere, so pull_max_particles defaults to 0; LAMA_PULL_MAX_PARTICLES (read when the engine is created) selects the pull
+    // form up to that many particles per device.
     const bool no_pull = count > d->pull_max_particles;
     const bool flat = d->scan_flat && sp.moving.l[6] == 0.0 && sp.moving.l[7] == 0.0;
     rp.pull_fallback = 0;
