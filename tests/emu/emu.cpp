@@ -414,8 +414,25 @@ int emu_segwalk_check(int r, uint32_t seed, int count, int side, int seg)
         for (int s0 = 0; s0 == 0 || s0 < n - 1; s0 += seg) {
             SegWalk w;
             w.init(fx, fy, tx, ty, s0, seg);
-            while (w.next()) {
-                ok = ok && ref.next() && w.i == ++i && (w.P & 0xFFFFu) == ref.x && (w.P >> 16) == ref.y;
+            if (s0 == 0) {   // the first segment of a group is walked with next() (run merging)
+                while (w.next()) ok = ok && ref.next() && w.i == ++i && (w.P & 0xFFFFu) == ref.x && (w.P >> 16) == ref.y;
+            } else {         // the other segments with the kernel's counter-driven loop: one step ahead of the cell being processed, no end test in the walk
+                int rem = w.iend - w.i;
+                if (rem > 0) {
+                    w.step();
+                    uint32_t P = w.P;
+                    for (;;) {
+                        const int pos = w.i;
+                        w.step();   // may land one cell past the segment (at most the beam's end cell): never processed
+                        const uint32_t Pn = w.P;
+                        ok = ok && ref.next() && pos == ++i && (P & 0xFFFFu) == ref.x && (P >> 16) == ref.y;
+                        if (--rem == 0) break;
+                        P = Pn;
+                    }
+                    // the look-ahead cell stays inside the bounding box of the beam's end cells
+                    const uint32_t lx = w.P & 0xFFFFu, ly = w.P >> 16;
+                    ok = ok && lx >= (fx < tx ? fx : tx) && lx <= (fx < tx ? tx : fx) && ly >= (fy < ty ? fy : ty) && ly <= (fy < ty ? ty : fy);
+                }
             }
         }
         if (ref.next()) ok = false;   // the segments must cover every interior cell
