@@ -80,3 +80,25 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
                            "-llama_b200", f"-Wl,-rpath,{lib_dir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_null_arguments_are_refused_not_dereferenced(api):
+    """every getter added in round 2 answers a null handle / null output with LAMA_ERR_ARG and a message (no CUDA call is made on that path)"""
+    import ctypes as C
+    L = api.lib()
+    null = C.c_void_p(None)
+    buf = (C.c_uint64 * 4)()
+    n = C.c_int(0)
+    calls = [
+        (L.lama_pf_get_memory_usage, (null, buf)),
+        (L.lama_pf_get_timestamps, (null, None, C.c_int(0), C.byref(n))),
+        (L.lama_pf_get_summary, (null, None)),
+        (L.lama_pf_get_resample_digest, (null, buf)),
+        (L.lama_pf_shard_stats, (null, buf)),
+        (L.lama_pf_shard_connect, (null, None)),
+    ]
+    for fn, args in calls:
+        fn.restype = C.c_int
+        rc = fn(*args)
+        assert rc < 0, fn.__name__
+        assert len(L.lama_last_error()) > 0
